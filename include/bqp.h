@@ -1,0 +1,132 @@
+/*
+ * bqp.h -- C ABI of the B200 batched QP-relaxation engine (libbqp.so).
+ *
+ * This is the drop-in boundary for miOSQP's hot path: every entry point below
+ * replaces one call the reference makes on its `osqp` object
+ * (file:line under /root/reference/miosqp/):
+ *
+ *   bqp_setup             <- osqp.OSQP().setup(P,q,A,l,u,**qp_settings)     workspace.py:63-68
+ *   bqp_update_q          <- solver.update(q=q)                             solver.py:185
+ *   bqp_solve_batch       <- Node.solve(): update(l,u)+warm_start(x,y)+solve()+clip+objective
+ *                            for B nodes of one problem at once              node.py:96-143
+ *   bqp_solve_multi       <- the same for nodes of several set-up problems in ONE launch
+ *                            (frontier of many MIQP instances, BASELINE cfg 2)
+ *   BQP_* status codes    <- osqp.constant('OSQP_*')                        node.py:88,128-129
+ *   bqp_free              <- garbage collection of the osqp object
+ *
+ * Conventions: plain pointers and sizes, no torch/numpy types.  All vectors
+ * are FP64 HOST buffers owned by the caller (the engine copies in/out and
+ * never keeps a caller pointer); batch arrays are node-major ([B][m], [B][n]).
+ * Return value 0 = OK, negative = bqp_error.  Per-node solver outcomes use
+ * OSQP's integer status codes in status[].  A handle is not thread-safe.
+ * There is NO CPU fallback: setup and every solve call fail with BQP_E_CUDA
+ * when no sm_100 device is usable.
+ */
+#ifndef BQP_H
+#define BQP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bqp_instance *bqp_handle;
+
+typedef enum {
+  BQP_OK = 0,
+  BQP_E_ARG = -1,        /* null pointer / bad dimension / bad setting */
+  BQP_E_BOUNDS = -2,     /* l > u in some row (osqp raises ValueError) */
+  BQP_E_NONCONVEX = -3,  /* reduced KKT matrix not positive definite */
+  BQP_E_CUDA = -4,       /* CUDA runtime error or no usable device */
+  BQP_E_ALLOC = -5,      /* out of host or device memory */
+  BQP_E_UNSUPPORTED = -6 /* setting outside the parity contract (e.g. adaptive_rho) or problem too large for one CTA */
+} bqp_error;
+
+/* OSQP status codes written to status[] (osqp.constant values) */
+enum {
+  BQP_SOLVED = 1, BQP_SOLVED_INACCURATE = 2, BQP_PRIMAL_INFEASIBLE_INACCURATE = 3,
+  BQP_DUAL_INFEASIBLE_INACCURATE = 4, BQP_MAX_ITER_REACHED = -2, BQP_PRIMAL_INFEASIBLE = -3,
+  BQP_DUAL_INFEASIBLE = -4, BQP_NON_CVX = -7, BQP_UNSOLVED = -10
+};
+
+typedef struct {
+  double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  int max_iter;
+  int scaling;            /* Ruiz passes (osqp default 10) */
+  int check_termination;  /* residual test period (osqp default 25), >= 1 */
+  int eq_rho;             /* 1: type rho per row ONCE at setup (equality x1e3, free rows RHO_MIN) */
+  int device;             /* CUDA device ordinal */
+} bqp_settings;
+
+/* QP  min 1/2 x'Px + q'x  s.t. l <= Ax <= u ;  P upper-triangular CSC, A CSC (m x n).
+ * For miOSQP, A/l/u are the EXTENDED data of data.py:5-33: the last n_int rows of A are
+ * I[i_idx,:]; i_idx (variable index per integer row, in row order) drives the in-kernel
+ * clip of node.py:131-136.  n_int = 0 gives a plain batched QP solver. */
+typedef struct {
+  int n, m;
+  const int *Pp, *Pi; const double *Px;
+  const int *Ap, *Ai; const double *Ax;
+  const double *q, *l, *u;
+  int n_int; const int *i_idx;
+} bqp_problem;
+
+/* per-node results beyond x,y (arrays of length B; any pointer may be NULL) */
+typedef struct {
+  int *status;        /* OSQP status code                         node.py:111 */
+  int *iters;         /* ADMM iterations                          node.py:118 */
+  double *obj;        /* osqp info.obj_val                                    */
+  double *pri_res;    /* osqp info.pri_res                                    */
+  double *dua_res;    /* osqp info.dua_res                                    */
+  double *lower;      /* 1/2 x'Px+q'x at the clipped x (node.lower); NaN unless status in {1,-2}  node.py:128-143 */
+} bqp_node_out;
+
+/* device-side timing of the last call, CUDA events on the engine's stream (milliseconds) */
+typedef struct {
+  double h2d_ms, kernel_ms, d2h_ms;
+  long long h2d_bytes, d2h_bytes;
+  int launches, tiles, tile_nodes, threads;
+  long long smem_bytes;
+  long long node_iters;     /* sum over nodes of ADMM iterations executed until that node terminated */
+  long long tile_iters;     /* sum over tiles of iterations the tile ran (= max over its nodes) */
+  long long stream_bytes;   /* matrix/factor bytes the kernel streamed: sum over tiles of iterations x per-iteration panel bytes (+ checks) */
+} bqp_timing;
+
+void bqp_default_settings(bqp_settings *s);
+int bqp_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out);
+int bqp_update_q(bqp_handle h, const double *q);
+int bqp_solve_batch(bqp_handle h, int B, const double *l, const double *u, const double *x0, const double *y0,
+                    double *x, double *y, const bqp_node_out *out);
+/* node b belongs to handles[b]; l[b],u[b],y0[b],y[b] have handles[b]->m entries, x0[b],x[b] have n.
+ * All handles must live on the same device. */
+int bqp_solve_multi(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                    const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                    const bqp_node_out *out);
+/* staged variant (inputs stay resident in HBM between runs; used to time the kernel alone):
+ * upload = pack + H2D, run = all kernels from the resident inputs (blocking), download = D2H + unpack */
+int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                     const double *const *x0, const double *const *y0);
+int bqp_batch_run(void);
+int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *out);
+int bqp_last_timing(bqp_timing *t);
+int bqp_free(bqp_handle h);
+
+/* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
+int bqp_set_tuning(int tile_nodes, int threads);
+
+/* introspection (tests, roofline arithmetic) */
+int bqp_get_dims(bqp_handle h, int *n, int *m, int *npad, long long *factor_bytes, long long *check_bytes);
+int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c);
+int bqp_device_count(void);
+const char *bqp_strerror(int code);
+const char *bqp_version(void);
+
+/* HOST-ONLY debug hooks for the layout tests (tests/test_host_layout.py): they run the host half of
+ * bqp_setup (scaling, rho typing, factor, panel layouts) without touching a device and apply the
+ * streamed panels / blocked factor with plain loops.  They are NOT a solve path: no ADMM runs here. */
+int bqp_debug_host_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out);
+int bqp_debug_host_kkt_solve(bqp_handle h, double *rhs_xz /* [n+m], scaled space, in place */);
+int bqp_debug_host_matvec(bqp_handle h, int which /*0: A x, 1: A' y, 2: P x*/, const double *in, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

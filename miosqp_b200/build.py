@@ -1,0 +1,61 @@
+"""
+Builds libbqp.so (the C-ABI engine of include/bqp.h) IN-TREE with nvcc for sm_100a.
+
+    python -m miosqp_b200.build [--force]
+
+The shared object lands next to this file (miosqp_b200/libbqp.so); it is git-ignored but
+travels to the GPU box with the gpurun snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libbqp.so")
+SOURCES = ["bqp_setup.cpp", "bqp_kernels.cu", "bqp_api.cu"]
+HEADERS = ["bqp_internal.h", os.path.join("..", "..", "include", "bqp.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-Xptxas", "-v"]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for d in [os.path.join(CSRC, s) for s in SOURCES + HEADERS]:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _stale():
+    # content hash, not mtimes: the gpurun snapshot does not preserve timestamps
+    if not os.path.exists(OUT) or not os.path.exists(OUT + ".sha256"):
+        return True
+    with open(OUT + ".sha256") as f:
+        return f.read().strip() != _digest()
+
+
+def build(force=False, verbose=False):
+    """Compile when sources are newer than the library.  Raises on failure (no fallback)."""
+    if not force and not _stale():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libbqp.so (see %s)" % log)
+    with open(OUT + ".sha256", "w") as f:
+        f.write(_digest())
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(OUT)

@@ -1,0 +1,488 @@
+// bqp_api.cu -- the C ABI of include/bqp.h: device residency of set-up problems, frontier batching
+// (tile construction, pinned staging, H2D / launch / D2H on one stream, CUDA-event timing).
+// There is no CPU solve path in this library: without a usable CUDA device setup and solve fail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "bqp_internal.h"
+
+using namespace bqp;
+
+struct bqp_instance {
+  HostInstance h;
+  bool on_device = false;
+  int device = 0;
+  DevInstance d{};
+  std::vector<void *> allocs;
+  double *d_q = nullptr;
+};
+
+namespace {
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) {                       \
+      g_last_cuda = e_;                            \
+      return e_ == cudaErrorMemoryAllocation ? BQP_E_ALLOC : BQP_E_CUDA; \
+    }                                              \
+  } while (0)
+
+cudaError_t g_last_cuda = cudaSuccess;
+int g_tune_tt = 0, g_tune_threads = 0;
+
+template <class Tp>
+int upload(bqp_instance *inst, const std::vector<Tp> &v, const Tp **out) {
+  void *p = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(Tp);
+  CK(cudaMalloc(&p, bytes));
+  inst->allocs.push_back(p);
+  if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  *out = (const Tp *)p;
+  return BQP_OK;
+}
+
+int upload_mat(bqp_instance *inst, const HostMat &M, DevMat *D) {
+  D->rows = M.rows; D->cols = M.cols; D->nslices = M.nslices;
+  int rc;
+  if ((rc = upload(inst, M.sptr, &D->sptr))) return rc;
+  if ((rc = upload(inst, M.iptr, &D->iptr))) return rc;
+  if ((rc = upload(inst, M.vals, &D->vals))) return rc;
+  if ((rc = upload(inst, M.idx, &D->idx))) return rc;
+  return BQP_OK;
+}
+
+// grow-only buffers of the (single, process-wide) batch context
+struct Buf {
+  void *p = nullptr; size_t cap = 0; bool pinned = false;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BQP_OK;
+    release();
+    size_t want = std::max(bytes, cap * 2);
+    if (pinned) CK(cudaHostAlloc(&p, want, cudaHostAllocDefault)); else CK(cudaMalloc(&p, want));
+    cap = want;
+    return BQP_OK;
+  }
+  void release() {
+    if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+  }
+};
+
+struct BatchCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  Buf h_in{nullptr, 0, true}, h_out{nullptr, 0, true}, h_ns{nullptr, 0, true}, h_ti{nullptr, 0, true};
+  Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
+  // description of the resident batch
+  int B = 0, ntiles = 0, tt = 0, threads = 0;
+  size_t smem = 0, in_doubles = 0, out_doubles = 0;
+  std::vector<bqp_instance *> node_inst;
+  std::vector<long long> out_off;
+  std::vector<DevTile> tiles;
+  std::vector<long long> tile_bytes_iter, tile_bytes_check;
+  std::vector<int> tile_check_every, tile_max_iter;
+  bqp_timing timing{};
+  bool resident = false, ran = false;
+};
+BatchCtx g;
+
+int ctx_init(int device) {
+  if (g.device == device && g.stream) return BQP_OK;
+  if (g.stream) {   // switching devices: drop everything
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts}) b->release();
+    for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
+    cudaStreamDestroy(g.stream); g.stream = nullptr;
+  }
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto &e : g.ev) CK(cudaEventCreate(&e));
+  g.device = device;
+  return BQP_OK;
+}
+
+int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int to_device(bqp_instance *inst) {
+  const HostInstance &h = inst->h;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || h.s.device < 0 || h.s.device >= ndev) return BQP_E_CUDA;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h.s.device));
+  if (prop.major < 10) return BQP_E_CUDA;   // sm_100a code only
+  CK(cudaSetDevice(h.s.device));
+  inst->device = h.s.device;
+  DevInstance &d = inst->d;
+  d.n = h.n; d.m = h.m; d.npad = h.npad; d.n_int = h.n_int;
+  int rc;
+  if ((rc = upload_mat(inst, h.At, &d.At))) return rc;
+  if ((rc = upload_mat(inst, h.Ab, &d.Ab))) return rc;
+  if ((rc = upload_mat(inst, h.Pm, &d.Pm))) return rc;
+  if ((rc = upload(inst, h.Lcol, &d.Lcol))) return rc;
+  if ((rc = upload(inst, h.Lrow, &d.Lrow))) return rc;
+  if ((rc = upload(inst, h.D2inv, &d.D2inv))) return rc;
+  if ((rc = upload(inst, h.rho, &d.rho))) return rc;
+  if ((rc = upload(inst, h.rho_inv, &d.rho_inv))) return rc;
+  if ((rc = upload(inst, h.q, &d.q))) return rc;
+  inst->d_q = const_cast<double *>(d.q);
+  if ((rc = upload(inst, h.D, &d.D))) return rc;
+  if ((rc = upload(inst, h.Dinv, &d.Dinv))) return rc;
+  if ((rc = upload(inst, h.E, &d.E))) return rc;
+  if ((rc = upload(inst, h.Einv, &d.Einv))) return rc;
+  if ((rc = upload(inst, h.i_idx, &d.i_idx))) return rc;
+  d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
+  d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
+  d.eps_pinf = h.s.eps_prim_inf; d.eps_dinf = h.s.eps_dual_inf;
+  d.max_iter = h.s.max_iter; d.check_every = h.s.check_termination;
+  inst->on_device = true;
+  return BQP_OK;
+}
+
+int max_tile_nodes(const HostInstance &h, int threads) {
+  int tt = kMaxTT;
+  while (tt > 1 && tile_smem_bytes(h.n, h.m, tt, threads) > (size_t)kMaxSmem) tt >>= 1;
+  return tile_smem_bytes(h.n, h.m, tt, threads) <= (size_t)kMaxSmem ? tt : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void bqp_default_settings(bqp_settings *s) {
+  if (!s) return;
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6; s->eps_abs = 1e-3; s->eps_rel = 1e-3;
+  s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4; s->max_iter = 4000; s->scaling = 10;
+  s->check_termination = 25; s->eq_rho = 1; s->device = 0;
+}
+
+int bqp_debug_host_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out) {
+  if (!out) return BQP_E_ARG;
+  *out = nullptr;
+  bqp_instance *inst = new (std::nothrow) bqp_instance();
+  if (!inst) return BQP_E_ALLOC;
+  int rc;
+  try { rc = host_setup(p, s, &inst->h); } catch (const std::bad_alloc &) { rc = BQP_E_ALLOC; }
+  if (rc) { delete inst; return rc; }
+  *out = inst;
+  return BQP_OK;
+}
+
+int bqp_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out) {
+  if (!out) return BQP_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { *out = nullptr; return BQP_E_CUDA; }
+  int rc = bqp_debug_host_setup(p, s, out);
+  if (rc) return rc;
+  if (max_tile_nodes((*out)->h, 64) == 0) { bqp_free(*out); *out = nullptr; return BQP_E_UNSUPPORTED; }
+  rc = to_device(*out);
+  if (rc) { bqp_free(*out); *out = nullptr; }
+  return rc;
+}
+
+int bqp_free(bqp_handle h) {
+  if (!h) return BQP_OK;
+  if (h->on_device) {
+    cudaSetDevice(h->device);
+    if (g.stream && g.device == h->device) cudaStreamSynchronize(g.stream);
+    for (void *p : h->allocs) cudaFree(p);
+    for (auto &ni : g.node_inst) if (ni == h) { g.resident = false; break; }
+  }
+  delete h;
+  return BQP_OK;
+}
+
+int bqp_update_q(bqp_handle h, const double *q) {
+  if (!h || !q) return BQP_E_ARG;
+  host_rescale_q(&h->h, q);
+  h->d.nq = h->h.nq;
+  if (h->on_device) {
+    CK(cudaSetDevice(h->device));
+    if (g.stream && g.device == h->device) CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpy(h->d_q, h->h.q.data(), sizeof(double) * h->h.n, cudaMemcpyHostToDevice));
+  }
+  return BQP_OK;
+}
+
+int bqp_set_tuning(int tile_nodes, int threads) {
+  if (tile_nodes != 0 && tile_nodes != 1 && tile_nodes != 2 && tile_nodes != 4 && tile_nodes != 8) return BQP_E_ARG;
+  if (threads != 0 && (threads % 32 != 0 || threads < 32 || threads > kMaxThreads)) return BQP_E_ARG;
+  g_tune_tt = tile_nodes; g_tune_threads = threads;
+  return BQP_OK;
+}
+
+int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                     const double *const *x0, const double *const *y0) {
+  if (B <= 0 || !handles || !l || !u || !x0 || !y0) return BQP_E_ARG;
+  g.resident = false; g.ran = false;
+  for (int b = 0; b < B; b++) {
+    if (!handles[b] || !l[b] || !u[b] || !x0[b] || !y0[b]) return BQP_E_ARG;
+    if (!handles[b]->on_device) return BQP_E_CUDA;
+    if (handles[b]->device != handles[0]->device) return BQP_E_ARG;
+    const int m = handles[b]->h.m;
+    for (int i = 0; i < m; i++)
+      if (l[b][i] > u[b][i]) return BQP_E_BOUNDS;   // osqp update_bounds raises
+  }
+  int rc = ctx_init(handles[0]->device);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  int ndev_sms = 148;
+  cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
+
+  // group nodes by instance, in first-appearance order
+  std::vector<bqp_instance *> uniq;
+  std::map<bqp_instance *, int> uid;
+  std::vector<std::vector<int>> members;
+  for (int b = 0; b < B; b++) {
+    auto it = uid.find(handles[b]);
+    if (it == uid.end()) { uid[handles[b]] = (int)uniq.size(); uniq.push_back(handles[b]); members.emplace_back(); it = uid.find(handles[b]); }
+    members[it->second].push_back(b);
+  }
+  // CTA shape: enough warps to give every 32-row slice of the widest panel its own warp
+  int threads = g_tune_threads;
+  if (!threads) {
+    int want = 2;
+    for (auto *inst : uniq) want = std::max(want, std::max(inst->h.Ab.nslices, inst->h.At.nslices));
+    threads = 32 * std::min(pow2ceil(want), kMaxThreads / 32);
+  }
+  // nodes per tile: as wide as shared memory allows, but narrow enough to spread a small frontier over the SMs
+  int tt_cap = kMaxTT;
+  for (auto *inst : uniq) {
+    int t = max_tile_nodes(inst->h, threads);
+    if (t == 0) return BQP_E_UNSUPPORTED;
+    tt_cap = std::min(tt_cap, t);
+  }
+  int tt = g_tune_tt ? std::min(g_tune_tt, tt_cap) : tt_cap;
+  if (!g_tune_tt) {
+    auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
+    while (tt > 1 && count_tiles(tt) < ndev_sms && count_tiles(tt / 2) <= 2LL * ndev_sms) tt >>= 1;
+    int widest = 1;
+    for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
+    tt = std::min(tt, pow2ceil(widest));
+  }
+  // tiles: split each instance's nodes evenly
+  g.tiles.clear(); g.node_inst.assign(B, nullptr); g.out_off.assign(B, 0);
+  g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_max_iter.clear();
+  std::vector<long long> in_off(B);
+  size_t in_d = 0, out_d = 0, work_d = 0, smem = 0;
+  for (int b = 0; b < B; b++) {
+    const HostInstance &h = handles[b]->h;
+    in_off[b] = (long long)in_d; g.out_off[b] = (long long)out_d; g.node_inst[b] = handles[b];
+    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n;
+  }
+  for (size_t k = 0; k < uniq.size(); k++) {
+    const HostInstance &h = uniq[k]->h;
+    const int cnt = (int)members[k].size(), nt = (cnt + tt - 1) / tt;
+    smem = std::max(smem, tile_smem_bytes(h.n, h.m, tt, threads));
+    for (int ti = 0; ti < nt; ti++) {
+      const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
+      DevTile t{};
+      t.inst = (int)k; t.nn = hi - lo;
+      for (int q = lo; q < hi; q++) {
+        const int b = members[k][q];
+        t.node[q - lo] = b; t.in_off[q - lo] = in_off[b]; t.out_off[q - lo] = g.out_off[b];
+      }
+      t.work_off = (long long)work_d;
+      work_d += tile_work_doubles(h.n, h.m, tt);
+      g.tiles.push_back(t);
+      g.tile_bytes_iter.push_back(h.factor_bytes());
+      g.tile_bytes_check.push_back(h.check_bytes());
+      g.tile_check_every.push_back(h.s.check_termination);
+      g.tile_max_iter.push_back(h.s.max_iter);
+    }
+  }
+  g.B = B; g.ntiles = (int)g.tiles.size(); g.tt = tt; g.threads = threads; g.smem = smem;
+  g.in_doubles = in_d; g.out_doubles = out_d;
+  if ((rc = g.h_in.reserve(in_d * 8))) return rc;
+  if ((rc = g.h_out.reserve(out_d * 8))) return rc;
+  if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
+  if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
+  if ((rc = g.d_in.reserve(in_d * 8))) return rc;
+  if ((rc = g.d_out.reserve(out_d * 8))) return rc;
+  if ((rc = g.d_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
+  if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
+  if ((rc = g.d_work.reserve(work_d * 8))) return rc;
+  if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size()))) return rc;
+  if ((rc = g.d_insts.reserve(sizeof(DevInstance) * uniq.size()))) return rc;
+  // pack the per-node inputs: l[m] u[m] x0[n] y0[m]
+  double *hin = (double *)g.h_in.p;
+  for (int b = 0; b < B; b++) {
+    const HostInstance &h = handles[b]->h;
+    double *p = hin + in_off[b];
+    std::memcpy(p, l[b], 8 * (size_t)h.m);
+    std::memcpy(p + h.m, u[b], 8 * (size_t)h.m);
+    std::memcpy(p + 2 * (size_t)h.m, x0[b], 8 * (size_t)h.n);
+    std::memcpy(p + 2 * (size_t)h.m + h.n, y0[b], 8 * (size_t)h.m);
+  }
+  std::vector<DevInstance> dinst(uniq.size());
+  for (size_t k = 0; k < uniq.size(); k++) dinst[k] = uniq[k]->d;
+  CK(cudaEventRecord(g.ev[0], g.stream));
+  CK(cudaMemcpyAsync(g.d_in.p, hin, in_d * 8, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  CK(cudaStreamSynchronize(g.stream));   // tiles / dinst are stack-lifetime host memory
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
+  g.timing = bqp_timing{};
+  g.timing.h2d_ms = ms;
+  g.timing.h2d_bytes = (long long)(in_d * 8 + sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
+  g.timing.tiles = g.ntiles; g.timing.tile_nodes = tt; g.timing.threads = threads; g.timing.smem_bytes = (long long)smem;
+  g.resident = true;
+  return BQP_OK;
+}
+
+int bqp_batch_run(void) {
+  if (!g.resident) return BQP_E_ARG;
+  CK(cudaSetDevice(g.device));
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  int rc = launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                       (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                       (int *)g.d_ti.p, g.smem, g.stream);
+  if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
+  g.timing.kernel_ms = ms;
+  g.timing.launches = 1;
+  g.ran = true;
+  return BQP_OK;
+}
+
+int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *out) {
+  if (!g.resident || !g.ran) return BQP_E_ARG;
+  CK(cudaSetDevice(g.device));
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaEventRecord(g.ev[3], g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
+  g.timing.d2h_ms = ms;
+  g.timing.d2h_bytes = (long long)(g.out_doubles * 8 + sizeof(NodeScalars) * (size_t)g.B + sizeof(int) * (size_t)g.ntiles);
+  const double *ho = (const double *)g.h_out.p;
+  const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
+  const int *ti = (const int *)g.h_ti.p;
+  long long node_iters = 0, tile_iters = 0, bytes = 0;
+  for (int b = 0; b < g.B; b++) {
+    const HostInstance &h = g.node_inst[b]->h;
+    if (x && x[b]) std::memcpy(x[b], ho + g.out_off[b], 8 * (size_t)h.n);
+    if (y && y[b]) std::memcpy(y[b], ho + g.out_off[b] + h.n, 8 * (size_t)h.m);
+    if (out) {
+      if (out->status) out->status[b] = hs[b].status;
+      if (out->iters) out->iters[b] = hs[b].iters;
+      if (out->obj) out->obj[b] = hs[b].obj;
+      if (out->pri_res) out->pri_res[b] = hs[b].pri_res;
+      if (out->dua_res) out->dua_res[b] = hs[b].dua_res;
+      if (out->lower) out->lower[b] = hs[b].lower;
+    }
+    node_iters += hs[b].iters;
+  }
+  for (int t = 0; t < g.ntiles; t++) {
+    tile_iters += ti[t];
+    const int ce = g.tile_check_every[t];
+    const long long checks = ti[t] / ce + ((ti[t] % ce) ? 1 : 0);
+    bytes += (long long)ti[t] * g.tile_bytes_iter[t] + checks * g.tile_bytes_check[t];
+  }
+  g.timing.node_iters = node_iters; g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
+  return BQP_OK;
+}
+
+int bqp_solve_multi(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                    const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                    const bqp_node_out *out) {
+  int rc = bqp_batch_upload(B, handles, l, u, x0, y0);
+  if (rc) return rc;
+  if ((rc = bqp_batch_run())) return rc;
+  return bqp_batch_download(x, y, out);
+}
+
+int bqp_solve_batch(bqp_handle h, int B, const double *l, const double *u, const double *x0, const double *y0,
+                    double *x, double *y, const bqp_node_out *out) {
+  if (!h || B <= 0 || !l || !u || !x0 || !y0) return BQP_E_ARG;
+  const int n = h->h.n, m = h->h.m;
+  std::vector<bqp_handle> hs(B, h);
+  std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
+  std::vector<double *> px(B), py(B);
+  for (int b = 0; b < B; b++) {
+    pl[b] = l + (size_t)b * m; pu[b] = u + (size_t)b * m; px0[b] = x0 + (size_t)b * n; py0[b] = y0 + (size_t)b * m;
+    px[b] = x ? x + (size_t)b * n : nullptr; py[b] = y ? y + (size_t)b * m : nullptr;
+  }
+  return bqp_solve_multi(B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), out);
+}
+
+int bqp_last_timing(bqp_timing *t) {
+  if (!t) return BQP_E_ARG;
+  *t = g.timing;
+  return BQP_OK;
+}
+
+int bqp_get_dims(bqp_handle h, int *n, int *m, int *npad, long long *factor_bytes, long long *check_bytes) {
+  if (!h) return BQP_E_ARG;
+  if (n) *n = h->h.n;
+  if (m) *m = h->h.m;
+  if (npad) *npad = h->h.npad;
+  if (factor_bytes) *factor_bytes = h->h.factor_bytes();
+  if (check_bytes) *check_bytes = h->h.check_bytes();
+  return BQP_OK;
+}
+
+int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c) {
+  if (!h) return BQP_E_ARG;
+  if (D) std::memcpy(D, h->h.D.data(), 8 * (size_t)h->h.n);
+  if (E) std::memcpy(E, h->h.E.data(), 8 * (size_t)h->h.m);
+  if (c) *c = h->h.c;
+  return BQP_OK;
+}
+
+int bqp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *bqp_strerror(int code) {
+  static char buf[160];
+  switch (code) {
+    case BQP_OK: return "ok";
+    case BQP_E_ARG: return "bad argument (null pointer, dimension or setting)";
+    case BQP_E_BOUNDS: return "lower bound greater than upper bound";
+    case BQP_E_NONCONVEX: return "reduced KKT matrix is not positive definite (non-convex problem)";
+    case BQP_E_CUDA:
+      std::snprintf(buf, sizeof buf, "CUDA error or no usable sm_100 device (%s)",
+                    g_last_cuda == cudaSuccess ? "no device" : cudaGetErrorString(g_last_cuda));
+      return buf;
+    case BQP_E_ALLOC: return "out of memory";
+    case BQP_E_UNSUPPORTED: return "unsupported setting or problem too large for one CTA's shared memory";
+  }
+  return "unknown error";
+}
+
+const char *bqp_version(void) { return "bqp 0.1 (sm_100a)"; }
+
+int bqp_debug_host_kkt_solve(bqp_handle h, double *rhs_xz) {
+  if (!h || !rhs_xz) return BQP_E_ARG;
+  host_kkt_solve(&h->h, rhs_xz);
+  return BQP_OK;
+}
+
+int bqp_debug_host_matvec(bqp_handle h, int which, const double *in, double *out) {
+  if (!h || !in || !out || which < 0 || which > 2) return BQP_E_ARG;
+  host_matvec(which == 0 ? h->h.Ab : (which == 1 ? h->h.At : h->h.Pm), in, out);
+  return BQP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// bqp_internal.h -- shared declarations of the B200 batched QP engine (host setup <-> kernels <-> C ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/bqp.h"
+
+namespace bqp {
+
+constexpr double kInfty = 1e30;          // OSQP_INFTY
+constexpr double kMinScaling = 1e-4;     // MIN_SCALING
+constexpr double kMaxScaling = 1e4;      // MAX_SCALING
+constexpr double kRhoMin = 1e-6;         // RHO_MIN
+constexpr double kRhoTol = 1e-4;         // RHO_TOL
+constexpr double kRhoEqFactor = 1e3;     // RHO_EQ_OVER_RHO_INEQ
+constexpr int kNB = 32;                  // dense-tail block size == warp width
+constexpr int kMaxTT = 8;                // widest node tile (nodes solved by one CTA)
+constexpr int kMaxThreads = 512;         // largest CTA of the ADMM kernel
+constexpr int kMaxSmem = 227 * 1024;     // opt-in dynamic shared memory per CTA on sm_100
+
+// Row-sliced matrix ("panel") format streamed by the kernel.  Rows are grouped into slices of
+// 32 (one per lane).  Slice s owns width[s] = sptr[s+1]-sptr[s] "entry rows" of 32 doubles:
+// vals[(sptr[s]+j)*32 + lane] is the j-th stored entry of row 32*s+lane, so a warp reads 256
+// contiguous bytes per step.  iptr[s] < 0 marks a DENSE slice (entry j multiplies column j, no
+// index stream); otherwise idx[(iptr[s]+j)*32 + lane] is the column.  Padding entries are 0.0 / column 0.
+struct HostMat {
+  int rows = 0, cols = 0, nslices = 0;
+  std::vector<int> sptr, iptr;
+  std::vector<double> vals;
+  std::vector<int> idx;
+  long long stream_bytes() const { return (long long)vals.size() * 8 + (long long)idx.size() * 4; }
+};
+
+struct DevMat {
+  int rows, cols, nslices;
+  const int *sptr, *iptr;
+  const double *vals;
+  const int *idx;
+};
+
+// Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
+// KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
+// streamed as the A panels and the dense trailing supernode L22 D2 L22' = P + sigma I + A' diag(rho) A).
+struct HostInstance {
+  int n = 0, m = 0, npad = 0, n_int = 0;
+  bqp_settings s{};
+  std::vector<double> D, Dinv, E, Einv;
+  double c = 1, cinv = 1;
+  std::vector<double> q;                 // scaled linear cost
+  double nq = 0;                         // || Dinv q ||_inf (scaled q), constant between update_q calls
+  std::vector<double> rho, rho_inv;
+  std::vector<int> i_idx;
+  HostMat At, Ab, Pm;                    // A' (n x m), A (m x n), P full symmetric (n x n); all scaled
+  // Blocked dense tail.  Lcol: block column J = rows J*32..npad of 32 columns, column-major (ld = npad-J*32);
+  // Lrow: block row J = 32 rows of columns 0..(J+1)*32, row-major (ld = (J+1)*32).  In BOTH, the 32x32
+  // diagonal block holds the strictly-lower part of inv(L22[J,J]) (unit diagonal implicit), so the
+  // in-block substitution is a mat-vec.
+  std::vector<double> Lcol, Lrow, D2inv;
+  long long factor_bytes() const {   // bytes one ADMM iteration streams: A', L fwd, L bwd, A, D2inv
+    return (long long)(Lcol.size() + Lrow.size() + D2inv.size()) * 8 + At.stream_bytes() + Ab.stream_bytes();
+  }
+  long long check_bytes() const {    // extra bytes of one termination check: P, A', A twice each (+ certificates)
+    return 2 * (Pm.stream_bytes() + At.stream_bytes() + Ab.stream_bytes());
+  }
+};
+
+int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *out);   // bqp_setup.cpp
+void host_rescale_q(HostInstance *h, const double *q);
+void host_kkt_solve(const HostInstance *h, double *rhs_xz);
+void host_matvec(const HostMat &M, const double *in, double *out);
+
+struct DevInstance {
+  int n, m, npad, n_int;
+  DevMat At, Ab, Pm;
+  const double *Lcol, *Lrow, *D2inv;
+  const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
+  const int *i_idx;
+  double c, cinv, nq;
+  double sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;
+  int max_iter, check_every;
+};
+
+// One CTA solves one tile = up to kMaxTT nodes of one instance.
+struct DevTile {
+  int inst, nn;
+  int node[kMaxTT];              // caller-side node index (scalar outputs)
+  long long in_off[kMaxTT];      // doubles into the packed input buffer: l[m] u[m] x0[n] y0[m]
+  long long out_off[kMaxTT];     // doubles into the packed output buffer: x[n] y[m]
+  long long work_off;            // doubles into the state workspace
+};
+
+struct NodeScalars {
+  int status, iters;
+  double obj, pri_res, dua_res, lower;
+};
+
+// state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each)
+inline size_t tile_work_doubles(int n, int m, int tt) { return (size_t)tt * (5 * (size_t)m + 2 * (size_t)n); }
+size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
+int launch_admm(int tt, int threads, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
+                double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes, void *stream);
+
+}  // namespace bqp

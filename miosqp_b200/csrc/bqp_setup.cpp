@@ -1,0 +1,370 @@
+// bqp_setup.cpp -- host side of bqp_setup(): what osqp.OSQP().setup() does once per (P, A)
+// (/root/reference/miosqp/workspace.py:63-68), re-designed for the batched sm_100a kernel:
+//   1. Ruiz equilibration + cost normalisation (OSQP paper, sec. 5.1)
+//   2. per-row rho typing, ONCE, from the root bounds (parity contract: no per-node re-typing)
+//   3. LDL^T of the quasi-definite KKT matrix in CONSTRAINTS-FIRST elimination order.  With the
+//      (2,2) block -diag(1/rho) eliminated first there is no fill in the first m columns:
+//        L = [[I, 0], [L21, L22]],  L21 = -A' diag(rho),  L22 D2 L22' = P + sigma I + A' diag(rho) A,
+//      so the sparse columns of L are the rows of A (streamed as the A / A' panels) and the
+//      trailing supernode L22 is dense (P = Pt Pt' is dense in every BASELINE config).
+//   4. the streaming layouts the kernel reads: 32-row sliced panels for A, A', P and 32x32-blocked
+//      column / row panels of L22 for the forward / backward sweeps.
+// Nothing here calls into oracle/.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "bqp_internal.h"
+
+namespace bqp {
+
+namespace {
+
+struct Csc {
+  int rows = 0, cols = 0;
+  std::vector<int> p, i;
+  std::vector<double> x;
+};
+
+void limit_scaling(double *v, int n) {
+  for (int k = 0; k < n; k++) {
+    if (v[k] < kMinScaling) v[k] = 1.0;
+    if (v[k] > kMaxScaling) v[k] = kMaxScaling;
+  }
+}
+
+void sym_col_norms(const Csc &P, std::vector<double> &out) {
+  std::fill(out.begin(), out.end(), 0.0);
+  for (int j = 0; j < P.cols; j++)
+    for (int k = P.p[j]; k < P.p[j + 1]; k++) {
+      int r = P.i[k];
+      double a = std::fabs(P.x[k]);
+      out[j] = std::max(out[j], a);
+      if (r != j) out[r] = std::max(out[r], a);
+    }
+}
+
+// Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation; scales P, A, q in place.
+void ruiz(Csc &P, Csc &A, std::vector<double> &q, int passes, HostInstance *h) {
+  const int n = h->n, m = h->m;
+  h->D.assign(n, 1.0);
+  h->E.assign(m, 1.0);
+  h->c = 1.0;
+  std::vector<double> dt(std::max(n, 1)), et(std::max(m, 1));
+  for (int it = 0; it < passes; it++) {
+    sym_col_norms(P, dt);
+    std::fill(et.begin(), et.end(), 0.0);
+    for (int j = 0; j < n; j++) {
+      double cn = 0;
+      for (int k = A.p[j]; k < A.p[j + 1]; k++) {
+        double a = std::fabs(A.x[k]);
+        cn = std::max(cn, a);
+        et[A.i[k]] = std::max(et[A.i[k]], a);
+      }
+      dt[j] = std::max(dt[j], cn);
+    }
+    limit_scaling(dt.data(), n);
+    limit_scaling(et.data(), m);
+    for (int j = 0; j < n; j++) dt[j] = 1.0 / std::sqrt(dt[j]);
+    for (int r = 0; r < m; r++) et[r] = 1.0 / std::sqrt(et[r]);
+    for (int j = 0; j < n; j++) {
+      for (int k = P.p[j]; k < P.p[j + 1]; k++) P.x[k] *= dt[P.i[k]] * dt[j];
+      for (int k = A.p[j]; k < A.p[j + 1]; k++) A.x[k] *= et[A.i[k]] * dt[j];
+      q[j] *= dt[j];
+      h->D[j] *= dt[j];
+    }
+    for (int r = 0; r < m; r++) h->E[r] *= et[r];
+    sym_col_norms(P, dt);
+    double mean = 0;
+    for (int j = 0; j < n; j++) mean += dt[j];
+    mean = n > 0 ? mean / n : 0.0;
+    double qn = 0;
+    for (int j = 0; j < n; j++) qn = std::max(qn, std::fabs(q[j]));
+    limit_scaling(&qn, 1);
+    double ct = std::max(mean, qn);
+    limit_scaling(&ct, 1);
+    ct = 1.0 / ct;
+    for (auto &v : P.x) v *= ct;
+    for (auto &v : q) v *= ct;
+    h->c *= ct;
+  }
+  h->Dinv.resize(n);
+  h->Einv.resize(m);
+  for (int j = 0; j < n; j++) h->Dinv[j] = 1.0 / h->D[j];
+  for (int r = 0; r < m; r++) h->Einv[r] = 1.0 / h->E[r];
+  h->cinv = 1.0 / h->c;
+}
+
+// rows[r] = sorted (col, val) list -> sliced panel format
+using RowList = std::vector<std::vector<std::pair<int, double>>>;
+
+void build_panel(const RowList &rows, int ncols, HostMat *M) {
+  const int nrows = (int)rows.size();
+  M->rows = nrows;
+  M->cols = ncols;
+  M->nslices = (nrows + 31) / 32;
+  M->sptr.assign(M->nslices + 1, 0);
+  M->iptr.assign(M->nslices, -1);
+  M->vals.clear();
+  M->idx.clear();
+  for (int s = 0; s < M->nslices; s++) {
+    int r0 = s * 32, r1 = std::min(nrows, r0 + 32);
+    size_t width = 0, nnz = 0;
+    for (int r = r0; r < r1; r++) {
+      width = std::max(width, rows[r].size());
+      nnz += rows[r].size();
+    }
+    // dense slice moves 8 B per (row, col); sparse moves 12 B per padded entry
+    bool dense = ncols > 0 && (size_t)ncols * 8 <= width * 12;
+    if (dense) width = ncols;
+    size_t base = M->vals.size();
+    M->vals.resize(base + width * 32, 0.0);
+    if (dense) {
+      for (int r = r0; r < r1; r++)
+        for (auto &e : rows[r]) M->vals[base + (size_t)e.first * 32 + (r - r0)] = e.second;
+    } else {
+      M->iptr[s] = (int)(M->idx.size() / 32);
+      size_t ibase = M->idx.size();
+      M->idx.resize(ibase + width * 32, 0);
+      for (int r = r0; r < r1; r++) {
+        size_t j = 0;
+        for (auto &e : rows[r]) {
+          M->vals[base + j * 32 + (r - r0)] = e.second;
+          M->idx[ibase + j * 32 + (r - r0)] = e.first;
+          j++;
+        }
+      }
+    }
+    M->sptr[s + 1] = (int)(M->vals.size() / 32);
+    (void)nnz;
+  }
+}
+
+}  // namespace
+
+void host_rescale_q(HostInstance *h, const double *q) {   // osqp update_lin_cost: q_scaled = c * D * q
+  h->nq = 0;
+  for (int j = 0; j < h->n; j++) {
+    h->q[j] = h->c * h->D[j] * q[j];
+    h->nq = std::max(h->nq, std::fabs(h->Dinv[j] * h->q[j]));
+  }
+}
+
+int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
+  if (!p || !s || !h) return BQP_E_ARG;
+  const int n = p->n, m = p->m;
+  if (n <= 0 || m < 0 || !p->Pp || !p->Ap || !p->q || (m > 0 && (!p->l || !p->u))) return BQP_E_ARG;
+  if (p->n_int < 0 || p->n_int > m || (p->n_int > 0 && !p->i_idx)) return BQP_E_ARG;
+  if (s->check_termination < 1 || s->max_iter < 1 || s->scaling < 0 || !(s->rho > 0) || !(s->sigma > 0) ||
+      !(s->alpha > 0 && s->alpha < 2))
+    return BQP_E_ARG;
+  for (int r = 0; r < m; r++)
+    if (p->l[r] > p->u[r]) return BQP_E_BOUNDS;
+  h->n = n; h->m = m; h->npad = ((n + kNB - 1) / kNB) * kNB; h->n_int = p->n_int; h->s = *s;
+  h->i_idx.assign(p->i_idx, p->i_idx + p->n_int);
+  for (int k = 0; k < p->n_int; k++)
+    if (h->i_idx[k] < 0 || h->i_idx[k] >= n) return BQP_E_ARG;
+
+  Csc P, A;
+  P.rows = P.cols = n;
+  P.p.assign(p->Pp, p->Pp + n + 1);
+  for (int j = 0; j < n; j++)            // keep the upper triangle only
+    for (int k = p->Pp[j]; k < p->Pp[j + 1]; k++)
+      if (p->Pi[k] < 0 || p->Pi[k] >= n) return BQP_E_ARG;
+  {
+    std::vector<int> np(n + 1, 0);
+    for (int j = 0; j < n; j++) {
+      np[j] = (int)P.i.size();
+      for (int k = p->Pp[j]; k < p->Pp[j + 1]; k++)
+        if (p->Pi[k] <= j) { P.i.push_back(p->Pi[k]); P.x.push_back(p->Px[k]); }
+    }
+    np[n] = (int)P.i.size();
+    P.p = np;
+  }
+  A.rows = m; A.cols = n;
+  A.p.assign(p->Ap, p->Ap + n + 1);
+  A.i.assign(p->Ai, p->Ai + p->Ap[n]);
+  A.x.assign(p->Ax, p->Ax + p->Ap[n]);
+  for (int v : A.i) if (v < 0 || v >= m) return BQP_E_ARG;
+  h->q.assign(p->q, p->q + n);
+
+  ruiz(P, A, h->q, s->scaling, h);
+
+  // rho typing on the SCALED, clamped root bounds
+  h->rho.resize(m); h->rho_inv.resize(m);
+  for (int r = 0; r < m; r++) {
+    double lo = std::max(p->l[r], -kInfty) * h->E[r], up = std::min(p->u[r], kInfty) * h->E[r];
+    double rho = s->rho;
+    if (s->eq_rho) {
+      if (lo < -kInfty * kMinScaling && up > kInfty * kMinScaling) rho = kRhoMin;
+      else if (up - lo < kRhoTol) rho = kRhoEqFactor * s->rho;
+    }
+    h->rho[r] = rho; h->rho_inv[r] = 1.0 / rho;
+  }
+
+  // row lists of A (m x n), A' (n x m) and full symmetric P (n x n)
+  RowList arows(m), atrows(n), prows(n);
+  for (int j = 0; j < n; j++)
+    for (int k = A.p[j]; k < A.p[j + 1]; k++) {
+      arows[A.i[k]].push_back({j, A.x[k]});
+      atrows[j].push_back({A.i[k], A.x[k]});
+    }
+  for (int j = 0; j < n; j++)
+    for (int k = P.p[j]; k < P.p[j + 1]; k++) {
+      int r = P.i[k];
+      prows[r].push_back({j, P.x[k]});
+      if (r != j) prows[j].push_back({r, P.x[k]});
+    }
+  auto by_col = [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; };
+  for (auto &r : arows) std::sort(r.begin(), r.end(), by_col);
+  for (auto &r : atrows) std::sort(r.begin(), r.end(), by_col);
+  for (auto &r : prows) std::sort(r.begin(), r.end(), by_col);
+  build_panel(arows, n, &h->Ab);
+  build_panel(atrows, m, &h->At);
+  build_panel(prows, n, &h->Pm);
+
+  // S = P + sigma I + A' diag(rho) A : dense lower triangle, column-major, padded with identity
+  const int np_ = h->npad;
+  std::vector<double> S((size_t)np_ * np_, 0.0);
+  auto Sat = [&](int r, int c) -> double & { return S[(size_t)c * np_ + r]; };
+  for (int j = 0; j < n; j++)
+    for (int k = P.p[j]; k < P.p[j + 1]; k++) Sat(j, P.i[k]) += P.x[k];   // (row j >= col i) lower copy of triu
+  for (int j = 0; j < n; j++) Sat(j, j) += s->sigma;
+  for (int j = n; j < np_; j++) Sat(j, j) = 1.0;
+  for (int r = 0; r < m; r++) {
+    const auto &row = arows[r];
+    const double rho = h->rho[r];
+    for (size_t a = 0; a < row.size(); a++) {
+      const double va = rho * row[a].second;
+      double *col = &S[(size_t)row[a].first * np_];
+      for (size_t b = a; b < row.size(); b++) col[row[b].first] += va * row[b].second;   // rows >= col
+    }
+  }
+  // in-place dense LDL^T (right-looking); afterwards S holds unit-lower L22 below the diagonal, D2 on it
+  h->D2inv.assign(np_, 1.0);
+  for (int j = 0; j < np_; j++) {
+    double d = Sat(j, j);
+    if (!(d > 0.0)) return BQP_E_NONCONVEX;
+    double dinv = 1.0 / d;
+    h->D2inv[j] = dinv;
+    double *cj = &S[(size_t)j * np_];
+    for (int k = j + 1; k < np_; k++) {
+      const double g = cj[k] * dinv;   // L[k][j]
+      if (g == 0.0) continue;
+      double *ck = &S[(size_t)k * np_];
+      for (int r = k; r < np_; r++) ck[r] -= cj[r] * g;   // S[r][k] -= (L[r][j] d) L[k][j]
+    }
+    for (int r = j + 1; r < np_; r++) cj[r] *= dinv;
+  }
+  // inverse of every 32x32 unit-lower diagonal block (strictly-lower part kept; unit diagonal implicit)
+  const int nb = np_ / kNB;
+  std::vector<double> Linv((size_t)nb * kNB * kNB, 0.0);   // [J][r][c]
+  for (int J = 0; J < nb; J++) {
+    const int r0 = J * kNB;
+    double *X = &Linv[(size_t)J * kNB * kNB];
+    for (int c = 0; c < kNB; c++)
+      for (int r = c + 1; r < kNB; r++) {
+        double acc = Sat(r0 + r, r0 + c);                  // k = c term: L[r][c] * X[c][c]
+        for (int k = c + 1; k < r; k++) acc += Sat(r0 + r, r0 + k) * X[k * kNB + c];
+        X[r * kNB + c] = -acc;
+      }
+  }
+  // blocked layouts
+  h->Lcol.clear(); h->Lrow.clear();
+  for (int J = 0; J < nb; J++) {          // block column J: rows J*32..npad, 32 columns, column-major
+    int r0 = J * kNB, ld = np_ - r0;
+    size_t base = h->Lcol.size();
+    h->Lcol.resize(base + (size_t)kNB * ld, 0.0);
+    const double *X = &Linv[(size_t)J * kNB * kNB];
+    for (int c = 0; c < kNB; c++) {
+      for (int r = c + 1; r < kNB; r++) h->Lcol[base + (size_t)c * ld + r] = X[r * kNB + c];
+      for (int r = r0 + kNB; r < np_; r++) h->Lcol[base + (size_t)c * ld + (r - r0)] = Sat(r, r0 + c);
+    }
+  }
+  for (int J = 0; J < nb; J++) {          // block row J: 32 rows, columns 0..(J+1)*32, row-major
+    int r0 = J * kNB, ld = (J + 1) * kNB;
+    size_t base = h->Lrow.size();
+    h->Lrow.resize(base + (size_t)kNB * ld, 0.0);
+    const double *X = &Linv[(size_t)J * kNB * kNB];
+    for (int rr = 0; rr < kNB; rr++) {
+      for (int cidx = 0; cidx < r0; cidx++) h->Lrow[base + (size_t)rr * ld + cidx] = Sat(r0 + rr, cidx);
+      for (int c = 0; c < rr; c++) h->Lrow[base + (size_t)rr * ld + r0 + c] = X[rr * kNB + c];
+    }
+  }
+  h->nq = 0;
+  for (int j = 0; j < n; j++) h->nq = std::max(h->nq, std::fabs(h->Dinv[j] * h->q[j]));
+  return BQP_OK;
+}
+
+// ---- host-only debug restatements of what the kernel does with the streamed layouts (tests only)
+void host_matvec(const HostMat &M, const double *in, double *out) {
+  for (int s = 0; s < M.nslices; s++) {
+    const int w = M.sptr[s + 1] - M.sptr[s];
+    for (int lane = 0; lane < 32; lane++) {
+      const int row = s * 32 + lane;
+      if (row >= M.rows) break;
+      double acc = 0;
+      for (int j = 0; j < w; j++) {
+        const double a = M.vals[((size_t)M.sptr[s] + j) * 32 + lane];
+        const int col = M.iptr[s] < 0 ? j : M.idx[((size_t)M.iptr[s] + j) * 32 + lane];
+        acc = std::fma(a, in[col], acc);
+      }
+      out[row] = acc;
+    }
+  }
+}
+
+void host_kkt_solve(const HostInstance *h, double *rhs) {
+  const int n = h->n, m = h->m, np_ = h->npad, nb = np_ / kNB;
+  std::vector<double> w(m), b(np_, 0.0), t(std::max(n, m));
+  // t2 = rhs_x + A' (rho o rhs_z)
+  for (int i = 0; i < m; i++) w[i] = h->rho[i] * rhs[n + i];
+  host_matvec(h->At, w.data(), t.data());
+  for (int j = 0; j < n; j++) b[j] = rhs[j] + t[j];
+  // forward sweep over block columns
+  size_t base = 0;
+  for (int J = 0; J < nb; J++) {
+    const int r0 = J * kNB, ld = np_ - r0;
+    const double *Lc = &h->Lcol[base];
+    double y[kNB];
+    for (int r = 0; r < kNB; r++) {
+      double acc = b[r0 + r];
+      for (int c = 0; c < r; c++) acc = std::fma(Lc[(size_t)c * ld + r], b[r0 + c], acc);
+      y[r] = acc;
+    }
+    for (int r = 0; r < kNB; r++) b[r0 + r] = y[r];
+    for (int r = r0 + kNB; r < np_; r++) {
+      double acc = 0;
+      for (int c = 0; c < kNB; c++) acc = std::fma(Lc[(size_t)c * ld + (r - r0)], y[c], acc);
+      b[r] -= acc;
+    }
+    base += (size_t)kNB * ld;
+  }
+  for (int j = 0; j < np_; j++) b[j] *= h->D2inv[j];
+  // backward sweep over block rows
+  std::vector<size_t> rbase(nb);
+  base = 0;
+  for (int J = 0; J < nb; J++) { rbase[J] = base; base += (size_t)kNB * (J + 1) * kNB; }
+  for (int J = nb - 1; J >= 0; J--) {
+    const int r0 = J * kNB, ld = (J + 1) * kNB;
+    const double *Lr = &h->Lrow[rbase[J]];
+    double x[kNB];
+    for (int c = 0; c < kNB; c++) {
+      double acc = b[r0 + c];
+      for (int rr = c + 1; rr < kNB; rr++) acc = std::fma(Lr[(size_t)rr * ld + r0 + c], b[r0 + rr], acc);
+      x[c] = acc;
+    }
+    for (int c = 0; c < kNB; c++) b[r0 + c] = x[c];
+    for (int cidx = 0; cidx < r0; cidx++) {
+      double acc = 0;
+      for (int rr = 0; rr < kNB; rr++) acc = std::fma(Lr[(size_t)rr * ld + cidx], x[rr], acc);
+      b[cidx] -= acc;
+    }
+  }
+  // nu = rho o (A xt - rhs_z)
+  host_matvec(h->Ab, b.data(), t.data());
+  for (int j = 0; j < n; j++) rhs[j] = b[j];
+  for (int i = 0; i < m; i++) rhs[n + i] = h->rho[i] * (t[i] - rhs[n + i]);
+}
+
+}  // namespace bqp

@@ -1,0 +1,309 @@
+"""
+ctypes binding of libbqp.so (include/bqp.h) -- the B200 batched QP-relaxation engine.
+
+`BatchedQP` is one set-up problem (what `osqp.OSQP().setup(...)` is for the reference,
+/root/reference/miosqp/workspace.py:63-68); `solve_batch` / `solve_multi` run the ADMM loops of
+many B&B nodes in one kernel launch (what the reference does one node at a time in
+/root/reference/miosqp/node.py:96-143).  There is no CPU fallback: if the library cannot be
+built or no B200 is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.sparse as spa
+
+from . import build as _build
+
+OSQP_INFTY = 1e30
+CONSTANTS = {
+    "OSQP_SOLVED": 1, "OSQP_SOLVED_INACCURATE": 2,
+    "OSQP_PRIMAL_INFEASIBLE_INACCURATE": 3, "OSQP_DUAL_INFEASIBLE_INACCURATE": 4,
+    "OSQP_MAX_ITER_REACHED": -2, "OSQP_PRIMAL_INFEASIBLE": -3, "OSQP_DUAL_INFEASIBLE": -4,
+    "OSQP_SIGINT": -5, "OSQP_TIME_LIMIT_REACHED": -6, "OSQP_NON_CVX": -7, "OSQP_UNSOLVED": -10,
+    "OSQP_INFTY": OSQP_INFTY, "OSQP_NAN": float("nan"),
+}
+
+# OSQP setting names understood by the engine, with OSQP's defaults
+DEFAULTS = dict(rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4,
+                eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25, eq_rho=1, device=0)
+# pre-0.1.3 names found in /root/reference/max_iter_examples/*.pickle
+ALIASES = {"eps_inf": "eps_prim_inf", "eps_unb": "eps_dual_inf"}
+# accepted and ignored (no effect on the iterates of the parity contract)
+IGNORED = {"verbose", "polish", "polishing", "warm_start", "time_limit", "linsys_solver", "delta",
+           "polish_refine_iter", "pol_refine_iter", "scaling_iter", "scaling_norm", "early_terminate",
+           "early_terminate_interval", "auto_rho", "adaptive_rho_interval", "adaptive_rho_fraction",
+           "adaptive_rho_tolerance"}
+
+
+class BqpError(RuntimeError):
+    pass
+
+
+class _Settings(C.Structure):
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+                ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+                ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+                ("max_iter", C.c_int), ("scaling", C.c_int), ("check_termination", C.c_int),
+                ("eq_rho", C.c_int), ("device", C.c_int)]
+
+
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class _Problem(C.Structure):
+    _fields_ = [("n", C.c_int), ("m", C.c_int),
+                ("Pp", _ip), ("Pi", _ip), ("Px", _dp),
+                ("Ap", _ip), ("Ai", _ip), ("Ax", _dp),
+                ("q", _dp), ("l", _dp), ("u", _dp),
+                ("n_int", C.c_int), ("i_idx", _ip)]
+
+
+class _NodeOut(C.Structure):
+    _fields_ = [("status", _ip), ("iters", _ip), ("obj", _dp), ("pri_res", _dp), ("dua_res", _dp), ("lower", _dp)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+                ("launches", C.c_int), ("tiles", C.c_int), ("tile_nodes", C.c_int), ("threads", C.c_int),
+                ("smem_bytes", C.c_longlong), ("node_iters", C.c_longlong), ("tile_iters", C.c_longlong),
+                ("stream_bytes", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch", "bqp_solve_multi",
+           "bqp_batch_upload", "bqp_batch_run", "bqp_batch_download", "bqp_last_timing", "bqp_free",
+           "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
+           "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_matvec"]
+
+_lib = None
+
+
+def lib():
+    """Load (building first when stale) libbqp.so.  Raises if it cannot be produced."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        pp = C.POINTER(C.c_void_p)
+        L.bqp_default_settings.argtypes = [C.POINTER(_Settings)]
+        L.bqp_setup.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), pp]
+        L.bqp_debug_host_setup.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), pp]
+        L.bqp_update_q.argtypes = [vp, _dp]
+        L.bqp_solve_batch.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(_NodeOut)]
+        L.bqp_solve_multi.argtypes = [C.c_int, pp, pp, pp, pp, pp, pp, pp, C.POINTER(_NodeOut)]
+        L.bqp_batch_upload.argtypes = [C.c_int, pp, pp, pp, pp, pp]
+        L.bqp_batch_run.argtypes = []
+        L.bqp_batch_download.argtypes = [pp, pp, C.POINTER(_NodeOut)]
+        L.bqp_last_timing.argtypes = [C.POINTER(Timing)]
+        L.bqp_free.argtypes = [vp]
+        L.bqp_set_tuning.argtypes = [C.c_int, C.c_int]
+        L.bqp_get_dims.argtypes = [vp, _ip, _ip, _ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.bqp_get_scaling.argtypes = [vp, _dp, _dp, _dp]
+        L.bqp_strerror.restype = C.c_char_p
+        L.bqp_strerror.argtypes = [C.c_int]
+        L.bqp_version.restype = C.c_char_p
+        L.bqp_debug_host_kkt_solve.argtypes = [vp, _dp]
+        L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = lib().bqp_strerror(rc).decode()
+    if rc in (-1, -2, -3, -6):     # osqp raises ValueError for bad data / l > u / non-convex
+        raise ValueError(msg)
+    raise BqpError(msg)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def normalize_settings(kw):
+    s = dict(DEFAULTS)
+    for k, v in kw.items():
+        k = ALIASES.get(k, k)
+        if k in s:
+            s[k] = v
+        elif k == "adaptive_rho":
+            if v:
+                raise ValueError("adaptive_rho is outside the engine's parity contract (rho is fixed; "
+                                 "every node is a pure function of (l,u,x0,y0))")
+        elif k == "scaled_termination":
+            if v:
+                raise ValueError("scaled_termination is not supported")
+        elif k in IGNORED:
+            continue
+        else:
+            raise TypeError("unknown OSQP setting %r" % k)
+    if isinstance(s["scaling"], bool):
+        s["scaling"] = 10 if s["scaling"] else 0
+    return s
+
+
+def set_tuning(tile_nodes=0, threads=0):
+    _check(lib().bqp_set_tuning(int(tile_nodes), int(threads)))
+
+
+def device_count():
+    return lib().bqp_device_count()
+
+
+def last_timing():
+    t = Timing()
+    _check(lib().bqp_last_timing(C.byref(t)))
+    return t.as_dict()
+
+
+class BatchResult(object):
+    """Per-node outputs of one batched solve (arrays of length B along axis 0)."""
+    __slots__ = ("x", "y", "status", "iters", "obj", "pri_res", "dua_res", "lower")
+
+
+class BatchedQP(object):
+    """One set-up QP family: P, A fixed; q updatable; l,u,x0,y0 per node."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.n = self.m = 0
+
+    def __del__(self):
+        self.free()
+
+    def free(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().bqp_free(self._h)
+            self._h = C.c_void_p()
+
+    def setup(self, P, q, A, l, u, i_idx=None, host_only=False, **settings):
+        s = normalize_settings(settings)
+        self.settings = s
+        P = spa.triu(spa.csc_matrix(P), format="csc")
+        A = spa.csc_matrix(A)
+        P.sort_indices()
+        A.sort_indices()
+        self.n, self.m = A.shape[1], A.shape[0]
+        if P.shape != (self.n, self.n):
+            raise ValueError("P must be n x n")
+        q = _f64(q); l = _f64(l); u = _f64(u)
+        if q.shape != (self.n,) or l.shape != (self.m,) or u.shape != (self.m,):
+            raise ValueError("q, l, u have inconsistent dimensions")
+        idx = np.ascontiguousarray(np.asarray(i_idx if i_idx is not None else [], dtype=np.int32))
+        Pp, Pi, Px = P.indptr.astype(np.int32), P.indices.astype(np.int32), _f64(P.data)
+        Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), _f64(A.data)
+        prob = _Problem(self.n, self.m, _i(Pp), _i(Pi), _d(Px), _i(Ap), _i(Ai), _d(Ax), _d(q), _d(l), _d(u),
+                        int(idx.size), _i(idx))
+        st = _Settings(**{k: s[k] for k, _ in _Settings._fields_})
+        self.free()
+        fn = lib().bqp_debug_host_setup if host_only else lib().bqp_setup
+        _check(fn(C.byref(prob), C.byref(st), C.byref(self._h)))
+        self.n_int = int(idx.size)
+        return self
+
+    def update_q(self, q):
+        q = _f64(q)
+        if q.shape != (self.n,):
+            raise ValueError("q must have length n")
+        _check(lib().bqp_update_q(self._h, _d(q)))
+
+    def dims(self):
+        n, m, npad = C.c_int(), C.c_int(), C.c_int()
+        fb, cb = C.c_longlong(), C.c_longlong()
+        _check(lib().bqp_get_dims(self._h, C.byref(n), C.byref(m), C.byref(npad), C.byref(fb), C.byref(cb)))
+        return dict(n=n.value, m=m.value, npad=npad.value, factor_bytes=fb.value, check_bytes=cb.value)
+
+    def scaling(self):
+        D = np.empty(self.n); E = np.empty(self.m); c = C.c_double()
+        _check(lib().bqp_get_scaling(self._h, _d(D), _d(E), C.byref(c)))
+        return D, E, c.value
+
+    def solve_batch(self, l, u, x0, y0):
+        """l,u,y0: [B][m]; x0: [B][n].  One launch for all B nodes."""
+        l = np.atleast_2d(_f64(l)); u = np.atleast_2d(_f64(u))
+        x0 = np.atleast_2d(_f64(x0)); y0 = np.atleast_2d(_f64(y0))
+        B = l.shape[0]
+        if l.shape != (B, self.m) or u.shape != (B, self.m) or y0.shape != (B, self.m) or x0.shape != (B, self.n):
+            raise ValueError("batch arrays have inconsistent dimensions")
+        r = _alloc_result(B, self.n, self.m)
+        out = _node_out(r)
+        _check(lib().bqp_solve_batch(self._h, B, _d(l), _d(u), _d(x0), _d(y0), _d(r.x), _d(r.y), C.byref(out)))
+        return r
+
+    # host-only debug hooks (layout tests)
+    def debug_kkt_solve(self, rhs):
+        b = _f64(rhs).copy()
+        _check(lib().bqp_debug_host_kkt_solve(self._h, _d(b)))
+        return b
+
+    def debug_matvec(self, which, v):
+        v = _f64(v)
+        out = np.zeros({0: self.m, 1: self.n, 2: self.n}[which])
+        _check(lib().bqp_debug_host_matvec(self._h, which, _d(v), _d(out)))
+        return out
+
+
+def _alloc_result(B, n, m):
+    r = BatchResult()
+    r.x = np.empty((B, n)); r.y = np.empty((B, m))
+    r.status = np.empty(B, np.int32); r.iters = np.empty(B, np.int32)
+    r.obj = np.empty(B); r.pri_res = np.empty(B); r.dua_res = np.empty(B); r.lower = np.empty(B)
+    return r
+
+
+def _node_out(r):
+    return _NodeOut(_i(r.status), _i(r.iters), _d(r.obj), _d(r.pri_res), _d(r.dua_res), _d(r.lower))
+
+
+class _Scalars(object):
+    __slots__ = ("status", "iters", "obj", "pri_res", "dua_res", "lower")
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+class ResidentBatch(object):
+    """Staged variant: upload once, run many times from HBM-resident inputs, download once."""
+
+    def __init__(self, qps, l, u, x0, y0):
+        self.qps = list(qps)
+        B = len(self.qps)
+        self._keep = [[_f64(a) for a in seq] for seq in (l, u, x0, y0)]
+        hs = (C.c_void_p * B)(*[q._h.value for q in self.qps])
+        _check(lib().bqp_batch_upload(B, hs, *[_ptr_array(k) for k in self._keep]))
+
+    def run(self):
+        _check(lib().bqp_batch_run())
+
+    def download(self):
+        B = len(self.qps)
+        xs = [np.empty(q.n) for q in self.qps]
+        ys = [np.empty(q.m) for q in self.qps]
+        sc = _Scalars()
+        sc.status = np.empty(B, np.int32); sc.iters = np.empty(B, np.int32)
+        sc.obj = np.empty(B); sc.pri_res = np.empty(B); sc.dua_res = np.empty(B); sc.lower = np.empty(B)
+        out = _node_out(sc)
+        _check(lib().bqp_batch_download(_ptr_array(xs), _ptr_array(ys), C.byref(out)))
+        return xs, ys, sc
+
+
+def solve_multi(qps, l, u, x0, y0):
+    """Nodes of several set-up problems in ONE launch.  All arguments are sequences of length B."""
+    rb = ResidentBatch(qps, l, u, x0, y0)
+    rb.run()
+    return rb.download()

@@ -45,3 +45,32 @@ CONFIGS = {
     "cfg2": dict(n=500, m=1000, p=50, density=0.7, seed=1, count=100),
     "cfg4": dict(n=2000, m=4000, p=200, density=0.05, seed=1, count=1),
 }
+
+
+def extend(pr):
+    """(P, q, A_ext, l_ext, u_ext, i_idx) exactly as Data/add_bounds builds them
+    (/root/reference/miosqp/data.py:5-33): integer-variable bound rows I[i_idx,:] appended below A."""
+    n = pr['A'].shape[1]
+    I_int = spa.identity(n, format='csc')[pr['i_idx'], :]
+    A = spa.vstack([pr['A'], I_int]).tocsc()
+    l = np.append(pr['l'], pr['i_l'])
+    u = np.append(pr['u'], pr['i_u'])
+    return pr['P'], pr['q'], A, l, u, np.asarray(pr['i_idx'])
+
+
+def branched_nodes(l_ext, u_ext, n_int, count, rng, depth=3):
+    """`count` synthetic B&B leaves of one instance: the root bounds with up to `depth` integer rows
+    fixed to one side, as add_left/add_right would (/root/reference/miosqp/workspace.py:157-203).
+    Node 0 is the root itself."""
+    m = l_ext.shape[0]
+    ls, us = [l_ext.copy()], [u_ext.copy()]
+    for _ in range(count - 1):
+        l = l_ext.copy(); u = u_ext.copy()
+        rows = m - n_int + rng.choice(n_int, size=min(depth, n_int), replace=False)
+        for r in rows:
+            if rng.random() < 0.5:
+                u[r] = np.floor(0.5 * (l_ext[r] + u_ext[r]))      # left child: u = floor(x)
+            else:
+                l[r] = np.ceil(0.5 * (l_ext[r] + u_ext[r]))       # right child: l = ceil(x)
+        ls.append(l); us.append(u)
+    return np.array(ls), np.array(us)

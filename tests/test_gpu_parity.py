@@ -1,0 +1,155 @@
+"""
+GPU parity: the CUDA engine (through the C ABI, include/bqp.h) against the CPU oracle on the same
+seeded inputs.  Tolerances (FP64): identical status and iteration count per node;
+|x - x_oracle|_inf <= 1e-9 (1 + |x_oracle|_inf), same for y; objective / residuals to 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from miosqp_b200 import engine, problems
+
+pytestmark = pytest.mark.gpu
+
+QP = dict(eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4)
+TOL = 1e-9
+
+
+def _close(a, b, tol=TOL):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    if ok.any():
+        scale = 1.0 + np.abs(b[ok]).max()
+        assert np.abs(a[ok] - b[ok]).max() <= tol * scale, (np.abs(a[ok] - b[ok]).max(), scale)
+
+
+def _compare(pr, count, seed, settings, warm="zero", tuning=(0, 0), oracle_mod=None):
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    n, m = A.shape[1], A.shape[0]
+    rng = np.random.default_rng(seed)
+    ls, us = problems.branched_nodes(l, u, len(i_idx), count, rng)
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **settings)
+    if warm == "root":
+        r = o.solve_node(l, u, np.zeros(n), np.zeros(m))
+        x0 = np.tile(np.nan_to_num(r.x), (count, 1)); y0 = np.tile(np.nan_to_num(r.y), (count, 1))
+    else:
+        x0 = np.zeros((count, n)); y0 = np.zeros((count, m))
+    xo, yo, so, io, extra = o.solve_batch(ls, us, x0, y0, threads=8)
+    engine.set_tuning(*tuning)
+    try:
+        e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **settings)
+        r = e.solve_batch(ls, us, x0, y0)
+    finally:
+        engine.set_tuning(0, 0)
+    assert list(r.status) == list(so), (list(r.status), list(so))
+    assert list(r.iters) == list(io), (list(r.iters), list(io))
+    # the reference clips integer entries after the solve (node.py:131-136); apply it to the oracle's x
+    for b in range(count):
+        if so[b] in (1, -2):
+            xo[b, i_idx] = np.minimum(np.maximum(xo[b, i_idx], ls[b, -len(i_idx):]), us[b, -len(i_idx):])
+    _close(r.x, xo); _close(r.y, yo)
+    _close(r.pri_res, extra["pri_res"]); _close(r.dua_res, extra["dua_res"])
+    fin = np.abs(extra["obj"]) < 1e29
+    _close(r.obj[fin], extra["obj"][fin])
+    Pd = P.toarray()
+    for b in range(count):
+        if so[b] in (1, -2):
+            lower = 0.5 * xo[b] @ Pd @ xo[b] + q @ xo[b]      # data.py:99-103
+            assert abs(r.lower[b] - lower) <= 1e-9 * (1 + abs(lower))
+        else:
+            assert np.isnan(r.lower[b])
+    return r, e
+
+
+def test_cfg1_root_and_leaves(oracle_mod):
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    _compare(pr, 12, 0, QP, oracle_mod=oracle_mod)
+
+
+def test_cfg1_known_answer(oracle_mod):
+    """Root relaxation objective of cfg 1 from exhaustive enumeration: -12.706728044."""
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)
+    r = e.solve_batch(l[None], u[None], np.zeros((1, 50)), np.zeros((1, 105)))
+    assert r.status[0] == 1
+    assert abs(r.lower[0] - (-12.706728044)) < 1e-6
+
+
+@pytest.mark.parametrize("tt,threads", [(1, 64), (2, 128), (4, 256), (8, 512), (8, 64)])
+def test_tile_shapes(oracle_mod, tt, threads):
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    _compare(pr, 11, 1, QP, tuning=(tt, threads), oracle_mod=oracle_mod)
+
+
+def test_warm_started_leaves(oracle_mod):
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    _compare(pr, 9, 2, QP, warm="root", oracle_mod=oracle_mod)
+
+
+def test_sparse_midsize(oracle_mod):
+    pr = problems.random_miqp(200, 300, 10, 0.05, seed=3)[0]
+    _compare(pr, 6, 3, QP, oracle_mod=oracle_mod)
+
+
+def test_dense_midsize_multiblock(oracle_mod):
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 10, 4, QP, warm="root", oracle_mod=oracle_mod)
+
+
+def test_infeasible_nodes(oracle_mod):
+    """Contradictory bounds on a general row give OSQP_PRIMAL_INFEASIBLE with NaN iterates."""
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    ls = np.tile(l, (3, 1)); us = np.tile(u, (3, 1))
+    ls[1, 0] = 50.0; us[1, 0] = 60.0          # row 0 cannot reach 50
+    ls[2, 1] = -60.0; us[2, 1] = -50.0
+    x0 = np.zeros((3, 50)); y0 = np.zeros((3, 105))
+    xo, yo, so, io, _ = o.solve_batch(ls, us, x0, y0)
+    r = e.solve_batch(ls, us, x0, y0)
+    assert list(so) == [1, -3, -3]
+    assert list(r.status) == list(so) and list(r.iters) == list(io)
+    assert np.isnan(r.x[1]).all() and np.isnan(r.y[2]).all() and np.isnan(r.lower[1])
+
+
+def test_bounds_error():
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    lb = l.copy(); lb[3] = u[3] + 1.0
+    with pytest.raises(ValueError):
+        e.solve_batch(lb[None], u[None], np.zeros((1, 50)), np.zeros((1, 105)))
+
+
+def test_multi_instance_one_launch(oracle_mod):
+    prs = problems.random_miqp(50, 100, 5, 0.7, seed=7, count=3)
+    qps, os_, L, U, X0, Y0 = [], [], [], [], [], []
+    rng = np.random.default_rng(5)
+    for pr in prs:
+        P, q, A, l, u, i_idx = problems.extend(pr)
+        e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+        o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+        ls, us = problems.branched_nodes(l, u, len(i_idx), 5, rng)
+        for b in range(5):
+            qps.append(e); os_.append(o); L.append(ls[b]); U.append(us[b]); X0.append(np.zeros(50)); Y0.append(np.zeros(105))
+    xs, ys, sc = engine.solve_multi(qps, L, U, X0, Y0)
+    xo, yo, so, io, _ = oracle_mod.solve_multi(os_, L, U, X0, Y0, threads=8)
+    assert list(sc.status) == list(so) and list(sc.iters) == list(io)
+    for b in range(len(qps)):
+        if so[b] in (1, -2):
+            _close(ys[b], yo[b])
+
+
+def test_update_q(oracle_mod):
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    q2 = q * 0.5 + 0.1
+    o.update(q=q2); e.update_q(q2)
+    ro = o.solve_node(l, u, np.zeros(50), np.zeros(105))
+    r = e.solve_batch(l[None], u[None], np.zeros((1, 50)), np.zeros((1, 105)))
+    assert r.status[0] == ro.info.status_val and r.iters[0] == ro.info.iter
+    _close(r.y[0], ro.y)
