@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""
+bench.py -- QP-relaxations/sec of the batched ADMM hot path (BASELINE.json metric).
+
+Workload (config "cfg2"): random_miqp n=500 m=1000 |i_idx|=50 density 0.7, 100 instances drawn by the
+reference generator (/root/reference/examples/random_miqp/run_example.py:71-83, np.random.seed(1)),
+each contributing the 8 leaves of its depth-3 B&B subtree on the three most fractional integer
+variables of its root relaxation, warm-started from the root's (x, y) exactly as
+Workspace.add_left/add_right create children (/root/reference/miosqp/workspace.py:157-203).
+One STEP = one pass of the hot path over that frontier batch: every leaf's full OSQP ADMM solve
+(Node.solve, /root/reference/miosqp/node.py:96-143), all leaves concurrently in one kernel launch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--instances I]
+
+value   : leaves solved per second, inputs resident in HBM, CUDA-event time of the launches.
+e2e     : the same through the public host-buffer call (pack + H2D + launch + D2H inside the timed region).
+roofline: algorithmic bytes / kernel time against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference: the CPU oracle (oracle/, a restatement of OSQP; the reference's own
+`osqp` dependency is not installable here) on all host threads over a bounded sample of the same leaves.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QP_SETTINGS = dict(eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4)   # run_example.py:113-116
+N_VAR, M_CON, P_INT, DENSITY = 500, 1000, 50, 0.7
+LEAF_DEPTH = 3
+
+
+def make_instances(count, seed):
+    from miosqp_b200 import problems
+    return [problems.extend(pr) for pr in problems.random_miqp(N_VAR, M_CON, P_INT, DENSITY, seed=seed, count=count)]
+
+
+def make_leaves(inst, x_root, y_root):
+    """8 leaves of the depth-3 subtree below the root on its 3 most fractional integer variables."""
+    P, q, A, l, u, i_idx = inst
+    m = l.shape[0]
+    n_int = len(i_idx)
+    xi = x_root[i_idx]
+    frac = np.abs(xi - np.round(xi))
+    order = np.argsort(-frac, kind="stable")[:LEAF_DEPTH]
+    L, U = [], []
+    for code in range(1 << LEAF_DEPTH):
+        ll = l.copy(); uu = u.copy()
+        for k, pos in enumerate(order):
+            row = m - n_int + pos
+            if (code >> k) & 1:
+                ll[row] = np.ceil(xi[pos])        # right child, workspace.py:189-190
+            else:
+                uu[row] = np.floor(xi[pos])       # left child, workspace.py:165-166
+        if np.any(ll > uu):                       # (integral root entry) keep the node valid
+            continue
+        L.append(ll); U.append(uu)
+    return L, U
+
+
+def algorithmic_bytes_per_node_iter(inst, T, check_every=25):
+    """8(2n+6m) + (2*12*nnzL + 16 N)/T + checks/25/T."""
+    P, q, A, l, u, i_idx = inst
+    n, m = A.shape[1], A.shape[0]
+    import scipy.sparse as spa
+    nnzA = A.nnz
+    nnz_triuP = spa.triu(P).nnz
+    nnzL = nnzA + n * (n - 1) // 2
+    N = n + m
+    return 8.0 * (2 * n + 6 * m) + (24.0 * nnzL + 16.0 * N) / T + 12.0 * (2 * nnzA + nnz_triuP) / check_every / T
+
+
+class ClockSampler(object):
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [v.strip() for v in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_oracle_sample(insts_nodes, threads, repeats=1):
+    """insts_nodes: list of (instance tuple, l, u, x0, y0).  Returns (seconds per pass, nodes, node_iters)."""
+    from oracle import oracle
+    solvers = {}
+    S, L, U, X0, Y0 = [], [], [], [], []
+    for inst, l, u, x0, y0 in insts_nodes:
+        key = id(inst)
+        if key not in solvers:
+            o = oracle.OSQP()
+            o.setup(inst[0], inst[1], inst[2], inst[3], inst[4], **QP_SETTINGS)
+            solvers[key] = o
+        S.append(solvers[key]); L.append(l); U.append(u); X0.append(x0); Y0.append(y0)
+    best = None
+    iters = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, _, st, it, _ = oracle.solve_multi(S, L, U, X0, Y0, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        iters = int(np.sum(it))
+    return best, len(S), iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=100)
+    ap.add_argument("--tile-nodes", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = host_cores()
+    workload = "random_miqp n=%d m=%d |i_idx|=%d density=%.1f, %d instances/GPU x %d leaves (depth-%d subtree, warm-started from the root)" % (
+        N_VAR, M_CON, P_INT, DENSITY, args.instances, 1 << LEAF_DEPTH, LEAF_DEPTH)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, cores, workload)
+
+    import torch
+    import torch.distributed as dist
+    from miosqp_b200 import engine
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- setup (untimed): instances, device-resident factors, root relaxations, leaf batch
+    t_setup = time.perf_counter()
+    insts = make_instances(args.instances, seed=1 + rank)
+    qps = [engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, device=local_rank, **QP_SETTINGS)
+           for (P, q, A, l, u, i_idx) in insts]
+    n, m = N_VAR, M_CON + P_INT
+    xs, ys, sc = engine.solve_multi(qps, [i[3] for i in insts], [i[4] for i in insts],
+                                    [np.zeros(n)] * len(insts), [np.zeros(m)] * len(insts))
+    root_iters = int(np.sum(sc.iters))
+    Q, L, U, X0, Y0, owner = [], [], [], [], [], []
+    for k, inst in enumerate(insts):
+        x_root = np.nan_to_num(xs[k]); y_root = np.nan_to_num(ys[k])
+        ll, uu = make_leaves(inst, x_root, y_root)
+        for a, b in zip(ll, uu):
+            Q.append(qps[k]); L.append(a); U.append(b); X0.append(x_root); Y0.append(y_root); owner.append(k)
+    B = len(Q)
+    engine.set_tuning(args.tile_nodes, args.threads)
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident measurement: inputs stay in HBM, one launch per step
+    rb = engine.ResidentBatch(Q, L, U, X0, Y0)
+    for _ in range(args.warmup):
+        rb.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rb.run()                                   # blocking; CUDA events on the engine's stream
+        kernel_ms.append(engine.last_timing()["kernel_ms"])
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    clocks = sampler.stop()
+    xs, ys, sc = rb.download()
+    tm = engine.last_timing()
+    dev_s = float(np.sum(kernel_ms)) / 1e3
+    node_iters = int(tm["node_iters"])
+
+    # ---- end to end through the public host-buffer API
+    for _ in range(min(args.warmup, 2)):
+        engine.solve_multi(Q, L, U, X0, Y0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        xs2, ys2, sc2 = engine.solve_multi(Q, L, U, X0, Y0)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tm2 = engine.last_timing()
+
+    # ---- max over ranks
+    times = torch.tensor([dev_s, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([B, node_iters], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    dev_s_max, e2e_s_max, wall_max = [float(v) for v in times.tolist()]
+    B_all, iters_all = [float(v) for v in counts.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        T = 1 << LEAF_DEPTH
+        bytes_per_ni = algorithmic_bytes_per_node_iter(insts[0], T)
+        launch_s = dev_s / args.steps
+        achieved = bytes_per_ni * node_iters / launch_s / 1e9
+        out = {
+            "metric": "QP-relaxations/sec", "value": B_all * args.steps / dev_s_max, "unit": "QP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "leaves_per_step": int(B_all), "qp_settings": QP_SETTINGS,
+                       "parallelism": "instances sharded across %d GPU(s), no data-path collective" % world,
+                       "l2": "inputs larger than L2 (%.0f MB of factors per GPU streamed every ADMM iteration)" % (
+                           sum(qp.dims()["factor_bytes"] for qp in qps) / 1e6),
+                       "tile_nodes": tm["tile_nodes"], "threads_per_cta": tm["threads"], "tiles": tm["tiles"],
+                       "smem_bytes_per_cta": tm["smem_bytes"]},
+            "admm_node_iters_per_s": iters_all * args.steps / dev_s_max,
+            "admm_iters_per_leaf": node_iters / float(B),
+            "status_counts": {str(k): int(v) for k, v in zip(*np.unique(sc.status, return_counts=True))},
+            "e2e": {"value": B_all * args.steps / e2e_s_max, "unit": "QP/s",
+                    "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"])},
+            "gpu_launches": args.steps * int(tm["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "traffic": None, "kernel": "admm_tile_kernel<%d>" % tm["tile_nodes"],
+                         "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_launch": node_iters,
+                         "launch_ms": 1e3 * launch_s,
+                         "streamed_bytes_per_launch": int(tm["stream_bytes"]),
+                         "streamed_gbs": tm["stream_bytes"] / launch_s / 1e9},
+            "setup_s": t_setup, "root_iters": root_iters, "wall_s_resident_loop": wall_max,
+        }
+        if not args.no_cpu_baseline:
+            S = min(B, 8 * cores)
+            sample = [(insts[owner[b]], L[b], U[b], X0[b], Y0[b]) for b in range(S)]
+            secs, nodes, its = run_oracle_sample(sample, cores)
+            out["cpu_baseline"] = {"value": nodes / secs, "unit": "QP/s", "cores": cores, "kind": "port",
+                                   "sample": "first %d leaves of the step's batch, CPU oracle (oracle/osqp_oracle.c), %d threads, %.1f s" % (
+                                       nodes, cores, secs),
+                                   "admm_node_iters_per_s": its / secs}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args, cores, workload):
+    """The reference's CPU path: its OSQP dependency is not installable here, so this times the CPU oracle
+    (a restatement of the same algorithm) on every host thread, on a bounded sample of the same leaves."""
+    from oracle import oracle
+    S_inst = max(1, min(args.instances, cores // 2))   # instances in the sample
+    insts = make_instances(S_inst, seed=1)
+    n, m = N_VAR, M_CON + P_INT
+    solvers = []
+    for inst in insts:
+        o = oracle.OSQP(); o.setup(inst[0], inst[1], inst[2], inst[3], inst[4], **QP_SETTINGS)
+        solvers.append(o)
+    xr, yr, st, it, _ = oracle.solve_multi(solvers, [i[3] for i in insts], [i[4] for i in insts],
+                                           [np.zeros(n)] * S_inst, [np.zeros(m)] * S_inst, threads=cores)
+    S, L, U, X0, Y0 = [], [], [], [], []
+    for k, inst in enumerate(insts):
+        x_root = np.nan_to_num(xr[k]); y_root = np.nan_to_num(yr[k])
+        ll, uu = make_leaves(inst, x_root, y_root)
+        for a, b in zip(ll, uu):
+            S.append(solvers[k]); L.append(a); U.append(b); X0.append(x_root); Y0.append(y_root)
+    for _ in range(min(args.warmup, 1)):
+        oracle.solve_multi(S, L, U, X0, Y0, threads=cores)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        _, _, st, it, _ = oracle.solve_multi(S, L, U, X0, Y0, threads=cores)
+        iters += int(np.sum(it))
+    secs = time.perf_counter() - t0
+    value = len(S) * args.steps / secs
+    sample = "%d leaves (first %d instances x 8) per step, CPU oracle, %d threads" % (len(S), S_inst, cores)
+    out = {"impl": "reference", "metric": "QP-relaxations/sec", "value": value, "unit": "QP/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "sample": sample, "qp_settings": QP_SETTINGS},
+           "admm_node_iters_per_s": iters / secs,
+           "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

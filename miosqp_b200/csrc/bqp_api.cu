@@ -85,6 +85,7 @@ struct BatchCtx {
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
+  bool use_stream = false; int nslots = 0, slot_bytes = 0;
   size_t smem = 0, in_doubles = 0, out_doubles = 0;
   std::vector<bqp_instance *> node_inst;
   std::vector<long long> out_off;
@@ -141,6 +142,20 @@ int to_device(bqp_instance *inst) {
   if ((rc = upload(inst, h.E, &d.E))) return rc;
   if ((rc = upload(inst, h.Einv, &d.Einv))) return rc;
   if ((rc = upload(inst, h.i_idx, &d.i_idx))) return rc;
+  d.stream = nullptr; d.groups = nullptr;
+  if (h.st.built) {
+    const unsigned char *dstream = nullptr;
+    const StreamGroup *dgroups = nullptr;
+    if ((rc = upload(inst, h.st.data, &dstream))) return rc;
+    if ((rc = upload(inst, h.st.groups, &dgroups))) return rc;
+    d.stream = dstream; d.groups = dgroups;
+    const HostStream &st = h.st;
+    d.g_at[0] = st.range[GK_AT][0]; d.g_at[1] = st.range[GK_AT][1];
+    d.g_fw[0] = st.fw[0]; d.g_fw[1] = st.fw[1];
+    d.g_bw[0] = st.bw[0]; d.g_bw[1] = st.bw[1];
+    d.g_ab[0] = st.range[GK_AB][0]; d.g_ab[1] = st.range[GK_AB][1];
+    d.g_pm[0] = st.range[GK_PM][0]; d.g_pm[1] = st.range[GK_PM][1];
+  }
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
   d.eps_pinf = h.s.eps_prim_inf; d.eps_dinf = h.s.eps_dual_inf;
@@ -248,28 +263,50 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     if (it == uid.end()) { uid[handles[b]] = (int)uniq.size(); uniq.push_back(handles[b]); members.emplace_back(); it = uid.find(handles[b]); }
     members[it->second].push_back(b);
   }
-  // CTA shape: enough warps to give every 32-row slice of the widest panel its own warp
+  // engine: the TMA-streamed kernel when every problem has a streamed layout (bqp_set_tuning(threads>0) forces
+  // the direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
+  bool use_stream = g_tune_threads == 0;
+  int slot_bytes = kStageValBytes;
+  for (auto *inst : uniq) {
+    const HostStream &st = inst->h.st;
+    if (!st.built || (int)st.groups.size() > 96 || st.range[GK_AT][1] - st.range[GK_AT][0] > 4) use_stream = false;
+    else slot_bytes = std::max(slot_bytes, st.slot_bytes);
+  }
+  auto stream_slots = [&](const HostInstance &h, int t) {
+    const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_bytes, 0);
+    return (int)std::min<long long>(8, ((long long)kMaxSmem - fixed) / slot_bytes);
+  };
   int threads = g_tune_threads;
-  if (!threads) {
+  if (!use_stream && !threads) {
     int want = 2;
     for (auto *inst : uniq) want = std::max(want, std::max(inst->h.Ab.nslices, inst->h.At.nslices));
     threads = 32 * std::min(pow2ceil(want), kMaxThreads / 32);
   }
-  // nodes per tile: as wide as shared memory allows, but narrow enough to spread a small frontier over the SMs
-  int tt_cap = kMaxTT;
+  if (use_stream) threads = 17 * 32;
+  // nodes per tile: as wide as shared memory allows ...
+  int tt_cap = kMaxTT, nslots = 8;
   for (auto *inst : uniq) {
-    int t = max_tile_nodes(inst->h, threads);
+    int t = 0;
+    if (use_stream) {
+      t = kMaxTT;
+      while (t > 1 && stream_slots(inst->h, t) < 4) t >>= 1;
+      if (stream_slots(inst->h, t) < 4) t = 0;
+    } else {
+      t = max_tile_nodes(inst->h, threads);
+    }
     if (t == 0) return BQP_E_UNSUPPORTED;
     tt_cap = std::min(tt_cap, t);
   }
-  int tt = g_tune_tt ? std::min(g_tune_tt, tt_cap) : tt_cap;
-  if (!g_tune_tt) {
+  int widest = 1;
+  for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
+  int tt = g_tune_tt ? std::min(g_tune_tt, tt_cap) : std::min(tt_cap, pow2ceil(widest));
+  if (!g_tune_tt) {   // ... but narrow enough to spread a small frontier over the SMs
     auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
-    while (tt > 1 && count_tiles(tt) < ndev_sms && count_tiles(tt / 2) <= 2LL * ndev_sms) tt >>= 1;
-    int widest = 1;
-    for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
-    tt = std::min(tt, pow2ceil(widest));
+    const long long target = use_stream ? ndev_sms / 2 : ndev_sms;
+    while (tt > 1 && count_tiles(tt) < target && count_tiles(tt / 2) <= 2LL * ndev_sms) tt >>= 1;
   }
+  if (use_stream)
+    for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
   // tiles: split each instance's nodes evenly
   g.tiles.clear(); g.node_inst.assign(B, nullptr); g.out_off.assign(B, 0);
   g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_max_iter.clear();
@@ -283,7 +320,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   for (size_t k = 0; k < uniq.size(); k++) {
     const HostInstance &h = uniq[k]->h;
     const int cnt = (int)members[k].size(), nt = (cnt + tt - 1) / tt;
-    smem = std::max(smem, tile_smem_bytes(h.n, h.m, tt, threads));
+    smem = std::max(smem, use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_bytes, nslots) : tile_smem_bytes(h.n, h.m, tt, threads));
     for (int ti = 0; ti < nt; ti++) {
       const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
       DevTile t{};
@@ -295,13 +332,14 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
       t.work_off = (long long)work_d;
       work_d += tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
-      g.tile_bytes_iter.push_back(h.factor_bytes());
-      g.tile_bytes_check.push_back(h.check_bytes());
+      g.tile_bytes_iter.push_back(use_stream ? h.st.iter_bytes : h.factor_bytes());
+      g.tile_bytes_check.push_back(use_stream ? h.st.check_bytes : h.check_bytes());
       g.tile_check_every.push_back(h.s.check_termination);
       g.tile_max_iter.push_back(h.s.max_iter);
     }
   }
   g.B = B; g.ntiles = (int)g.tiles.size(); g.tt = tt; g.threads = threads; g.smem = smem;
+  g.use_stream = use_stream; g.nslots = nslots; g.slot_bytes = slot_bytes;
   g.in_doubles = in_d; g.out_doubles = out_d;
   if ((rc = g.h_in.reserve(in_d * 8))) return rc;
   if ((rc = g.h_out.reserve(out_d * 8))) return rc;
@@ -346,9 +384,13 @@ int bqp_batch_run(void) {
   if (!g.resident) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
   CK(cudaEventRecord(g.ev[1], g.stream));
-  int rc = launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
-                       (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
-                       (int *)g.d_ti.p, g.smem, g.stream);
+  int rc = g.use_stream
+               ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
+                                    g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p,
+                                    (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
+               : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                             (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                             (int *)g.d_ti.p, g.smem, g.stream);
   if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaStreamSynchronize(g.stream));
@@ -479,10 +521,28 @@ int bqp_debug_host_kkt_solve(bqp_handle h, double *rhs_xz) {
   return BQP_OK;
 }
 
+int bqp_debug_host_stream_kkt_solve(bqp_handle h, double *rhs_xz) {
+  if (!h || !rhs_xz) return BQP_E_ARG;
+  return host_stream_kkt_solve(&h->h, rhs_xz);
+}
+
 int bqp_debug_host_matvec(bqp_handle h, int which, const double *in, double *out) {
-  if (!h || !in || !out || which < 0 || which > 2) return BQP_E_ARG;
+  if (!h || !in || !out || which < 0 || which > 3) return BQP_E_ARG;
+  if (which == 3) return host_stream_matvec_P(&h->h, in, out);
   host_matvec(which == 0 ? h->h.Ab : (which == 1 ? h->h.At : h->h.Pm), in, out);
   return BQP_OK;
 }
 
 }  // extern "C"
+
+extern "C" int bqp_debug_dump_groups(bqp_handle h) {
+  if (!h) return BQP_E_ARG;
+  const HostStream &st = h->h.st;
+  std::printf("built=%d groups=%zu slot_bytes=%d iter_bytes=%lld\n", (int)st.built, st.groups.size(), st.slot_bytes, st.iter_bytes);
+  for (size_t g = 0; g < st.groups.size(); g++) {
+    const StreamGroup &G = st.groups[g];
+    std::printf("g%2zu kind=%d row0=%4d nsl=%2d sparse=%d qch=[%d %d %d %d] qcol0=[%d %d %d %d] off=%lld\n", g, G.kind, G.row0, G.nsl,
+                G.sparse, G.qch[0], G.qch[1], G.qch[2], G.qch[3], G.qcol0[0], G.qcol0[1], G.qcol0[2], G.qcol0[3], G.data_off);
+  }
+  return BQP_OK;
+}

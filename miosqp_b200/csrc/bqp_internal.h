@@ -39,6 +39,33 @@ struct DevMat {
   const int *idx;
 };
 
+// ---- streamed layout of the sm_100a TMA kernel (bqp_stream.cu) ------------------------------------------
+// Everything one ADMM iteration touches is laid out ONCE, in consumption order, as a sequence of GROUPS.
+// A group is up to 16 row slices (32 rows each; slice i belongs to consumer warp i, warps 4q..4q+3 form
+// QUAD q).  Its data is a sequence of fixed-size STAGES, one TMA bulk copy each:
+//   stage = vals[4 warps][kKC entry-rows][32 lanes] (f64)  (+ idx[4][kKC][32] (i32) when the group is sparse)
+// ordered by (chunk c, quad q) for every quad with c < qch[q].  Dense groups multiply entry-row e of quad q
+// with element in_off + qcol0[q] + e of the input vector; sparse groups with in_off + idx.
+constexpr int kKC = 16;
+constexpr int kStageValBytes = 4 * kKC * 32 * 8;   // 16 KiB
+constexpr int kStageIdxBytes = 4 * kKC * 32 * 4;   //  8 KiB
+enum { GK_AT = 0, GK_FWD_D = 1, GK_FWD_U = 2, GK_BWD_D = 3, GK_BWD_U = 4, GK_AB = 5, GK_PM = 6 };
+struct StreamGroup {
+  int kind, row0, nsl, in_off, sparse;
+  int qch[4], qcol0[4];
+  long long data_off;   // bytes into the instance's stream buffer
+};
+struct HostStream {
+  bool built = false;
+  int tri_nb = 0;
+  std::vector<StreamGroup> groups;
+  int range[7][2] = {};              // [kind] -> [first, last) group index (FWD/BWD kinds D and U interleaved: see fw, bw)
+  int fw[2] = {0, 0}, bw[2] = {0, 0};
+  std::vector<unsigned char> data;
+  long long iter_bytes = 0, check_bytes = 0;   // bytes streamed by one iteration / one termination check
+  int slot_bytes = kStageValBytes;
+};
+
 // Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
 // KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
 // streamed as the A panels and the dense trailing supernode L22 D2 L22' = P + sigma I + A' diag(rho) A).
@@ -57,6 +84,7 @@ struct HostInstance {
   // diagonal block holds the strictly-lower part of inv(L22[J,J]) (unit diagonal implicit), so the
   // in-block substitution is a mat-vec.
   std::vector<double> Lcol, Lrow, D2inv;
+  HostStream st;                         // streamed layout (built for problems large enough for the TMA kernel)
   long long factor_bytes() const {   // bytes one ADMM iteration streams: A', L fwd, L bwd, A, D2inv
     return (long long)(Lcol.size() + Lrow.size() + D2inv.size()) * 8 + At.stream_bytes() + Ab.stream_bytes();
   }
@@ -69,9 +97,14 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *out); 
 void host_rescale_q(HostInstance *h, const double *q);
 void host_kkt_solve(const HostInstance *h, double *rhs_xz);
 void host_matvec(const HostMat &M, const double *in, double *out);
+int host_stream_kkt_solve(const HostInstance *h, double *rhs_xz);
+int host_stream_matvec_P(const HostInstance *h, const double *in, double *out);
 
 struct DevInstance {
   int n, m, npad, n_int;
+  // streamed layout (TMA kernel)
+  const unsigned char *stream; const StreamGroup *groups;
+  int g_at[2], g_fw[2], g_bw[2], g_ab[2], g_pm[2];
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -98,6 +131,10 @@ struct NodeScalars {
 // state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each)
 inline size_t tile_work_doubles(int n, int m, int tt) { return (size_t)tt * (5 * (size_t)m + 2 * (size_t)n); }
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
+size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots);          // bqp_stream.cu
+int launch_admm_stream(int tt, int slot_bytes, int nslots, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
+                       size_t smem_bytes, void *stream);
 int launch_admm(int tt, int threads, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
                 double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes, void *stream);
 

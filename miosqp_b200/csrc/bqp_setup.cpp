@@ -12,6 +12,7 @@
 // Nothing here calls into oracle/.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "bqp_internal.h"
@@ -138,6 +139,165 @@ void build_panel(const RowList &rows, int ncols, HostMat *M) {
     M->sptr[s + 1] = (int)(M->vals.size() / 32);
     (void)nnz;
   }
+}
+
+}  // namespace
+
+
+// ------------------------------------------------------------------------------------------------------
+// Streamed layout (see bqp_internal.h): groups of <= 16 slices, fixed-size stages in (chunk, quad) order.
+namespace {
+
+using Entry = std::pair<int, double>;
+using Row = std::vector<Entry>;
+
+// rows: 32*nsl entry lists (absolute columns of the input vector, sorted by column)
+void add_group(HostStream &st, int kind, int row0, const std::vector<const Row *> &rows) {
+  static const Row empty;
+  StreamGroup G{};
+  G.kind = kind; G.row0 = row0; G.nsl = (int)rows.size() / 32; G.in_off = 0;
+  int clo[4], chi[4], mlen[4];
+  long long dense_stages = 0, sparse_stages = 0;
+  for (int q = 0; q < 4; q++) {
+    clo[q] = 1 << 30; chi[q] = -1; mlen[q] = 0;
+    for (int r = q * 128; r < std::min<int>((q + 1) * 128, (int)rows.size()); r++) {
+      const Row &R = rows[r] ? *rows[r] : empty;
+      if (R.empty()) continue;
+      clo[q] = std::min(clo[q], R.front().first);
+      chi[q] = std::max(chi[q], R.back().first + 1);
+      mlen[q] = std::max(mlen[q], (int)R.size());
+    }
+    if (chi[q] < 0) { clo[q] = 0; chi[q] = 0; }
+    // a quad that owns slices must still see the group (its warps arrive on the barriers) only if it has data
+    dense_stages += (chi[q] - clo[q] + kKC - 1) / kKC;
+    sparse_stages += (mlen[q] + kKC - 1) / kKC;
+  }
+  G.sparse = sparse_stages * (kStageValBytes + kStageIdxBytes) < dense_stages * kStageValBytes ? 1 : 0;
+  for (int q = 0; q < 4; q++) {
+    G.qcol0[q] = G.sparse ? 0 : clo[q];
+    G.qch[q] = G.sparse ? (mlen[q] + kKC - 1) / kKC : (chi[q] - clo[q] + kKC - 1) / kKC;
+  }
+  G.data_off = (long long)st.data.size();
+  const int sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
+  if (G.sparse) st.slot_bytes = std::max(st.slot_bytes, sb);
+  int maxc = std::max(std::max(G.qch[0], G.qch[1]), std::max(G.qch[2], G.qch[3]));
+  std::vector<size_t> cursor(rows.size(), 0);   // dense mode: next entry of each row not yet emitted
+  for (int c = 0; c < maxc; c++)
+    for (int q = 0; q < 4; q++) {
+      if (c >= G.qch[q]) continue;
+      const size_t base = st.data.size();
+      st.data.resize(base + sb, 0);
+      double *vals = reinterpret_cast<double *>(st.data.data() + base);
+      int *idx = reinterpret_cast<int *>(st.data.data() + base + kStageValBytes);
+      for (int wq = 0; wq < 4; wq++)
+        for (int lane = 0; lane < 32; lane++) {
+          const size_t r = (size_t)(q * 4 + wq) * 32 + lane;
+          if (r >= rows.size() || !rows[r]) continue;
+          const Row &R = *rows[r];
+          if (G.sparse) {
+            for (int j = 0; j < kKC; j++) {
+              const size_t e = (size_t)c * kKC + j;
+              if (e >= R.size()) break;
+              vals[(wq * kKC + j) * 32 + lane] = R[e].second;
+              idx[(wq * kKC + j) * 32 + lane] = R[e].first;
+            }
+          } else {
+            const int col0 = G.qcol0[q] + c * kKC;
+            size_t &k = cursor[r];
+            while (k < R.size() && R[k].first < col0 + kKC) {
+              vals[(wq * kKC + (R[k].first - col0)) * 32 + lane] = R[k].second;
+              k++;
+            }
+          }
+        }
+    }
+  st.groups.push_back(G);
+}
+
+// split `rows` (a multiple of 32 entries is not required) into groups of <= 16 slices of similar size
+void add_panel(HostStream &st, int kind, int row0, const std::vector<const Row *> &rows_in) {
+  std::vector<const Row *> rows(rows_in);
+  while (rows.size() % 32) rows.push_back(nullptr);
+  const int nsl = (int)rows.size() / 32;
+  if (nsl == 0) return;
+  const int ng = (nsl + 15) / 16, spg = (nsl + ng - 1) / ng;
+  for (int g = 0; g < ng; g++) {
+    const int s0 = g * spg, s1 = std::min(nsl, s0 + spg);
+    if (s0 >= s1) break;
+    std::vector<const Row *> sub(rows.begin() + (size_t)s0 * 32, rows.begin() + (size_t)s1 * 32);
+    add_group(st, kind, row0 + s0 * 32, sub);
+  }
+}
+
+long long bytes_of(const HostStream &st, int g0, int g1) {
+  long long b = 0;
+  for (int g = g0; g < g1; g++) {
+    const StreamGroup &G = st.groups[g];
+    b += (long long)(G.qch[0] + G.qch[1] + G.qch[2] + G.qch[3]) * (kStageValBytes + (G.sparse ? kStageIdxBytes : 0));
+  }
+  return b;
+}
+
+// S: dense column-major npad x npad holding unit-lower L22 strictly below the diagonal
+void build_stream(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &atrows,
+                  const std::vector<Row> &prows, const std::vector<double> &S, int tri_nb) {
+  HostStream &st = h->st;
+  const int np_ = h->npad;
+  st = HostStream();
+  st.tri_nb = tri_nb;
+  auto L = [&](int r, int c) -> double { return S[(size_t)c * np_ + r]; };
+  auto ptrs = [](const std::vector<Row> &v) { std::vector<const Row *> p; for (auto &r : v) p.push_back(&r); return p; };
+  st.range[GK_AT][0] = (int)st.groups.size();
+  add_panel(st, GK_AT, 0, ptrs(atrows));
+  st.range[GK_AT][1] = (int)st.groups.size();
+  // triangular sweeps over super-blocks of tri_nb columns with explicitly inverted diagonal super-blocks
+  const int nsb = (np_ + tri_nb - 1) / tri_nb;
+  std::vector<std::vector<double>> Xs(nsb);
+  for (int J = 0; J < nsb; J++) {
+    const int r0 = J * tri_nb, nbj = std::min(tri_nb, np_ - r0);
+    std::vector<double> &X = Xs[J];
+    X.assign((size_t)nbj * nbj, 0.0);   // row-major inverse of the unit-lower diagonal super-block
+    for (int c = 0; c < nbj; c++) {
+      X[(size_t)c * nbj + c] = 1.0;
+      for (int r = c + 1; r < nbj; r++) {
+        double acc = 0;
+        for (int k = c; k < r; k++) acc += L(r0 + r, r0 + k) * X[(size_t)k * nbj + c];
+        X[(size_t)r * nbj + c] = -acc;
+      }
+    }
+  }
+  st.fw[0] = (int)st.groups.size();
+  for (int J = 0; J < nsb; J++) {
+    const int r0 = J * tri_nb, nbj = std::min(tri_nb, np_ - r0);
+    std::vector<Row> d(nbj), u(std::max(0, np_ - r0 - nbj));
+    for (int r = 0; r < nbj; r++)
+      for (int c = 0; c <= r; c++) d[r].push_back({r0 + c, Xs[J][(size_t)r * nbj + c]});
+    for (int r = r0 + nbj; r < np_; r++)
+      for (int c = 0; c < nbj; c++) u[r - r0 - nbj].push_back({r0 + c, L(r, r0 + c)});
+    add_panel(st, GK_FWD_D, r0, ptrs(d));
+    add_panel(st, GK_FWD_U, r0 + nbj, ptrs(u));
+  }
+  st.fw[1] = st.bw[0] = (int)st.groups.size();
+  for (int J = nsb - 1; J >= 0; J--) {
+    const int r0 = J * tri_nb, nbj = std::min(tri_nb, np_ - r0);
+    std::vector<Row> d(nbj), u(r0);
+    for (int c = 0; c < nbj; c++)
+      for (int rr = c; rr < nbj; rr++) d[c].push_back({r0 + rr, Xs[J][(size_t)rr * nbj + c]});
+    for (int c = 0; c < r0; c++)
+      for (int rr = 0; rr < nbj; rr++) u[c].push_back({r0 + rr, L(r0 + rr, c)});
+    add_panel(st, GK_BWD_D, r0, ptrs(d));
+    add_panel(st, GK_BWD_U, 0, ptrs(u));
+  }
+  st.bw[1] = (int)st.groups.size();
+  st.range[GK_AB][0] = (int)st.groups.size();
+  add_panel(st, GK_AB, 0, ptrs(arows));
+  st.range[GK_AB][1] = st.range[GK_PM][0] = (int)st.groups.size();
+  add_panel(st, GK_PM, 0, ptrs(prows));
+  st.range[GK_PM][1] = (int)st.groups.size();
+  st.iter_bytes = bytes_of(st, st.range[GK_AT][0], st.range[GK_AB][1]);
+  st.check_bytes = 2 * (bytes_of(st, st.range[GK_AT][0], st.range[GK_AT][1]) + bytes_of(st, st.range[GK_AB][0], st.range[GK_AB][1]) +
+                        bytes_of(st, st.range[GK_PM][0], st.range[GK_PM][1]));
+  st.built = true;
 }
 
 }  // namespace
@@ -293,6 +453,14 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
   }
   h->nq = 0;
   for (int j = 0; j < n; j++) h->nq = std::max(h->nq, std::fabs(h->Dinv[j] * h->q[j]));
+  // streamed layout for the TMA kernel (problems with at least 4 slices of variables)
+  h->st = HostStream();
+  if (h->At.nslices >= 4) {
+    int tri_nb = 128;
+    if (const char *e = std::getenv("BQP_TRI_NB")) tri_nb = std::atoi(e);
+    tri_nb = std::max(32, std::min(512, (tri_nb / 32) * 32));
+    build_stream(h, arows, atrows, prows, S, tri_nb);
+  }
   return BQP_OK;
 }
 
@@ -365,6 +533,77 @@ void host_kkt_solve(const HostInstance *h, double *rhs) {
   host_matvec(h->Ab, b.data(), t.data());
   for (int j = 0; j < n; j++) rhs[j] = b[j];
   for (int i = 0; i < m; i++) rhs[n + i] = h->rho[i] * (t[i] - rhs[n + i]);
+}
+
+// ---- host-only debug restatement of the streamed layout (tests only): what consume_group computes
+static void host_group_apply(const HostStream &st, const StreamGroup &G, const double *in, double *acc) {
+  const int nrows = G.nsl * 32;
+  for (int r = 0; r < nrows; r++) acc[r] = 0.0;
+  const unsigned char *p = st.data.data() + G.data_off;
+  const int sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
+  const int maxc = std::max(std::max(G.qch[0], G.qch[1]), std::max(G.qch[2], G.qch[3]));
+  for (int c = 0; c < maxc; c++)
+    for (int q = 0; q < 4; q++) {
+      if (c >= G.qch[q]) continue;
+      const double *vals = reinterpret_cast<const double *>(p);
+      const int *idx = reinterpret_cast<const int *>(p + kStageValBytes);
+      for (int wq = 0; wq < 4; wq++)
+        for (int j = 0; j < kKC; j++)
+          for (int lane = 0; lane < 32; lane++) {
+            const int r = (q * 4 + wq) * 32 + lane;
+            if (r >= nrows) continue;
+            const int col = G.sparse ? idx[(wq * kKC + j) * 32 + lane] : G.qcol0[q] + c * kKC + j;
+            acc[r] = std::fma(vals[(wq * kKC + j) * 32 + lane], in[G.in_off + col], acc[r]);
+          }
+      p += sb;
+    }
+}
+
+int host_stream_kkt_solve(const HostInstance *h, double *rhs) {
+  const HostStream &st = h->st;
+  if (!st.built) return BQP_E_UNSUPPORTED;
+  const int n = h->n, m = h->m, np_ = h->npad;
+  std::vector<double> w(m + 64, 0.0), b(np_ + 64, 0.0), acc(16 * 32), t(m + 64, 0.0);
+  for (int i = 0; i < m; i++) w[i] = h->rho[i] * rhs[n + i];
+  for (int g = st.range[GK_AT][0]; g < st.range[GK_AT][1]; g++) {
+    const StreamGroup &G = st.groups[g];
+    host_group_apply(st, G, w.data(), acc.data());
+    for (int r = 0; r < G.nsl * 32; r++) if (G.row0 + r < n) b[G.row0 + r] = rhs[G.row0 + r] + acc[r];
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    const int g0 = pass ? st.bw[0] : st.fw[0], g1 = pass ? st.bw[1] : st.fw[1];
+    if (pass) for (int j = 0; j < np_; j++) b[j] *= h->D2inv[j];
+    for (int g = g0; g < g1; g++) {
+      const StreamGroup &G = st.groups[g];
+      host_group_apply(st, G, b.data(), acc.data());
+      const bool diag = (G.kind == GK_FWD_D || G.kind == GK_BWD_D);
+      for (int r = 0; r < G.nsl * 32; r++) {
+        if (G.row0 + r >= np_) continue;
+        if (diag) b[G.row0 + r] = acc[r]; else b[G.row0 + r] -= acc[r];
+      }
+    }
+  }
+  for (int g = st.range[GK_AB][0]; g < st.range[GK_AB][1]; g++) {
+    const StreamGroup &G = st.groups[g];
+    host_group_apply(st, G, b.data(), acc.data());
+    for (int r = 0; r < G.nsl * 32; r++) if (G.row0 + r < m) t[G.row0 + r] = acc[r];
+  }
+  for (int j = 0; j < n; j++) rhs[j] = b[j];
+  for (int i = 0; i < m; i++) rhs[n + i] = h->rho[i] * (t[i] - rhs[n + i]);
+  return BQP_OK;
+}
+
+int host_stream_matvec_P(const HostInstance *h, const double *in, double *out) {
+  const HostStream &st = h->st;
+  if (!st.built) return BQP_E_UNSUPPORTED;
+  std::vector<double> v(h->npad + 64, 0.0), acc(16 * 32);
+  for (int j = 0; j < h->n; j++) v[j] = in[j];
+  for (int g = st.range[GK_PM][0]; g < st.range[GK_PM][1]; g++) {
+    const StreamGroup &G = st.groups[g];
+    host_group_apply(st, G, v.data(), acc.data());
+    for (int r = 0; r < G.nsl * 32; r++) if (G.row0 + r < h->n) out[G.row0 + r] = acc[r];
+  }
+  return BQP_OK;
 }
 
 }  // namespace bqp

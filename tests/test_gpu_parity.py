@@ -153,3 +153,42 @@ def test_update_q(oracle_mod):
     r = e.solve_batch(l[None], u[None], np.zeros((1, 50)), np.zeros((1, 105)))
     assert r.status[0] == ro.info.status_val and r.iters[0] == ro.info.iter
     _close(r.y[0], ro.y)
+
+
+# ---------------------------------------------------------------- TMA-streamed kernel (bqp_stream.cu)
+@pytest.mark.parametrize("tt", [1, 2, 4, 8])
+def test_stream_kernel_tile_widths(oracle_mod, tt):
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == 17 * 32       # 16 consumer warps + the TMA producer warp
+
+
+def test_stream_kernel_sparse_groups(oracle_mod):
+    pr = problems.random_miqp(400, 600, 20, 0.03, seed=8)[0]
+    _compare(pr, 5, 7, QP, oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == 17 * 32
+
+
+def test_stream_vs_direct_kernel_same_results():
+    """Both kernels implement the same iteration; statuses and iteration counts must agree."""
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    ls, us = problems.branched_nodes(l, u, len(i_idx), 7, np.random.default_rng(3))
+    x0 = np.zeros((7, 130)); y0 = np.zeros((7, 210))
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    r1 = e.solve_batch(ls, us, x0, y0)
+    engine.set_tuning(0, 256)
+    try:
+        r2 = e.solve_batch(ls, us, x0, y0)
+        assert engine.last_timing()["threads"] == 256
+    finally:
+        engine.set_tuning(0, 0)
+    assert list(r1.status) == list(r2.status) and list(r1.iters) == list(r2.iters)
+    _close(r1.x, r2.x); _close(r1.y, r2.y); _close(r1.lower, r2.lower)
+
+
+def test_cfg2_size_leaves(oracle_mod):
+    """BASELINE cfg 2 shape (n=500, m=1000, |i_idx|=50): 8 leaves of one instance in one tile."""
+    pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
+    _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == 17 * 32
