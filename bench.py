@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sort", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +198,11 @@ def main():
                                     [np.zeros(n)] * len(insts), [np.zeros(m)] * len(insts))
     root_iters = int(np.sum(sc.iters))
     Q, L, U, X0, Y0, owner = [], [], [], [], [], []
-    for k, inst in enumerate(insts):
+    # longest-first submission: a leaf's ADMM iteration count correlates with its parent's, and tiles are scheduled in
+    # submission order, so the instances whose root needed most iterations go first (shorter tail when tiles > SMs)
+    order = np.argsort(-sc.iters, kind="stable") if not args.no_sort else np.arange(len(insts))
+    for k in order:
+        inst = insts[k]
         x_root = np.nan_to_num(xs[k]); y_root = np.nan_to_num(ys[k])
         ll, uu = make_leaves(inst, x_root, y_root)
         for a, b in zip(ll, uu):
@@ -277,6 +282,7 @@ def main():
                        "smem_bytes_per_cta": tm["smem_bytes"]},
             "admm_node_iters_per_s": iters_all * args.steps / dev_s_max,
             "admm_iters_per_leaf": node_iters / float(B),
+            "admm_iters_max": int(np.max(sc.iters)), "admm_iters_median": float(np.median(sc.iters)),
             "status_counts": {str(k): int(v) for k, v in zip(*np.unique(sc.status, return_counts=True))},
             "e2e": {"value": B_all * args.steps / e2e_s_max, "unit": "QP/s",
                     "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"])},

@@ -273,8 +273,9 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     else slot_bytes = std::max(slot_bytes, st.slot_bytes);
   }
   auto stream_slots = [&](const HostInstance &h, int t) {
-    const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_bytes, 0);
-    return (int)std::min<long long>(8, ((long long)kMaxSmem - fixed) / slot_bytes);
+    // slots PER QUAD (the kernel keeps one ring per quad of consumer warps)
+    const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_bytes, 0) + 1024;
+    return (int)std::min<long long>(8, ((long long)kMaxSmem - fixed) / ((kStreamWarps / 4) * (long long)slot_bytes));
   };
   int threads = g_tune_threads;
   if (!use_stream && !threads) {
@@ -282,15 +283,15 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     for (auto *inst : uniq) want = std::max(want, std::max(inst->h.Ab.nslices, inst->h.At.nslices));
     threads = 32 * std::min(pow2ceil(want), kMaxThreads / 32);
   }
-  if (use_stream) threads = 17 * 32;
+  if (use_stream) threads = (kStreamWarps + 1) * 32;
   // nodes per tile: as wide as shared memory allows ...
   int tt_cap = kMaxTT, nslots = 8;
   for (auto *inst : uniq) {
     int t = 0;
     if (use_stream) {
       t = kMaxTT;
-      while (t > 1 && stream_slots(inst->h, t) < 4) t >>= 1;
-      if (stream_slots(inst->h, t) < 4) t = 0;
+      while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
+      if (stream_slots(inst->h, t) < 2) t = 0;
     } else {
       t = max_tile_nodes(inst->h, threads);
     }

@@ -41,14 +41,16 @@ struct DevMat {
 
 // ---- streamed layout of the sm_100a TMA kernel (bqp_stream.cu) ------------------------------------------
 // Everything one ADMM iteration touches is laid out ONCE, in consumption order, as a sequence of GROUPS.
-// A group is up to 16 row slices (32 rows each; slice i belongs to consumer warp i, warps 4q..4q+3 form
+// A group is up to kStreamWarps row slices (32 rows each; slice i belongs to consumer warp i, warps 4q..4q+3 form
 // QUAD q).  Its data is a sequence of fixed-size STAGES, one TMA bulk copy each:
 //   stage = vals[4 warps][kKC entry-rows][32 lanes] (f64)  (+ idx[4][kKC][32] (i32) when the group is sparse)
-// ordered by (chunk c, quad q) for every quad with c < qch[q].  Dense groups multiply entry-row e of quad q
+// ordered quad by quad (all qch[0] chunks of quad 0, then quad 1, ...): every quad is an independent stream with
+// its own ring of shared-memory slots and its own producer lane.  Dense groups multiply entry-row e of quad q
 // with element in_off + qcol0[q] + e of the input vector; sparse groups with in_off + idx.
 constexpr int kKC = 16;
-constexpr int kStageValBytes = 4 * kKC * 32 * 8;   // 16 KiB
-constexpr int kStageIdxBytes = 4 * kKC * 32 * 4;   //  8 KiB
+constexpr int kStreamWarps = 12;                    // consumer warps of the TMA kernel (3 quads) = slices per group
+constexpr int kStageValBytes = 4 * kKC * 32 * 8;   // 8 KiB
+constexpr int kStageIdxBytes = 4 * kKC * 32 * 4;   // 4 KiB
 enum { GK_AT = 0, GK_FWD_D = 1, GK_FWD_U = 2, GK_BWD_D = 3, GK_BWD_U = 4, GK_AB = 5, GK_PM = 6 };
 struct StreamGroup {
   int kind, row0, nsl, in_off, sparse;
@@ -128,8 +130,8 @@ struct NodeScalars {
   double obj, pri_res, dua_res, lower;
 };
 
-// state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each)
-inline size_t tile_work_doubles(int n, int m, int tt) { return (size_t)tt * (5 * (size_t)m + 2 * (size_t)n); }
+// state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each); P x scratch (n rows)
+inline size_t tile_work_doubles(int n, int m, int tt) { return (size_t)tt * (5 * (size_t)m + 3 * (size_t)n); }
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

@@ -182,9 +182,9 @@ void add_group(HostStream &st, int kind, int row0, const std::vector<const Row *
   if (G.sparse) st.slot_bytes = std::max(st.slot_bytes, sb);
   int maxc = std::max(std::max(G.qch[0], G.qch[1]), std::max(G.qch[2], G.qch[3]));
   std::vector<size_t> cursor(rows.size(), 0);   // dense mode: next entry of each row not yet emitted
-  for (int c = 0; c < maxc; c++)
-    for (int q = 0; q < 4; q++) {
-      if (c >= G.qch[q]) continue;
+  (void)maxc;
+  for (int q = 0; q < 4; q++)
+    for (int c = 0; c < G.qch[q]; c++) {
       const size_t base = st.data.size();
       st.data.resize(base + sb, 0);
       double *vals = reinterpret_cast<double *>(st.data.data() + base);
@@ -204,8 +204,13 @@ void add_group(HostStream &st, int kind, int row0, const std::vector<const Row *
           } else {
             const int col0 = G.qcol0[q] + c * kKC;
             size_t &k = cursor[r];
+            // register-blocked dense layout: consumer lane (kp = lane'>>3, r8 = lane'&7) owns rows r8+8i (i<4) of
+            // the slice and the columns 4j+kp of the chunk; rows (0,1) and (2,3) are two 16-byte vectors laid out
+            // [j][pair][lane] so that each LDS.128 of a warp is bank-conflict free
             while (k < R.size() && R[k].first < col0 + kKC) {
-              vals[(wq * kKC + (R[k].first - col0)) * 32 + lane] = R[k].second;
+              const int dc = R[k].first - col0, j = dc >> 2, kp = dc & 3;
+              const int lane2 = (lane & 7) + 8 * kp, i = lane >> 3;
+              vals[(size_t)wq * (kKC * 32) + (((size_t)j * 2 + (i >> 1)) * 32 + lane2) * 2 + (i & 1)] = R[k].second;
               k++;
             }
           }
@@ -214,13 +219,13 @@ void add_group(HostStream &st, int kind, int row0, const std::vector<const Row *
   st.groups.push_back(G);
 }
 
-// split `rows` (a multiple of 32 entries is not required) into groups of <= 16 slices of similar size
+// split `rows` (a multiple of 32 entries is not required) into groups of <= kStreamWarps slices of similar size
 void add_panel(HostStream &st, int kind, int row0, const std::vector<const Row *> &rows_in) {
   std::vector<const Row *> rows(rows_in);
   while (rows.size() % 32) rows.push_back(nullptr);
   const int nsl = (int)rows.size() / 32;
   if (nsl == 0) return;
-  const int ng = (nsl + 15) / 16, spg = (nsl + ng - 1) / ng;
+  const int ng = (nsl + kStreamWarps - 1) / kStreamWarps, spg = (nsl + ng - 1) / ng;
   for (int g = 0; g < ng; g++) {
     const int s0 = g * spg, s1 = std::min(nsl, s0 + spg);
     if (s0 >= s1) break;
@@ -458,7 +463,7 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
   if (h->At.nslices >= 4) {
     int tri_nb = 128;
     if (const char *e = std::getenv("BQP_TRI_NB")) tri_nb = std::atoi(e);
-    tri_nb = std::max(32, std::min(512, (tri_nb / 32) * 32));
+    tri_nb = std::max(32, std::min(32 * kStreamWarps, (tri_nb / 32) * 32));
     build_stream(h, arows, atrows, prows, S, tri_nb);
   }
   return BQP_OK;
@@ -542,19 +547,30 @@ static void host_group_apply(const HostStream &st, const StreamGroup &G, const d
   const unsigned char *p = st.data.data() + G.data_off;
   const int sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
   const int maxc = std::max(std::max(G.qch[0], G.qch[1]), std::max(G.qch[2], G.qch[3]));
-  for (int c = 0; c < maxc; c++)
-    for (int q = 0; q < 4; q++) {
-      if (c >= G.qch[q]) continue;
+  (void)maxc;
+  for (int q = 0; q < 4; q++)
+    for (int c = 0; c < G.qch[q]; c++) {
       const double *vals = reinterpret_cast<const double *>(p);
       const int *idx = reinterpret_cast<const int *>(p + kStageValBytes);
-      for (int wq = 0; wq < 4; wq++)
-        for (int j = 0; j < kKC; j++)
-          for (int lane = 0; lane < 32; lane++) {
-            const int r = (q * 4 + wq) * 32 + lane;
-            if (r >= nrows) continue;
-            const int col = G.sparse ? idx[(wq * kKC + j) * 32 + lane] : G.qcol0[q] + c * kKC + j;
-            acc[r] = std::fma(vals[(wq * kKC + j) * 32 + lane], in[G.in_off + col], acc[r]);
-          }
+      for (int wq = 0; wq < 4; wq++) {
+        if (G.sparse) {
+          for (int j = 0; j < kKC; j++)
+            for (int lane = 0; lane < 32; lane++) {
+              const int r = (q * 4 + wq) * 32 + lane;
+              if (r >= nrows) continue;
+              acc[r] = std::fma(vals[(wq * kKC + j) * 32 + lane], in[G.in_off + idx[(wq * kKC + j) * 32 + lane]], acc[r]);
+            }
+        } else {
+          for (int j = 0; j < kKC / 4; j++)
+            for (int lane2 = 0; lane2 < 32; lane2++)
+              for (int i = 0; i < 4; i++) {
+                const int r = (q * 4 + wq) * 32 + (lane2 & 7) + 8 * i;
+                if (r >= nrows) continue;
+                const int col = G.qcol0[q] + c * kKC + 4 * j + (lane2 >> 3);
+                acc[r] = std::fma(vals[(size_t)wq * (kKC * 32) + (((size_t)j * 2 + (i >> 1)) * 32 + lane2) * 2 + (i & 1)], in[G.in_off + col], acc[r]);
+              }
+        }
+      }
       p += sb;
     }
 }
@@ -563,7 +579,7 @@ int host_stream_kkt_solve(const HostInstance *h, double *rhs) {
   const HostStream &st = h->st;
   if (!st.built) return BQP_E_UNSUPPORTED;
   const int n = h->n, m = h->m, np_ = h->npad;
-  std::vector<double> w(m + 64, 0.0), b(np_ + 64, 0.0), acc(16 * 32), t(m + 64, 0.0);
+  std::vector<double> w(m + 64, 0.0), b(np_ + 64, 0.0), acc(kStreamWarps * 32), t(m + 64, 0.0);
   for (int i = 0; i < m; i++) w[i] = h->rho[i] * rhs[n + i];
   for (int g = st.range[GK_AT][0]; g < st.range[GK_AT][1]; g++) {
     const StreamGroup &G = st.groups[g];
@@ -596,7 +612,7 @@ int host_stream_kkt_solve(const HostInstance *h, double *rhs) {
 int host_stream_matvec_P(const HostInstance *h, const double *in, double *out) {
   const HostStream &st = h->st;
   if (!st.built) return BQP_E_UNSUPPORTED;
-  std::vector<double> v(h->npad + 64, 0.0), acc(16 * 32);
+  std::vector<double> v(h->npad + 64, 0.0), acc(kStreamWarps * 32);
   for (int j = 0; j < h->n; j++) v[j] = in[j];
   for (int g = st.range[GK_PM][0]; g < st.range[GK_PM][1]; g++) {
     const StreamGroup &G = st.groups[g];

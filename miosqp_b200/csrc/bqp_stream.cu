@@ -7,9 +7,10 @@
 // CONSUMPTION ORDER (HostStream, bqp_internal.h) and streamed through a ring of shared-memory stages by
 // cp.async.bulk (TMA, 1-D) + mbarrier:
 //
-//   warp 16, lane 0 : producer.  Walks the same control flow as the consumers and issues one bulk copy
-//                     per stage (16 KiB of values, + 8 KiB of column indices for sparse groups).
-//   warps 0..15     : consumers.  Warp w owns slice w (32 rows, lane = row) of the current group; the four
+//   warp 12         : producer.  Lane q feeds quad q: it walks the same control flow as the consumers and issues
+//                     one bulk copy per stage (8 KiB of values, + 4 KiB of column indices for sparse groups)
+//                     into quad q's private ring of slots (canonical full/empty mbarrier pipeline per quad).
+//   warps 0..11     : consumers.  Warp w owns slice w (32 rows, lane = row) of the current group; the four
 //                     warps of a quad share a stage.  One matrix entry is read from shared memory once and
 //                     used for all T nodes (vectors are [row][T], node index fastest).
 //
@@ -19,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "bqp_internal.h"
 
@@ -26,7 +28,7 @@ namespace bqp {
 
 namespace {
 
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = kStreamWarps;
 constexpr int kConsumers = kConsumerWarps * 32;
 constexpr int kStreamThreads = kConsumers + 32;
 constexpr int kRed = 16;          // reduced quantities per termination check
@@ -62,21 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s at 2 GHz
-  }
-}
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void wait_issued(const uint32_t *issued, uint32_t s) {
-  if ((int32_t)(ld_acquire_u32(issued) - s) > 0) return;
-  const long long t0 = clock64();
-  while ((int32_t)(ld_acquire_u32(issued) - s) <= 0) {
-    if (clock64() - t0 > 8000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -122,36 +109,51 @@ struct StreamShared {
   double fin[kRed][kMaxTT];
   int status[kMaxTT], iters[kMaxTT], newly[kMaxTT];
   int remaining;
-  uint32_t issued;
   StreamGroup groups[kMaxGroups];
 };
 
+constexpr int kQuads = kConsumerWarps / 4;
+
+// Per-quad ring state.  A consumer warp tracks the ring of its own quad; producer lane q tracks quad q's.
 struct Ring {
-  unsigned char *base;
-  uint64_t *full, *empty;
-  uint32_t *issued;   // number of stages the producer has issued so far (shared memory, release/acquire)
+  unsigned char *base;      // first slot of this quad
+  uint64_t *full, *empty;   // [nslots] each, this quad's barriers
   int nslots, slot_bytes;
-  uint32_t seq;   // next stage sequence number; advances identically in every thread
+  int slot;                 // next slot to fill / consume
+  uint32_t phase;           // parity of the current pass over the ring
+  __device__ __forceinline__ void advance() {
+    if (++slot == nslots) { slot = 0; phase ^= 1; }
+  }
 };
 
-// producer: one bulk copy per stage of group G, in (chunk, quad) order
-__device__ __forceinline__ void produce_group(const StreamGroup &G, const unsigned char *__restrict__ stream, Ring &R, int lane) {
-  const uint32_t sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
-  const unsigned char *src = stream + G.data_off;
-  const int maxc = max(max(G.qch[0], G.qch[1]), max(G.qch[2], G.qch[3]));
-  for (int c = 0; c < maxc; c++)
-    for (int q = 0; q < 4; q++) {
-      if (c >= G.qch[q]) continue;
-      const uint32_t slot = R.seq % (uint32_t)R.nslots, k = R.seq / (uint32_t)R.nslots;
-      if (lane == 0) {
-        if (k > 0) mbar_wait(R.empty + slot, (k - 1) & 1);
-        mbar_expect_tx(R.full + slot, sb);
-        tma_load_1d(R.base + (size_t)slot * R.slot_bytes, src, sb, R.full + slot);
-        st_release_u32(R.issued, R.seq + 1);
+__device__ __forceinline__ void l2_prefetch(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+// producer lane q (< kQuads): one bulk copy per stage of quad q of group G.  Optional L2 prefetch `prefetch_ahead`
+// bytes further down the (cyclic) per-iteration stream.
+__device__ __forceinline__ void produce_group(const StreamGroup &G, const unsigned char *__restrict__ stream, long long iter_bytes,
+                                              long long prefetch_ahead, Ring &R, int lane) {
+  if (lane < kQuads) {
+    const uint32_t sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
+    int before = 0;
+    for (int q = 0; q < lane; q++) before += G.qch[q];
+    const long long off0 = G.data_off + (long long)before * sb;
+    const unsigned char *src = stream + off0;
+    const int nch = G.qch[lane];
+    for (int c = 0; c < nch; c++) {
+      mbar_wait(R.empty + R.slot, R.phase ^ 1);     // passes at once on the first lap
+      mbar_expect_tx(R.full + R.slot, sb);
+      tma_load_1d(R.base + (size_t)R.slot * R.slot_bytes, src, sb, R.full + R.slot);
+      if (prefetch_ahead > 0 && G.data_off < iter_bytes) {
+        long long o = off0 + (long long)c * sb + prefetch_ahead;
+        if (o >= iter_bytes) o -= iter_bytes;
+        if (o + sb <= iter_bytes) l2_prefetch(stream + o, sb);
       }
       src += sb;
-      R.seq++;
+      R.advance();
     }
+  }
   __syncwarp();   // keep the producer warp converged: its lanes take the CTA-wide barriers together
 }
 
@@ -160,43 +162,77 @@ template <int T>
 __device__ __forceinline__ void consume_group(const StreamGroup &G, const double *__restrict__ in, Ring &R, int warp, int lane,
                                               double (&acc)[T]) {
   const int q = warp >> 2, wq = warp & 3;
-  const int q0 = G.qch[0], q1 = G.qch[1], q2 = G.qch[2], q3 = G.qch[3];
   const int myc = G.qch[q];
+  const int kp = lane >> 3;
+  double acc4[4][T];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int t = 0; t < T; t++) acc4[i][t] = 0.0;
   if (myc > 0) {
     const double *inq = in + (size_t)(G.in_off + (G.sparse ? 0 : G.qcol0[q])) * T;
     for (int c = 0; c < myc; c++) {
-      // stages issued before (c, q): all (c', q') with c' < c, and (c, q') with q' < q
-      uint32_t s = R.seq + min(q0, c) + min(q1, c) + min(q2, c) + min(q3, c);
-      if (q > 0) s += (q0 > c);
-      if (q > 1) s += (q1 > c);
-      if (q > 2) s += (q2 > c);
-      const uint32_t slot = s % (uint32_t)R.nslots, k = s / (uint32_t)R.nslots;
-      // The ring is shared by the four quads, so this quad may get here before the producer has even armed use k
-      // of the slot; a parity wait would then alias with use k-2.  Gate on the issue counter first.
-      wait_issued(R.issued, s);
-      mbar_wait(R.full + slot, k & 1);
+      const int slot = R.slot;
+      mbar_wait(R.full + slot, R.phase);
       const unsigned char *stage = R.base + (size_t)slot * R.slot_bytes;
-      const double *v = reinterpret_cast<const double *>(stage) + (wq * kKC) * 32 + lane;
-      double a[kKC];
-#pragma unroll
-      for (int j = 0; j < kKC; j++) a[j] = v[j * 32];
       if (!G.sparse) {
-        const double *x = inq + (size_t)c * kKC * T;
+        // register-blocked dense stage: this lane owns rows r8+8i (i<4) and the columns 4j+kp of the chunk
+        const double *v = reinterpret_cast<const double *>(stage) + (size_t)wq * (kKC * 32) + lane * 2;
+        const double *x = inq + ((size_t)c * kKC + kp) * T;
 #pragma unroll
-        for (int j = 0; j < kKC; j++) fma_row<T>(a[j], x + j * T, acc);
+        for (int j = 0; j < kKC / 4; j++) {
+          const double2 a01 = *reinterpret_cast<const double2 *>(v + j * 128);
+          const double2 a23 = *reinterpret_cast<const double2 *>(v + j * 128 + 64);
+          double xv[T];
+          if constexpr (T == 1) {
+            xv[0] = x[(size_t)j * 4 * T];
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; t += 2) {
+              const double2 w = *reinterpret_cast<const double2 *>(x + (size_t)j * 4 * T + t);
+              xv[t] = w.x; xv[t + 1] = w.y;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < T; t++) {
+            acc4[0][t] = fma(a01.x, xv[t], acc4[0][t]);
+            acc4[1][t] = fma(a01.y, xv[t], acc4[1][t]);
+            acc4[2][t] = fma(a23.x, xv[t], acc4[2][t]);
+            acc4[3][t] = fma(a23.y, xv[t], acc4[3][t]);
+          }
+        }
       } else {
+        const double *v = reinterpret_cast<const double *>(stage) + (wq * kKC) * 32 + lane;
         const int *ix = reinterpret_cast<const int *>(stage + kStageValBytes) + (wq * kKC) * 32 + lane;
+        double a[kKC];
         int col[kKC];
 #pragma unroll
-        for (int j = 0; j < kKC; j++) col[j] = ix[j * 32];
+        for (int j = 0; j < kKC; j++) { a[j] = v[j * 32]; col[j] = ix[j * 32]; }
 #pragma unroll
         for (int j = 0; j < kKC; j++) fma_row<T>(a[j], inq + (size_t)col[j] * T, acc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(R.empty + slot);
+      R.advance();
     }
   }
-  R.seq += q0 + q1 + q2 + q3;
+  if (myc > 0 && !G.sparse) {
+    // combine the four column parts (lanes kp = 0..3 of every r8) in a fixed order; lane (kp, r8) keeps row r8+8kp
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        double v = acc4[i][t];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc4[i][t] = v;
+      }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const double lo = kp & 1 ? acc4[1][t] : acc4[0][t], hi = kp & 1 ? acc4[3][t] : acc4[2][t];
+      acc[t] += kp & 2 ? hi : lo;
+    }
+  }
 }
 
 template <int T, int OP>   // OP 0: max, 1: sum, 2: min
@@ -218,7 +254,7 @@ template <int T>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                    double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
-                   int *__restrict__ tile_iters, int nslots, int slot_bytes) {
+                   int *__restrict__ tile_iters, int nslots, int slot_bytes, long long prefetch_ahead) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp == kConsumerWarps;
@@ -227,7 +263,6 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
     S.tile = tiles[blockIdx.x];
     S.I = insts[S.tile.inst];
     S.remaining = S.tile.nn;
-    S.issued = 0;
   }
   if (tid < kMaxTT) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
   __syncthreads();
@@ -238,19 +273,21 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   const int mvec = ((m > np ? m : np) + kKC + 15) & ~15;
   size_t off = (sizeof(StreamShared) + 15) & ~size_t(15);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off);
-  off += sizeof(uint64_t) * 2 * (size_t)nslots;
+  off += sizeof(uint64_t) * 2 * (size_t)kQuads * nslots;
   off = (off + 15) & ~size_t(15);
   double *vin = reinterpret_cast<double *>(smem_raw + off);   // [mvec][T]
   double *bb = vin + (size_t)mvec * T;                        // [np + kKC][T]
   double *red = bb + (size_t)(np + kKC) * T;                  // [kRed][16][T]
   off += ((size_t)mvec + np + kKC + (size_t)kRed * kConsumerWarps) * T * 8;
   off = (off + 127) & ~size_t(127);
+  // rings: quad q owns slots [q*nslots, (q+1)*nslots); consumer warps look at their quad, producer lane q at quad q
+  const int rq = producer ? (lane < kQuads ? lane : 0) : (warp >> 2);
   Ring R;
-  R.base = smem_raw + off;
-  R.full = bars; R.empty = bars + nslots; R.issued = &S.issued;
-  R.nslots = nslots; R.slot_bytes = slot_bytes; R.seq = 0;
+  R.base = smem_raw + off + (size_t)rq * nslots * slot_bytes;
+  R.full = bars + (size_t)rq * nslots; R.empty = bars + (size_t)(kQuads + rq) * nslots;
+  R.nslots = nslots; R.slot_bytes = slot_bytes; R.slot = 0; R.phase = 0;
   if (tid == 0) {
-    for (int s = 0; s < nslots; s++) { mbar_init(R.full + s, 1); mbar_init(R.empty + s, 4); }
+    for (int s = 0; s < kQuads * nslots; s++) { mbar_init(bars + s, 1); mbar_init(bars + kQuads * nslots + s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -258,11 +295,12 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
 
   const int max_iter = I.max_iter, check_every = I.check_every;
   const unsigned char *stream = I.stream;
+  const long long iter_bytes = S.groups[I.g_pm[0]].data_off;   // A', L fwd, L bwd, A: what one iteration streams
 
   // =============================================================== producer warp: mirror of the consumer control flow
   if (producer) {
     auto produce = [&](const int (&range)[2]) {
-      for (int g = range[0]; g < range[1]; g++) produce_group(S.groups[g], stream, R, lane);
+      for (int g = range[0]; g < range[1]; g++) produce_group(S.groups[g], stream, iter_bytes, prefetch_ahead, R, lane);
     };
     produce(I.g_ab);                                   // prologue: z = A x
     for (int iter = 1; iter <= max_iter; iter++) {
@@ -281,7 +319,7 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   // =============================================================== consumer warps
   double *W = work + S.tile.work_off;
   double *gx = W, *gdx = gx + (size_t)n * T, *gz = gdx + (size_t)n * T, *gy = gz + (size_t)m * T,
-         *gl = gy + (size_t)m * T, *gu = gl + (size_t)m * T, *gdy = gu + (size_t)m * T;
+         *gl = gy + (size_t)m * T, *gu = gl + (size_t)m * T, *gdy = gu + (size_t)m * T, *gpx = gdy + (size_t)m * T;
   const double alpha = I.alpha, sigma = I.sigma;
 
   // ---- prologue (node.py:102-105)
@@ -408,9 +446,18 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
       // P x and A' y share the row ownership (both have n rows): group k of P pairs with group k of A'
       double dr[T], b1[T], b2[T], quad[T], lin[T];
       zero<T>(dr); zero<T>(b1); zero<T>(b2); zero<T>(quad); zero<T>(lin);
-      double px[4][T];   // up to 4 groups of n-row matrices (n <= 2048)
+      // P x goes through a per-tile scratch row (same thread writes and reads it back) to keep registers free
       const int npm = I.g_pm[1] - I.g_pm[0];
-      for (int k = 0; k < npm; k++) { zero<T>(px[k]); consume_group<T>(S.groups[I.g_pm[0] + k], bb, R, warp, lane, px[k]); }
+      for (int k = 0; k < npm; k++) {
+        const StreamGroup &G = S.groups[I.g_pm[0] + k];
+        double px[T]; zero<T>(px);
+        consume_group<T>(G, bb, R, warp, lane, px);
+        const int j = G.row0 + warp * 32 + lane;
+        if (warp < G.nsl && j < n) {
+#pragma unroll
+          for (int t = 0; t < T; t++) gpx[(size_t)j * T + t] = px[t];
+        }
+      }
       for (int k = 0; k < npm; k++) {
         const StreamGroup &G = S.groups[I.g_at[0] + k];
         double aty[T]; zero<T>(aty);
@@ -420,11 +467,11 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
           const double qj = __ldg(I.q + j), di = __ldg(I.Dinv + j);
 #pragma unroll
           for (int t = 0; t < T; t++) {
-            const double xj = bb[(size_t)j * T + t];
-            dr[t] = fmax(dr[t], fabs(di * (px[k][t] + qj + aty[t])));
-            b1[t] = fmax(b1[t], fabs(di * px[k][t]));
+            const double xj = bb[(size_t)j * T + t], pxj = gpx[(size_t)j * T + t];
+            dr[t] = fmax(dr[t], fabs(di * (pxj + qj + aty[t])));
+            b1[t] = fmax(b1[t], fabs(di * pxj));
             b2[t] = fmax(b2[t], fabs(di * aty[t]));
-            quad[t] += xj * px[k][t];
+            quad[t] += xj * pxj;
             lin[t] += qj * xj;
           }
         }
@@ -684,11 +731,11 @@ size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots) {
   const int np = ((n + kNB - 1) / kNB) * kNB;
   const int mvec = ((m > np ? m : np) + kKC + 15) & ~15;
   size_t off = (sizeof(StreamShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * 2 * (size_t)nslots;
+  off += sizeof(uint64_t) * 2 * (size_t)kQuads * nslots;
   off = (off + 15) & ~size_t(15);
   off += ((size_t)mvec + np + kKC + (size_t)kRed * kConsumerWarps) * tt * 8;
   off = (off + 127) & ~size_t(127);
-  return off + (size_t)nslots * slot_bytes;
+  return off + (size_t)kQuads * nslots * slot_bytes;
 }
 
 template <int T>
@@ -696,7 +743,9 @@ static int launch_t(int slot_bytes, int nslots, const DevInstance *d_insts, cons
                     double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(admm_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return BQP_E_CUDA;
-  admm_stream_kernel<T><<<ntiles, kStreamThreads, smem, st>>>(d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, slot_bytes);
+  long long prefetch_ahead = 0;   // experiment knob: L2 prefetch distance of the producer warp (KiB), off by default
+  if (const char *pk = getenv("BQP_PREFETCH_KB")) prefetch_ahead = 1024LL * atoll(pk);
+  admm_stream_kernel<T><<<ntiles, kStreamThreads, smem, st>>>(d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, slot_bytes, prefetch_ahead);
   return cudaGetLastError() == cudaSuccess ? BQP_OK : BQP_E_CUDA;
 }
 

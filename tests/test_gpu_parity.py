@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 QP = dict(eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4)
 TOL = 1e-9
+STREAM_THREADS = 13 * 32   # 12 consumer warps + 1 TMA producer warp (bqp_stream.cu)
 
 
 def _close(a, b, tol=TOL):
@@ -160,13 +161,13 @@ def test_update_q(oracle_mod):
 def test_stream_kernel_tile_widths(oracle_mod, tt):
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == 17 * 32       # 16 consumer warps + the TMA producer warp
+    assert engine.last_timing()["threads"] == STREAM_THREADS       # consumer warps + the TMA producer warp
 
 
 def test_stream_kernel_sparse_groups(oracle_mod):
     pr = problems.random_miqp(400, 600, 20, 0.03, seed=8)[0]
     _compare(pr, 5, 7, QP, oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == 17 * 32
+    assert engine.last_timing()["threads"] == STREAM_THREADS
 
 
 def test_stream_vs_direct_kernel_same_results():
@@ -191,4 +192,4 @@ def test_cfg2_size_leaves(oracle_mod):
     """BASELINE cfg 2 shape (n=500, m=1000, |i_idx|=50): 8 leaves of one instance in one tile."""
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
     _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == 17 * 32
+    assert engine.last_timing()["threads"] == STREAM_THREADS

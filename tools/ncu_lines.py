@@ -29,18 +29,18 @@ def main():
     # offset -> (inner line, outer line) for the kernel matching pat
     line_of = {}
     in_k = False
-    cur = (0, 0)
+    cur = (("", 0), ("", 0))
     for ln in sass.splitlines():
         if ln.startswith(".text."):
             in_k = pat in ln
             continue
         if not in_k:
             continue
-        m = re.search(r'//## File "[^"]*", line (\d+)(.*)', ln)
+        m = re.search(r'//## File "([^"]*)", line (\d+)(.*)', ln)
         if m:
-            inner = int(m.group(1))
-            outers = re.findall(r'line (\d+)', m.group(2))
-            cur = (inner, int(outers[-1]) if outers else inner)
+            inner = (os.path.basename(m.group(1)), int(m.group(2)))
+            outers = re.findall(r'File "([^"]*)", line (\d+)', m.group(3))
+            cur = (inner, (os.path.basename(outers[-1][0]), int(outers[-1][1])) if outers else inner)
             continue
         m = re.match(r'\s+/\*([0-9a-f]+)\*/\s+(.*?);', ln)
         if m:
@@ -63,17 +63,26 @@ def main():
             base = addr
         s = int(r[si] or 0)
         total += s
-        (inner, outer), txt = line_of.get(addr - base, ((0, 0), r[1]))
+        (inner, outer), txt = line_of.get(addr - base, ((("", 0), ("", 0)), r[1]))
         inner_s[inner] += s
         outer_s[outer] += s
         op_s[txt.split()[0] if not txt.startswith("@") else txt.split()[1]] += s
-    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "miosqp_b200", "csrc", "bqp_kernels.cu")).read().splitlines()
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "miosqp_b200", "csrc")
+    srcs = {}
+
+    def text(fl):
+        f, line = fl
+        if f not in srcs:
+            try:
+                srcs[f] = open(os.path.join(csrc, f)).read().splitlines()
+            except OSError:
+                srcs[f] = []
+        return srcs[f][line - 1].strip()[:100] if 0 < line <= len(srcs[f]) else ""
     print("total samples", total)
     for name, ctr in (("kernel-level line (call site)", outer_s), ("innermost line", inner_s)):
         print("== by", name)
-        for line, s in ctr.most_common(top):
-            txt = src[line - 1].strip()[:100] if 0 < line <= len(src) else ""
-            print("%6.2f%%  L%-4d %s" % (100.0 * s / max(total, 1), line, txt))
+        for fl, s in ctr.most_common(top):
+            print("%6.2f%%  %s:%-4d %s" % (100.0 * s / max(total, 1), fl[0], fl[1], text(fl)))
     print("== by opcode")
     for op, s in op_s.most_common(15):
         print("%6.2f%%  %s" % (100.0 * s / max(total, 1), op))
