@@ -123,6 +123,7 @@ const char *bqp_version(void);
  * bqp_setup (scaling, rho typing, factor, panel layouts) without touching a device and apply the
  * streamed panels / blocked factor with plain loops.  They are NOT a solve path: no ADMM runs here. */
 int bqp_debug_host_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out);
+int bqp_debug_dump_groups(bqp_handle h);   /* prints the streamed group table to stdout */
 int bqp_debug_host_kkt_solve(bqp_handle h, double *rhs_xz /* [n+m], scaled space, in place */);
 int bqp_debug_host_stream_kkt_solve(bqp_handle h, double *rhs_xz /* same, through the TMA kernel's streamed layout */);
 int bqp_debug_host_matvec(bqp_handle h, int which /*0: A x, 1: A' y, 2: P x, 3: P x via the streamed layout*/, const double *in, double *out);

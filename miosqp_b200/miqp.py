@@ -1,0 +1,122 @@
+"""
+MIOSQP -- the reference's public API (/root/reference/miosqp/solver.py:32-212) on the batched CUDA engine.
+
+    m = MIOSQP(); m.setup(P, q, A, l, u, i_idx, i_l, i_u, settings, qp_settings)
+    res = m.solve();  m.update_vectors(q=..., l=..., u=...);  m.set_x0(x0)
+
+`solve()` alternates (1) one engine launch over every open leaf that has no result yet and (2) a host replay of
+the reference's sequential loop over the cached results (tree.py).  `solve_many` drives several MIQPs in
+lock-step so that ONE launch per B&B step covers the frontiers of all of them (BASELINE config 2: 100 instances).
+"""
+from __future__ import print_function
+
+from time import perf_counter, time
+
+import numpy as np
+
+from . import engine
+from .problem_data import Data
+from .results import Results
+from .tree import Workspace
+
+
+class MIOSQP(object):
+    def __init__(self):
+        self.data = None
+        self.work = None
+
+    def setup(self, P, q, A, l, u, i_idx, i_l, i_u, settings, qp_settings):
+        start = time()
+        if i_l is None:
+            i_l = -np.inf * np.ones(len(i_idx))
+        if i_u is None:
+            i_u = np.inf * np.ones(len(i_idx))
+        self.data = Data(P, q, A, l, u, i_idx, i_l, i_u)
+        self.work = Workspace(self.data, settings, qp_settings)
+        self.work.setup_time = time() - start
+
+    # -- one B&B replay step over cached results; returns False when the chosen leaf still needs the engine
+    def _replay(self):
+        work = self.work
+        while work.can_continue():
+            if work.pending():
+                return True            # unsolved leaves in the frontier: batch them before choosing
+            leaf = work.choose_leaf(work.settings['tree_explor_rule'])
+            leaf.solve()
+            work.bound_and_branch(leaf)
+            if work.settings['verbose'] and work.iter_num % work.settings['print_interval'] == 0:
+                work.print_progress(leaf)
+            work.iter_num += 1
+        return False
+
+    def _begin(self):
+        self._t0 = time()
+        if self.work.settings['verbose']:
+            self.work.print_headline()
+
+    def _finish(self):
+        work = self.work
+        work.osqp_iter_avg = work.osqp_iter / work.iter_num
+        work.get_return_status()
+        work.get_return_solution()
+        if work.settings['verbose']:
+            work.print_footer()
+        work.solve_time = time() - self._t0
+        if work.first_run:
+            work.first_run = 0
+            work.run_time = work.setup_time + work.solve_time
+        else:
+            work.run_time = work.solve_time
+        if work.settings['verbose']:
+            print("Elapsed time: %.4es" % work.run_time)
+        return Results(work.x, work.upper_glob, work.run_time, work.status, work.osqp_solve_time, work.osqp_iter_avg)
+
+    def solve(self):
+        self._begin()
+        while self._replay():
+            self.work.solve_pending()
+        return self._finish()
+
+    def update_vectors(self, q=None, l=None, u=None):
+        work = self.work
+        work.data.update_vectors(q, l, u)
+        if q is not None:
+            work.solver.update_q(q)          # factor kept; only the scaled linear cost is re-uploaded
+        work.reset()
+        work.solve_time = 0.
+        work.run_time = 0.
+
+    def set_x0(self, x0):
+        self.work.set_x0(x0)
+
+
+def solve_many(solvers, on_batch=None):
+    """Solve several set-up MIOSQP objects together: every step flattens the unsolved leaves of ALL frontiers into
+    one node batch (one kernel launch).  Each instance's result is identical to its own `solve()`.
+    `on_batch(n_nodes, seconds)` is called after every launch (benchmarks)."""
+    for s in solvers:
+        s._begin()
+    active = list(solvers)
+    while active:
+        active = [s for s in active if s._replay()]
+        nodes, owners = [], []
+        for s in active:
+            for nd in s.work.pending():
+                nodes.append(nd); owners.append(s.work)
+        if not nodes:
+            continue
+        # longest-first submission: children of slow-converging parents go first (tile order = submission order)
+        order = sorted(range(len(nodes)), key=lambda k: -getattr(nodes[k], "parent_iters", 0))
+        nodes = [nodes[k] for k in order]; owners = [owners[k] for k in order]
+        t0 = perf_counter()
+        xs, ys, sc = engine.solve_multi([w.solver for w in owners], [nd.l for nd in nodes], [nd.u for nd in nodes],
+                                        [nd.x for nd in nodes], [nd.y for nd in nodes])
+        dt = perf_counter() - t0
+        Workspace.absorb(nodes, xs, ys, sc, dt)
+        for w in set(owners):
+            w.batches += 1
+        for w in owners:
+            w.batched_nodes += 1
+        if on_batch is not None:
+            on_batch(len(nodes), dt)
+    return [s._finish() for s in solvers]

@@ -1,0 +1,44 @@
+"""
+MIQP problem data in the layout the engine receives.
+
+Mirrors what /root/reference/miosqp/data.py builds (add_bounds :5-33, Data :78-126): the integer-variable
+bounds i_l <= x[i_idx] <= i_u become |i_idx| identity rows appended BELOW A (in i_idx order, unsorted), so a
+B&B node only ever differs from the root in the last n_int entries of l and u.
+"""
+import numpy as np
+import scipy.sparse as spa
+
+
+def add_bounds(i_idx, l_new, u_new, A, l, u):
+    """Append the rows I[i_idx, :] with bounds (l_new, u_new) to l <= A x <= u."""
+    n = A.shape[1]
+    rows = spa.identity(n, format="csc")[i_idx, :]
+    return spa.vstack([A, rows]).tocsc(), np.append(l, l_new), np.append(u, u_new)
+
+
+class Data(object):
+    """P, q and the EXTENDED A, l, u of one MIQP; n, m (original rows) and n_int."""
+
+    def __init__(self, P, q, A, l, u, i_idx, i_l, i_u):
+        self.m, self.n = A.shape
+        self.n_int = len(i_idx)
+        self.A, self.l, self.u = add_bounds(i_idx, i_l, i_u, A, l, u)
+        self.P = P.tocsc()
+        self.q = q
+        self.i_idx, self.i_l, self.i_u = i_idx, i_l, i_u
+
+    def compute_obj_val(self, x):
+        """1/2 x'Px + q'x with the full symmetric P (data.py:99-103)."""
+        return .5 * np.dot(x, self.P.dot(x)) + np.dot(self.q, x)
+
+    def update_vectors(self, q=None, l=None, u=None):
+        """Replace q and the ORIGINAL rows of l, u in place; dimension errors as data.py:105-126."""
+        for name, vec, size in (("q", q, self.n), ("l", l, self.m), ("u", u, self.m)):
+            if vec is not None and len(vec) != size:
+                raise ValueError('Wrong %s dimension!' % name)
+        if q is not None:
+            self.q = q
+        if l is not None:
+            self.l[:self.m] = l
+        if u is not None:
+            self.u[:self.m] = u

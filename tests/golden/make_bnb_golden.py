@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""
+Generates tests/golden/bnb_*.json: the UNMODIFIED reference package (/root/reference/miosqp) run in THIS
+container on top of the CPU oracle through tests/osqp_shim (the reference's own `osqp` dependency is not
+installable here), recording per problem the sequence of branching decisions (constr_idx, nextvar_idx), the
+final status, upper_glob, x and the node / ADMM iteration counters.
+
+    python tests/golden/make_bnb_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "osqp_shim"))
+sys.path.insert(0, "/root/reference")
+
+import osqp  # noqa: E402  (the shim)
+osqp.set_backend("oracle")
+import miosqp as ref  # noqa: E402
+from miosqp import workspace as ref_ws  # noqa: E402
+from miosqp_b200 import problems  # noqa: E402
+
+CASES = {
+    "cfg1_seed1": dict(n=50, m=100, p=5, density=0.7, seed=1),
+    "cfg1_seed2": dict(n=50, m=100, p=5, density=0.7, seed=2),
+    "cfg1_seed3": dict(n=50, m=100, p=5, density=0.7, seed=3),
+    "small_seed5": dict(n=30, m=60, p=8, density=0.5, seed=5),
+    "mid_seed7": dict(n=120, m=200, p=10, density=0.7, seed=7),
+}
+
+
+def run_reference(pr, settings, qp_settings, x0=None):
+    decisions = []
+    orig = ref_ws.Workspace.branch
+
+    def branch(self, leaf):
+        self.pick_nextvar(leaf)
+        decisions.append((int(leaf.constr_idx), int(leaf.nextvar_idx)))
+        self.add_left(leaf)
+        self.add_right(leaf)
+    ref_ws.Workspace.branch = branch
+    try:
+        m = ref.MIOSQP()
+        m.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'], settings, qp_settings)
+        if x0 is not None:
+            m.set_x0(x0)
+        res = m.solve()
+    finally:
+        ref_ws.Workspace.branch = orig
+    w = m.work
+    return dict(decisions=decisions, status=res.status, upper_glob=float(res.upper_glob),
+                x=[float(v) for v in res.x], iter_num=int(w.iter_num), osqp_iter=int(w.osqp_iter),
+                osqp_iter_avg=float(res.osqp_iter_avg), lower_glob=float(w.lower_glob))
+
+
+def main():
+    out = {}
+    for name, c in CASES.items():
+        pr = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"])[0]
+        out[name] = dict(case=c, result=run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS),
+                                                       dict(problems.RANDOM_MIQP_QP_SETTINGS)))
+        r = out[name]["result"]
+        print(name, r["status"], r["upper_glob"], "nodes", r["iter_num"] - 1, "admm", r["osqp_iter"], "branchings", len(r["decisions"]))
+    with open(os.path.join(HERE, "bnb_random_miqp.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

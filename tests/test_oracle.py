@@ -1,0 +1,152 @@
+"""
+The CPU oracle (oracle/osqp_oracle.c) against reference-independent known answers.  The reference's own
+arithmetic lives in PyPI `osqp`, which is not installable here and ships no golden vectors in the reference
+tree (PARITY UNPINNED, see oracle header), so the oracle is pinned by: closed-form QPs, KKT optimality of its
+output, LDL' reconstruction, OSQP's documented status semantics, and the exhaustive-enumeration optimum of
+BASELINE config 1.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as spa
+
+from miosqp_b200 import problems
+from oracle import oracle
+
+QP = dict(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)
+
+
+def _solve(P, q, A, l, u, **kw):
+    o = oracle.OSQP()
+    s = dict(QP); s.update(kw)
+    o.setup(spa.csc_matrix(P), np.asarray(q, float), spa.csc_matrix(A), np.asarray(l, float), np.asarray(u, float), **s)
+    return o, o.solve()
+
+
+def test_box_qp_closed_form():
+    # min 1/2 x'x - c'x  s.t. 0 <= x <= 1  ->  x = clip(c, 0, 1)
+    c = np.array([-0.5, 0.3, 1.7, 0.999])
+    o, r = _solve(np.eye(4), -c, np.eye(4), np.zeros(4), np.ones(4))
+    assert r.info.status_val == 1
+    assert np.abs(r.x - np.clip(c, 0, 1)).max() < 1e-6
+    # multipliers: y = c - x on active bounds (sign: positive at upper bound)
+    assert np.abs(r.y - (c - np.clip(c, 0, 1))).max() < 1e-5
+
+
+def test_equality_constrained_closed_form():
+    # min 1/2 x'Px + q'x s.t. a'x = b  ->  KKT system
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((5, 5)); P = M @ M.T + np.eye(5); q = rng.standard_normal(5)
+    a = rng.standard_normal((1, 5)); b = np.array([0.7])
+    K = np.block([[P, a.T], [a, np.zeros((1, 1))]])
+    sol = np.linalg.solve(K, np.r_[-q, b])
+    o, r = _solve(P, q, a, b, b)
+    assert r.info.status_val == 1
+    assert np.abs(r.x - sol[:5]).max() < 1e-6 and abs(r.y[0] - sol[5]) < 1e-5
+
+
+def test_primal_infeasible_and_dual_infeasible_status():
+    # x <= -1 and x >= 1 cannot hold together
+    A = np.array([[1.0], [1.0]])
+    o, r = _solve(np.eye(1), [0.0], A, [-np.inf, 1.0], [-1.0, np.inf], eps_abs=1e-4, eps_rel=1e-4)
+    assert r.info.status_val == oracle.constant("OSQP_PRIMAL_INFEASIBLE")
+    assert np.isnan(r.x).all()
+    # unbounded below along x2 (P singular there, q2 < 0, no upper bound)
+    P = np.diag([1.0, 0.0]); A = np.eye(2)
+    o, r = _solve(P, [0.0, -1.0], A, [-1.0, 0.0], [1.0, np.inf], eps_abs=1e-4, eps_rel=1e-4)
+    assert r.info.status_val == oracle.constant("OSQP_DUAL_INFEASIBLE")
+
+
+def test_max_iter_status_and_iteration_granularity():
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, _ = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, eps_abs=1e-9, eps_rel=1e-9, max_iter=60)
+    r = o.solve()
+    assert r.info.status_val in (oracle.constant("OSQP_MAX_ITER_REACHED"), oracle.constant("OSQP_SOLVED_INACCURATE"))
+    assert r.info.iter == 60
+    o2 = oracle.OSQP(); o2.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3)
+    r2 = o2.solve()
+    assert r2.info.status_val == 1 and r2.info.iter % 25 == 0      # termination is only tested every 25 iterations
+
+
+def test_kkt_optimality_random_qp():
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, _ = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, **QP)
+    r = o.solve()
+    assert r.info.status_val == 1
+    Pd = P.toarray(); Ad = A.toarray()
+    assert np.abs(Pd @ r.x + q + Ad.T @ r.y).max() < 1e-6                 # stationarity
+    z = Ad @ r.x
+    assert (z >= l - 1e-6).all() and (z <= u + 1e-6).all()               # primal feasibility
+    assert (r.y[(z > l + 1e-5) & (z < u - 1e-5)] ** 2).max() < 1e-10     # complementarity
+    assert (r.y[np.abs(z - u) < 1e-7] >= -1e-8).all() and (r.y[np.abs(z - l) < 1e-7] <= 1e-8).all()
+
+
+def test_cfg1_fingerprints_and_root_relaxation():
+    """BASELINE.md known answer: root relaxation objective -12.706728044."""
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    assert list(pr["i_idx"]) == [27, 35, 40, 38, 2]
+    assert abs(pr["P"].data.sum() - 15878.928065531603) < 1e-6 and abs(pr["q"].sum() - 1.245233404579) < 1e-9
+    P, q, A, l, u, _ = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, **QP)
+    r = o.solve()
+    assert abs(r.info.obj_val - (-12.706728044)) < 1e-6
+    assert np.abs(r.x[pr["i_idx"]] - np.array([0, 0, 0, 0.392675, 0.013816])).max() < 1e-4
+
+
+def test_cfg1_exhaustive_enumeration_optimum():
+    """All 2^5 binary assignments solved as QPs: optimum -12.420811293 at all-zero."""
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, **QP)
+    L, U = [], []
+    for code in range(32):
+        ll, uu = l.copy(), u.copy()
+        for k in range(5):
+            ll[100 + k] = uu[100 + k] = (code >> k) & 1
+        L.append(ll); U.append(uu)
+    x, y, st, it, extra = o.solve_batch(np.array(L), np.array(U), np.zeros((32, 50)), np.zeros((32, 105)), threads=8)
+    assert (st == 1).all()
+    objs = extra["obj"]
+    assert int(np.argmin(objs)) == 0 and abs(objs.min() - (-12.420811293)) < 1e-6
+    assert abs(np.sort(objs)[1] - (-12.035724881)) < 1e-6
+
+
+def test_ldl_reconstruction_and_scaling():
+    pr = problems.random_miqp(30, 60, 4, 0.5, seed=2)[0]
+    P, q, A, l, u, _ = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3, sigma=1e-6, rho=0.1)
+    n, m, N, nnzL = o.dims()
+    perm, Lp, Li, Lx, Dd = o.factor()
+    L = spa.csc_matrix((Lx, Li, Lp), shape=(N, N)).toarray() + np.eye(N)
+    K = L @ np.diag(Dd) @ L.T
+    b = np.random.default_rng(1).standard_normal(N)
+    sol = o.kkt_solve(b)
+    Kfull = np.zeros((N, N)); Kfull[np.ix_(perm, perm)] = K
+    assert np.abs(Kfull @ sol - b).max() < 1e-8 * (1 + np.abs(b).max()) * 1e3
+    D, E, c = o.scaling()
+    assert (D > 0).all() and (E > 0).all() and c > 0
+    assert (Dd[:0] if False else True)
+    # quasi-definite: n positive and m negative pivots
+    assert (Dd > 0).sum() == n and (Dd < 0).sum() == m
+
+
+def test_pure_function_of_node_inputs():
+    """Parity contract: a node's result depends on (l,u,x0,y0) only -- not on what was solved before."""
+    pr = problems.random_miqp(50, 100, 5, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3)
+    ls, us = problems.branched_nodes(l, u, 5, 4, np.random.default_rng(0))
+    a = [o.solve_node(ls[k], us[k], np.zeros(50), np.zeros(105)) for k in range(4)]
+    b = [o.solve_node(ls[k], us[k], np.zeros(50), np.zeros(105)) for k in (3, 2, 1, 0)][::-1]
+    for ra, rb in zip(a, b):
+        assert ra.info.iter == rb.info.iter and np.array_equal(ra.x, rb.x)
+
+
+def test_bounds_validation():
+    pr = problems.random_miqp(20, 30, 3, 0.5, seed=3)[0]
+    P, q, A, l, u, _ = problems.extend(pr)
+    o = oracle.OSQP(); o.setup(P, q, A, l, u)
+    bad = l.copy(); bad[0] = u[0] + 1
+    with pytest.raises(ValueError):
+        o.update(l=bad, u=u)
