@@ -71,10 +71,18 @@ class MIOSQP(object):
             print("Elapsed time: %.4es" % work.run_time)
         return Results(work.x, work.upper_glob, work.run_time, work.status, work.osqp_solve_time, work.osqp_iter_avg)
 
-    def solve(self):
+    def solve(self, dist_ctx=None):
+        """dist_ctx = (rank, world, group): split every frontier batch across the ranks' GPUs (config 4); all ranks
+        replay the same tree and agree on the incumbent with one all-reduce(MIN) per B&B step."""
         self._begin()
         while self._replay():
-            self.work.solve_pending()
+            self.work.solve_pending(dist_ctx)
+            if dist_ctx is not None:
+                from . import sharding
+                best, same = sharding.agree_incumbent(self.work.upper_glob, group=dist_ctx[2],
+                                                      device=dist_ctx[3] if len(dist_ctx) > 3 else None)
+                if not same:
+                    raise RuntimeError("replicated B&B replays diverged: incumbent %r vs global %r" % (self.work.upper_glob, best))
         return self._finish()
 
     def update_vectors(self, q=None, l=None, u=None):

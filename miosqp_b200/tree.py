@@ -105,15 +105,36 @@ class Workspace(object):
             share = seconds * float(scalars.iters[k]) / total
             node.cached = (int(scalars.status[k]), int(scalars.iters[k]), share, xs[k], ys[k])
 
-    def solve_pending(self):
+    def solve_pending(self, dist_ctx=None):
+        """One launch over every unsolved open leaf.  With dist_ctx = (rank, world, group) the batch is dealt
+        round-robin to the ranks, each solves its share on its own GPU, and one all-gather returns all results."""
         nodes = self.pending()
-        if nodes:
-            t0 = perf_counter()
-            xs, ys, sc = engine.solve_multi([self.solver] * len(nodes), [nd.l for nd in nodes], [nd.u for nd in nodes],
-                                            [nd.x for nd in nodes], [nd.y for nd in nodes])
-            self.absorb(nodes, xs, ys, sc, perf_counter() - t0)
-            self.batches += 1
-            self.batched_nodes += len(nodes)
+        if not nodes:
+            return 0
+        t0 = perf_counter()
+        if dist_ctx is None:
+            mine = list(range(len(nodes)))
+        else:
+            from . import sharding
+            rank, world, group = dist_ctx
+            mine = sharding.split_nodes(len(nodes), rank, world)
+        local = {}
+        if mine:
+            sub = [nodes[k] for k in mine]
+            xs, ys, sc = engine.solve_multi([self.solver] * len(sub), [nd.l for nd in sub], [nd.u for nd in sub],
+                                            [nd.x for nd in sub], [nd.y for nd in sub])
+            dt = perf_counter() - t0
+            total = float(max(1, int(np.sum(sc.iters))))
+            for j, k in enumerate(mine):
+                local[k] = (int(sc.status[j]), int(sc.iters[j]), dt * float(sc.iters[j]) / total, xs[j], ys[j])
+        if dist_ctx is not None:
+            merged = sharding.exchange_node_results(local, len(nodes), rank, world, group)
+        else:
+            merged = [local[k] for k in range(len(nodes))]
+        for node, res in zip(nodes, merged):
+            node.cached = res
+        self.batches += 1
+        self.batched_nodes += len(nodes)
         return len(nodes)
 
     # ------------------------------------------------------------------ reference logic, replayed

@@ -1,0 +1,81 @@
+"""
+N > 1 host logic on CPU: two processes, gloo backend, the oracle-backed stand-in engine.
+  * instance sharding (config 2): each rank solves its block of MIQPs, results gathered -> equal to golden.
+  * frontier splitting (config 4): both ranks replay one tree, each solving half of every batch; node results
+    cross with one all-gather, the incumbent is agreed with one all-reduce(MIN) -> equal to golden on both ranks.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, mode, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_engine
+    import miosqp_b200
+    from miosqp_b200 import engine, problems, sharding
+    engine.BatchedQP = fake_engine.FakeBatchedQP
+    engine.solve_multi = fake_engine.solve_multi
+    golden = json.load(open(os.path.join(HERE, "golden", "bnb_random_miqp.json")))
+    names = sorted(golden)
+
+    def build(name):
+        c = golden[name]["case"]
+        pr = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"])[0]
+        m = miosqp_b200.MIOSQP()
+        m.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+        return m
+
+    if mode == "instances":
+        lo, hi = sharding.shard_range(len(names), rank, world)
+        mine = [build(n) for n in names[lo:hi]]
+        res = miosqp_b200.solve_many(mine)
+        local = [(n, r.status, float(r.upper_glob), [list(d) for d in m.work.decisions])
+                 for n, m, r in zip(names[lo:hi], mine, res)]
+        allres = sharding.gather_results(local)
+    else:
+        m = build("small_seed5")
+        r = m.solve(dist_ctx=(rank, world, None))
+        allres = [("small_seed5", r.status, float(r.upper_glob), [list(d) for d in m.work.decisions], m.work.batched_nodes)]
+    with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
+        json.dump(allres, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["instances", "frontier"])
+def test_two_rank_gloo(tmp_path, mode):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + (0 if mode == "instances" else 1)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    golden = json.load(open(os.path.join(HERE, "golden", "bnb_random_miqp.json")))
+    outs = [json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r))) for r in range(2)]
+    assert outs[0] == outs[1]                      # every rank ends with the same, complete answer
+    for rec in outs[0]:
+        g = golden[rec[0]]["result"]
+        assert rec[1] == g["status"]
+        assert abs(rec[2] - g["upper_glob"]) < 1e-12
+        assert rec[3] == [list(d) for d in g["decisions"]]
+    if mode == "instances":
+        assert [rec[0] for rec in outs[0]] == sorted(golden)
+
+
+def test_shard_helpers():
+    from miosqp_b200 import sharding
+    for n in (0, 1, 7, 100):
+        for w in (1, 2, 4, 8):
+            parts = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+            assert sorted(sum((sharding.split_nodes(n, r, w) for r in range(w)), [])) == list(range(n))
