@@ -268,6 +268,15 @@ def main():
         T = 1 << LEAF_DEPTH
         bytes_per_ni = algorithmic_bytes_per_node_iter(insts[0], T)
         launch_s = dev_s / args.steps
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read+write of ONE launch of this kernel, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f)
+            if tr["kernel"] == ("admm_stream_kernel<%d>" % tm["tile_nodes"]) and tr["grid"] == tm["tiles"]:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                traffic_src = tr["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         achieved = bytes_per_ni * node_iters / launch_s / 1e9
         out = {
             "metric": "QP-relaxations/sec", "value": B_all * args.steps / dev_s_max, "unit": "QP/s",
@@ -290,7 +299,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "traffic": None, "kernel": "admm_tile_kernel<%d>" % tm["tile_nodes"],
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": ("admm_stream_kernel<%d>" if tm["threads"] == 416 else "admm_tile_kernel<%d>") % tm["tile_nodes"],
                          "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_launch": node_iters,
                          "launch_ms": 1e3 * launch_s,
                          "streamed_bytes_per_launch": int(tm["stream_bytes"]),

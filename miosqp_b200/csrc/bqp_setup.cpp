@@ -461,7 +461,7 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
   // streamed layout for the TMA kernel (problems with at least 4 slices of variables)
   h->st = HostStream();
   if (h->At.nslices >= 4) {
-    int tri_nb = 128;
+    int tri_nb = 256;   // measured best on B200 for n = 500 (fewer, fatter diagonal groups)
     if (const char *e = std::getenv("BQP_TRI_NB")) tri_nb = std::atoi(e);
     tri_nb = std::max(32, std::min(32 * kStreamWarps, (tri_nb / 32) * 32));
     build_stream(h, arows, atrows, prows, S, tri_nb);
