@@ -269,7 +269,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   int slot_bytes = kStageValBytes;
   for (auto *inst : uniq) {
     const HostStream &st = inst->h.st;
-    if (!st.built || (int)st.groups.size() > 96 || st.range[GK_AT][1] - st.range[GK_AT][0] > 4) use_stream = false;
+    if (!st.built || (int)st.groups.size() > 96) use_stream = false;   // 96 = groups cached in shared memory
     else slot_bytes = std::max(slot_bytes, st.slot_bytes);
   }
   auto stream_slots = [&](const HostInstance &h, int t) {
