@@ -269,15 +269,14 @@ def main():
         bytes_per_ni = algorithmic_bytes_per_node_iter(insts[0], T)
         launch_s = dev_s / args.steps
         traffic, traffic_src = None, None
-        try:   # dram__bytes_read+write of ONE launch of this kernel, from the committed ncu --set full capture
+        try:   # dram__bytes_read+write summed over the launches of ONE step, from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 tr = json.load(f)
-            if tr["kernel"] == ("admm_stream_kernel<%d>" % tm["tile_nodes"]) and tr["grid"] == tm["tiles"]:
+            if tr["kernel"] == ("admm_stream_kernel<%d>" % tm["tile_nodes"]) and tr["launches_per_step"] == tm["launches"]:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
                 traffic_src = tr["source"]
         except (OSError, KeyError, ValueError):
             pass
-        achieved = bytes_per_ni * node_iters / launch_s / 1e9
         out = {
             "metric": "QP-relaxations/sec", "value": B_all * args.steps / dev_s_max, "unit": "QP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -301,9 +300,10 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": ("admm_stream_kernel<%d>" if tm["threads"] == 416 else "admm_tile_kernel<%d>") % tm["tile_nodes"],
-                         "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_launch": node_iters,
-                         "launch_ms": 1e3 * launch_s,
-                         "streamed_bytes_per_launch": int(tm["stream_bytes"]),
+                         "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_step": node_iters,
+                         "launches_per_step": int(tm["launches"]), "step_kernel_ms": 1e3 * launch_s,
+                         "note": "one step = %d launches of the same kernel (rounds of 100 ADMM iterations, re-tiled in between); achieved, traffic and streamed bytes are per step" % int(tm["launches"]),
+                         "streamed_bytes_per_step": int(tm["stream_bytes"]),
                          "streamed_gbs": tm["stream_bytes"] / launch_s / 1e9},
             "setup_s": t_setup, "root_iters": root_iters, "wall_s_resident_loop": wall_max,
         }

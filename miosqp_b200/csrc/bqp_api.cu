@@ -85,13 +85,16 @@ struct BatchCtx {
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
-  bool use_stream = false; int nslots = 0, slot_bytes = 0;
+  bool use_stream = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0;
+  int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
+  std::vector<long long> in_off, state_off;
+  Buf d_state;
   size_t smem = 0, in_doubles = 0, out_doubles = 0;
   std::vector<bqp_instance *> node_inst;
   std::vector<long long> out_off;
   std::vector<DevTile> tiles;
   std::vector<long long> tile_bytes_iter, tile_bytes_check;
-  std::vector<int> tile_check_every, tile_max_iter;
+  std::vector<int> tile_check_every;
   bqp_timing timing{};
   bool resident = false, ran = false;
 };
@@ -102,7 +105,7 @@ int ctx_init(int device) {
   if (g.stream) {   // switching devices: drop everything
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
-    for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts}) b->release();
+    for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state}) b->release();
     for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
     cudaStreamDestroy(g.stream); g.stream = nullptr;
   }
@@ -142,7 +145,7 @@ int to_device(bqp_instance *inst) {
   if ((rc = upload(inst, h.E, &d.E))) return rc;
   if ((rc = upload(inst, h.Einv, &d.Einv))) return rc;
   if ((rc = upload(inst, h.i_idx, &d.i_idx))) return rc;
-  d.stream = nullptr; d.groups = nullptr;
+  d.stream = nullptr; d.groups = nullptr; d.w_in_stage = 0;
   if (h.st.built) {
     const unsigned char *dstream = nullptr;
     const StreamGroup *dgroups = nullptr;
@@ -155,6 +158,9 @@ int to_device(bqp_instance *inst) {
     d.g_bw[0] = st.bw[0]; d.g_bw[1] = st.bw[1];
     d.g_ab[0] = st.range[GK_AB][0]; d.g_ab[1] = st.range[GK_AB][1];
     d.g_pm[0] = st.range[GK_PM][0]; d.g_pm[1] = st.range[GK_PM][1];
+    d.w_in_stage = 1;
+    for (int g = d.g_at[0]; g < d.g_at[1]; g++) if (st.groups[g].sparse) d.w_in_stage = 0;
+    if (const char *e = std::getenv("BQP_W_IN_STAGE")) if (std::atoi(e) == 0) d.w_in_stage = 0;
   }
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
@@ -236,6 +242,111 @@ int bqp_set_tuning(int tile_nodes, int threads) {
   return BQP_OK;
 }
 
+// ---- per-launch planning: tile (a capacity-bounded subset of) the still-running nodes, choose T / ring depth, upload
+// the tile table.  Nodes are grouped by (problem, iterations done so far); groups with the least progress go first, and
+// when more tiles exist than the GPU holds at once (`capacity`) the rest wait for the next launch -- so every launch is
+// one full wave, and stragglers are re-tiled ever narrower as the frontier drains.  `scheduled` returns the chosen nodes.
+static int plan_round(const std::vector<int> &alive, const std::vector<int> &progress, std::vector<int> *scheduled) {
+  int ndev_sms = 148;
+  cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
+  const bool use_stream = g.use_stream, w_in_stage = g.w_in_stage;
+  const bool rounds = use_stream && g.round_iters > 0;
+  const int capacity = rounds ? ndev_sms : (1 << 30);   // streamed kernel: one 13-warp CTA per SM (registers, smem)
+  // groups in (progress, first appearance) order
+  std::vector<bqp_instance *> uniq;
+  std::map<std::pair<int, bqp_instance *>, int> gid;
+  std::vector<std::vector<int>> members;
+  std::vector<int> gprog;
+  {
+    std::vector<int> order(alive);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return progress[a] < progress[b]; });
+    for (int b : order) {
+      bqp_instance *h = g.node_inst[b];
+      auto key = std::make_pair(progress[b], h);
+      auto it = gid.find(key);
+      if (it == gid.end()) { gid[key] = (int)members.size(); members.emplace_back(); uniq.push_back(h); gprog.push_back(progress[b]); it = gid.find(key); }
+      members[it->second].push_back(b);
+    }
+  }
+  const int slot_bytes = g.stage_bytes;
+  auto slot_size = [&](int t) { return slot_bytes + (w_in_stage ? kKC * t * 8 : 0); };
+  auto stream_slots = [&](const HostInstance &h, int t) {   // slots PER QUAD (one ring per quad of consumer warps)
+    const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_size(t), 0, w_in_stage) + 1024;
+    return (int)std::min<long long>(8, ((long long)kMaxSmem - fixed) / ((kStreamWarps / 4) * (long long)slot_size(t)));
+  };
+  // nodes per tile: as wide as shared memory allows ...
+  int tt_cap = kMaxTT, nslots = 8;
+  for (auto *inst : uniq) {
+    int t = 0;
+    if (use_stream) {
+      t = kMaxTT;
+      while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
+      if (t == kMaxTT) t = kMaxTT / 2;                         // T=8 is FP64/smem-issue bound per SM
+      if (stream_slots(inst->h, t) < 2) t = 0;
+    } else {
+      t = max_tile_nodes(inst->h, g.threads);
+    }
+    if (t == 0) return BQP_E_UNSUPPORTED;
+    tt_cap = std::min(tt_cap, t);
+  }
+  int widest = 1;
+  for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
+  int tt = g_tune_tt ? std::min(g_tune_tt, use_stream ? kMaxTT : tt_cap) : std::min(tt_cap, pow2ceil(widest));
+  if (g_tune_tt && use_stream)
+    for (auto *inst : uniq) while (tt > 1 && stream_slots(inst->h, tt) < 2) tt >>= 1;
+  if (!g_tune_tt) {   // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small
+    auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
+    while (tt > 1 && count_tiles(tt / 2) <= ndev_sms) tt >>= 1;
+  }
+  if (use_stream)
+    for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
+  // tiles: split each group's nodes evenly; stop at capacity (whole groups only, so siblings stay in the same launch)
+  g.tiles.clear();
+  g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear();
+  scheduled->clear();
+  std::vector<DevInstance> dinst;
+  std::map<bqp_instance *, int> inst_slot;
+  size_t work_d = 0, smem = 0;
+  for (size_t k = 0; k < members.size(); k++) {
+    const HostInstance &h = uniq[k]->h;
+    const int cnt = (int)members[k].size(), nt = (cnt + tt - 1) / tt;
+    if (!g.tiles.empty() && (long long)g.tiles.size() + nt > capacity) break;
+    auto is = inst_slot.find(uniq[k]);
+    if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
+    smem = std::max(smem, use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads));
+    for (int ti = 0; ti < nt; ti++) {
+      const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
+      DevTile t{};
+      t.inst = is->second; t.nn = hi - lo;
+      t.iter_begin = gprog[k];
+      t.iter_end = rounds ? std::min(gprog[k] + g.round_iters, h.s.max_iter) : h.s.max_iter;
+      for (int q = lo; q < hi; q++) {
+        const int b = members[k][q];
+        t.node[q - lo] = b; t.in_off[q - lo] = g.in_off[b]; t.out_off[q - lo] = g.out_off[b]; t.state_off[q - lo] = g.state_off[b];
+        scheduled->push_back(b);
+      }
+      t.work_off = (long long)work_d;
+      work_d += tile_work_doubles(h.n, h.m, tt);
+      g.tiles.push_back(t);
+      g.tile_bytes_iter.push_back(use_stream ? h.st.iter_bytes : h.factor_bytes());
+      g.tile_bytes_check.push_back(use_stream ? h.st.check_bytes : h.check_bytes());
+      g.tile_check_every.push_back(h.s.check_termination);
+    }
+  }
+  g.ntiles = (int)g.tiles.size(); g.tt = tt; g.smem = smem; g.nslots = nslots; g.slot_bytes = use_stream ? slot_size(tt) : slot_bytes;
+  int rc;
+  if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
+  if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
+  if ((rc = g.d_work.reserve(work_d * 8))) return rc;
+  if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size()))) return rc;
+  if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size()))) return rc;
+  CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));   // tiles / dinst are stack-lifetime host memory
+  g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
+  return BQP_OK;
+}
+
 int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
                      const double *const *x0, const double *const *y0) {
   if (B <= 0 || !handles || !l || !u || !x0 || !y0) return BQP_E_ARG;
@@ -251,132 +362,70 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   int rc = ctx_init(handles[0]->device);
   if (rc) return rc;
   CK(cudaSetDevice(g.device));
-  int ndev_sms = 148;
-  cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
 
-  // group nodes by instance, in first-appearance order
-  std::vector<bqp_instance *> uniq;
-  std::map<bqp_instance *, int> uid;
-  std::vector<std::vector<int>> members;
-  for (int b = 0; b < B; b++) {
-    auto it = uid.find(handles[b]);
-    if (it == uid.end()) { uid[handles[b]] = (int)uniq.size(); uniq.push_back(handles[b]); members.emplace_back(); it = uid.find(handles[b]); }
-    members[it->second].push_back(b);
-  }
   // engine: the TMA-streamed kernel when every problem has a streamed layout (bqp_set_tuning(threads>0) forces
   // the direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
-  bool use_stream = g_tune_threads == 0;
-  int slot_bytes = kStageValBytes;
-  for (auto *inst : uniq) {
-    const HostStream &st = inst->h.st;
-    if (!st.built || (int)st.groups.size() > 96) use_stream = false;   // 96 = groups cached in shared memory
-    else slot_bytes = std::max(slot_bytes, st.slot_bytes);
-  }
-  auto stream_slots = [&](const HostInstance &h, int t) {
-    // slots PER QUAD (the kernel keeps one ring per quad of consumer warps)
-    const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_bytes, 0) + 1024;
-    return (int)std::min<long long>(8, ((long long)kMaxSmem - fixed) / ((kStreamWarps / 4) * (long long)slot_bytes));
-  };
-  int threads = g_tune_threads;
-  if (!use_stream && !threads) {
-    int want = 2;
-    for (auto *inst : uniq) want = std::max(want, std::max(inst->h.Ab.nslices, inst->h.At.nslices));
-    threads = 32 * std::min(pow2ceil(want), kMaxThreads / 32);
-  }
-  if (use_stream) threads = (kStreamWarps + 1) * 32;
-  // nodes per tile: as wide as shared memory allows ...
-  int tt_cap = kMaxTT, nslots = 8;
-  for (auto *inst : uniq) {
-    int t = 0;
-    if (use_stream) {
-      t = kMaxTT;
-      while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
-      if (stream_slots(inst->h, t) < 2) t = 0;
-    } else {
-      t = max_tile_nodes(inst->h, threads);
-    }
-    if (t == 0) return BQP_E_UNSUPPORTED;
-    tt_cap = std::min(tt_cap, t);
-  }
-  int widest = 1;
-  for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
-  int tt = g_tune_tt ? std::min(g_tune_tt, tt_cap) : std::min(tt_cap, pow2ceil(widest));
-  if (!g_tune_tt) {   // ... but narrow enough to spread a small frontier over the SMs
-    auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
-    const long long target = use_stream ? ndev_sms / 2 : ndev_sms;
-    while (tt > 1 && count_tiles(tt) < target && count_tiles(tt / 2) <= 2LL * ndev_sms) tt >>= 1;
-  }
-  if (use_stream)
-    for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
-  // tiles: split each instance's nodes evenly
-  g.tiles.clear(); g.node_inst.assign(B, nullptr); g.out_off.assign(B, 0);
-  g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_max_iter.clear();
-  std::vector<long long> in_off(B);
-  size_t in_d = 0, out_d = 0, work_d = 0, smem = 0;
+  g.use_stream = g_tune_threads == 0;
+  g.stage_bytes = kStageValBytes;
+  g.w_in_stage = true;
+  g.max_iter_all = 0; g.round_ok = true;
+  int check0 = handles[0]->h.s.check_termination, want = 2;
   for (int b = 0; b < B; b++) {
     const HostInstance &h = handles[b]->h;
-    in_off[b] = (long long)in_d; g.out_off[b] = (long long)out_d; g.node_inst[b] = handles[b];
-    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n;
+    const HostStream &st = h.st;
+    if (!st.built || (int)st.groups.size() > 96) g.use_stream = false;   // 96 = groups cached in shared memory
+    else g.stage_bytes = std::max(g.stage_bytes, st.slot_bytes);
+    if (!handles[b]->d.w_in_stage) g.w_in_stage = false;
+    g.max_iter_all = std::max(g.max_iter_all, h.s.max_iter);
+    if (h.s.check_termination != check0) g.round_ok = false;
+    want = std::max(want, std::max(h.Ab.nslices, h.At.nslices));
   }
-  for (size_t k = 0; k < uniq.size(); k++) {
-    const HostInstance &h = uniq[k]->h;
-    const int cnt = (int)members[k].size(), nt = (cnt + tt - 1) / tt;
-    smem = std::max(smem, use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_bytes, nslots) : tile_smem_bytes(h.n, h.m, tt, threads));
-    for (int ti = 0; ti < nt; ti++) {
-      const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
-      DevTile t{};
-      t.inst = (int)k; t.nn = hi - lo;
-      for (int q = lo; q < hi; q++) {
-        const int b = members[k][q];
-        t.node[q - lo] = b; t.in_off[q - lo] = in_off[b]; t.out_off[q - lo] = g.out_off[b];
-      }
-      t.work_off = (long long)work_d;
-      work_d += tile_work_doubles(h.n, h.m, tt);
-      g.tiles.push_back(t);
-      g.tile_bytes_iter.push_back(use_stream ? h.st.iter_bytes : h.factor_bytes());
-      g.tile_bytes_check.push_back(use_stream ? h.st.check_bytes : h.check_bytes());
-      g.tile_check_every.push_back(h.s.check_termination);
-      g.tile_max_iter.push_back(h.s.max_iter);
-    }
+  if (!g.use_stream) g.w_in_stage = false;
+  g.threads = g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
+  // rounds: the streamed kernel runs `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
+  // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
+  g.round_iters = 0;
+  if (g.use_stream && g.round_ok) {
+    int r = 100;
+    if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
+    g.round_iters = r <= 0 ? 0 : ((r + check0 - 1) / check0) * check0;
   }
-  g.B = B; g.ntiles = (int)g.tiles.size(); g.tt = tt; g.threads = threads; g.smem = smem;
-  g.use_stream = use_stream; g.nslots = nslots; g.slot_bytes = slot_bytes;
-  g.in_doubles = in_d; g.out_doubles = out_d;
+
+  g.node_inst.assign(B, nullptr); g.in_off.assign(B, 0); g.out_off.assign(B, 0); g.state_off.assign(B, 0);
+  size_t in_d = 0, out_d = 0, st_d = 0;
+  for (int b = 0; b < B; b++) {
+    const HostInstance &h = handles[b]->h;
+    g.in_off[b] = (long long)in_d; g.out_off[b] = (long long)out_d; g.state_off[b] = (long long)st_d; g.node_inst[b] = handles[b];
+    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
+  }
+  g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
   if ((rc = g.h_in.reserve(in_d * 8))) return rc;
   if ((rc = g.h_out.reserve(out_d * 8))) return rc;
   if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
-  if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
   if ((rc = g.d_in.reserve(in_d * 8))) return rc;
   if ((rc = g.d_out.reserve(out_d * 8))) return rc;
   if ((rc = g.d_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
-  if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
-  if ((rc = g.d_work.reserve(work_d * 8))) return rc;
-  if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size()))) return rc;
-  if ((rc = g.d_insts.reserve(sizeof(DevInstance) * uniq.size()))) return rc;
+  if ((rc = g.d_state.reserve(std::max<size_t>(st_d, 1) * 8))) return rc;
   // pack the per-node inputs: l[m] u[m] x0[n] y0[m]
   double *hin = (double *)g.h_in.p;
   for (int b = 0; b < B; b++) {
     const HostInstance &h = handles[b]->h;
-    double *p = hin + in_off[b];
+    double *p = hin + g.in_off[b];
     std::memcpy(p, l[b], 8 * (size_t)h.m);
     std::memcpy(p + h.m, u[b], 8 * (size_t)h.m);
     std::memcpy(p + 2 * (size_t)h.m, x0[b], 8 * (size_t)h.n);
     std::memcpy(p + 2 * (size_t)h.m + h.n, y0[b], 8 * (size_t)h.m);
   }
-  std::vector<DevInstance> dinst(uniq.size());
-  for (size_t k = 0; k < uniq.size(); k++) dinst[k] = uniq[k]->d;
   CK(cudaEventRecord(g.ev[0], g.stream));
   CK(cudaMemcpyAsync(g.d_in.p, hin, in_d * 8, cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
   CK(cudaEventRecord(g.ev[1], g.stream));
-  CK(cudaStreamSynchronize(g.stream));   // tiles / dinst are stack-lifetime host memory
+  CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
   g.timing = bqp_timing{};
   g.timing.h2d_ms = ms;
-  g.timing.h2d_bytes = (long long)(in_d * 8 + sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
-  g.timing.tiles = g.ntiles; g.timing.tile_nodes = tt; g.timing.threads = threads; g.timing.smem_bytes = (long long)smem;
+  g.timing.h2d_bytes = (long long)(in_d * 8);
+  g.timing.threads = g.threads;
   g.resident = true;
   return BQP_OK;
 }
@@ -384,21 +433,55 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
 int bqp_batch_run(void) {
   if (!g.resident) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
+  std::vector<int> alive(g.B), progress(g.B, 0), scheduled;
+  for (int b = 0; b < g.B; b++) alive[b] = b;
+  long long tile_iters = 0, bytes = 0, h2d_extra = 0;
+  int launches = 0, first_tiles = 0, first_tt = 0;
+  long long first_smem = 0;
   CK(cudaEventRecord(g.ev[1], g.stream));
-  int rc = g.use_stream
-               ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
-                                    g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p,
-                                    (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
-               : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
-                             (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
-                             (int *)g.d_ti.p, g.smem, g.stream);
-  if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
+  while (!alive.empty()) {
+    int rc = plan_round(alive, progress, &scheduled);
+    if (rc) return rc;
+    h2d_extra += g.round_h2d_bytes;
+    if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; }
+    rc = g.use_stream
+             ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, g.w_in_stage ? 1 : 0, (double *)g.d_state.p,
+                                  (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
+                                  (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
+             : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                           (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                           (int *)g.d_ti.p, g.smem, g.stream);
+    if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
+    launches++;
+    CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
+    const int *ti = (const int *)g.h_ti.p;
+    for (int t = 0; t < g.ntiles; t++) {
+      tile_iters += ti[t];
+      const int ce = g.tile_check_every[t];
+      bytes += (long long)ti[t] * g.tile_bytes_iter[t] + (long long)(ti[t] / ce + ((ti[t] % ce) ? 1 : 0)) * g.tile_bytes_check[t];
+    }
+    std::vector<char> done(g.B, 0);
+    for (int b : scheduled) {
+      if (hs[b].status == BQP_UNSOLVED) progress[b] = hs[b].iters;   // iterations completed so far (its tile's iter_end)
+      else done[b] = 1;
+    }
+    std::vector<int> next;
+    for (int b : alive) if (!done[b]) next.push_back(b);
+    if (next.size() == alive.size() && scheduled.empty()) return BQP_E_CUDA;
+    alive.swap(next);
+  }
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
   g.timing.kernel_ms = ms;
-  g.timing.launches = 1;
+  g.timing.launches = launches;
+  g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
+  g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
+  g.round_h2d_total = h2d_extra;
   g.ran = true;
   return BQP_OK;
 }
@@ -409,17 +492,16 @@ int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *o
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaEventRecord(g.ev[3], g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
   g.timing.d2h_ms = ms;
-  g.timing.d2h_bytes = (long long)(g.out_doubles * 8 + sizeof(NodeScalars) * (size_t)g.B + sizeof(int) * (size_t)g.ntiles);
+  g.timing.d2h_bytes = (long long)(g.out_doubles * 8 + sizeof(NodeScalars) * (size_t)g.B);
+  g.timing.h2d_bytes = (long long)(g.in_doubles * 8) + g.round_h2d_total;
   const double *ho = (const double *)g.h_out.p;
   const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
-  const int *ti = (const int *)g.h_ti.p;
-  long long node_iters = 0, tile_iters = 0, bytes = 0;
+  long long node_iters = 0;
   for (int b = 0; b < g.B; b++) {
     const HostInstance &h = g.node_inst[b]->h;
     if (x && x[b]) std::memcpy(x[b], ho + g.out_off[b], 8 * (size_t)h.n);
@@ -434,13 +516,7 @@ int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *o
     }
     node_iters += hs[b].iters;
   }
-  for (int t = 0; t < g.ntiles; t++) {
-    tile_iters += ti[t];
-    const int ce = g.tile_check_every[t];
-    const long long checks = ti[t] / ce + ((ti[t] % ce) ? 1 : 0);
-    bytes += (long long)ti[t] * g.tile_bytes_iter[t] + checks * g.tile_bytes_check[t];
-  }
-  g.timing.node_iters = node_iters; g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
+  g.timing.node_iters = node_iters;
   return BQP_OK;
 }
 

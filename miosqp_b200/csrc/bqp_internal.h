@@ -107,6 +107,7 @@ struct DevInstance {
   // streamed layout (TMA kernel)
   const unsigned char *stream; const StreamGroup *groups;
   int g_at[2], g_fw[2], g_bw[2], g_ab[2], g_pm[2];
+  int w_in_stage;   // 1: every A' group is dense -> its input vector chunks ride in the TMA stages (no m x T vector in smem)
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -119,9 +120,11 @@ struct DevInstance {
 // One CTA solves one tile = up to kMaxTT nodes of one instance.
 struct DevTile {
   int inst, nn;
+  int iter_begin, iter_end;      // this launch runs ADMM iterations iter_begin+1 .. iter_end of the tile's nodes (a round)
   int node[kMaxTT];              // caller-side node index (scalar outputs)
   long long in_off[kMaxTT];      // doubles into the packed input buffer: l[m] u[m] x0[n] y0[m]
   long long out_off[kMaxTT];     // doubles into the packed output buffer: x[n] y[m]
+  long long state_off[kMaxTT];   // doubles into the ADMM state buffer (scaled x[n] z[m] y[m]) used to resume a node
   long long work_off;            // doubles into the state workspace
 };
 
@@ -130,11 +133,18 @@ struct NodeScalars {
   double obj, pri_res, dua_res, lower;
 };
 
-// state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each); P x scratch (n rows)
-inline size_t tile_work_doubles(int n, int m, int tt) { return (size_t)tt * (5 * (size_t)m + 3 * (size_t)n); }
+// state workspace of one tile, [row][T] node-fastest: x, dx (n rows each); z, y, l, u, dy (m rows each); P x scratch
+// (n rows); then, 16-byte aligned, the A' input vector w = rho z - y (m + 32 rows, zero padded) for the TMA kernel
+#ifdef __CUDACC__
+#define BQP_HD __host__ __device__
+#else
+#define BQP_HD
+#endif
+BQP_HD inline size_t tile_w_offset(int n, int m, int tt) { return ((size_t)tt * (5 * (size_t)m + 3 * (size_t)n) + 1) & ~size_t(1); }
+inline size_t tile_work_doubles(int n, int m, int tt) { return (tile_w_offset(n, m, tt) + (size_t)tt * ((size_t)m + 32) + 1) & ~size_t(1); }
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
-size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots);          // bqp_stream.cu
-int launch_admm_stream(int tt, int slot_bytes, int nslots, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
+int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                        const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                        size_t smem_bytes, void *stream);
 int launch_admm(int tt, int threads, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,

@@ -168,6 +168,7 @@ void add_group(HostStream &st, int kind, int row0, const std::vector<const Row *
       mlen[q] = std::max(mlen[q], (int)R.size());
     }
     if (chi[q] < 0) { clo[q] = 0; chi[q] = 0; }
+    clo[q] &= ~3;   // 32-byte aligned first column (the A' input chunk is fetched by TMA from global memory)
     // a quad that owns slices must still see the group (its warps arrive on the barriers) only if it has data
     dense_stages += (chi[q] - clo[q] + kKC - 1) / kKC;
     sparse_stages += (mlen[q] + kKC - 1) / kKC;

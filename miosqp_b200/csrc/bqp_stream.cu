@@ -130,21 +130,27 @@ __device__ __forceinline__ void l2_prefetch(const void *src_gmem, uint32_t bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
-// producer lane q (< kQuads): one bulk copy per stage of quad q of group G.  Optional L2 prefetch `prefetch_ahead`
-// bytes further down the (cyclic) per-iteration stream.
+// producer lane q (< kQuads): one bulk copy per stage of quad q of group G.  When `wsrc` is given (A' groups in
+// w-in-stage mode) a second, small bulk copy appends the kKC rows of the input vector w = rho z - y that the stage
+// multiplies, fetched from the tile's global workspace (written by the consumers, published through `wbar`).
+// Optional L2 prefetch `prefetch_ahead` bytes further down the (cyclic) per-iteration stream.
 __device__ __forceinline__ void produce_group(const StreamGroup &G, const unsigned char *__restrict__ stream, long long iter_bytes,
-                                              long long prefetch_ahead, Ring &R, int lane) {
+                                              long long prefetch_ahead, const double *wsrc, int T, Ring &R, int lane) {
   if (lane < kQuads) {
     const uint32_t sb = kStageValBytes + (G.sparse ? kStageIdxBytes : 0);
+    const uint32_t wb = wsrc ? (uint32_t)(kKC * T * 8) : 0u;
     int before = 0;
     for (int q = 0; q < lane; q++) before += G.qch[q];
     const long long off0 = G.data_off + (long long)before * sb;
     const unsigned char *src = stream + off0;
+    const double *w = wsrc ? wsrc + (size_t)(G.in_off + G.qcol0[lane]) * T : nullptr;
     const int nch = G.qch[lane];
     for (int c = 0; c < nch; c++) {
       mbar_wait(R.empty + R.slot, R.phase ^ 1);     // passes at once on the first lap
-      mbar_expect_tx(R.full + R.slot, sb);
-      tma_load_1d(R.base + (size_t)R.slot * R.slot_bytes, src, sb, R.full + R.slot);
+      mbar_expect_tx(R.full + R.slot, sb + wb);
+      unsigned char *dst = R.base + (size_t)R.slot * R.slot_bytes;
+      tma_load_1d(dst, src, sb, R.full + R.slot);
+      if (wb) tma_load_1d(dst + kStageValBytes, w + (size_t)c * kKC * T, wb, R.full + R.slot);
       if (prefetch_ahead > 0 && G.data_off < iter_bytes) {
         long long o = off0 + (long long)c * sb + prefetch_ahead;
         if (o >= iter_bytes) o -= iter_bytes;
@@ -160,7 +166,7 @@ __device__ __forceinline__ void produce_group(const StreamGroup &G, const unsign
 // consumer: acc += (this warp's slice of group G) * in
 template <int T>
 __device__ __forceinline__ void consume_group(const StreamGroup &G, const double *__restrict__ in, Ring &R, int warp, int lane,
-                                              double (&acc)[T]) {
+                                              double (&acc)[T], bool wtail = false) {
   const int q = warp >> 2, wq = warp & 3;
   const int myc = G.qch[q];
   const int kp = lane >> 3;
@@ -178,7 +184,9 @@ __device__ __forceinline__ void consume_group(const StreamGroup &G, const double
       if (!G.sparse) {
         // register-blocked dense stage: this lane owns rows r8+8i (i<4) and the columns 4j+kp of the chunk
         const double *v = reinterpret_cast<const double *>(stage) + (size_t)wq * (kKC * 32) + lane * 2;
-        const double *x = inq + ((size_t)c * kKC + kp) * T;
+        // input rows of this chunk: from the vector in shared memory, or from the stage's own tail (w-in-stage A')
+        const double *x = wtail ? reinterpret_cast<const double *>(stage + kStageValBytes) + kp * T
+                                : inq + ((size_t)c * kKC + kp) * T;
 #pragma unroll
         for (int j = 0; j < kKC / 4; j++) {
           const double2 a01 = *reinterpret_cast<const double2 *>(v + j * 128);
@@ -254,7 +262,8 @@ template <int T>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                    double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
-                   int *__restrict__ tile_iters, int nslots, int slot_bytes, long long prefetch_ahead) {
+                   int *__restrict__ tile_iters, int nslots, int slot_bytes, int w_in_stage, long long prefetch_ahead,
+                   double *__restrict__ state) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp == kConsumerWarps;
@@ -268,12 +277,14 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   __syncthreads();
   const DevInstance &I = S.I;
   const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn;
+  const int iter_begin = S.tile.iter_begin, iter_end = S.tile.iter_end;   // this round's slice of the ADMM loop
   const int ngroups = I.g_pm[1];
   for (int g = tid; g < ngroups; g += blockDim.x) S.groups[g] = I.groups[g];
-  const int mvec = ((m > np ? m : np) + kKC + 15) & ~15;
+  const int mvec = w_in_stage ? 0 : ((m > np ? m : np) + kKC + 15) & ~15;   // A' input vector in smem only when needed
   size_t off = (sizeof(StreamShared) + 15) & ~size_t(15);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off);
-  off += sizeof(uint64_t) * 2 * (size_t)kQuads * nslots;
+  uint64_t *wbar = bars + 2 * (size_t)kQuads * nslots;       // "w published" (consumers -> producer), w-in-stage mode
+  off += sizeof(uint64_t) * (2 * (size_t)kQuads * nslots + 2);
   off = (off + 15) & ~size_t(15);
   double *vin = reinterpret_cast<double *>(smem_raw + off);   // [mvec][T]
   double *bb = vin + (size_t)mvec * T;                        // [np + kKC][T]
@@ -288,6 +299,7 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   R.nslots = nslots; R.slot_bytes = slot_bytes; R.slot = 0; R.phase = 0;
   if (tid == 0) {
     for (int s = 0; s < kQuads * nslots; s++) { mbar_init(bars + s, 1); mbar_init(bars + kQuads * nslots + s, 4); }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -297,27 +309,44 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   const unsigned char *stream = I.stream;
   const long long iter_bytes = S.groups[I.g_pm[0]].data_off;   // A', L fwd, L bwd, A: what one iteration streams
 
+  double *W = work + S.tile.work_off;
+  double *gw = W + tile_w_offset(n, m, T);             // A' input vector in global memory (w-in-stage mode)
+
   // =============================================================== producer warp: mirror of the consumer control flow
   if (producer) {
     auto produce = [&](const int (&range)[2]) {
-      for (int g = range[0]; g < range[1]; g++) produce_group(S.groups[g], stream, iter_bytes, prefetch_ahead, R, lane);
+      for (int g = range[0]; g < range[1]; g++)
+        produce_group(S.groups[g], stream, iter_bytes, prefetch_ahead, nullptr, T, R, lane);
     };
-    produce(I.g_ab);                                   // prologue: z = A x
-    for (int iter = 1; iter <= max_iter; iter++) {
+    uint32_t wphase = 0;
+    auto produce_at = [&]() {        // every pass over A' waits for the consumers to have published its input vector
+      if (w_in_stage) { mbar_wait(wbar, wphase); wphase ^= 1; }
+      for (int g = I.g_at[0]; g < I.g_at[1]; g++)
+        produce_group(S.groups[g], stream, iter_bytes, prefetch_ahead, w_in_stage ? gw : nullptr, T, R, lane);
+    };
+    if (iter_begin == 0) produce(I.g_ab);              // prologue: z = A x (a resumed round restores z instead)
+    for (int iter = iter_begin + 1; iter <= iter_end; iter++) {
       const bool do_check = (iter % check_every == 0) || iter == max_iter;
-      produce(I.g_at); produce(I.g_fw); produce(I.g_bw); produce(I.g_ab);
+      produce_at(); produce(I.g_fw); produce(I.g_bw); produce(I.g_ab);
       if (!do_check) continue;
-      produce(I.g_pm); produce(I.g_at); produce(I.g_ab);     // P x, A' y, A x
-      produce(I.g_at); produce(I.g_pm); produce(I.g_ab);     // A' dy, P dx, A dx
+      produce(I.g_pm); produce_at(); produce(I.g_ab);        // P x, A' y, A x
+      produce_at(); produce(I.g_pm); produce(I.g_ab);        // A' dy, P dx, A dx
       __syncthreads();                                       // decision published by the consumers
-      if (S.remaining == 0) break;
+      if (S.remaining == 0 || iter == iter_end) break;
     }
     produce(I.g_pm);                                   // epilogue objective
     return;
   }
 
   // =============================================================== consumer warps
-  double *W = work + S.tile.work_off;
+  // wv: where the A' input vector is written.  publish_w(): make it visible to the producer's TMA reads (generic ->
+  // async proxy fence by every writer, consumer barrier, one arrival on wbar); plain consumer barrier otherwise.
+  double *const wv = w_in_stage ? gw : vin;
+  auto publish_w = [&]() {
+    if (w_in_stage) asm volatile("fence.proxy.async;" ::: "memory");
+    consumer_bar();
+    if (w_in_stage && tid == 0) mbar_arrive(wbar);
+  };
   double *gx = W, *gdx = gx + (size_t)n * T, *gz = gdx + (size_t)n * T, *gy = gz + (size_t)m * T,
          *gl = gy + (size_t)m * T, *gu = gl + (size_t)m * T, *gdy = gu + (size_t)m * T, *gpx = gdy + (size_t)m * T;
   const double alpha = I.alpha, sigma = I.sigma;
@@ -338,13 +367,25 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
   for (int e = tid; e < (np + kKC) * T; e += kConsumers) {
     const int j = e / T, t = e - j * T;
     double xv = 0.0;
-    if (j < n && t < nn) xv = __ldg(I.Dinv + j) * in[S.tile.in_off[t] + 2 * (size_t)m + j];
+    if (j < n && t < nn)
+      xv = iter_begin == 0 ? __ldg(I.Dinv + j) * in[S.tile.in_off[t] + 2 * (size_t)m + j] : state[S.tile.state_off[t] + j];
     bb[e] = xv;
     if (j < n) gx[e] = xv;
   }
-  for (int e = tid + m * T; e < mvec * T; e += kConsumers) vin[e] = 0.0;
+  if (iter_begin > 0) {   // resumed round: z and y continue from the saved ADMM state, w = rho z - y
+    for (int e = tid; e < m * T; e += kConsumers) {
+      const int i = e / T, t = e - i * T;
+      double zv = 0.0, yv = 0.0;
+      if (t < nn) { const double *sp = state + S.tile.state_off[t] + n; zv = sp[i]; yv = sp[m + i]; }
+      gz[e] = zv; gy[e] = yv;
+    }
+  }
+  for (int e = tid + m * T; e < (w_in_stage ? m + 32 : mvec) * T; e += kConsumers) wv[e] = 0.0;
   consumer_bar();
-  for (int g = I.g_ab[0]; g < I.g_ab[1]; g++) {   // z = A x ; vin = rho z - y
+  if (iter_begin > 0) {
+    for (int e = tid; e < m * T; e += kConsumers) wv[e] = __ldg(I.rho + e / T) * gz[e] - gy[e];
+  }
+  for (int g = I.g_ab[0]; g < (iter_begin == 0 ? I.g_ab[1] : I.g_ab[0]); g++) {   // z = A x ; w = rho z - y
     const StreamGroup &G = S.groups[g];
     double acc[T]; zero<T>(acc);
     consume_group<T>(G, bb, R, warp, lane, acc);
@@ -354,20 +395,20 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
 #pragma unroll
       for (int t = 0; t < T; t++) {
         gz[(size_t)i * T + t] = acc[t];
-        vin[(size_t)i * T + t] = rho * acc[t] - gy[(size_t)i * T + t];
+        wv[(size_t)i * T + t] = rho * acc[t] - gy[(size_t)i * T + t];
       }
     }
   }
-  consumer_bar();
+  publish_w();
 
   int iter = 0;
-  for (iter = 1; iter <= max_iter; iter++) {
+  for (iter = iter_begin + 1; iter <= iter_end; iter++) {
     const bool do_check = (iter % check_every == 0) || iter == max_iter;
     // ---- b = sigma x - q + A'(rho z - y)
     for (int g = I.g_at[0]; g < I.g_at[1]; g++) {
       const StreamGroup &G = S.groups[g];
       double acc[T]; zero<T>(acc);
-      consume_group<T>(G, vin, R, warp, lane, acc);
+      consume_group<T>(G, vin, R, warp, lane, acc, w_in_stage != 0);
       const int j = G.row0 + warp * 32 + lane;
       if (warp < G.nsl && j < n) {
         const double qj = __ldg(I.q + j);
@@ -431,17 +472,17 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
           const double dy = rho * (zr - zn), yn = yv + dy;
           gz[e] = zn; gy[e] = yn;
           if (do_check) gdy[e] = dy;
-          vin[e] = rho * zn - yn;
+          wv[e] = rho * zn - yn;
         }
       }
     }
+    if (!do_check) { publish_w(); continue; }
     consumer_bar();
-    if (!do_check) continue;
 
     // ---- termination check (update_info + check_termination)
     for (int e = tid; e < n * T; e += kConsumers) bb[e] = gx[e];
-    for (int e = tid; e < m * T; e += kConsumers) vin[e] = gy[e];
-    consumer_bar();
+    for (int e = tid; e < m * T; e += kConsumers) wv[e] = gy[e];
+    publish_w();
     {
       // P x and A' y share the row ownership (both have n rows): group k of P pairs with group k of A'
       double dr[T], b1[T], b2[T], quad[T], lin[T];
@@ -461,7 +502,7 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
       for (int k = 0; k < npm; k++) {
         const StreamGroup &G = S.groups[I.g_at[0] + k];
         double aty[T]; zero<T>(aty);
-        consume_group<T>(G, vin, R, warp, lane, aty);
+        consume_group<T>(G, vin, R, warp, lane, aty, w_in_stage != 0);
         const int j = G.row0 + warp * 32 + lane;
         if (warp < G.nsl && j < n) {
           const double qj = __ldg(I.q + j), di = __ldg(I.Dinv + j);
@@ -519,7 +560,7 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
             if (up > kInfty * kMinScaling) {
               if (lo < -kInfty * kMinScaling) d = 0.0; else d = fmin(d, 0.0);
             } else if (lo < -kInfty * kMinScaling) d = fmax(d, 0.0);
-            vin[e] = d;
+            wv[e] = d;
             ndy[t] = fmax(ndy[t], fabs(ei * d));
             lhs[t] += up * fmax(d, 0.0) + lo * fmin(d, 0.0);
           }
@@ -543,14 +584,14 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
       red_put<T, 0>(ndx, red, 10, warp, lane);
       red_put<T, 1>(qdx, red, 11, warp, lane);
     }
-    consumer_bar();
+    publish_w();   // projected dy is the next A' input
     {
       double t1[T], t2[T];
       zero<T>(t1); zero<T>(t2);
       for (int g = I.g_at[0]; g < I.g_at[1]; g++) {
         const StreamGroup &G = S.groups[g];
         double atd[T]; zero<T>(atd);
-        consume_group<T>(G, vin, R, warp, lane, atd);
+        consume_group<T>(G, vin, R, warp, lane, atd, w_in_stage != 0);
         const int j = G.row0 + warp * 32 + lane;
         if (warp < G.nsl && j < n) {
           const double di = __ldg(I.Dinv + j);
@@ -664,12 +705,20 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
       for (int i = tid; i < m; i += kConsumers) oy[i] = bad ? NAN : I.cinv * __ldg(I.E + i) * gy[(size_t)i * T + t];
     }
     __syncthreads();   // with the producer warp: it reads S.remaining after this barrier
-    if (S.remaining == 0) break;
-    for (int e = tid; e < m * T; e += kConsumers) vin[e] = __ldg(I.rho + e / T) * gz[e] - gy[e];
-    consumer_bar();
+    if (S.remaining == 0 || iter == iter_end) break;
+    for (int e = tid; e < m * T; e += kConsumers) wv[e] = __ldg(I.rho + e / T) * gz[e] - gy[e];
+    publish_w();
   }
   consumer_bar();
-  if (tid == 0) tile_iters[blockIdx.x] = iter > max_iter ? max_iter : iter;
+  if (tid == 0) tile_iters[blockIdx.x] = (iter > iter_end ? iter_end : iter) - iter_begin;
+  // nodes still running when this round's iteration budget ends: save the scaled ADMM state for the next round
+  for (int t = 0; t < nn; t++) {
+    if (S.status[t] != BQP_UNSOLVED) continue;
+    double *sp = state + S.tile.state_off[t];
+    for (int j = tid; j < n; j += kConsumers) sp[j] = gx[(size_t)j * T + t];
+    for (int i = tid; i < m; i += kConsumers) { sp[n + i] = gz[(size_t)i * T + t]; sp[n + m + i] = gy[(size_t)i * T + t]; }
+    if (tid == 0) { NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.pri_res = r.dua_res = r.lower = NAN; ns[S.tile.node[t]] = r; }
+  }
 
   // ---- epilogue (node.py:128-143): clip integer entries, lower = 1/2 x'Px + q'x at the clipped point
   for (int t = 0; t < nn; t++) {
@@ -727,11 +776,11 @@ admm_stream_kernel(const DevInstance *__restrict__ insts, const DevTile *__restr
 
 }  // namespace
 
-size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots) {
+size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage) {
   const int np = ((n + kNB - 1) / kNB) * kNB;
-  const int mvec = ((m > np ? m : np) + kKC + 15) & ~15;
+  const int mvec = w_in_stage ? 0 : ((m > np ? m : np) + kKC + 15) & ~15;
   size_t off = (sizeof(StreamShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * 2 * (size_t)kQuads * nslots;
+  off += sizeof(uint64_t) * (2 * (size_t)kQuads * nslots + 2);
   off = (off + 15) & ~size_t(15);
   off += ((size_t)mvec + np + kKC + (size_t)kRed * kConsumerWarps) * tt * 8;
   off = (off + 127) & ~size_t(127);
@@ -739,25 +788,25 @@ size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots) {
 }
 
 template <int T>
-static int launch_t(int slot_bytes, int nslots, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
+static int launch_t(int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
                     double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(admm_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return BQP_E_CUDA;
   long long prefetch_ahead = 0;   // experiment knob: L2 prefetch distance of the producer warp (KiB), off by default
   if (const char *pk = getenv("BQP_PREFETCH_KB")) prefetch_ahead = 1024LL * atoll(pk);
-  admm_stream_kernel<T><<<ntiles, kStreamThreads, smem, st>>>(d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, slot_bytes, prefetch_ahead);
+  admm_stream_kernel<T><<<ntiles, kStreamThreads, smem, st>>>(d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, slot_bytes, w_in_stage, prefetch_ahead, d_state);
   return cudaGetLastError() == cudaSuccess ? BQP_OK : BQP_E_CUDA;
 }
 
-int launch_admm_stream(int tt, int slot_bytes, int nslots, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                        const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                        size_t smem_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (tt) {
-    case 1: return launch_t<1>(slot_bytes, nslots, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-    case 2: return launch_t<2>(slot_bytes, nslots, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-    case 4: return launch_t<4>(slot_bytes, nslots, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-    case 8: return launch_t<8>(slot_bytes, nslots, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+    case 1: return launch_t<1>(slot_bytes, nslots, w_in_stage, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+    case 2: return launch_t<2>(slot_bytes, nslots, w_in_stage, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+    case 4: return launch_t<4>(slot_bytes, nslots, w_in_stage, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+    case 8: return launch_t<8>(slot_bytes, nslots, w_in_stage, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
   }
   return BQP_E_ARG;
 }

@@ -193,3 +193,25 @@ def test_cfg2_size_leaves(oracle_mod):
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
     _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
     assert engine.last_timing()["threads"] == STREAM_THREADS
+
+
+def test_rounds_and_retiling_are_bit_identical(monkeypatch):
+    """The streamed kernel runs in rounds of BQP_ROUND_ITERS iterations; between rounds finished nodes drop out and
+    the rest are re-tiled (other tile widths, other tile mates), resuming from the saved ADMM state.  The result of
+    every node must not depend on that: bit-identical to one uninterrupted launch."""
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    ls, us = problems.branched_nodes(l, u, len(i_idx), 13, np.random.default_rng(11))
+    x0 = np.zeros((13, 130)); y0 = np.zeros((13, 210))
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    monkeypatch.setenv("BQP_ROUND_ITERS", "0")
+    r0 = e.solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["launches"] == 1
+    for rounds in ("25", "50", "250"):
+        monkeypatch.setenv("BQP_ROUND_ITERS", rounds)
+        r1 = e.solve_batch(ls, us, x0, y0)
+        if int(rounds) < int(r0.iters.max()):
+            assert engine.last_timing()["launches"] > 1
+        assert np.array_equal(r0.status, r1.status) and np.array_equal(r0.iters, r1.iters)
+        for a, b in ((r0.x, r1.x), (r0.y, r1.y), (r0.lower, r1.lower), (r0.obj, r1.obj), (r0.pri_res, r1.pri_res)):
+            assert np.array_equal(a, b, equal_nan=True)
