@@ -154,6 +154,62 @@ def run_oracle_sample(insts_nodes, threads, repeats=1):
     return best, len(S), iters
 
 
+def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, dev_s_max, e2e_s_max, wall_max,
+                 tm, tm2, iters, status, factor_mb, inst0, clocks, t_setup, root_iters):
+    """The JSON line of the bench contract (kept separate from the GPU code so that it is unit-tested on CPU)."""
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    T = 1 << LEAF_DEPTH
+    bytes_per_ni = algorithmic_bytes_per_node_iter(inst0, T)
+    step_s = dev_s / args.steps
+    streamed = tm["threads"] == 416
+    kernel = ("admm_stream_kernel<%d>" if streamed else "admm_tile_kernel<%d>") % tm["tile_nodes"]
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read+write summed over the launches of ONE step, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        if tr["kernel"] == kernel and tr["launches_per_step"] == tm["launches"]:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_src = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
+    achieved = bytes_per_ni * node_iters / step_s / 1e9
+    return {
+        "metric": "QP-relaxations/sec", "value": B_all * args.steps / dev_s_max, "unit": "QP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "leaves_per_step": int(B_all), "qp_settings": QP_SETTINGS,
+                   "parallelism": "instances sharded across %d GPU(s), no data-path collective" % world,
+                   "l2": "inputs larger than L2 (%.0f MB of factors per GPU streamed every ADMM iteration)" % factor_mb,
+                   "tile_nodes": tm["tile_nodes"], "threads_per_cta": tm["threads"], "tiles_first_launch": tm["tiles"],
+                   "smem_bytes_per_cta": tm["smem_bytes"]},
+        "admm_node_iters_per_s": iters_all * args.steps / dev_s_max,
+        "admm_iters_per_leaf": node_iters / float(B),
+        "admm_iters_max": int(np.max(iters)), "admm_iters_median": float(np.median(iters)),
+        "status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
+        "e2e": {"value": B_all * args.steps / e2e_s_max, "unit": "QP/s",
+                "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"])},
+        "gpu_launches": args.steps * int(tm["launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                     "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_step": node_iters,
+                     "launches_per_step": int(tm["launches"]), "step_kernel_ms": 1e3 * step_s,
+                     "note": "one step = %d launches of the same kernel (rounds of ADMM iterations, re-tiled in between); "
+                             "achieved, traffic and streamed bytes are per step" % int(tm["launches"]),
+                     "streamed_bytes_per_step": int(tm["stream_bytes"]),
+                     "streamed_gbs": tm["stream_bytes"] / step_s / 1e9},
+        "setup_s": t_setup, "root_iters": root_iters, "wall_s_resident_loop": wall_max,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -258,55 +314,9 @@ def main():
     B_all, iters_all = [float(v) for v in counts.tolist()]
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        T = 1 << LEAF_DEPTH
-        bytes_per_ni = algorithmic_bytes_per_node_iter(insts[0], T)
-        launch_s = dev_s / args.steps
-        traffic, traffic_src = None, None
-        try:   # dram__bytes_read+write summed over the launches of ONE step, from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                tr = json.load(f)
-            if tr["kernel"] == ("admm_stream_kernel<%d>" % tm["tile_nodes"]) and tr["launches_per_step"] == tm["launches"]:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                traffic_src = tr["source"]
-        except (OSError, KeyError, ValueError):
-            pass
-        out = {
-            "metric": "QP-relaxations/sec", "value": B_all * args.steps / dev_s_max, "unit": "QP/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "leaves_per_step": int(B_all), "qp_settings": QP_SETTINGS,
-                       "parallelism": "instances sharded across %d GPU(s), no data-path collective" % world,
-                       "l2": "inputs larger than L2 (%.0f MB of factors per GPU streamed every ADMM iteration)" % (
-                           sum(qp.dims()["factor_bytes"] for qp in qps) / 1e6),
-                       "tile_nodes": tm["tile_nodes"], "threads_per_cta": tm["threads"], "tiles": tm["tiles"],
-                       "smem_bytes_per_cta": tm["smem_bytes"]},
-            "admm_node_iters_per_s": iters_all * args.steps / dev_s_max,
-            "admm_iters_per_leaf": node_iters / float(B),
-            "admm_iters_max": int(np.max(sc.iters)), "admm_iters_median": float(np.median(sc.iters)),
-            "status_counts": {str(k): int(v) for k, v in zip(*np.unique(sc.status, return_counts=True))},
-            "e2e": {"value": B_all * args.steps / e2e_s_max, "unit": "QP/s",
-                    "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"])},
-            "gpu_launches": args.steps * int(tm["launches"]),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": ("admm_stream_kernel<%d>" if tm["threads"] == 416 else "admm_tile_kernel<%d>") % tm["tile_nodes"],
-                         "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_step": node_iters,
-                         "launches_per_step": int(tm["launches"]), "step_kernel_ms": 1e3 * launch_s,
-                         "note": "one step = %d launches of the same kernel (rounds of 100 ADMM iterations, re-tiled in between); achieved, traffic and streamed bytes are per step" % int(tm["launches"]),
-                         "streamed_bytes_per_step": int(tm["stream_bytes"]),
-                         "streamed_gbs": tm["stream_bytes"] / launch_s / 1e9},
-            "setup_s": t_setup, "root_iters": root_iters, "wall_s_resident_loop": wall_max,
-        }
+        out = build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, dev_s_max, e2e_s_max, wall_max,
+                           tm, tm2, np.asarray(sc.iters), np.asarray(sc.status),
+                           sum(qp.dims()["factor_bytes"] for qp in qps) / 1e6, insts[0], clocks, t_setup, root_iters)
         if not args.no_cpu_baseline:
             S = min(B, 8 * cores)
             sample = [(insts[owner[b]], L[b], U[b], X0[b], Y0[b]) for b in range(S)]
@@ -327,6 +337,8 @@ def reference_arm(args, cores, workload):
     (a restatement of the same algorithm) on every host thread, on a bounded sample of the same leaves."""
     from oracle import oracle
     S_inst = max(1, min(args.instances, cores // 2))   # instances in the sample
+    if os.environ.get("BENCH_REFERENCE_MAX_INSTANCES"):   # tests: smaller sample
+        S_inst = max(1, min(S_inst, int(os.environ["BENCH_REFERENCE_MAX_INSTANCES"])))
     insts = make_instances(S_inst, seed=1)
     n, m = N_VAR, M_CON + P_INT
     solvers = []
