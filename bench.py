@@ -167,8 +167,7 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
     T = 1 << LEAF_DEPTH
     bytes_per_ni = algorithmic_bytes_per_node_iter(inst0, T)
     step_s = dev_s / args.steps
-    streamed = tm["threads"] == 416
-    kernel = ("admm_stream_kernel<%d>" if streamed else "admm_tile_kernel<%d>") % tm["tile_nodes"]
+    kernel = {0: "admm_tile_kernel<%d>", 1: "admm_stream_kernel<%d>", 2: "admm_panel_kernel<%d>"}[int(tm.get("kernel", 1))] % tm["tile_nodes"]
     traffic, traffic_src = None, None
     try:   # dram__bytes_read+write summed over the launches of ONE step, from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -188,7 +187,7 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
                    "parallelism": "instances sharded across %d GPU(s), no data-path collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB of factors per GPU streamed every ADMM iteration)" % factor_mb,
                    "tile_nodes": tm["tile_nodes"], "threads_per_cta": tm["threads"], "tiles_first_launch": tm["tiles"],
-                   "smem_bytes_per_cta": tm["smem_bytes"]},
+                   "smem_bytes_per_cta": tm["smem_bytes"], "ring_slots": int(tm.get("ring_slots", 0))},
         "admm_node_iters_per_s": iters_all * args.steps / dev_s_max,
         "admm_iters_per_leaf": node_iters / float(B),
         "admm_iters_max": int(np.max(iters)), "admm_iters_median": float(np.median(iters)),

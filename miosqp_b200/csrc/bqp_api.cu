@@ -85,7 +85,7 @@ struct BatchCtx {
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
-  bool use_stream = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0;
+  bool use_stream = false, use_panel = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0;
   int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
   std::vector<long long> in_off, state_off;
   Buf d_state;
@@ -93,7 +93,7 @@ struct BatchCtx {
   std::vector<bqp_instance *> node_inst;
   std::vector<long long> out_off;
   std::vector<DevTile> tiles;
-  std::vector<long long> tile_bytes_iter, tile_bytes_check;
+  std::vector<long long> tile_bytes_iter, tile_bytes_check, tile_bytes_launch;
   std::vector<int> tile_check_every;
   bqp_timing timing{};
   bool resident = false, ran = false;
@@ -161,6 +161,13 @@ int to_device(bqp_instance *inst) {
     d.w_in_stage = 1;
     for (int g = d.g_at[0]; g < d.g_at[1]; g++) if (st.groups[g].sparse) d.w_in_stage = 0;
     if (const char *e = std::getenv("BQP_W_IN_STAGE")) if (std::atoi(e) == 0) d.w_in_stage = 0;
+  }
+  d.pstream = nullptr; d.p_nw = d.p_npm = d.p_npa = 0; d.p_panel_doubles = d.p_offA = d.p_offP = 0;
+  if (h.pn.built) {
+    const double *dp = nullptr;
+    if ((rc = upload(inst, h.pn.data, &dp))) return rc;
+    d.pstream = dp; d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
+    d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
   }
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
@@ -249,9 +256,15 @@ int bqp_set_tuning(int tile_nodes, int threads) {
 static int plan_round(const std::vector<int> &alive, const std::vector<int> &progress, std::vector<int> *scheduled) {
   int ndev_sms = 148;
   cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
-  const bool use_stream = g.use_stream, w_in_stage = g.w_in_stage;
-  const bool rounds = use_stream && g.round_iters > 0;
-  const int capacity = rounds ? ndev_sms : (1 << 30);   // streamed kernel: one 13-warp CTA per SM (registers, smem)
+  const bool use_stream = g.use_stream, use_panel = g.use_panel, w_in_stage = g.w_in_stage;
+  const bool rounds = (use_stream || use_panel) && g.round_iters > 0;
+  const int capacity = rounds ? ndev_sms : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
+  auto panel_slots = [&](const HostInstance &h, int t) {   // ring slots (one panel each) that fit beside the vectors
+    const long long fixed = (long long)panel_smem_bytes(h.npad, t, 0) + 256;
+    long long cap = 12;
+    if (const char *e = std::getenv("BQP_PANEL_SLOTS")) cap = std::max(4, std::atoi(e));   // experiment knob (ring depth)
+    return (int)std::min<long long>(cap, ((long long)kMaxSmem - fixed) / h.pn.panel_bytes());
+  };
   // groups in (progress, first appearance) order
   std::vector<bqp_instance *> uniq;
   std::map<std::pair<int, bqp_instance *>, int> gid;
@@ -278,7 +291,11 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   int tt_cap = kMaxTT, nslots = 8;
   for (auto *inst : uniq) {
     int t = 0;
-    if (use_stream) {
+    if (use_panel) {
+      t = 4;
+      while (t > 1 && panel_slots(inst->h, t) < 4) t >>= 1;   // pass 2 holds up to 3 panels; the rest are in flight
+      if (panel_slots(inst->h, t) < 4) t = 0;
+    } else if (use_stream) {
       t = kMaxTT;
       while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
       if (t == kMaxTT) t = kMaxTT / 2;                         // T=8 is FP64/smem-issue bound per SM
@@ -291,18 +308,22 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   }
   int widest = 1;
   for (auto &mb : members) widest = std::max<int>(widest, (int)mb.size());
-  int tt = g_tune_tt ? std::min(g_tune_tt, use_stream ? kMaxTT : tt_cap) : std::min(tt_cap, pow2ceil(widest));
+  int tt = g_tune_tt ? std::min(g_tune_tt, use_panel ? tt_cap : (use_stream ? kMaxTT : tt_cap)) : std::min(tt_cap, pow2ceil(widest));
   if (g_tune_tt && use_stream)
     for (auto *inst : uniq) while (tt > 1 && stream_slots(inst->h, tt) < 2) tt >>= 1;
   if (!g_tune_tt) {   // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small
     auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
     while (tt > 1 && count_tiles(tt / 2) <= ndev_sms) tt >>= 1;
   }
-  if (use_stream)
+  if (use_panel) {
+    nslots = 12;
+    for (auto *inst : uniq) nslots = std::min(nslots, panel_slots(inst->h, tt));
+  } else if (use_stream)
     for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
   // tiles: split each group's nodes evenly; stop at capacity (whole groups only, so siblings stay in the same launch)
   g.tiles.clear();
-  g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear();
+  g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_bytes_launch.clear();
+  g.nw_max = 0;
   scheduled->clear();
   std::vector<DevInstance> dinst;
   std::map<bqp_instance *, int> inst_slot;
@@ -313,7 +334,9 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     if (!g.tiles.empty() && (long long)g.tiles.size() + nt > capacity) break;
     auto is = inst_slot.find(uniq[k]);
     if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
-    smem = std::max(smem, use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads));
+    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, tt, nslots)
+                          : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
+    if (use_panel) g.nw_max = std::max(g.nw_max, h.pn.nw);
     for (int ti = 0; ti < nt; ti++) {
       const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
       DevTile t{};
@@ -326,10 +349,11 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
         scheduled->push_back(b);
       }
       t.work_off = (long long)work_d;
-      work_d += tile_work_doubles(h.n, h.m, tt);
+      work_d += use_panel ? panel_work_doubles(h.npad, h.m, tt) : tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
-      g.tile_bytes_iter.push_back(use_stream ? h.st.iter_bytes : h.factor_bytes());
-      g.tile_bytes_check.push_back(use_stream ? h.st.check_bytes : h.check_bytes());
+      g.tile_bytes_iter.push_back(use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
+      g.tile_bytes_check.push_back(use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
+      g.tile_bytes_launch.push_back(use_panel ? h.pn.launch_bytes() : 0);
       g.tile_check_every.push_back(h.s.check_termination);
     }
   }
@@ -366,6 +390,11 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   // engine: the TMA-streamed kernel when every problem has a streamed layout (bqp_set_tuning(threads>0) forces
   // the direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
   g.use_stream = g_tune_threads == 0;
+  g.use_panel = g_tune_threads == 0;
+  if (const char *e = std::getenv("BQP_KERNEL")) {        // tests / A-B runs: "panel" (default when possible), "stream", "direct"
+    if (!std::strcmp(e, "stream")) g.use_panel = false;
+    else if (!std::strcmp(e, "direct")) g.use_panel = g.use_stream = false;
+  }
   g.stage_bytes = kStageValBytes;
   g.w_in_stage = true;
   g.max_iter_all = 0; g.round_ok = true;
@@ -373,6 +402,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   for (int b = 0; b < B; b++) {
     const HostInstance &h = handles[b]->h;
     const HostStream &st = h.st;
+    if (!h.pn.built) g.use_panel = false;
     if (!st.built || (int)st.groups.size() > 96) g.use_stream = false;   // 96 = groups cached in shared memory
     else g.stage_bytes = std::max(g.stage_bytes, st.slot_bytes);
     if (!handles[b]->d.w_in_stage) g.w_in_stage = false;
@@ -380,12 +410,13 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     if (h.s.check_termination != check0) g.round_ok = false;
     want = std::max(want, std::max(h.Ab.nslices, h.At.nslices));
   }
+  if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
-  g.threads = g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
+  g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
   // rounds: the streamed kernel runs `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
   // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
   g.round_iters = 0;
-  if (g.use_stream && g.round_ok) {
+  if ((g.use_stream || g.use_panel) && g.round_ok) {
     int r = 100;
     if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
     g.round_iters = r <= 0 ? 0 : ((r + check0 - 1) / check0) * check0;
@@ -436,15 +467,19 @@ int bqp_batch_run(void) {
   std::vector<int> alive(g.B), progress(g.B, 0), scheduled;
   for (int b = 0; b < g.B; b++) alive[b] = b;
   long long tile_iters = 0, bytes = 0, h2d_extra = 0;
-  int launches = 0, first_tiles = 0, first_tt = 0;
+  int launches = 0, first_tiles = 0, first_tt = 0, first_slots = 0;
   long long first_smem = 0;
   CK(cudaEventRecord(g.ev[1], g.stream));
   while (!alive.empty()) {
     int rc = plan_round(alive, progress, &scheduled);
     if (rc) return rc;
     h2d_extra += g.round_h2d_bytes;
-    if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; }
-    rc = g.use_stream
+    if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
+    rc = g.use_panel
+             ? launch_admm_panel(g.tt, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
+                                 g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                                 (int *)g.d_ti.p, g.smem, g.stream)
+         : g.use_stream
              ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, g.w_in_stage ? 1 : 0, (double *)g.d_state.p,
                                   (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
                                   (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
@@ -461,7 +496,7 @@ int bqp_batch_run(void) {
     for (int t = 0; t < g.ntiles; t++) {
       tile_iters += ti[t];
       const int ce = g.tile_check_every[t];
-      bytes += (long long)ti[t] * g.tile_bytes_iter[t] + (long long)(ti[t] / ce + ((ti[t] % ce) ? 1 : 0)) * g.tile_bytes_check[t];
+      bytes += (long long)ti[t] * g.tile_bytes_iter[t] + (long long)(ti[t] / ce + ((ti[t] % ce) ? 1 : 0)) * g.tile_bytes_check[t] + g.tile_bytes_launch[t];
     }
     std::vector<char> done(g.B, 0);
     for (int b : scheduled) {
@@ -480,6 +515,9 @@ int bqp_batch_run(void) {
   g.timing.kernel_ms = ms;
   g.timing.launches = launches;
   g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
+  if (g.use_panel) g.timing.threads = (g.nw_max + kPanelUpdWarps + 1) * 32;
+  g.timing.kernel = g.use_panel ? 2 : (g.use_stream ? 1 : 0);
+  g.timing.ring_slots = first_slots;
   g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
   g.round_h2d_total = h2d_extra;
   g.ran = true;
@@ -603,9 +641,15 @@ int bqp_debug_host_stream_kkt_solve(bqp_handle h, double *rhs_xz) {
   return host_stream_kkt_solve(&h->h, rhs_xz);
 }
 
+int bqp_debug_host_panel_kkt_solve(bqp_handle h, double *rhs_xz) {
+  if (!h || !rhs_xz) return BQP_E_ARG;
+  return host_panel_kkt_solve(&h->h, rhs_xz);
+}
+
 int bqp_debug_host_matvec(bqp_handle h, int which, const double *in, double *out) {
-  if (!h || !in || !out || which < 0 || which > 3) return BQP_E_ARG;
+  if (!h || !in || !out || which < 0 || which > 4) return BQP_E_ARG;
   if (which == 3) return host_stream_matvec_P(&h->h, in, out);
+  if (which == 4) return host_panel_matvec_P(&h->h, in, out);
   host_matvec(which == 0 ? h->h.Ab : (which == 1 ? h->h.At : h->h.Pm), in, out);
   return BQP_OK;
 }

@@ -68,6 +68,30 @@ struct HostStream {
   int slot_bytes = kStageValBytes;
 };
 
+// ---- row-panel layout of the fused single-pass kernel (bqp_panel.cu) -------------------------------------
+// For problems whose A is dense enough to be stored dense (every BASELINE random_miqp config at density 0.7) one ADMM
+// iteration is restated as   x~ = M b,  z~ = A x~,  b' = sigma x - q + A'(rho z - y)   with M = (P + sigma I + A' rho A)^-1
+// formed explicitly on the host, and A streamed ONCE per iteration: each PANEL (kPanelRows rows x npad columns, one
+// TMA bulk copy) is used while it sits in shared memory first for its rows of A x~ and then, after the per-row z/y
+// update, for its contribution to A' w.  Consumer warp w owns columns 32w..32w+31; its lane (rg = lane>>3, cg = lane&7)
+// owns rows 2rg, 2rg+1 and columns 4cg..4cg+3 of that tile.  Storage of panel k (doubles):
+//   k*8*npad + ((w*4 + b)*32 + lane)*2 + a   holds   X[8k + 2rg + a][32w + 4cg + b]
+// so every warp-wide 16-byte load is 512 contiguous bytes.  Matrices in stream order: M (npad rows), A (m rows padded to
+// 8), P full symmetric (npad rows; termination checks and the final objective only).
+constexpr int kPanelRows = 8;
+constexpr int kPanelMaxWarps = 16;                  // consumer warps = column tiles of 32  (npad <= 512)
+constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin
+struct HostPanels {
+  bool built = false;
+  int nw = 0, npm = 0, npa = 0;                     // column tiles; panels of M (and P); panels of A
+  long long panel_doubles = 0, offA = 0, offP = 0;  // doubles
+  std::vector<double> data;
+  long long panel_bytes() const { return panel_doubles * 8; }
+  long long iter_bytes() const { return (long long)(npm + npa) * panel_bytes(); }          // M + A
+  long long check_bytes() const { return (long long)(2 * npa + npm) * panel_bytes(); }     // A twice + P
+  long long launch_bytes() const { return (long long)(npa + npm) * panel_bytes(); }        // prologue A pass + objective P pass
+};
+
 // Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
 // KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
 // streamed as the A panels and the dense trailing supernode L22 D2 L22' = P + sigma I + A' diag(rho) A).
@@ -87,6 +111,7 @@ struct HostInstance {
   // in-block substitution is a mat-vec.
   std::vector<double> Lcol, Lrow, D2inv;
   HostStream st;                         // streamed layout (built for problems large enough for the TMA kernel)
+  HostPanels pn;                         // row-panel layout of the fused single-pass kernel (dense A, npad <= 512)
   long long factor_bytes() const {   // bytes one ADMM iteration streams: A', L fwd, L bwd, A, D2inv
     return (long long)(Lcol.size() + Lrow.size() + D2inv.size()) * 8 + At.stream_bytes() + Ab.stream_bytes();
   }
@@ -101,6 +126,8 @@ void host_kkt_solve(const HostInstance *h, double *rhs_xz);
 void host_matvec(const HostMat &M, const double *in, double *out);
 int host_stream_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_stream_matvec_P(const HostInstance *h, const double *in, double *out);
+int host_panel_kkt_solve(const HostInstance *h, double *rhs_xz);
+int host_panel_matvec_P(const HostInstance *h, const double *in, double *out);
 
 struct DevInstance {
   int n, m, npad, n_int;
@@ -108,6 +135,8 @@ struct DevInstance {
   const unsigned char *stream; const StreamGroup *groups;
   int g_at[2], g_fw[2], g_bw[2], g_ab[2], g_pm[2];
   int w_in_stage;   // 1: every A' group is dense -> its input vector chunks ride in the TMA stages (no m x T vector in smem)
+  // row-panel layout (fused single-pass kernel)
+  const double *pstream; int p_nw, p_npm, p_npa; long long p_panel_doubles, p_offA, p_offP;
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -142,6 +171,12 @@ struct NodeScalars {
 #endif
 BQP_HD inline size_t tile_w_offset(int n, int m, int tt) { return ((size_t)tt * (5 * (size_t)m + 3 * (size_t)n) + 1) & ~size_t(1); }
 inline size_t tile_work_doubles(int n, int m, int tt) { return (tile_w_offset(n, m, tt) + (size_t)tt * ((size_t)m + 32) + 1) & ~size_t(1); }
+// panel kernel: z, y, l, u, dy (m padded to 8 rows each); dx, Px, A'y, A'dy, P dx (npad rows each)
+inline size_t panel_work_doubles(int npad, int m, int tt) { return (size_t)tt * (5 * (size_t)((m + 7) & ~7) + 5 * (size_t)npad); }
+size_t panel_smem_bytes(int npad, int tt, int nslots);                                // bqp_panel.cu
+int launch_admm_panel(int tt, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
+                      size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

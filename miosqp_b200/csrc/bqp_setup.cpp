@@ -308,6 +308,75 @@ void build_stream(HostInstance *h, const std::vector<Row> &arows, const std::vec
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------
+// Row-panel layout of the fused single-pass kernel (bqp_internal.h, bqp_panel.cu).
+namespace {
+
+// X: dense row-major rows x npad (rows beyond `rows` and columns beyond the data are zero) -> panels appended to pn.data
+void append_panels(HostPanels &pn, const std::vector<double> &X, int rows, int npad) {
+  const int npanels = (rows + kPanelRows - 1) / kPanelRows, nw = npad / 32;
+  const size_t base = pn.data.size();
+  pn.data.resize(base + (size_t)npanels * kPanelRows * npad, 0.0);
+  for (int k = 0; k < npanels; k++)
+    for (int w = 0; w < nw; w++)
+      for (int b = 0; b < 4; b++)
+        for (int lane = 0; lane < 32; lane++)
+          for (int a = 0; a < 2; a++) {
+            const int r = k * kPanelRows + 2 * (lane >> 3) + a, c = 32 * w + 4 * (lane & 7) + b;
+            if (r < rows) pn.data[base + (size_t)k * kPanelRows * npad + (((size_t)w * 4 + b) * 32 + lane) * 2 + a] = X[(size_t)r * npad + c];
+          }
+}
+
+// S: column-major npad x npad, unit-lower L22 strictly below the diagonal (after the LDL' above); D2inv its inverse pivots
+void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &prows, const std::vector<double> &S) {
+  const int n = h->n, m = h->m, np_ = h->npad;
+  HostPanels &pn = h->pn;
+  pn = HostPanels();
+  // X = inv(L22) (unit lower, row-major, leading n x n block), row by row: X[r][:] = e_r - sum_{k<r} L[r][k] X[k][:]
+  std::vector<double> X((size_t)n * n, 0.0);
+  for (int r = 0; r < n; r++) {
+    double *xr = &X[(size_t)r * n];
+    for (int k = 0; k < r; k++) {
+      const double l = S[(size_t)k * np_ + r];
+      if (l == 0.0) continue;
+      const double *xk = &X[(size_t)k * n];
+      for (int c = 0; c <= k; c++) xr[c] -= l * xk[c];
+    }
+    xr[r] = 1.0;
+  }
+  // M = X' D2^-1 X  (lower triangle accumulated by rank-1 updates with the rows of X, then mirrored)
+  std::vector<double> M((size_t)np_ * np_, 0.0);
+  for (int k = 0; k < n; k++) {
+    const double *xk = &X[(size_t)k * n];
+    const double d = h->D2inv[k];
+    for (int i = 0; i <= k; i++) {
+      const double f = xk[i] * d;
+      if (f == 0.0) continue;
+      double *mi = &M[(size_t)i * np_];
+      for (int j = 0; j <= i; j++) mi[j] += f * xk[j];
+    }
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < i; j++) M[(size_t)j * np_ + i] = M[(size_t)i * np_ + j];
+  std::vector<double> Ad((size_t)std::max(m, 1) * np_, 0.0), Pd((size_t)np_ * np_, 0.0);
+  for (int r = 0; r < m; r++)
+    for (auto &e : arows[r]) Ad[(size_t)r * np_ + e.first] = e.second;
+  for (int r = 0; r < n; r++)
+    for (auto &e : prows[r]) Pd[(size_t)r * np_ + e.first] = e.second;
+  pn.nw = np_ / 32;
+  pn.panel_doubles = (long long)kPanelRows * np_;
+  pn.npm = np_ / kPanelRows;
+  pn.npa = (m + kPanelRows - 1) / kPanelRows;
+  append_panels(pn, M, np_, np_);
+  pn.offA = (long long)pn.data.size();
+  append_panels(pn, Ad, m, np_);
+  pn.offP = (long long)pn.data.size();
+  append_panels(pn, Pd, np_, np_);
+  pn.built = true;
+}
+
+}  // namespace
+
 void host_rescale_q(HostInstance *h, const double *q) {   // osqp update_lin_cost: q_scaled = c * D * q
   h->nq = 0;
   for (int j = 0; j < h->n; j++) {
@@ -467,6 +536,15 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     tri_nb = std::max(32, std::min(32 * kStreamWarps, (tri_nb / 32) * 32));
     build_stream(h, arows, atrows, prows, S, tri_nb);
   }
+  // row-panel layout for the fused single-pass kernel: A stored dense, so only when A is dense enough that one dense
+  // pass (8 m n bytes) beats two sparse ones (24 nnz bytes), and the variables fit the 16 column tiles of one CTA
+  h->pn = HostPanels();
+  {
+    double min_density = 0.34;
+    if (const char *e = std::getenv("BQP_PANEL_MIN_DENSITY")) min_density = std::atof(e);
+    const double density = (m > 0) ? (double)A.x.size() / ((double)m * n) : 1.0;
+    if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density) build_panels(h, arows, prows, S);
+  }
   return BQP_OK;
 }
 
@@ -607,6 +685,53 @@ int host_stream_kkt_solve(const HostInstance *h, double *rhs) {
   }
   for (int j = 0; j < n; j++) rhs[j] = b[j];
   for (int i = 0; i < m; i++) rhs[n + i] = h->rho[i] * (t[i] - rhs[n + i]);
+  return BQP_OK;
+}
+
+// what the panel kernel computes for one KKT solve, from the panel data: b = rhs_x + A'(rho rhs_z); x~ = M b;
+// nu = rho (A x~ - rhs_z).  Lane-level summation order is not reproduced (plain loops): a layout check.
+int host_panel_kkt_solve(const HostInstance *h, double *rhs) {
+  const HostPanels &pn = h->pn;
+  if (!pn.built) return BQP_E_UNSUPPORTED;
+  const int n = h->n, m = h->m, np_ = h->npad;
+  auto at = [&](long long off, int r, int c) -> double {
+    const int k = r / kPanelRows, rr = r % kPanelRows, w = c / 32, cc = c % 32;
+    const int lane = (rr >> 1) * 8 + (cc >> 2), b = cc & 3, a = rr & 1;
+    return pn.data[(size_t)off + (size_t)k * kPanelRows * np_ + (((size_t)w * 4 + b) * 32 + lane) * 2 + a];
+  };
+  std::vector<double> b(np_, 0.0), xt(np_, 0.0);
+  for (int j = 0; j < n; j++) b[j] = rhs[j];
+  for (int i = 0; i < m; i++) {
+    const double w = h->rho[i] * rhs[n + i];
+    for (int j = 0; j < np_; j++) b[j] = std::fma(at(pn.offA, i, j), w, b[j]);
+  }
+  for (int r = 0; r < np_; r++) {
+    double acc = 0;
+    for (int j = 0; j < np_; j++) acc = std::fma(at(0, r, j), b[j], acc);
+    xt[r] = acc;
+  }
+  for (int i = 0; i < m; i++) {
+    double acc = 0;
+    for (int j = 0; j < np_; j++) acc = std::fma(at(pn.offA, i, j), xt[j], acc);
+    rhs[n + i] = h->rho[i] * (acc - rhs[n + i]);
+  }
+  for (int j = 0; j < n; j++) rhs[j] = xt[j];
+  return BQP_OK;
+}
+
+int host_panel_matvec_P(const HostInstance *h, const double *in, double *out) {
+  const HostPanels &pn = h->pn;
+  if (!pn.built) return BQP_E_UNSUPPORTED;
+  const int np_ = h->npad;
+  for (int r = 0; r < h->n; r++) {
+    double acc = 0;
+    for (int c = 0; c < h->n; c++) {
+      const int k = r / kPanelRows, rr = r % kPanelRows, w = c / 32, cc = c % 32;
+      const int lane = (rr >> 1) * 8 + (cc >> 2), b = cc & 3, a = rr & 1;
+      acc = std::fma(pn.data[(size_t)pn.offP + (size_t)k * kPanelRows * np_ + (((size_t)w * 4 + b) * 32 + lane) * 2 + a], in[c], acc);
+    }
+    out[r] = acc;
+  }
   return BQP_OK;
 }
 

@@ -68,7 +68,7 @@ class Timing(C.Structure):
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
                 ("launches", C.c_int), ("tiles", C.c_int), ("tile_nodes", C.c_int), ("threads", C.c_int),
                 ("smem_bytes", C.c_longlong), ("node_iters", C.c_longlong), ("tile_iters", C.c_longlong),
-                ("stream_bytes", C.c_longlong)]
+                ("stream_bytes", C.c_longlong), ("kernel", C.c_int), ("ring_slots", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -78,6 +78,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_batch_upload", "bqp_batch_run", "bqp_batch_download", "bqp_last_timing", "bqp_free",
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
+           "bqp_debug_host_panel_kkt_solve",
            "bqp_debug_host_matvec"]
 
 _lib = None
@@ -110,6 +111,7 @@ def lib():
         L.bqp_version.restype = C.c_char_p
         L.bqp_debug_host_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_stream_kkt_solve.argtypes = [vp, _dp]
+        L.bqp_debug_host_panel_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
         _lib = L
     return _lib
@@ -257,9 +259,14 @@ class BatchedQP(object):
         _check(lib().bqp_debug_host_stream_kkt_solve(self._h, _d(b)))
         return b
 
+    def debug_panel_kkt_solve(self, rhs):
+        b = _f64(rhs).copy()
+        _check(lib().bqp_debug_host_panel_kkt_solve(self._h, _d(b)))
+        return b
+
     def debug_matvec(self, which, v):
         v = _f64(v)
-        out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n}[which])
+        out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n, 4: self.n}[which])
         _check(lib().bqp_debug_host_matvec(self._h, which, _d(v), _d(out)))
         return out
 

@@ -45,7 +45,7 @@ def test_no_cpu_fallback():
         engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, eps_abs=1e-3)
 
 
-@pytest.mark.parametrize("shape", [(50, 100, 5, 0.7), (130, 200, 10, 0.7), (200, 300, 10, 0.05), (300, 77, 5, 0.5)])
+@pytest.mark.parametrize("shape", [(50, 100, 5, 0.7), (130, 200, 10, 0.7), (200, 300, 10, 0.05), (300, 77, 5, 0.5), (500, 1000, 50, 0.7)])
 def test_host_layouts_reproduce_oracle_kkt_solve(oracle_mod, shape):
     n, m, p, d = shape
     P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(n, m, p, d, seed=1)[0])
@@ -63,6 +63,13 @@ def test_host_layouts_reproduce_oracle_kkt_solve(oracle_mod, shape):
     if n >= 97:                                                                # streamed layout is built from 4 slices up
         assert np.abs(e.debug_stream_kkt_solve(b) - ref).max() <= 1e-11 * scale
         assert np.array_equal(e.debug_matvec(2, x), e.debug_matvec(3, x))
+    if 64 <= e.dims()['npad'] <= 512 and d >= 0.34:                                     # row panels of the fused single-pass kernel
+        got = e.debug_panel_kkt_solve(b)                                       # explicit reduced inverse instead of sweeps
+        assert np.abs(got - ref).max() <= 1e-10 * scale
+        assert np.abs(e.debug_matvec(4, x) - e.debug_matvec(2, x)).max() <= 1e-12 * (1 + np.abs(e.debug_matvec(2, x)).max())
+    else:
+        with pytest.raises(ValueError):                                       # BQP_E_UNSUPPORTED: no panel layout built
+            e.debug_panel_kkt_solve(b)
 
 
 def o_scaled_A(o, e, x):

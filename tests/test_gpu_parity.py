@@ -15,6 +15,11 @@ TOL = 1e-9
 STREAM_THREADS = 13 * 32   # 12 consumer warps + 1 TMA producer warp (bqp_stream.cu)
 
 
+def panel_threads(n):
+    """fused single-pass kernel (bqp_panel.cu): one consumer warp per 32 columns + 3 update warps + TMA producer warp"""
+    return ((n + 31) // 32 + 4) * 32
+
+
 def _close(a, b, tol=TOL):
     a = np.asarray(a, float); b = np.asarray(b, float)
     assert np.array_equal(np.isnan(a), np.isnan(b))
@@ -156,9 +161,46 @@ def test_update_q(oracle_mod):
     _close(r.y[0], ro.y)
 
 
+# ---------------------------------------------------------------- fused single-pass panel kernel (bqp_panel.cu)
+@pytest.mark.parametrize("tt", [1, 2, 4])
+def test_panel_kernel_tile_widths(oracle_mod, tt):
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(130)
+    assert engine.last_timing()["tile_nodes"] == tt
+
+
+def test_panel_kernel_cold_start_and_infeasible(oracle_mod):
+    """zero warm start (prologue z = A x0 pass) and contradictory bounds (certificate path) through the panel kernel"""
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 7, 12, QP, oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(130)
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    ls = np.tile(l, (3, 1)); us = np.tile(u, (3, 1))
+    ls[1, 0] = 500.0; us[1, 0] = 600.0
+    ls[2, 5] = -600.0; us[2, 5] = -500.0
+    x0 = np.zeros((3, 130)); y0 = np.zeros((3, 210))
+    xo, yo, so, io, _ = o.solve_batch(ls, us, x0, y0)
+    r = e.solve_batch(ls, us, x0, y0)
+    assert list(so)[1:] == [-3, -3]
+    assert list(r.status) == list(so) and list(r.iters) == list(io)
+    assert np.isnan(r.x[1]).all() and np.isnan(r.y[2]).all() and np.isnan(r.lower[1])
+    _close(r.y[0], yo[0])
+
+
+def test_panel_kernel_max_iter(oracle_mod):
+    """nodes that run into max_iter (incl. the x10 'inaccurate' pass) agree with the oracle"""
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 6, 13, dict(QP, max_iter=60, eps_abs=1e-6, eps_rel=1e-6), oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(130)
+
+
 # ---------------------------------------------------------------- TMA-streamed kernel (bqp_stream.cu)
 @pytest.mark.parametrize("tt", [1, 2, 4, 8])
-def test_stream_kernel_tile_widths(oracle_mod, tt):
+def test_stream_kernel_tile_widths(oracle_mod, tt, monkeypatch):
+    monkeypatch.setenv("BQP_KERNEL", "stream")
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
     assert engine.last_timing()["threads"] == STREAM_THREADS       # consumer warps + the TMA producer warp
@@ -170,14 +212,20 @@ def test_stream_kernel_sparse_groups(oracle_mod):
     assert engine.last_timing()["threads"] == STREAM_THREADS
 
 
-def test_stream_vs_direct_kernel_same_results():
-    """Both kernels implement the same iteration; statuses and iteration counts must agree."""
+def test_three_kernels_same_results(monkeypatch):
+    """All kernels implement the same iteration; statuses and iteration counts must agree."""
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     P, q, A, l, u, i_idx = problems.extend(pr)
     ls, us = problems.branched_nodes(l, u, len(i_idx), 7, np.random.default_rng(3))
     x0 = np.zeros((7, 130)); y0 = np.zeros((7, 210))
     e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    r0 = e.solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["threads"] == panel_threads(130)
+    monkeypatch.setenv("BQP_KERNEL", "stream")
     r1 = e.solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["threads"] == STREAM_THREADS
+    assert list(r0.status) == list(r1.status) and list(r0.iters) == list(r1.iters)
+    _close(r0.x, r1.x); _close(r0.y, r1.y); _close(r0.lower, r1.lower)
     engine.set_tuning(0, 256)
     try:
         r2 = e.solve_batch(ls, us, x0, y0)
@@ -192,10 +240,18 @@ def test_cfg2_size_leaves(oracle_mod):
     """BASELINE cfg 2 shape (n=500, m=1000, |i_idx|=50): 8 leaves of one instance in one tile."""
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
     _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(500)
+
+
+def test_cfg2_size_leaves_stream_kernel(oracle_mod, monkeypatch):
+    monkeypatch.setenv("BQP_KERNEL", "stream")
+    pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
+    _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
     assert engine.last_timing()["threads"] == STREAM_THREADS
 
 
-def test_rounds_and_retiling_are_bit_identical(monkeypatch):
+@pytest.mark.parametrize("kernel", ["panel", "stream"])
+def test_rounds_and_retiling_are_bit_identical(monkeypatch, kernel):
     """The streamed kernel runs in rounds of BQP_ROUND_ITERS iterations; between rounds finished nodes drop out and
     the rest are re-tiled (other tile widths, other tile mates), resuming from the saved ADMM state.  The result of
     every node must not depend on that: bit-identical to one uninterrupted launch."""
@@ -204,6 +260,7 @@ def test_rounds_and_retiling_are_bit_identical(monkeypatch):
     ls, us = problems.branched_nodes(l, u, len(i_idx), 13, np.random.default_rng(11))
     x0 = np.zeros((13, 130)); y0 = np.zeros((13, 210))
     e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    monkeypatch.setenv("BQP_KERNEL", kernel)
     monkeypatch.setenv("BQP_ROUND_ITERS", "0")
     r0 = e.solve_batch(ls, us, x0, y0)
     assert engine.last_timing()["launches"] == 1
