@@ -85,7 +85,7 @@ struct BatchCtx {
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
-  bool use_stream = false, use_panel = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0;
+  bool use_stream = false, use_panel = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
   int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
   std::vector<long long> in_off, state_off;
   Buf d_state;
@@ -258,12 +258,20 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
   const bool use_stream = g.use_stream, use_panel = g.use_panel, w_in_stage = g.w_in_stage;
   const bool rounds = (use_stream || use_panel) && g.round_iters > 0;
-  const int capacity = rounds ? ndev_sms : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
-  auto panel_slots = [&](const HostInstance &h, int t) {   // ring slots (one panel each) that fit beside the vectors
-    const long long fixed = (long long)panel_smem_bytes(h.npad, t, 0) + 256;
-    long long cap = 12;
+  // panel kernel: problems wider than one CTA's consumer warps run as cluster pairs (2 SMs per tile)
+  int cs = 1;
+  if (use_panel) {
+    for (int b : alive) if (g.node_inst[b]->h.pn.nw > kPanelCtaWarps) cs = 2;
+    if (const char *e = std::getenv("BQP_PANEL_CLUSTER")) { const int v = std::atoi(e); if (v == 2 || (v == 1 && cs == 1)) cs = v; }
+  }
+  g.cs = cs;
+  const int capacity = rounds ? ndev_sms / cs : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
+  auto panel_slots = [&](const HostInstance &h, int t) {   // ring slots (this CTA's share of one panel each) beside the vectors
+    const long long fixed = (long long)panel_smem_bytes(h.npad, t, 0, cs) + 256;
+    const long long sb = (long long)(cs == 2 ? (h.pn.nw + 1) / 2 : h.pn.nw) * kPanelRows * 32 * 8;
+    long long cap = 16;
     if (const char *e = std::getenv("BQP_PANEL_SLOTS")) cap = std::max(4, std::atoi(e));   // experiment knob (ring depth)
-    return (int)std::min<long long>(cap, ((long long)kMaxSmem - fixed) / h.pn.panel_bytes());
+    return (int)std::min<long long>(cap, ((long long)kMaxSmem - fixed) / sb);
   };
   // groups in (progress, first appearance) order
   std::vector<bqp_instance *> uniq;
@@ -282,6 +290,8 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     }
   }
   const int slot_bytes = g.stage_bytes;
+  if (use_panel && cs == 1)
+    for (int b : alive) if (g.node_inst[b]->h.pn.nw > kPanelCtaWarps) return BQP_E_UNSUPPORTED;
   auto slot_size = [&](int t) { return slot_bytes + (w_in_stage ? kKC * t * 8 : 0); };
   auto stream_slots = [&](const HostInstance &h, int t) {   // slots PER QUAD (one ring per quad of consumer warps)
     const long long fixed = (long long)stream_smem_bytes(h.n, h.m, t, slot_size(t), 0, w_in_stage) + 1024;
@@ -316,7 +326,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     while (tt > 1 && count_tiles(tt / 2) <= ndev_sms) tt >>= 1;
   }
   if (use_panel) {
-    nslots = 12;
+    nslots = 16;
     for (auto *inst : uniq) nslots = std::min(nslots, panel_slots(inst->h, tt));
   } else if (use_stream)
     for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
@@ -334,7 +344,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     if (!g.tiles.empty() && (long long)g.tiles.size() + nt > capacity) break;
     auto is = inst_slot.find(uniq[k]);
     if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
-    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, tt, nslots)
+    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, tt, nslots, cs)
                           : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
     if (use_panel) g.nw_max = std::max(g.nw_max, h.pn.nw);
     for (int ti = 0; ti < nt; ti++) {
@@ -349,7 +359,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
         scheduled->push_back(b);
       }
       t.work_off = (long long)work_d;
-      work_d += use_panel ? panel_work_doubles(h.npad, h.m, tt) : tile_work_doubles(h.n, h.m, tt);
+      work_d += use_panel ? cs * panel_work_doubles(h.npad, h.m, tt) : tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
       g.tile_bytes_iter.push_back(use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
       g.tile_bytes_check.push_back(use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
@@ -476,7 +486,7 @@ int bqp_batch_run(void) {
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
     rc = g.use_panel
-             ? launch_admm_panel(g.tt, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
+             ? launch_admm_panel(g.tt, g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
                                  g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
                                  (int *)g.d_ti.p, g.smem, g.stream)
          : g.use_stream
@@ -515,7 +525,7 @@ int bqp_batch_run(void) {
   g.timing.kernel_ms = ms;
   g.timing.launches = launches;
   g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
-  if (g.use_panel) g.timing.threads = (g.nw_max + kPanelUpdWarps + 1) * 32;
+  if (g.use_panel) g.timing.threads = ((g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max) + kPanelUpdWarps + 1) * 32;
   g.timing.kernel = g.use_panel ? 2 : (g.use_stream ? 1 : 0);
   g.timing.ring_slots = first_slots;
   g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;

@@ -79,7 +79,8 @@ struct HostStream {
 // so every warp-wide 16-byte load is 512 contiguous bytes.  Matrices in stream order: M (npad rows), A (m rows padded to
 // 8), P full symmetric (npad rows; termination checks and the final objective only).
 constexpr int kPanelRows = 8;
-constexpr int kPanelMaxWarps = 16;                  // consumer warps = column tiles of 32  (npad <= 512)
+constexpr int kPanelMaxWarps = 16;                  // column tiles of 32 (npad <= 512), one consumer warp each
+constexpr int kPanelCtaWarps = 8;                   // consumer warps per CTA; wider problems run as a cluster pair of CTAs
 constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin
 struct HostPanels {
   bool built = false;
@@ -171,10 +172,10 @@ struct NodeScalars {
 #endif
 BQP_HD inline size_t tile_w_offset(int n, int m, int tt) { return ((size_t)tt * (5 * (size_t)m + 3 * (size_t)n) + 1) & ~size_t(1); }
 inline size_t tile_work_doubles(int n, int m, int tt) { return (tile_w_offset(n, m, tt) + (size_t)tt * ((size_t)m + 32) + 1) & ~size_t(1); }
-// panel kernel: z, y, l, u, dy (m padded to 8 rows each); dx, Px, A'y, A'dy, P dx (npad rows each)
-inline size_t panel_work_doubles(int npad, int m, int tt) { return (size_t)tt * (5 * (size_t)((m + 7) & ~7) + 5 * (size_t)npad); }
-size_t panel_smem_bytes(int npad, int tt, int nslots);                                // bqp_panel.cu
-int launch_admm_panel(int tt, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+// panel kernel, per CTA: z, y, l, u, dy (m padded to 8 rows each); dx, Px, A'y, A'dy, P dx, x snapshot (npad rows each)
+BQP_HD inline size_t panel_work_doubles(int npad, int m, int tt) { return (size_t)tt * (5 * (size_t)((m + 7) & ~7) + 6 * (size_t)npad); }
+size_t panel_smem_bytes(int npad, int tt, int nslots, int cs);                        // bqp_panel.cu
+int launch_admm_panel(int tt, int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu

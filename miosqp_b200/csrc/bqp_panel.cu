@@ -1,23 +1,28 @@
 // bqp_panel.cu -- fused single-pass batched ADMM kernel for sm_100a (dense A, npad <= 512).
 //
-// Same node-tile ownership as the other kernels (one CTA = up to T <= 4 B&B leaves of one problem, whole OSQP loop
+// Same node-tile ownership as the other kernels (a tile = up to T <= 4 B&B leaves of one problem, whole OSQP loop
 // in-kernel; /root/reference/miosqp/node.py:96-143), but the iteration is restated so that A is streamed from HBM ONCE
 // per ADMM iteration instead of twice (A' then A) and the triangular sweeps disappear:
 //
 //     x~ = M b                         M = (P + sigma I + A' rho A)^-1, explicit, one dependency-free mat-vec
 //     z~ = A x~ ; z,y update ; b' = sigma x - q + A'(rho z - y)     ONE pass over A
 //
-// Every matrix is cut into row PANELS (kPanelRows rows x npad columns, bqp_internal.h), one TMA bulk copy each into a ring
-// of shared-memory slots.  While panel k of A sits in shared memory it is used twice:
+// Every matrix is cut into row PANELS (kPanelRows rows x npad columns, bqp_internal.h), streamed by TMA bulk copies
+// into a ring of shared-memory slots.  While panel k of A sits in shared memory it is used twice:
 //   pass 1   z~_I = A_I x~            consumer warp w owns columns 32w..32w+31 (x~ in registers), partial sums are
 //                                     reduced over the 8 column lanes by a transposing shuffle tree and handed to the
-//   update   z_I, y_I, w_I            UPDATE WARP (one lane per (row, node)), which adds the 16 warp partials in a fixed
-//                                     order, applies the projection / dual update and publishes w_I = rho z_I - y_I;
+//   update   z_I, y_I, w_I            UPDATE WARPS (one lane per (row, node)), which add the warp partials in a fixed
+//                                     order, apply the projection / dual update and publish w_I = rho z_I - y_I;
 //   pass 2   b' += A_I' w_I           same panel, accumulators stay in consumer registers for the whole pass.
-// pass 2 of panel k is software-pipelined behind pass 1 of panel k+1, so the update warp's latency is hidden.
-// Roles: warps [0, NW) consumers (NW = npad/32), warp NW the update warp, warp NW+1 the TMA producer (one lane).
-// Synchronisation is mbarrier-only inside a pass (full/empty per ring slot, "partials full" / "update done" per panel
-// parity); CTA-wide named barriers only at termination checks.
+// pass 2 runs LAG panels behind pass 1, so the update latency is hidden.
+//
+// Problems wider than 8 column tiles run as a CLUSTER OF TWO CTAs (one SM each): CTA r streams and multiplies only
+// its half of the columns of every panel (half the HBM stream, shared-memory traffic and FP64 work per SM, 168 registers
+// per thread), the per-warp partial sums of pass 1 are written into BOTH CTAs' shared memory (st.shared::cluster + remote
+// mbarrier arrive over DSMEM), and both CTAs run the (cheap) row-space update redundantly, so nothing else crosses.
+// Roles per CTA: warps [0, NWc) consumers, kPanelUpdWarps update warps, one TMA producer warp (one lane).
+// Synchronisation inside a pass is mbarrier-only (full/empty per ring slot, "partials full" / "update done" per
+// hand-off buffer); named barriers only at termination checks.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -32,8 +37,11 @@ namespace {
 constexpr int kPR = kPanelRows;
 constexpr int kColQ = 9;          // column-space reductions per termination check
 constexpr int kFin = 16;
+constexpr int kFinP = 9;          // row-space quantities each update warp accumulates
+constexpr int kHB = kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b
+constexpr int kPanelThreads = (kPanelCtaWarps + kPanelUpdWarps + 1) * 32;
 
-// ------------------------------------------------------------------ mbarrier / TMA wrappers (PTX); barriers by shared-window address
+// ------------------------------------------------------------------ mbarrier / TMA / cluster wrappers (PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -44,25 +52,44 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// flow-control-only arrive on a peer barrier (no data rides on it): relaxed, so it does not wait for this thread's
+// earlier global stores the way a cluster-scope release would
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+  if constexpr (CLUSTER) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
 // Bounded wait: a broken protocol traps (reported as a CUDA error) instead of hanging the GPU.
+template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait<CLUSTER>(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s at 2 GHz
+  while (!mbar_try_wait<CLUSTER>(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz
   }
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
@@ -74,10 +101,24 @@ __device__ __forceinline__ void l2_prefetch(const void *src_gmem, uint32_t bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// DSMEM store that signals the peer's mbarrier when it has landed (complete_tx of 8 bytes): data and notification in one
+// asynchronous operation, so the sender needs no cluster-scope fence (a release.cluster arrive costs a MEMBAR.ALL.GPU)
+__device__ __forceinline__ void st_async_remote_f64(uint32_t raddr, double v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
+}
 
-// Position of element (column j, node t) in the shared-memory column vectors xs / xts / vs.  Consumer lane (cw, cg) reads
-// its columns 32cw+4cg+b with one 16-byte load per (b, node pair): the 8 column lanes must hit 8 consecutive 16-byte
-// words, so the vector is stored [cw][b][node pair][cg][2] instead of [j][t].
+// Position of element (column j, node t) in the shared-memory column vectors xs / xts / vs: [column tile][b][node pair]
+// [column lane][2], the order in which a consumer lane (columns 32w + 4cg + b) reads its 16-byte pieces.
 template <int T>
 __device__ __forceinline__ int vidx(int j, int t) {
   const int cwb = ((j >> 5) << 2) + (j & 3), cg = (j >> 2) & 7;
@@ -85,7 +126,6 @@ __device__ __forceinline__ int vidx(int j, int t) {
   else return ((cwb * (T / 2) + (t >> 1)) * 8 + cg) * 2 + (t & 1);
 }
 
-constexpr int kFinP = 9;   // row-space quantities each update warp accumulates
 struct PanelShared {
   DevInstance I;
   DevTile tile;
@@ -95,13 +135,15 @@ struct PanelShared {
   int remaining;
 };
 
-// everything a role needs to find its way around shared memory
+// everything a role needs to find its way around shared memory (u32 = shared-window addresses; *_r = the same object in
+// the peer CTA of the pair, mapped with mapa)
 struct Lay {
-  uint32_t full, empty, pf, ud;          // shared-window addresses of the barrier arrays: [nslots], [nslots], [NB], [NB]
-  double *xs, *xts, *vs, *part, *ubuf;   // [np][T] x3, [NB][NW][8T], [NB][8T]
+  uint32_t full, empty, pf, ud, udp, ck; // barrier arrays: [nslots], [nslots], [kHB], [kHB], [kHB], [1]
+  uint32_t pf_r, udp_r, ck_r, part_r, red_r;
+  double *xs, *xts, *vs, *part, *ubuf, *red;   // [np][T] x3, [kHB][NW][8T], [kHB][8T], [kColQ][NW][T]
   unsigned char *ring;
   uint32_t ring_u32;
-  int nslots, slot_bytes, nw, np;
+  int nslots, slot_bytes, nw, nwc, w0, np;    // nw: column tiles of the problem; nwc, w0: this CTA's share
 };
 
 // ---- transposing shuffle reduction over the 8 column lanes (lane bits 0..2).  C values per lane go in; after the three
@@ -123,39 +165,54 @@ __device__ __forceinline__ void tstep(double *a, int lane, int &idx) {
   }
 }
 
-// LAG = how many panels pass 2 runs behind pass 1 (the update warps' latency it hides), LAG < NB.
-// NB = kPanelUpdWarps hand-off buffers (partials, u, "partials full" / "update done" barriers): buffer b = panel % NB always
-// belongs to update warp b, so every barrier is waited on strictly phase by phase by a single warp.
-template <int T, int LAG>
+// LAG = how many panels pass 2 runs behind pass 1 (the update latency it hides), LAG < kHB.  CS = CTAs per tile.
+template <int T, int LAG, int CS>
 struct Consumer {
-  static constexpr int NB = kPanelUpdWarps;
-  static_assert(LAG < NB, "pass 2 may lag at most NB - 1 panels");
+  static_assert(LAG < kHB, "pass 2 may lag at most kHB - 1 panels");
   Lay L;
   int cw, lane, rg, cg;
   int slot; uint32_t phase;          // ring position of the next pass-1 panel
   int slot2;                         // ring position of the next pass-2 panel
-  int g, gb;                         // global panel counter (same sequence in the update warps), g % NB
+  int g, gb;                         // global panel counter (same sequence in the update warps), g % kHB
   int ud_g, ud_b; uint32_t ud_ph;    // next panel whose "update done" barrier this thread has not observed yet
+  int up_g, up_b; uint32_t up_ph;    // the same for the peer CTA's update warps (flow control of the DSMEM partials)
   bool writer;
 
   __device__ __forceinline__ void wait_ud(int target) {
     while (ud_g <= target) {
       mbar_wait(L.ud + 8u * ud_b, ud_ph);
       ud_g++;
-      if (++ud_b == NB) { ud_b = 0; ud_ph ^= 1u; }
+      if (++ud_b == kHB) { ud_b = 0; ud_ph ^= 1u; }
     }
   }
-  __device__ __forceinline__ int col0() const { return 32 * cw + 4 * cg; }
-  // one pass over `npanels` panels: pass 1 with the column vector `vsrc` (shared memory, vidx layout; this lane reads its
-  // own 4 columns); with PASS2 the per-row values published by the update warps are multiplied back into acc (this
-  // lane's 4 columns x T nodes) LAG panels later.
+  __device__ __forceinline__ void wait_udp(int target) {   // the peer's update warp has read our partials of that panel
+    if constexpr (CS == 2) {
+      while (up_g <= target) {
+        mbar_wait(L.udp + 8u * up_b, up_ph);
+        up_g++;
+        if (++up_b == kHB) { up_b = 0; up_ph ^= 1u; }
+      }
+    }
+  }
+  __device__ __forceinline__ int col0() const { return 32 * (L.w0 + cw) + 4 * cg; }   // first of this lane's 4 columns
+  // one pass over `npanels` panels: pass 1 with the column vector `vsrc` (shared memory, vidx layout; this lane keeps its
+  // own 4 columns x T nodes in registers); with PASS2 the per-row values published by the update warps are multiplied
+  // back into acc (this lane's 4 columns x T nodes) LAG panels later.
   template <bool PASS2>
   __device__ __forceinline__ void pass(int npanels, const double *vsrc, double (&acc)[4][T]) {
     const int g0 = g;
-    const int aoff = ((cw * 4) * 32 + lane) * 16;   // bytes
-    const double *xp = vsrc + (T == 1 ? (cw * 32 + cg) : (cw * 4 * (T / 2) * 8 + cg) * 2);   // vidx(32cw+4cg, 0)
+    const int aoff = ((cw * 4) * 32 + lane) * 16;   // bytes into the slot
+    double xv[4][T];
+    {
+      const int c0 = col0();
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int t = 0; t < T; t++) xv[b][t] = vsrc[vidx<T>(c0 + b, t)];
+    }
     int g2b = gb;
     slot2 = slot;
+    const int wg = L.w0 + cw;
     const int nsteps = npanels + (PASS2 ? LAG : 0);
     for (int k = 0; k < nsteps; k++) {
       if (k < npanels) {
@@ -166,37 +223,31 @@ struct Consumer {
         for (int b = 0; b < 4; b++) a[b] = ap[b * 32];
         double zp[2 * T];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          double xv[T];
-          if constexpr (T == 1) {
-            xv[0] = xp[b * 8];
-          } else {
+        for (int t = 0; t < T; t++) { zp[t] = a[0].x * xv[0][t]; zp[T + t] = a[0].y * xv[0][t]; }
 #pragma unroll
-            for (int t = 0; t < T; t += 2) {
-              const double2 v = *reinterpret_cast<const double2 *>(xp + (b * (T / 2) + (t >> 1)) * 16);
-              xv[t] = v.x; xv[t + 1] = v.y;
-            }
-          }
+        for (int b = 1; b < 4; b++)
 #pragma unroll
-          for (int t = 0; t < T; t++) {
-            if (b == 0) { zp[t] = a[0].x * xv[t]; zp[T + t] = a[0].y * xv[t]; }
-            else { zp[t] = fma(a[b].x, xv[t], zp[t]); zp[T + t] = fma(a[b].y, xv[t], zp[T + t]); }
-          }
-        }
+          for (int t = 0; t < T; t++) { zp[t] = fma(a[b].x, xv[b][t], zp[t]); zp[T + t] = fma(a[b].y, xv[b][t], zp[T + t]); }
         int idx = 0;
         tstep<2 * T, 1>(zp, lane, idx);
         tstep<T, 2>(zp, lane, idx);
         tstep<(T >= 4 ? T / 2 : 1), 4>(zp, lane, idx);
-        wait_ud(g - NB);                      // the update warp has consumed this partials buffer (panel g - NB)
-        if (writer) L.part[(gb * L.nw + cw) * (kPR * T) + 2 * rg * T + idx] = zp[0];
+        wait_ud(g - kHB); wait_udp(g - kHB);   // the update warps of both CTAs have consumed this partials buffer
+        if (writer) {
+          const int pi = (gb * L.nw + wg) * (kPR * T) + 2 * rg * T + idx;
+          L.part[pi] = zp[0];
+          if constexpr (CS == 2) st_async_remote_f64(L.part_r + 8u * pi, zp[0], L.pf_r + 8u * gb);
+        }
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(L.pf + 8u * gb);
+          // pair: the barrier also counts the bytes the peer's consumer warps store into our buffer (posted by warp 0)
+          if (CS == 2 && cw == 0) mbar_expect_tx(L.pf + 8u * gb, (uint32_t)((L.nw - L.nwc) * (kPR * T) * 8));
+          else mbar_arrive(L.pf + 8u * gb);
           if (!PASS2) mbar_arrive(L.empty + 8u * slot);
         }
         if (++slot == L.nslots) { slot = 0; phase ^= 1u; }
         g++;
-        if (++gb == NB) gb = 0;
+        if (++gb == kHB) gb = 0;
       }
       if (PASS2 && k >= LAG) {
         wait_ud(g0 + k - LAG);
@@ -223,7 +274,7 @@ struct Consumer {
         __syncwarp();
         if (lane == 0) mbar_arrive(L.empty + 8u * slot2);
         if (++slot2 == L.nslots) slot2 = 0;
-        if (++g2b == NB) g2b = 0;
+        if (++g2b == kHB) g2b = 0;
       }
     }
   }
@@ -265,7 +316,7 @@ __device__ __forceinline__ double reduce_warp(double v) { return reduce_same_nod
 enum { PM_M = 0, PM_A_INIT, PM_A_RESUME, PM_A_ITER, PM_A_CHK1, PM_A_CHK2, PM_P_CHK, PM_P_OBJ };
 
 struct WorkPtrs {
-  double *gz, *gy, *gl, *gu, *gdy, *gdx, *gpx, *gaty, *gatd, *gpdx;
+  double *gz, *gy, *gl, *gu, *gdy, *gdx, *gpx, *gaty, *gatd, *gpdx, *gsx;
 };
 
 // accumulators of an update warp (one lane per (row-in-panel, node)), reduced over rows at decision time
@@ -273,15 +324,15 @@ struct RowAcc {
   double pr, a1, a2, vu, vl, ndy, lhs, quad, lin;
 };
 
-// Update warps: warp uw handles the panels whose hand-off buffer is uw (global panel counter % NB).  Within one pass
-// that is every NB-th panel starting at some class c = k % NB: `cls` (set by pass()) names it, so that sums over rows
-// can be combined class by class -- a fixed order whatever ran earlier in the launch.
-template <int T, int LAG>
+// Update warps: warp uw handles the panels whose hand-off buffer is uw (global panel counter % kHB), so it waits on its
+// "partials full" barrier strictly phase by phase.  Within one pass that is every kHB-th panel starting at some class
+// c = k % kHB: `cls` (set by pass()) names it, so that sums over rows can be combined class by class -- a fixed order
+// whatever ran earlier in the launch.  With CS == 2 both CTAs of the pair run this redundantly on identical inputs.
+template <int T, int CS>
 struct Updater {
-  static constexpr int NB = kPanelUpdWarps;
   Lay L;
   int lane, uw;
-  int g, gb, cls; uint32_t gph;      // global panel counter, g % NB, class of the last pass, parity (g / NB) & 1
+  int g, gb, cls; uint32_t gph;      // global panel counter, g % kHB, class of the last pass, parity (g / kHB) & 1
   bool active;
 
   template <int MODE>
@@ -292,7 +343,7 @@ struct Updater {
     constexpr bool kPass2 = kIsA || MODE == PM_P_CHK;
     const int r = lane / T, t = lane % T;
     const double alpha = I.alpha, oma = 1.0 - I.alpha;
-    cls = uw - gb; if (cls < 0) cls += NB;   // this warp's panels of the pass: k = cls, cls + NB, ...
+    cls = uw - gb; if (cls < 0) cls += kHB;   // this warp's panels of the pass: k = cls, cls + kHB, ...
     for (int k = 0; k < npanels; k++) {
       if (gb == uw) {
         const int row = k * kPR + r;
@@ -369,26 +420,30 @@ struct Updater {
         }
         if constexpr (kPass2) { if (active) L.ubuf[gb * (kPR * T) + lane] = u; }
         __syncwarp();
-        if (lane == 0) mbar_arrive(L.ud + 8u * gb);
+        if (lane == 0) {
+          mbar_arrive(L.ud + 8u * gb);
+          if constexpr (CS == 2) mbar_arrive_remote_relaxed(L.udp_r + 8u * gb);
+        }
       }
       g++;
-      if (++gb == NB) { gb = 0; gph ^= 1u; }
+      if (++gb == kHB) { gb = 0; gph ^= 1u; }
     }
   }
 };
 
-template <int T, int LAG>
-__global__ void __launch_bounds__((kPanelMaxWarps + kPanelUpdWarps + 1) * 32, 1)
+template <int T, int LAG, int CS>
+__global__ void __launch_bounds__(kPanelThreads, 1)
 admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                   double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
                   int *__restrict__ tile_iters, int nslots, double *__restrict__ state, int prefetch_panels) {
-  constexpr int NB = kPanelUpdWarps;
   constexpr int KU = kPanelUpdWarps;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = CS == 2 ? cluster_ctarank() : 0u, peer = rank ^ 1u;
+  const int tile_id = blockIdx.x / CS;
   PanelShared &S = *reinterpret_cast<PanelShared *>(smem_raw);
   if (tid == 0) {
-    S.tile = tiles[blockIdx.x];
+    S.tile = tiles[tile_id];
     S.I = insts[S.tile.inst];
     S.remaining = S.tile.nn;
   }
@@ -398,37 +453,52 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, NW = I.p_nw;
   const int npm = I.p_npm, npa = I.p_npa;
   const int iter_begin = S.tile.iter_begin, iter_end = S.tile.iter_end;
-  const int slot_bytes = (int)(I.p_panel_doubles * 8);
-  if (warp >= NW + KU + 1) return;             // CTA sized for the widest problem of the launch
-  const int nthr_cu = (NW + KU) * 32, nthr_all = (NW + KU + 1) * 32;
-  const bool is_update = warp >= NW && warp < NW + KU, is_producer = warp == NW + KU;
+  // this CTA's share of the column tiles
+  const int nwh = CS == 2 ? (NW + 1) / 2 : NW;
+  const int w0 = rank == 0 ? 0 : nwh, NWc = rank == 0 ? nwh : NW - nwh;
+  const int slot_bytes = NWc * (kPR * 32 * 8);
+  const int nwslots = (int)(blockDim.x >> 5) - KU - 1;     // consumer warp slots of this launch
+  const int nthr_cu = (NWc + KU) * 32, nthr_all = (NWc + KU + 1) * 32;
+  const bool is_consumer = warp < NWc, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
 
   Lay L;
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
   L.full = smem_u32(smem_raw + off);
-  L.empty = L.full + 8u * nslots; L.pf = L.empty + 8u * nslots; L.ud = L.pf + 8u * NB;
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 2 * NB);
+  L.empty = L.full + 8u * nslots; L.pf = L.empty + 8u * nslots; L.ud = L.pf + 8u * kHB; L.udp = L.ud + 8u * kHB;
+  L.ck = L.udp + 8u * kHB;
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * kHB + 1);
   off = (off + 15) & ~size_t(15);
   L.xs = reinterpret_cast<double *>(smem_raw + off);
   L.xts = L.xs + (size_t)np * T;
   L.vs = L.xts + (size_t)np * T;
   L.part = L.vs + (size_t)np * T;
-  L.ubuf = L.part + (size_t)NB * NW * kPR * T;
-  off += ((size_t)3 * np * T + (size_t)NB * NW * kPR * T + (size_t)NB * kPR * T) * 8;
+  L.ubuf = L.part + (size_t)kHB * NW * kPR * T;
+  L.red = L.ubuf + (size_t)kHB * kPR * T;
+  off += ((size_t)3 * np * T + (size_t)kHB * NW * kPR * T + (size_t)kHB * kPR * T + (size_t)kColQ * NW * T) * 8;
   off = (off + 127) & ~size_t(127);
   L.ring = smem_raw + off;
   L.ring_u32 = smem_u32(L.ring);
-  L.nslots = nslots; L.slot_bytes = slot_bytes; L.nw = NW; L.np = np;
+  L.nslots = nslots; L.slot_bytes = slot_bytes; L.nw = NW; L.nwc = NWc; L.w0 = w0; L.np = np;
+  if constexpr (CS == 2) {
+    L.pf_r = mapa(L.pf, peer); L.udp_r = mapa(L.udp, peer); L.ck_r = mapa(L.ck, peer);
+    L.part_r = mapa(smem_u32(L.part), peer); L.red_r = mapa(smem_u32(L.red), peer);
+  } else {
+    L.pf_r = L.udp_r = L.ck_r = L.part_r = L.red_r = 0;
+  }
   if (tid == 0) {
-    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, NW); }
-    for (int s = 0; s < NB; s++) { mbar_init(L.pf + 8u * s, NW); mbar_init(L.ud + 8u * s, 1); }
+    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, NWc); }
+    // "partials full" / check barriers: one arrival per LOCAL consumer warp; the peer's share arrives as transaction bytes
+    for (int s = 0; s < kHB; s++) { mbar_init(L.pf + 8u * s, NWc); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); }
+    mbar_init(L.ck, NWc);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  named_bar(1, nthr_all);
+  if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs exist before anyone arrives
+  if (!is_consumer && !is_update && !is_producer) return;            // CTA sized for the widest problem of the launch
 
   const int max_iter = I.max_iter, check_every = I.check_every;
-  const double *pM = I.pstream, *pA = I.pstream + I.p_offA, *pP = I.pstream + I.p_offP;
+  const double *pM = I.pstream + (size_t)w0 * (kPR * 32), *pA = I.pstream + I.p_offA + (size_t)w0 * (kPR * 32),
+               *pP = I.pstream + I.p_offP + (size_t)w0 * (kPR * 32);
 
   // =============================================================== producer warp: mirror of the pass sequence
   if (is_producer) {
@@ -468,15 +538,16 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   WorkPtrs W;
   {
     const size_t m8 = (size_t)((m + 7) & ~7);
-    double *p = work + S.tile.work_off;
+    double *p = work + S.tile.work_off + (size_t)rank * panel_work_doubles(np, m, T);   // each CTA of a pair keeps its own copy
     W.gz = p; p += m8 * T; W.gy = p; p += m8 * T; W.gl = p; p += m8 * T; W.gu = p; p += m8 * T; W.gdy = p; p += m8 * T;
     W.gdx = p; p += (size_t)np * T; W.gpx = p; p += (size_t)np * T; W.gaty = p; p += (size_t)np * T;
-    W.gatd = p; p += (size_t)np * T; W.gpdx = p;
+    W.gatd = p; p += (size_t)np * T; W.gpdx = p; p += (size_t)np * T; W.gsx = p;
   }
   const double sigma = I.sigma;
+  const int ctid = is_consumer ? tid : NWc * 32 + (tid - nwslots * 32);   // dense index over consumer + update threads
 
   // ---- prologue (node.py:102-105): bounds, warm start (or the saved state of a resumed round)
-  for (int e = tid; e < m * T; e += nthr_cu) {
+  for (int e = ctid; e < m * T; e += nthr_cu) {
     const int i = e / T, t = e - i * T;
     double lo = -kInfty, up = kInfty, yv = 0.0, zv = 0.0;
     if (t < nn) {
@@ -489,7 +560,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     const double ei = __ldg(I.E + i);
     W.gl[e] = ei * lo; W.gu[e] = ei * up; W.gy[e] = yv; W.gz[e] = zv;
   }
-  for (int e = tid; e < np * T; e += nthr_cu) {
+  for (int e = ctid; e < np * T; e += nthr_cu) {
     const int j = e / T, t = e - j * T;
     double xv = 0.0;
     if (j < n && t < nn)
@@ -542,49 +613,59 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
               : (status == BQP_DUAL_INFEASIBLE || status == BQP_DUAL_INFEASIBLE_INACCURATE) ? -kInfty
               : (status == BQP_NON_CVX ? NAN : obj);
       r.lower = NAN;
-      ns[S.tile.node[t]] = r;
+      if (rank == 0) ns[S.tile.node[t]] = r;
       atomicSub(&S.remaining, 1);
     }
   };
-  // unscaled iterates of the nodes that terminated at this check (consumers + update warps)
+  // unscaled iterates of the nodes that terminated at this check (consumers + update warps): a private copy per CTA (the
+  // objective operand of the epilogue), and the caller's buffers from CTA 0
   auto snapshot = [&]() {
     for (int t = 0; t < nn; t++) {
       if (!S.newly[t]) continue;
       const int st = S.status[t];
       const bool bad = !(st == BQP_SOLVED || st == BQP_SOLVED_INACCURATE || st == BQP_MAX_ITER_REACHED);
-      double *ox = out + S.tile.out_off[t], *oy = ox + n;
-      for (int j = tid; j < n; j += nthr_cu) ox[j] = bad ? NAN : __ldg(I.D + j) * L.xs[vidx<T>(j, t)];
-      for (int i = tid; i < m; i += nthr_cu) oy[i] = bad ? NAN : I.cinv * __ldg(I.E + i) * W.gy[(size_t)i * T + t];
+      double *ox = out + S.tile.out_off[t], *oy = ox + n, *sx = W.gsx + (size_t)t * np;
+      for (int j = ctid; j < n; j += nthr_cu) {
+        const double v = bad ? NAN : __ldg(I.D + j) * L.xs[vidx<T>(j, t)];
+        sx[j] = v;
+        if (rank == 0) ox[j] = v;
+      }
+      if (rank == 0)
+        for (int i = ctid; i < m; i += nthr_cu) oy[i] = bad ? NAN : I.cinv * __ldg(I.E + i) * W.gy[(size_t)i * T + t];
     }
   };
   // end of the launch, both roles: save the state of unfinished nodes, clip + stage the objective operand
   auto finish_common = [&](int iter) {
-    if (tid == 0) tile_iters[blockIdx.x] = (iter > iter_end ? iter_end : iter) - iter_begin;
-    for (int t = 0; t < nn; t++) {
-      if (S.status[t] != BQP_UNSOLVED) continue;
-      double *sp = state + S.tile.state_off[t];
-      for (int j = tid; j < n; j += nthr_cu) sp[j] = L.xs[vidx<T>(j, t)];
-      for (int i = tid; i < m; i += nthr_cu) { sp[n + i] = W.gz[(size_t)i * T + t]; sp[n + m + i] = W.gy[(size_t)i * T + t]; }
-      if (tid == 0) { NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.pri_res = r.dua_res = r.lower = NAN; ns[S.tile.node[t]] = r; }
+    if (ctid == 0 && rank == 0) tile_iters[tile_id] = (iter > iter_end ? iter_end : iter) - iter_begin;
+    if (rank == 0) {
+      for (int t = 0; t < nn; t++) {
+        if (S.status[t] != BQP_UNSOLVED) continue;
+        double *sp = state + S.tile.state_off[t];
+        for (int j = ctid; j < n; j += nthr_cu) sp[j] = L.xs[vidx<T>(j, t)];
+        for (int i = ctid; i < m; i += nthr_cu) { sp[n + i] = W.gz[(size_t)i * T + t]; sp[n + m + i] = W.gy[(size_t)i * T + t]; }
+        if (ctid == 0) { NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.pri_res = r.dua_res = r.lower = NAN; ns[S.tile.node[t]] = r; }
+      }
     }
     // epilogue (node.py:128-143): clip integer entries, lower = 1/2 x'Px + q'x at the clipped point
     for (int t = 0; t < nn; t++) {
       const int st = S.status[t];
       if (!(st == BQP_SOLVED || st == BQP_MAX_ITER_REACHED)) continue;
-      double *ox = out + S.tile.out_off[t];
+      double *ox = out + S.tile.out_off[t], *sx = W.gsx + (size_t)t * np;
       const double *p = in + S.tile.in_off[t];
-      for (int k = tid; k < I.n_int; k += nthr_cu) {
+      for (int k = ctid; k < I.n_int; k += nthr_cu) {
         const int j = __ldg(I.i_idx + k), row = m - I.n_int + k;
-        ox[j] = fmin(fmax(ox[j], p[row]), p[m + row]);
+        const double v = fmin(fmax(sx[j], p[row]), p[m + row]);
+        sx[j] = v;
+        if (rank == 0) ox[j] = v;
       }
     }
     named_bar(2, nthr_cu);
-    for (int e = tid; e < np * T; e += nthr_cu) {
+    for (int e = ctid; e < np * T; e += nthr_cu) {
       const int j = e / T, t = e - j * T;
       double v = 0.0;
       if (j < n && t < nn) {
         const int st = S.status[t];
-        if (st == BQP_SOLVED || st == BQP_MAX_ITER_REACHED) v = __ldg(I.Dinv + j) * out[S.tile.out_off[t] + j];
+        if (st == BQP_SOLVED || st == BQP_MAX_ITER_REACHED) v = __ldg(I.Dinv + j) * W.gsx[(size_t)t * np + j];
       }
       L.xs[vidx<T>(j, t)] = v;
     }
@@ -593,11 +674,12 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
 
   if (is_update) {
     // ============================================================= update warps
-    Updater<T, LAG> U;
-    U.L = L; U.lane = lane; U.uw = warp - NW; U.g = 0; U.gb = 0; U.cls = 0; U.gph = 0; U.active = lane < kPR * T;
+    Updater<T, CS> U;
+    U.L = L; U.lane = lane; U.uw = warp - nwslots; U.g = 0; U.gb = 0; U.cls = 0; U.gph = 0; U.active = lane < kPR * T;
+    uint32_t ck_ph = 0;
     RowAcc R;
     auto reset = [&]() { R.pr = R.a1 = R.a2 = R.ndy = R.lhs = R.quad = R.lin = 0.0; R.vu = -INFINITY; R.vl = INFINITY; };
-    // this warp's row-space accumulators -> finp[uw] (one value per node)
+    // this warp's row-space accumulators -> finp (one value per node)
     auto publish_rows = [&](int cls_sum) {
       const double v[kFinP] = {reduce_same_node<T, 0>(R.pr), reduce_same_node<T, 0>(R.a1), reduce_same_node<T, 0>(R.a2),
                                reduce_same_node<T, 0>(R.ndy), reduce_same_node<T, 1>(R.lhs), reduce_same_node<T, 0>(R.vu),
@@ -621,22 +703,22 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       const int cls_chk2 = U.cls;
       U.template pass<PM_P_CHK>(S, W, npm, true, R);
       publish_rows(cls_chk2);
-      named_bar(2, nthr_cu);     // A'y, A'dy, P dx, P x are in the workspace; row-space partials in finp
-      named_bar(2, nthr_cu);     // consumers have reduced the column-space quantities per warp into `part`
+      named_bar(3, KU * 32);     // row-space partials of every update warp are in finp
       if (U.uw == 0) {
+        mbar_wait(L.ck, ck_ph);   // every consumer warp (of both CTAs) has delivered its column-space partials
         for (int idx = lane; idx < kColQ * T; idx += 32) {
           const int q = idx / T, t = idx - q * T;
           const bool is_sum = (q == 3 || q == 4 || q == 8);
-          double rr = L.part[((size_t)q * NW) * T + t];
+          double rr = L.red[((size_t)q * NW) * T + t];
           for (int w = 1; w < NW; w++) {
-            const double v = L.part[((size_t)q * NW + w) * T + t];
+            const double v = L.red[((size_t)q * NW + w) * T + t];
             rr = is_sum ? rr + v : fmax(rr, v);
           }
           // slots: 0 dr, 1 |Px|, 2 |A'y|, 3 quad, 4 lin, 5 t1 -> fin[12], 6 t2 -> fin[13], 7 ndx -> fin[10], 8 qdx -> fin[11]
           const int slot = q < 5 ? q : (q == 5 ? 12 : (q == 6 ? 13 : (q == 7 ? 10 : 11)));
           S.fin[slot][t] = rr;
         }
-        if (lane < T) {   // row-space quantities: the update warps' partials in warp order
+        if (lane < T) {   // row-space quantities: maxima in any order, the sum class by class
           double pr = S.finp[0][0][lane], a1 = S.finp[0][1][lane], a2 = S.finp[0][2][lane], ndy = S.finp[0][3][lane],
                  lhs = S.finp[0][4][lane], vu = S.finp[0][5][lane], vl = S.finp[0][6][lane];
           for (int w = 1; w < KU; w++) {
@@ -650,6 +732,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         __syncwarp();
         if (lane < T) decide(lane, iter);
       }
+      ck_ph ^= 1u;
       named_bar(2, nthr_cu);     // decision visible to the consumers
       snapshot();
       named_bar(1, nthr_all);    // ... and to the producer
@@ -659,8 +742,8 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     reset();
     U.template pass<PM_P_OBJ>(S, W, npm, false, R);
     publish_rows(U.cls);
-    named_bar(3, KU * 32);       // update warps only
-    if (U.uw == 0 && lane < nn) {
+    named_bar(3, KU * 32);
+    if (U.uw == 0 && lane < nn && rank == 0) {
       const int st = S.status[lane];
       if (st == BQP_SOLVED || st == BQP_MAX_ITER_REACHED) {
         double qd = S.finp[0][7][lane], ln = S.finp[0][8][lane];
@@ -672,10 +755,11 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   }
 
   // =============================================================== consumer warps
-  Consumer<T, LAG> C;
+  Consumer<T, LAG, CS> C;
   C.L = L; C.cw = warp; C.lane = lane; C.rg = lane >> 3; C.cg = lane & 7;
-  C.slot = 0; C.slot2 = 0; C.phase = 0; C.g = 0; C.gb = 0; C.ud_g = 0; C.ud_b = 0; C.ud_ph = 0;
+  C.slot = 0; C.slot2 = 0; C.phase = 0; C.g = 0; C.gb = 0; C.ud_g = 0; C.ud_b = 0; C.ud_ph = 0; C.up_g = 0; C.up_b = 0; C.up_ph = 0;
   C.writer = T >= 4 ? true : (T == 2 ? (lane & 4) == 0 : (lane & 6) == 0);
+  const int wg = w0 + warp;      // this warp's column tile
   double acc[4][T];
   // b' = sigma x - q + A'(rho z - y) for this warp's columns, from the pass-2 accumulators, into vs (read back by the
   // same warp only: the M pass input)
@@ -712,6 +796,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
 #pragma unroll
         for (int t = 0; t < T; t++) gvec[o + b * T + t] = acc[b][t];
     }
+    __syncwarp();
   };
   zero4<T>(acc);
   C.template pass<true>(npa, L.xs, acc);            // z = A x0 (first round) ; A'(rho z - y)
@@ -736,18 +821,24 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     zero4<T>(acc);
     C.template pass<true>(npm, L.xs, acc);
     C.allreduce_rg(acc); store_cols(W.gpdx);
-    named_bar(2, nthr_cu);
     {
-      // column-space quantities: lane <-> column 32*warp + lane (the same partition for every tile width)
-      const int j = warp * 32 + lane;
-      const bool in = j < n;
-      const double di = in ? __ldg(I.Dinv + j) : 0.0, dj = in ? __ldg(I.D + j) : 0.0, qj = in ? __ldg(I.q + j) : 0.0;
-      auto put = [&](int q, int t, double v) { if (lane == 0) L.part[((size_t)q * NW + warp) * T + t] = v; };
+      // column-space quantities: lane <-> column 32 * (column tile) + lane (the same partition for every tile width).
+      // Everything read here was written by this warp (store_cols) or by update warps whose panels it has waited for.
+      const int j = wg * 32 + lane;
+      const bool inr = j < n;
+      const double di = inr ? __ldg(I.Dinv + j) : 0.0, dj = inr ? __ldg(I.D + j) : 0.0, qj = inr ? __ldg(I.q + j) : 0.0;
+      auto put = [&](int q, int t, double v) {
+        if (lane == 0) {
+          const int ri = (q * NW + wg) * T + t;
+          L.red[ri] = v;
+          if constexpr (CS == 2) st_async_remote_f64(L.red_r + 8u * ri, v, L.ck_r);
+        }
+      };
 #pragma unroll
       for (int t = 0; t < T; t++) {
         const size_t e = (size_t)j * T + t;
-        const double px = in ? W.gpx[e] : 0.0, aty = in ? W.gaty[e] : 0.0, xj = in ? L.xs[vidx<T>(j, t)] : 0.0,
-                     dxj = in ? W.gdx[e] : 0.0, atd = in ? W.gatd[e] : 0.0, pdx = in ? W.gpdx[e] : 0.0;
+        const double px = inr ? W.gpx[e] : 0.0, aty = inr ? W.gaty[e] : 0.0, xj = inr ? L.xs[vidx<T>(j, t)] : 0.0,
+                     dxj = inr ? W.gdx[e] : 0.0, atd = inr ? W.gatd[e] : 0.0, pdx = inr ? W.gpdx[e] : 0.0;
         put(0, t, reduce_warp<0>(fabs(di * (px + qj + aty))));
         put(1, t, reduce_warp<0>(fabs(di * px)));
         put(2, t, reduce_warp<0>(fabs(di * aty)));
@@ -758,8 +849,11 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         put(7, t, reduce_warp<0>(fabs(dj * dxj)));
         put(8, t, reduce_warp<1>(qj * dxj));
       }
+      if (lane == 0) {
+        if (CS == 2 && warp == 0) mbar_expect_tx(L.ck, (uint32_t)((NW - NWc) * kColQ * T * 8));
+        else mbar_arrive(L.ck);
+      }
     }
-    named_bar(2, nthr_cu);     // partials ready for the update warp
     named_bar(2, nthr_cu);     // decision made
     snapshot();
     named_bar(1, nthr_all);
@@ -767,47 +861,57 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   }
   finish_common(iter);
   C.template pass<false>(npm, L.xs, acc);           // P x at the clipped point (sums taken by the update warps)
+  C.wait_ud(C.g - 1); C.wait_udp(C.g - 1);   // the update warps of both CTAs are done with our partials: safe to leave the cluster
 }
 
 }  // namespace
 
-static int panel_nb(int) { return kPanelUpdWarps; }   // hand-off buffers
-
-size_t panel_smem_bytes(int npad, int tt, int nslots) {
-  const int nw = npad / 32, nb = panel_nb(tt);
+size_t panel_smem_bytes(int npad, int tt, int nslots, int cs) {
+  const int nw = npad / 32;
+  const int nwc = cs == 2 ? (nw + 1) / 2 : nw;
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 2 * (size_t)nb);
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * (size_t)kHB + 1);
   off = (off + 15) & ~size_t(15);
-  off += ((size_t)3 * npad * tt + (size_t)nb * nw * kPR * tt + (size_t)nb * kPR * tt) * 8;
+  off += ((size_t)3 * npad * tt + (size_t)kHB * nw * kPR * tt + (size_t)kHB * kPR * tt + (size_t)kColQ * nw * tt) * 8;
   off = (off + 127) & ~size_t(127);
-  return off + (size_t)nslots * kPR * npad * 8;
+  return off + (size_t)nslots * nwc * (kPR * 32 * 8);
 }
 
-template <int T, int LAG>
+template <int T, int LAG, int CS>
 static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                     const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem,
                     cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<T, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<T, LAG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return BQP_E_CUDA;
   int prefetch_panels = 0;   // L2 prefetch distance of the producer, in panels (experiment knob)
   if (const char *pk = getenv("BQP_PANEL_PREFETCH")) prefetch_panels = atoi(pk);
-  admm_panel_kernel<T, LAG><<<ntiles, (nw_max + kPanelUpdWarps + 1) * 32, smem, st>>>(d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters,
-                                                                                       nslots, d_state, prefetch_panels);
-  return cudaGetLastError() == cudaSuccess ? BQP_OK : BQP_E_CUDA;
+  const int nwc = CS == 2 ? (nw_max + 1) / 2 : nw_max;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ntiles * CS), 1, 1);
+  cfg.blockDim = dim3((unsigned)((nwc + kPanelUpdWarps + 1) * 32), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, admm_panel_kernel<T, LAG, CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
+                         prefetch_panels);
+  return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? BQP_OK : BQP_E_CUDA;
 }
 
-// T = 4: pass 2 runs one panel behind pass 1 (the FP64 work of a panel covers the update latency, and shared memory only
-// holds 5 panels); narrower tiles: two panels behind.
-int launch_admm_panel(int tt, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+// cs = CTAs per tile (1, or 2 = a cluster pair splitting the columns).  Pass 2 runs two panels behind pass 1.
+int launch_admm_panel(int tt, int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (nw_max < 1 || nw_max > kPanelMaxWarps) return BQP_E_ARG;
-  switch (tt) {
-    case 1: return launch_p<1, 2>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-    case 2: return launch_p<2, 2>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-    case 4: return launch_p<4, 1>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  }
+  if (nw_max < 1 || nw_max > kPanelMaxWarps || (cs != 1 && cs != 2) || (cs == 1 && nw_max > kPanelCtaWarps)) return BQP_E_ARG;
+#define BQP_PANEL_CASE(TT, CC)                                                                                              \
+  if (tt == TT && cs == CC)                                                                                                  \
+    return launch_p<TT, 2, CC>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  BQP_PANEL_CASE(1, 1) BQP_PANEL_CASE(2, 1) BQP_PANEL_CASE(4, 1)
+  BQP_PANEL_CASE(1, 2) BQP_PANEL_CASE(2, 2) BQP_PANEL_CASE(4, 2)
+#undef BQP_PANEL_CASE
   return BQP_E_ARG;
 }
 

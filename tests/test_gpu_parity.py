@@ -15,9 +15,14 @@ TOL = 1e-9
 STREAM_THREADS = 13 * 32   # 12 consumer warps + 1 TMA producer warp (bqp_stream.cu)
 
 
-def panel_threads(n):
-    """fused single-pass kernel (bqp_panel.cu): one consumer warp per 32 columns + 3 update warps + TMA producer warp"""
-    return ((n + 31) // 32 + 4) * 32
+def panel_threads(n, cluster=None):
+    """fused single-pass kernel (bqp_panel.cu): one consumer warp per 32 columns (split over a cluster pair of CTAs
+    beyond 8 column tiles) + 3 update warps + TMA producer warp"""
+    nw = (n + 31) // 32
+    if cluster is None:
+        cluster = 2 if nw > 8 else 1
+    nwc = (nw + 1) // 2 if cluster == 2 else nw
+    return (nwc + 4) * 32
 
 
 def _close(a, b, tol=TOL):
@@ -188,6 +193,23 @@ def test_panel_kernel_cold_start_and_infeasible(oracle_mod):
     assert list(r.status) == list(so) and list(r.iters) == list(io)
     assert np.isnan(r.x[1]).all() and np.isnan(r.y[2]).all() and np.isnan(r.lower[1])
     _close(r.y[0], yo[0])
+
+
+@pytest.mark.parametrize("tt", [1, 2, 4])
+def test_panel_kernel_cluster_pair_uneven_split(oracle_mod, tt, monkeypatch):
+    """n = 130 has 5 column tiles: forced onto a cluster pair, CTA 0 takes 3 and CTA 1 takes 2 of them"""
+    monkeypatch.setenv("BQP_PANEL_CLUSTER", "2")
+    pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
+    _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(130, cluster=2)
+    _compare(pr, 6, 13, dict(QP, max_iter=60, eps_abs=1e-6, eps_rel=1e-6), tuning=(tt, 0), oracle_mod=oracle_mod)
+
+
+def test_panel_kernel_cluster_pair_cfg2_cold(oracle_mod):
+    """cfg 2 shape through the cluster pair (16 column tiles, 8 per CTA), cold start"""
+    pr = problems.random_miqp(500, 1000, 50, 0.7, seed=2)[0]
+    _compare(pr, 5, 21, QP, oracle_mod=oracle_mod)
+    assert engine.last_timing()["threads"] == panel_threads(500)
 
 
 def test_panel_kernel_max_iter(oracle_mod):
