@@ -266,8 +266,8 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   }
   g.cs = cs;
   const int capacity = rounds ? ndev_sms / cs : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
-  auto panel_slots = [&](const HostInstance &h, int t) {   // ring slots (this CTA's share of one panel each) beside the vectors
-    const long long fixed = (long long)panel_smem_bytes(h.npad, t, 0, cs) + 256;
+  auto panel_slots = [&](const HostInstance &h) {   // ring slots (this CTA's share of one panel each) beside the vectors
+    const long long fixed = (long long)panel_smem_bytes(h.npad, 0, cs) + 256;
     const long long sb = (long long)(cs == 2 ? (h.pn.nw + 1) / 2 : h.pn.nw) * kPanelRows * 32 * 8;
     long long cap = 16;
     if (const char *e = std::getenv("BQP_PANEL_SLOTS")) cap = std::max(4, std::atoi(e));   // experiment knob (ring depth)
@@ -302,9 +302,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   for (auto *inst : uniq) {
     int t = 0;
     if (use_panel) {
-      t = 4;
-      while (t > 1 && panel_slots(inst->h, t) < 4) t >>= 1;   // pass 2 holds up to 3 panels; the rest are in flight
-      if (panel_slots(inst->h, t) < 4) t = 0;
+      t = panel_slots(inst->h) >= 4 ? kPanelT : 0;   // pass 2 holds 2 panels; the rest are in flight
     } else if (use_stream) {
       t = kMaxTT;
       while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
@@ -327,7 +325,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   }
   if (use_panel) {
     nslots = 16;
-    for (auto *inst : uniq) nslots = std::min(nslots, panel_slots(inst->h, tt));
+    for (auto *inst : uniq) nslots = std::min(nslots, panel_slots(inst->h));
   } else if (use_stream)
     for (auto *inst : uniq) nslots = std::min(nslots, stream_slots(inst->h, tt));
   // tiles: split each group's nodes evenly; stop at capacity (whole groups only, so siblings stay in the same launch)
@@ -344,7 +342,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     if (!g.tiles.empty() && (long long)g.tiles.size() + nt > capacity) break;
     auto is = inst_slot.find(uniq[k]);
     if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
-    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, tt, nslots, cs)
+    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, nslots, cs)
                           : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
     if (use_panel) g.nw_max = std::max(g.nw_max, h.pn.nw);
     for (int ti = 0; ti < nt; ti++) {
@@ -359,7 +357,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
         scheduled->push_back(b);
       }
       t.work_off = (long long)work_d;
-      work_d += use_panel ? cs * panel_work_doubles(h.npad, h.m, tt) : tile_work_doubles(h.n, h.m, tt);
+      work_d += use_panel ? cs * panel_work_doubles(h.npad, h.m) : tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
       g.tile_bytes_iter.push_back(use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
       g.tile_bytes_check.push_back(use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
@@ -486,7 +484,7 @@ int bqp_batch_run(void) {
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
     rc = g.use_panel
-             ? launch_admm_panel(g.tt, g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
+             ? launch_admm_panel(g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
                                  g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
                                  (int *)g.d_ti.p, g.smem, g.stream)
          : g.use_stream

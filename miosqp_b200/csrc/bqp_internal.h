@@ -71,14 +71,17 @@ struct HostStream {
 // ---- row-panel layout of the fused single-pass kernel (bqp_panel.cu) -------------------------------------
 // For problems whose A is dense enough to be stored dense (every BASELINE random_miqp config at density 0.7) one ADMM
 // iteration is restated as   x~ = M b,  z~ = A x~,  b' = sigma x - q + A'(rho z - y)   with M = (P + sigma I + A' rho A)^-1
-// formed explicitly on the host, and A streamed ONCE per iteration: each PANEL (kPanelRows rows x npad columns, one
-// TMA bulk copy) is used while it sits in shared memory first for its rows of A x~ and then, after the per-row z/y
-// update, for its contribution to A' w.  Consumer warp w owns columns 32w..32w+31; its lane (rg = lane>>3, cg = lane&7)
-// owns rows 2rg, 2rg+1 and columns 4cg..4cg+3 of that tile.  Storage of panel k (doubles):
-//   k*8*npad + ((w*4 + b)*32 + lane)*2 + a   holds   X[8k + 2rg + a][32w + 4cg + b]
-// so every warp-wide 16-byte load is 512 contiguous bytes.  Matrices in stream order: M (npad rows), A (m rows padded to
-// 8), P full symmetric (npad rows; termination checks and the final objective only).
-constexpr int kPanelRows = 8;
+// formed explicitly on the host, and A streamed ONCE per iteration: each PANEL (kPanelRows rows x npad columns) is
+// used while it sits in shared memory first for its rows of A x~ and then, after the per-row z/y update, for its
+// contribution to A' w.  Consumer warp w owns the column tile 32w..32w+31 and multiplies it with FP64 mma.sync.m8n8k4
+// (the up to kPanelT nodes of the tile are the N dimension), so a tile of a panel is stored as the 8 A-fragments of
+// pass 1:   k*16*npad + w*512 + h*256 + ks*32 + lane   holds   X[16k + 8h + (lane>>2)][32w + 4ks + (lane&3)]
+// (a warp-wide 8-byte load is 256 contiguous bytes; the transposed fragments of pass 2 read the same 2 KB without bank
+// conflicts).  The tiles of one panel are contiguous in w, so a CTA streaming columns [32 w0, 32 (w0+nwc)) of every
+// panel issues one TMA bulk copy per panel.  Matrices in stream order: M (npad rows), A (m rows padded to 8), P full
+// symmetric (npad rows; termination checks and the final objective only).
+constexpr int kPanelRows = 16;                      // two 8-row mma tiles: one hand-off to the update warps per 16 rows
+constexpr int kPanelT = 8;                          // nodes per tile of the panel kernel (N of the mma)
 constexpr int kPanelMaxWarps = 16;                  // column tiles of 32 (npad <= 512), one consumer warp each
 constexpr int kPanelCtaWarps = 8;                   // consumer warps per CTA; wider problems run as a cluster pair of CTAs
 constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin
@@ -172,10 +175,10 @@ struct NodeScalars {
 #endif
 BQP_HD inline size_t tile_w_offset(int n, int m, int tt) { return ((size_t)tt * (5 * (size_t)m + 3 * (size_t)n) + 1) & ~size_t(1); }
 inline size_t tile_work_doubles(int n, int m, int tt) { return (tile_w_offset(n, m, tt) + (size_t)tt * ((size_t)m + 32) + 1) & ~size_t(1); }
-// panel kernel, per CTA: z, y, l, u, dy (m padded to 8 rows each); dx, Px, A'y, A'dy, P dx, x snapshot (npad rows each)
-BQP_HD inline size_t panel_work_doubles(int npad, int m, int tt) { return (size_t)tt * (5 * (size_t)((m + 7) & ~7) + 6 * (size_t)npad); }
-size_t panel_smem_bytes(int npad, int tt, int nslots, int cs);                        // bqp_panel.cu
-int launch_admm_panel(int tt, int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+// panel kernel, per CTA, [row][kPanelT]: z, y, l, u, dy (m padded to whole panels); dx, Px, A'y, A'dy, P dx, x, x snapshot (npad rows each)
+BQP_HD inline size_t panel_work_doubles(int npad, int m) { return (size_t)kPanelT * (5 * (size_t)((m + kPanelRows - 1) / kPanelRows * kPanelRows) + 7 * (size_t)npad); }
+size_t panel_smem_bytes(int npad, int nslots, int cs);                                // bqp_panel.cu
+int launch_admm_panel(int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu

@@ -1,25 +1,30 @@
 // bqp_panel.cu -- fused single-pass batched ADMM kernel for sm_100a (dense A, npad <= 512).
 //
-// Same node-tile ownership as the other kernels (a tile = up to T <= 4 B&B leaves of one problem, whole OSQP loop
-// in-kernel; /root/reference/miosqp/node.py:96-143), but the iteration is restated so that A is streamed from HBM ONCE
-// per ADMM iteration instead of twice (A' then A) and the triangular sweeps disappear:
+// Same node-tile ownership as the other kernels (a tile = up to 8 B&B leaves of one problem, whole OSQP loop in-kernel;
+// /root/reference/miosqp/node.py:96-143), but the iteration is restated so that A is streamed from HBM ONCE per ADMM
+// iteration instead of twice (A' then A) and the triangular sweeps disappear:
 //
 //     x~ = M b                         M = (P + sigma I + A' rho A)^-1, explicit, one dependency-free mat-vec
 //     z~ = A x~ ; z,y update ; b' = sigma x - q + A'(rho z - y)     ONE pass over A
 //
-// Every matrix is cut into row PANELS (kPanelRows rows x npad columns, bqp_internal.h), streamed by TMA bulk copies
+// Every matrix is cut into row PANELS (kPanelRows = 8 rows x npad columns, bqp_internal.h), streamed by TMA bulk copies
 // into a ring of shared-memory slots.  While panel k of A sits in shared memory it is used twice:
-//   pass 1   z~_I = A_I x~            consumer warp w owns columns 32w..32w+31 (x~ in registers), partial sums are
-//                                     reduced over the 8 column lanes by a transposing shuffle tree and handed to the
-//   update   z_I, y_I, w_I            UPDATE WARPS (one lane per (row, node)), which add the warp partials in a fixed
+//   pass 1   z~_I = A_I x~            consumer warp w owns columns 32w..32w+31; the [8 rows x 32 cols] x [32 cols x 8 nodes]
+//                                     product is 8 FP64 mma.sync.m8n8k4 (the 8 leaves of the tile are the N dimension, so
+//                                     the hardware does the reduction over columns: no shuffles), partial sums go to the
+//   update   z_I, y_I, w_I            UPDATE WARPS (one lane per (row, node pair)), which add the warp partials in a fixed
 //                                     order, apply the projection / dual update and publish w_I = rho z_I - y_I;
-//   pass 2   b' += A_I' w_I           same panel, accumulators stay in consumer registers for the whole pass.
-// pass 2 runs LAG panels behind pass 1, so the update latency is hidden.
+//   pass 2   b' += A_I' w_I           same panel read transposed from shared memory: 8 more mma.sync per warp, the
+//                                     [32 cols x 8 nodes] accumulators stay in registers for the whole pass.
+// pass 2 runs LAG panels behind pass 1, so the update latency is hidden.  (FP64 mma.sync issues at the same 64 FMA/clk/SM
+// as DFMA on B200 -- tools/micro/dmma_rate.cu -- but with 1/8 of the instructions; the vector-FMA version of this kernel
+// was instruction-issue bound at a quarter of the HBM roofline.)
 //
 // Problems wider than 8 column tiles run as a CLUSTER OF TWO CTAs (one SM each): CTA r streams and multiplies only
-// its half of the columns of every panel (half the HBM stream, shared-memory traffic and FP64 work per SM, 168 registers
-// per thread), the per-warp partial sums of pass 1 are written into BOTH CTAs' shared memory (st.shared::cluster + remote
-// mbarrier arrive over DSMEM), and both CTAs run the (cheap) row-space update redundantly, so nothing else crosses.
+// its half of the columns of every panel (half the HBM stream, shared-memory traffic and FP64 work per SM), the per-warp
+// partial sums of pass 1 are written into BOTH CTAs' shared memory (st.async over DSMEM, completing transaction bytes on
+// the peer's mbarrier: no cluster-scope fence anywhere in the loop), and both CTAs run the (cheap) row-space update
+// redundantly, so nothing else crosses.
 // Roles per CTA: warps [0, NWc) consumers, kPanelUpdWarps update warps, one TMA producer warp (one lane).
 // Synchronisation inside a pass is mbarrier-only (full/empty per ring slot, "partials full" / "update done" per
 // hand-off buffer); named barriers only at termination checks.
@@ -27,6 +32,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 #include "bqp_internal.h"
 
@@ -34,12 +40,16 @@ namespace bqp {
 
 namespace {
 
+constexpr int T8 = kPanelT;       // nodes per tile = N of the mma
 constexpr int kPR = kPanelRows;
 constexpr int kColQ = 9;          // column-space reductions per termination check
 constexpr int kFin = 16;
 constexpr int kFinP = 9;          // row-space quantities each update warp accumulates
-constexpr int kHB = kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b
+constexpr int kHBmul = 1;
+constexpr int kHB = kHBmul * kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b % kPanelUpdWarps
+constexpr int kPH = kPanelRows / 8;            // 8-row mma tiles per panel
 constexpr int kPanelThreads = (kPanelCtaWarps + kPanelUpdWarps + 1) * 32;
+constexpr int kTileDoubles = kPR * 32;   // one column tile of one panel
 
 // ------------------------------------------------------------------ mbarrier / TMA / cluster wrappers (PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,42 +63,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // flow-control-only arrive on a peer barrier (no data rides on it): relaxed, so it does not wait for this thread's
-// earlier global stores the way a cluster-scope release would
+// earlier global stores the way a cluster-scope release would (that compiles to MEMBAR.ALL.GPU)
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t rbar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
-template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  if constexpr (CLUSTER) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
   return ok != 0;
 }
 // Bounded wait: a broken protocol traps (reported as a CUDA error) instead of hanging the GPU.
-template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait<CLUSTER>(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait<CLUSTER>(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz
   }
 }
@@ -112,26 +108,22 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 // DSMEM store that signals the peer's mbarrier when it has landed (complete_tx of 8 bytes): data and notification in one
-// asynchronous operation, so the sender needs no cluster-scope fence (a release.cluster arrive costs a MEMBAR.ALL.GPU)
+// asynchronous operation, so the sender needs no cluster-scope fence
 __device__ __forceinline__ void st_async_remote_f64(uint32_t raddr, double v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
 }
-
-// Position of element (column j, node t) in the shared-memory column vectors xs / xts / vs: [column tile][b][node pair]
-// [column lane][2], the order in which a consumer lane (columns 32w + 4cg + b) reads its 16-byte pieces.
-template <int T>
-__device__ __forceinline__ int vidx(int j, int t) {
-  const int cwb = ((j >> 5) << 2) + (j & 3), cg = (j >> 2) & 7;
-  if constexpr (T == 1) return cwb * 8 + cg;
-  else return ((cwb * (T / 2) + (t >> 1)) * 8 + cg) * 2 + (t & 1);
+// D (8x8) += A (8x4, row) * B (4x8, col), FP64.  Fragments: A: lane holds A[lane>>2][lane&3]; B: B[lane&3][lane>>2];
+// C/D: rows lane>>2, columns 2*(lane&3), 2*(lane&3)+1.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
 struct PanelShared {
   DevInstance I;
   DevTile tile;
-  double fin[kFin][4];
-  double finp[kPanelUpdWarps][kFinP][4];
-  int status[4], iters[4], newly[4];
+  double fin[kFin][T8];
+  double finp[kPanelUpdWarps][kFinP][T8];
+  int status[T8], iters[T8], newly[T8];
   int remaining;
 };
 
@@ -140,43 +132,32 @@ struct PanelShared {
 struct Lay {
   uint32_t full, empty, pf, ud, udp, ck; // barrier arrays: [nslots], [nslots], [kHB], [kHB], [kHB], [1]
   uint32_t pf_r, udp_r, ck_r, part_r, red_r;
-  double *xs, *xts, *vs, *part, *ubuf, *red;   // [np][T] x3, [kHB][NW][8T], [kHB][8T], [kColQ][NW][T]
+  double *xts, *vs;                      // x~ and b for THIS CTA's columns: [32 NWc][8]
+  double *part, *ubuf, *red;             // [kHB][NW][32 lanes][2], [kHB][8 rows][8], [kColQ][NW][8]
   unsigned char *ring;
   uint32_t ring_u32;
   int nslots, slot_bytes, nw, nwc, w0, np;    // nw: column tiles of the problem; nwc, w0: this CTA's share
 };
 
-// ---- transposing shuffle reduction over the 8 column lanes (lane bits 0..2).  C values per lane go in; after the three
-// steps every (row, node) sum lives in exactly one lane of each group of 8 (duplicated when 2T < 8): idx says which.
-template <int C, int MK>
-__device__ __forceinline__ void tstep(double *a, int lane, int &idx) {
-  if constexpr (C >= 2) {
-    constexpr int H = C / 2;
-    const bool up = (lane & MK) != 0;
-#pragma unroll
-    for (int i = 0; i < H; i++) {
-      const double send = up ? a[i] : a[i + H];
-      const double keep = up ? a[i + H] : a[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, MK);
-    }
-    if (up) idx += H;
-  } else {
-    a[0] += __shfl_xor_sync(0xffffffffu, a[0], MK);
-  }
-}
-
 // LAG = how many panels pass 2 runs behind pass 1 (the update latency it hides), LAG < kHB.  CS = CTAs per tile.
-template <int T, int LAG, int CS>
+#ifdef BQP_PANEL_TIMERS
+#define TSTAMP(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define TSTAMP(i) do { } while (0)
+#endif
+template <int LAG, int CS>
 struct Consumer {
   static_assert(LAG < kHB, "pass 2 may lag at most kHB - 1 panels");
   Lay L;
-  int cw, lane, rg, cg;
+#ifdef BQP_PANEL_TIMERS
+  long long tacc[8], tlast;
+#endif
+  int cw, lane;
   int slot; uint32_t phase;          // ring position of the next pass-1 panel
   int slot2;                         // ring position of the next pass-2 panel
   int g, gb;                         // global panel counter (same sequence in the update warps), g % kHB
   int ud_g, ud_b; uint32_t ud_ph;    // next panel whose "update done" barrier this thread has not observed yet
   int up_g, up_b; uint32_t up_ph;    // the same for the peer CTA's update warps (flow control of the DSMEM partials)
-  bool writer;
 
   __device__ __forceinline__ void wait_ud(int target) {
     while (ud_g <= target) {
@@ -194,146 +175,137 @@ struct Consumer {
       }
     }
   }
-  __device__ __forceinline__ int col0() const { return 32 * (L.w0 + cw) + 4 * cg; }   // first of this lane's 4 columns
-  // one pass over `npanels` panels: pass 1 with the column vector `vsrc` (shared memory, vidx layout; this lane keeps its
-  // own 4 columns x T nodes in registers); with PASS2 the per-row values published by the update warps are multiplied
-  // back into acc (this lane's 4 columns x T nodes) LAG panels later.
+  // one pass over `npanels` panels.  pass 1 multiplies with the column vector src ([column - src_col0][8 nodes]; this
+  // warp's 32 columns are held as 8 B fragments); with PASS2 the per-row values published by the update warps are
+  // multiplied back into acc (C fragments: column 32 wg + 8 mt + (lane >> 2), nodes 2 (lane & 3) + {0, 1}) LAG panels later.
   template <bool PASS2>
-  __device__ __forceinline__ void pass(int npanels, const double *vsrc, double (&acc)[4][T]) {
+  __device__ __forceinline__ void pass(int npanels, const double *src, int src_col0, double (&acc)[4][2]) {
+    double acc1[4][2];     // second accumulator set of pass 2 (rows 4..7 of every panel): independent mma chains
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) { acc1[mt][0] = 0.0; acc1[mt][1] = 0.0; }
     const int g0 = g;
-    const int aoff = ((cw * 4) * 32 + lane) * 16;   // bytes into the slot
-    double xv[4][T];
-    {
-      const int c0 = col0();
+    const int wg = L.w0 + cw, gq = lane >> 2, tq = lane & 3;
+    double bx[8];
 #pragma unroll
-      for (int b = 0; b < 4; b++)
-#pragma unroll
-        for (int t = 0; t < T; t++) xv[b][t] = vsrc[vidx<T>(c0 + b, t)];
-    }
+    for (int ks = 0; ks < 8; ks++) bx[ks] = src[(size_t)(32 * wg + 4 * ks + tq - src_col0) * T8 + gq];
+    // pass-2 A fragment (A' as the row operand): element (row 4 kk + tq, column 8 mt + gq) of the tile
+    const int a2 = (gq >> 2) * 32 + tq * 4 + (gq & 3);
     int g2b = gb;
     slot2 = slot;
-    const int wg = L.w0 + cw;
     const int nsteps = npanels + (PASS2 ? LAG : 0);
     for (int k = 0; k < nsteps; k++) {
       if (k < npanels) {
+        TSTAMP(7);
         mbar_wait(L.full + 8u * slot, phase);
-        const double2 *ap = reinterpret_cast<const double2 *>(L.ring + (size_t)slot * L.slot_bytes + aoff);
-        double2 a[4];
+        TSTAMP(0);
+        const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)slot * L.slot_bytes) + cw * kTileDoubles + lane;
+        // independent mma (their latency, not their issue rate, is what a dependent chain would pay), then a fixed tree
+        double c0[kPH][2];
 #pragma unroll
-        for (int b = 0; b < 4; b++) a[b] = ap[b * 32];
-        double zp[2 * T];
+        for (int h = 0; h < kPH; h++) {
+          double cc[8][2];
 #pragma unroll
-        for (int t = 0; t < T; t++) { zp[t] = a[0].x * xv[0][t]; zp[T + t] = a[0].y * xv[0][t]; }
+          for (int ks = 0; ks < 8; ks++) { cc[ks][0] = 0.0; cc[ks][1] = 0.0; dmma(cc[ks], sp[h * 256 + ks * 32], bx[ks]); }
 #pragma unroll
-        for (int b = 1; b < 4; b++)
-#pragma unroll
-          for (int t = 0; t < T; t++) { zp[t] = fma(a[b].x, xv[b][t], zp[t]); zp[T + t] = fma(a[b].y, xv[b][t], zp[T + t]); }
-        int idx = 0;
-        tstep<2 * T, 1>(zp, lane, idx);
-        tstep<T, 2>(zp, lane, idx);
-        tstep<(T >= 4 ? T / 2 : 1), 4>(zp, lane, idx);
+          for (int i = 0; i < 2; i++) c0[h][i] = ((cc[0][i] + cc[1][i]) + (cc[2][i] + cc[3][i])) + ((cc[4][i] + cc[5][i]) + (cc[6][i] + cc[7][i]));
+        }
+        TSTAMP(1);
         wait_ud(g - kHB); wait_udp(g - kHB);   // the update warps of both CTAs have consumed this partials buffer
-        if (writer) {
-          const int pi = (gb * L.nw + wg) * (kPR * T) + 2 * rg * T + idx;
-          L.part[pi] = zp[0];
-          if constexpr (CS == 2) st_async_remote_f64(L.part_r + 8u * pi, zp[0], L.pf_r + 8u * gb);
+        TSTAMP(2);
+#pragma unroll
+        for (int h = 0; h < kPH; h++) {
+          const int pi = (((gb * L.nw + wg) * kPH + h) * 32 + lane) * 2;
+          *reinterpret_cast<double2 *>(L.part + pi) = make_double2(c0[h][0], c0[h][1]);
+          if constexpr (CS == 2) {
+            st_async_remote_f64(L.part_r + 8u * pi, c0[h][0], L.pf_r + 8u * gb);
+            st_async_remote_f64(L.part_r + 8u * pi + 8u, c0[h][1], L.pf_r + 8u * gb);
+          }
         }
         __syncwarp();
         if (lane == 0) {
           // pair: the barrier also counts the bytes the peer's consumer warps store into our buffer (posted by warp 0)
-          if (CS == 2 && cw == 0) mbar_expect_tx(L.pf + 8u * gb, (uint32_t)((L.nw - L.nwc) * (kPR * T) * 8));
+          if (CS == 2 && cw == 0) mbar_expect_tx(L.pf + 8u * gb, (uint32_t)((L.nw - L.nwc) * kPH * 32 * 16));
           else mbar_arrive(L.pf + 8u * gb);
           if (!PASS2) mbar_arrive(L.empty + 8u * slot);
         }
         if (++slot == L.nslots) { slot = 0; phase ^= 1u; }
         g++;
         if (++gb == kHB) gb = 0;
+        TSTAMP(3);
       }
       if (PASS2 && k >= LAG) {
         wait_ud(g0 + k - LAG);
-        const double *up = L.ubuf + g2b * (kPR * T) + 2 * rg * T;
-        double u[2 * T];
-        if constexpr (T == 1) {
-          const double2 v = *reinterpret_cast<const double2 *>(up);
-          u[0] = v.x; u[1] = v.y;
-        } else {
+        TSTAMP(4);
+        const double *up = L.ubuf + g2b * (kPR * T8);
+        const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)slot2 * L.slot_bytes) + cw * kTileDoubles + a2;
 #pragma unroll
-          for (int i = 0; i < 2 * T; i += 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(up + i);
-            u[i] = v.x; u[i + 1] = v.y;
+        for (int h = 0; h < kPH; h++) {
+          const double bu0 = up[(h * 8 + tq) * T8 + gq], bu1 = up[(h * 8 + 4 + tq) * T8 + gq];
+#pragma unroll
+          for (int mt = 0; mt < 4; mt++) {
+            dmma(acc[mt], sp[h * 256 + mt * 64], bu0);
+            dmma(acc1[mt], sp[h * 256 + mt * 64 + 16], bu1);
           }
         }
-        const double2 *ap = reinterpret_cast<const double2 *>(L.ring + (size_t)slot2 * L.slot_bytes + aoff);
-        double2 a[4];
-#pragma unroll
-        for (int b = 0; b < 4; b++) a[b] = ap[b * 32];
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int t = 0; t < T; t++) { acc[b][t] = fma(a[b].x, u[t], acc[b][t]); acc[b][t] = fma(a[b].y, u[T + t], acc[b][t]); }
         __syncwarp();
+        TSTAMP(5);
         if (lane == 0) mbar_arrive(L.empty + 8u * slot2);
         if (++slot2 == L.nslots) slot2 = 0;
         if (++g2b == kHB) g2b = 0;
+        TSTAMP(6);
       }
     }
-  }
-  // column sums of pass 2 live spread over the 4 row groups of the warp: butterfly all-reduce (lane bits 3, 4)
-  __device__ __forceinline__ void allreduce_rg(double (&acc)[4][T]) {
+    if (PASS2) {
 #pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        double v = acc[b][t];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        acc[b][t] = v;
-      }
+      for (int mt = 0; mt < 4; mt++) { acc[mt][0] += acc1[mt][0]; acc[mt][1] += acc1[mt][1]; }
+    }
   }
 };
 
-template <int T>
-__device__ __forceinline__ void zero4(double (&a)[4][T]) {
+__device__ __forceinline__ void zero4(double (&a)[4][2]) {
 #pragma unroll
-  for (int b = 0; b < 4; b++)
-#pragma unroll
-    for (int t = 0; t < T; t++) a[b][t] = 0.0;
+  for (int b = 0; b < 4; b++) { a[b][0] = 0.0; a[b][1] = 0.0; }
 }
 
-// reduce v over the lanes that hold the same node (lane % T): xor masks 16 .. T
-template <int T, int OP>   // OP 0: max, 1: sum, 2: min
-__device__ __forceinline__ double reduce_same_node(double v) {
+template <int OP>   // OP 0: max, 1: sum, 2: min
+__device__ __forceinline__ double red_op(double v, double w) { return OP == 0 ? fmax(v, w) : (OP == 1 ? v + w : fmin(v, w)); }
+// reduce over the 8 rows of a panel: lanes with the same lane & 3 (xor masks 16, 8, 4)
+template <int OP>
+__device__ __forceinline__ double reduce_rows(double v) {
 #pragma unroll
-  for (int o = 16; o >= T; o >>= 1) {
-    const double w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = OP == 0 ? fmax(v, w) : (OP == 1 ? v + w : fmin(v, w));
-  }
+  for (int o = 16; o >= 4; o >>= 1) v = red_op<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 template <int OP>
-__device__ __forceinline__ double reduce_warp(double v) { return reduce_same_node<1, OP>(v); }
+__device__ __forceinline__ double reduce_warp(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = red_op<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 
 enum { PM_M = 0, PM_A_INIT, PM_A_RESUME, PM_A_ITER, PM_A_CHK1, PM_A_CHK2, PM_P_CHK, PM_P_OBJ };
 
-struct WorkPtrs {
-  double *gz, *gy, *gl, *gu, *gdy, *gdx, *gpx, *gaty, *gatd, *gpdx, *gsx;
+struct WorkPtrs {   // per-CTA workspace in global memory (L2 resident), every vector [row][8 nodes]
+  double *gz, *gy, *gl, *gu, *gdy, *gdx, *gpx, *gaty, *gatd, *gpdx, *gxs, *gsx;
 };
 
-// accumulators of an update warp (one lane per (row-in-panel, node)), reduced over rows at decision time
+// accumulators of an update warp lane (one row of every panel it handles, two nodes), reduced over rows at decision time
 struct RowAcc {
-  double pr, a1, a2, vu, vl, ndy, lhs, quad, lin;
+  double pr[2], a1[2], a2[2], vu[2], vl[2], ndy[2], lhs[2], quad[2], lin[2];
 };
 
 // Update warps: warp uw handles the panels whose hand-off buffer is uw (global panel counter % kHB), so it waits on its
 // "partials full" barrier strictly phase by phase.  Within one pass that is every kHB-th panel starting at some class
 // c = k % kHB: `cls` (set by pass()) names it, so that sums over rows can be combined class by class -- a fixed order
 // whatever ran earlier in the launch.  With CS == 2 both CTAs of the pair run this redundantly on identical inputs.
-template <int T, int CS>
+// Lane <-> (row lane >> 2 of the panel, nodes 2 (lane & 3) and 2 (lane & 3) + 1): the C fragment layout of pass 1.
+template <int CS>
 struct Updater {
   Lay L;
   int lane, uw;
-  int g, gb, cls; uint32_t gph;      // global panel counter, g % kHB, class of the last pass, parity (g / kHB) & 1
-  bool active;
+  int gb, cls;                       // global panel counter % kPanelUpdWarps at the start of the next pass; class of the last pass
+  int bsel; uint32_t ph;             // this warp's next hand-off buffer is uw + kPanelUpdWarps * bsel, its phase parity ph
+  struct Pre { double2 s0, s1, s2, s3; double rho, rinv, ei; };
 
   template <int MODE>
   __device__ __forceinline__ void pass(const PanelShared &S, const WorkPtrs &W, int npanels, bool do_check, RowAcc &R) {
@@ -341,102 +313,136 @@ struct Updater {
     const int m = I.m, n = I.n;
     constexpr bool kIsA = (MODE == PM_A_INIT || MODE == PM_A_RESUME || MODE == PM_A_ITER || MODE == PM_A_CHK1 || MODE == PM_A_CHK2);
     constexpr bool kPass2 = kIsA || MODE == PM_P_CHK;
-    const int r = lane / T, t = lane % T;
+    const int r = lane >> 2, tp = lane & 3;
     const double alpha = I.alpha, oma = 1.0 - I.alpha;
-    cls = uw - gb; if (cls < 0) cls += kHB;   // this warp's panels of the pass: k = cls, cls + kHB, ...
-    for (int k = 0; k < npanels; k++) {
-      if (gb == uw) {
-        const int row = k * kPR + r;
-        const bool live = active && (kIsA ? row < m : row < L.np);
-        const int e = k * (kPR * T) + lane;        // row * T + t
-        const int ev = vidx<T>(row, t);            // same element in the shared-memory column vectors
-        // ---- operands that do not depend on the partial sums: fetched before the wait
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, rho = 0, rinv = 0, ei = 0;
-        if (live) {
-          if constexpr (MODE == PM_A_ITER) { s0 = W.gz[e]; s1 = W.gy[e]; s2 = W.gl[e]; s3 = W.gu[e]; rho = __ldg(I.rho + row); rinv = __ldg(I.rho_inv + row); }
-          if constexpr (MODE == PM_A_INIT) { s1 = W.gy[e]; rho = __ldg(I.rho + row); }
-          if constexpr (MODE == PM_A_RESUME) { s0 = W.gz[e]; s1 = W.gy[e]; rho = __ldg(I.rho + row); }
-          if constexpr (MODE == PM_A_CHK1) { s0 = W.gz[e]; s1 = W.gy[e]; ei = __ldg(I.Einv + row); }
-          if constexpr (MODE == PM_A_CHK2) { s0 = W.gdy[e]; s2 = W.gl[e]; s3 = W.gu[e]; ei = __ldg(I.Einv + row); rho = __ldg(I.E + row); }
-          if constexpr (MODE == PM_M) { s0 = L.xs[ev]; }
-          if constexpr (MODE == PM_P_CHK) { s0 = W.gdx[e]; }
-          if constexpr (MODE == PM_P_OBJ) { s0 = L.xs[ev]; s1 = row < n ? __ldg(I.q + row) : 0.0; }
-        }
-        mbar_wait(L.pf + 8u * gb, gph);
-        double sum = 0.0;
-        if (active) {   // the NW warp partials in a fixed order: four interleaved chains, then a fixed tree
-          const double *pp = L.part + gb * L.nw * (kPR * T) + lane;
-          double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    const int jlo = 32 * L.w0, jhi = 32 * (L.w0 + L.nwc);     // rows of x~ this CTA's consumers read
+    constexpr int KU = kPanelUpdWarps;
+    cls = uw - gb; if (cls < 0) cls += KU;   // this warp's panels of the pass: k = cls, cls + KU, ...
+    // operands that do not depend on the partial sums.  They are fetched one owned panel AHEAD (right after the previous
+    // panel is handed over), so their L2 / HBM latency never sits between "partials full" and "update done".
+    auto load_state = [&](int k, int h) {
+      Pre p;
+      p.s0 = p.s1 = p.s2 = p.s3 = make_double2(0, 0); p.rho = p.rinv = p.ei = 0.0;
+      const int row = k * kPR + h * 8 + r;
+      if (k < npanels && (kIsA ? row < m : row < L.np)) {
+        const int e2 = row * (T8 / 2) + tp;
+        auto ld2 = [&](const double *v) { return reinterpret_cast<const double2 *>(v)[e2]; };
+        if constexpr (MODE == PM_A_ITER) { p.s0 = ld2(W.gz); p.s1 = ld2(W.gy); p.s2 = ld2(W.gl); p.s3 = ld2(W.gu); p.rho = __ldg(I.rho + row); p.rinv = __ldg(I.rho_inv + row); }
+        if constexpr (MODE == PM_A_INIT) { p.s1 = ld2(W.gy); p.rho = __ldg(I.rho + row); }
+        if constexpr (MODE == PM_A_RESUME) { p.s0 = ld2(W.gz); p.s1 = ld2(W.gy); p.rho = __ldg(I.rho + row); }
+        if constexpr (MODE == PM_A_CHK1) { p.s0 = ld2(W.gz); p.s1 = ld2(W.gy); p.ei = __ldg(I.Einv + row); }
+        if constexpr (MODE == PM_A_CHK2) { p.s0 = ld2(W.gdy); p.s2 = ld2(W.gl); p.s3 = ld2(W.gu); p.ei = __ldg(I.Einv + row); p.rho = __ldg(I.E + row); }
+        if constexpr (MODE == PM_M) { p.s0 = ld2(W.gxs); }
+        if constexpr (MODE == PM_P_CHK) { p.s0 = ld2(W.gdx); }
+        if constexpr (MODE == PM_P_OBJ) { p.s0 = ld2(W.gxs); p.rho = row < n ? __ldg(I.q + row) : 0.0; }
+      }
+      return p;
+    };
+    Pre nxt[kPH];
+#pragma unroll
+    for (int h = 0; h < kPH; h++) nxt[h] = load_state(cls, h);
+    for (int k = cls; k < npanels; k += KU) {
+      Pre cur[kPH];
+#pragma unroll
+      for (int h = 0; h < kPH; h++) { cur[h] = nxt[h]; nxt[h] = load_state(k + KU, h); }
+      const int hb = uw + KU * bsel;              // hand-off buffer of this panel
+      mbar_wait(L.pf + 8u * hb, ph);
+#pragma unroll
+      for (int h = 0; h < kPH; h++) {
+        const int row = k * kPR + h * 8 + r;
+        const bool live = kIsA ? row < m : row < L.np;
+        const int e2 = row * (T8 / 2) + tp;         // double2 index of (row, nodes 2tp, 2tp+1) in a [row][8] vector
+        auto st2 = [&](double *v, double a, double b) { reinterpret_cast<double2 *>(v)[e2] = make_double2(a, b); };
+        const double rho = cur[h].rho, rinv = cur[h].rinv, ei = cur[h].ei;
+        double sum[2];
+        {   // the NW warp partials in a fixed order: four interleaved chains, then a fixed tree
+          const double2 *pp = reinterpret_cast<const double2 *>(L.part) + (hb * L.nw * kPH + h) * 32 + lane;
+          double2 c0 = make_double2(0, 0), c1 = c0, c2 = c0, c3 = c0;
           int w = 0;
           for (; w + 4 <= L.nw; w += 4) {
-            c0 += pp[(w + 0) * (kPR * T)]; c1 += pp[(w + 1) * (kPR * T)];
-            c2 += pp[(w + 2) * (kPR * T)]; c3 += pp[(w + 3) * (kPR * T)];
+            const double2 p0 = pp[(w + 0) * (kPH * 32)], p1 = pp[(w + 1) * (kPH * 32)], p2 = pp[(w + 2) * (kPH * 32)], p3 = pp[(w + 3) * (kPH * 32)];
+            c0.x += p0.x; c0.y += p0.y; c1.x += p1.x; c1.y += p1.y; c2.x += p2.x; c2.y += p2.y; c3.x += p3.x; c3.y += p3.y;
           }
-          for (; w < L.nw; w++) c0 += pp[w * (kPR * T)];
-          sum = (c0 + c1) + (c2 + c3);
+          for (; w < L.nw; w++) { const double2 p0 = pp[w * (kPH * 32)]; c0.x += p0.x; c0.y += p0.y; }
+          sum[0] = (c0.x + c1.x) + (c2.x + c3.x);
+          sum[1] = (c0.y + c1.y) + (c2.y + c3.y);
         }
-        double u = 0.0;
+        double u[2] = {0.0, 0.0};
         if (live) {
+          const double a0[2] = {cur[h].s0.x, cur[h].s0.y}, a1[2] = {cur[h].s1.x, cur[h].s1.y}, a2[2] = {cur[h].s2.x, cur[h].s2.y},
+                       a3[2] = {cur[h].s3.x, cur[h].s3.y};
           if constexpr (MODE == PM_M) {
-            const double xn = alpha * sum + oma * s0;
-            L.xs[ev] = xn; L.xts[ev] = sum;
-            if (do_check) W.gdx[e] = xn - s0;
+            const double xn0 = alpha * sum[0] + oma * a0[0], xn1 = alpha * sum[1] + oma * a0[1];
+            st2(W.gxs, xn0, xn1);
+            if (row >= jlo && row < jhi) reinterpret_cast<double2 *>(L.xts)[(row - jlo) * (T8 / 2) + tp] = make_double2(sum[0], sum[1]);
+            if (do_check) st2(W.gdx, xn0 - a0[0], xn1 - a0[1]);
           } else if constexpr (MODE == PM_A_ITER) {
-            const double zr = alpha * sum + oma * s0;
-            double zn = zr + rinv * s1;
-            zn = fmin(fmax(zn, s2), s3);
-            const double dy = rho * (zr - zn), yn = s1 + dy;
-            W.gz[e] = zn; W.gy[e] = yn;
-            if (do_check) W.gdy[e] = dy;
-            u = fma(rho, zn, -yn);
+            double zn[2], yn[2], dy[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const double zr = alpha * sum[i] + oma * a0[i];
+              double z = zr + rinv * a1[i];
+              z = fmin(fmax(z, a2[i]), a3[i]);
+              dy[i] = rho * (zr - z); yn[i] = a1[i] + dy[i]; zn[i] = z;
+              u[i] = fma(rho, z, -yn[i]);
+            }
+            st2(W.gz, zn[0], zn[1]); st2(W.gy, yn[0], yn[1]);
+            if (do_check) st2(W.gdy, dy[0], dy[1]);
           } else if constexpr (MODE == PM_A_INIT) {
-            W.gz[e] = sum;
-            u = fma(rho, sum, -s1);
+            st2(W.gz, sum[0], sum[1]);
+            u[0] = fma(rho, sum[0], -a1[0]); u[1] = fma(rho, sum[1], -a1[1]);
           } else if constexpr (MODE == PM_A_RESUME) {
-            u = fma(rho, s0, -s1);
+            u[0] = fma(rho, a0[0], -a1[0]); u[1] = fma(rho, a0[1], -a1[1]);
           } else if constexpr (MODE == PM_A_CHK1) {
-            R.pr = fmax(R.pr, fabs(ei * (sum - s0)));
-            R.a1 = fmax(R.a1, fabs(ei * sum));
-            R.a2 = fmax(R.a2, fabs(ei * s0));
-            u = s1;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              R.pr[i] = fmax(R.pr[i], fabs(ei * (sum[i] - a0[i])));
+              R.a1[i] = fmax(R.a1[i], fabs(ei * sum[i]));
+              R.a2[i] = fmax(R.a2[i], fabs(ei * a0[i]));
+              u[i] = a1[i];
+            }
           } else if constexpr (MODE == PM_A_CHK2) {
-            const double v = ei * sum;
-            if (s3 < kInfty * kMinScaling) R.vu = fmax(R.vu, v);
-            if (s2 > -kInfty * kMinScaling) R.vl = fmin(R.vl, v);
-            double d = s0;
-            if (s3 > kInfty * kMinScaling) {
-              if (s2 < -kInfty * kMinScaling) d = 0.0; else d = fmin(d, 0.0);
-            } else if (s2 < -kInfty * kMinScaling) d = fmax(d, 0.0);
-            R.ndy = fmax(R.ndy, fabs(rho * d));       // rho holds E[row] in this mode
-            R.lhs += s3 * fmax(d, 0.0) + s2 * fmin(d, 0.0);
-            u = d;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const double v = ei * sum[i];
+              if (a3[i] < kInfty * kMinScaling) R.vu[i] = fmax(R.vu[i], v);
+              if (a2[i] > -kInfty * kMinScaling) R.vl[i] = fmin(R.vl[i], v);
+              double d = a0[i];
+              if (a3[i] > kInfty * kMinScaling) {
+                if (a2[i] < -kInfty * kMinScaling) d = 0.0; else d = fmin(d, 0.0);
+              } else if (a2[i] < -kInfty * kMinScaling) d = fmax(d, 0.0);
+              R.ndy[i] = fmax(R.ndy[i], fabs(rho * d));       // rho holds E[row] in this mode
+              R.lhs[i] += a3[i] * fmax(d, 0.0) + a2[i] * fmin(d, 0.0);
+              u[i] = d;
+            }
           } else if constexpr (MODE == PM_P_CHK) {
-            W.gpx[e] = sum;
-            u = s0;
+            st2(W.gpx, sum[0], sum[1]);
+            u[0] = a0[0]; u[1] = a0[1];
           } else if constexpr (MODE == PM_P_OBJ) {
-            R.quad += s0 * sum;
-            R.lin += s1 * s0;
+#pragma unroll
+            for (int i = 0; i < 2; i++) { R.quad[i] += a0[i] * sum[i]; R.lin[i] += rho * a0[i]; }   // rho holds q[row]
           }
         }
-        if constexpr (kPass2) { if (active) L.ubuf[gb * (kPR * T) + lane] = u; }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(L.ud + 8u * gb);
-          if constexpr (CS == 2) mbar_arrive_remote_relaxed(L.udp_r + 8u * gb);
-        }
+        if constexpr (kPass2) reinterpret_cast<double2 *>(L.ubuf)[hb * (kPR * T8 / 2) + h * 32 + lane] = make_double2(u[0], u[1]);
       }
-      g++;
-      if (++gb == kHB) { gb = 0; gph ^= 1u; }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(L.ud + 8u * hb);
+        if constexpr (CS == 2) mbar_arrive_remote_relaxed(L.udp_r + 8u * hb);
+      }
+      if constexpr (kHBmul == 1) { ph ^= 1u; } else { if (bsel) ph ^= 1u; bsel ^= 1; }
     }
+    gb = (gb + npanels) % KU;
   }
 };
 
-template <int T, int LAG, int CS>
+template <int LAG, int CS>
 __global__ void __launch_bounds__(kPanelThreads, 1)
 admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                   double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
                   int *__restrict__ tile_iters, int nslots, double *__restrict__ state, int prefetch_panels) {
   constexpr int KU = kPanelUpdWarps;
+  constexpr int T = T8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = CS == 2 ? cluster_ctarank() : 0u, peer = rank ^ 1u;
@@ -447,7 +453,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     S.I = insts[S.tile.inst];
     S.remaining = S.tile.nn;
   }
-  if (tid < 4) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
+  if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
   __syncthreads();
   const DevInstance &I = S.I;
   const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, NW = I.p_nw;
@@ -456,7 +462,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   // this CTA's share of the column tiles
   const int nwh = CS == 2 ? (NW + 1) / 2 : NW;
   const int w0 = rank == 0 ? 0 : nwh, NWc = rank == 0 ? nwh : NW - nwh;
-  const int slot_bytes = NWc * (kPR * 32 * 8);
+  const int slot_bytes = NWc * (kTileDoubles * 8);
   const int nwslots = (int)(blockDim.x >> 5) - KU - 1;     // consumer warp slots of this launch
   const int nthr_cu = (NWc + KU) * 32, nthr_all = (NWc + KU + 1) * 32;
   const bool is_consumer = warp < NWc, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
@@ -468,13 +474,12 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   L.ck = L.udp + 8u * kHB;
   off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * kHB + 1);
   off = (off + 15) & ~size_t(15);
-  L.xs = reinterpret_cast<double *>(smem_raw + off);
-  L.xts = L.xs + (size_t)np * T;
-  L.vs = L.xts + (size_t)np * T;
-  L.part = L.vs + (size_t)np * T;
-  L.ubuf = L.part + (size_t)kHB * NW * kPR * T;
+  L.xts = reinterpret_cast<double *>(smem_raw + off);
+  L.vs = L.xts + (size_t)nwh * 32 * T;
+  L.part = L.vs + (size_t)nwh * 32 * T;
+  L.ubuf = L.part + (size_t)kHB * NW * 64 * kPH;
   L.red = L.ubuf + (size_t)kHB * kPR * T;
-  off += ((size_t)3 * np * T + (size_t)kHB * NW * kPR * T + (size_t)kHB * kPR * T + (size_t)kColQ * NW * T) * 8;
+  off += ((size_t)2 * nwh * 32 * T + (size_t)kHB * NW * 64 * kPH + (size_t)kHB * kPR * T + (size_t)kColQ * NW * T) * 8;
   off = (off + 127) & ~size_t(127);
   L.ring = smem_raw + off;
   L.ring_u32 = smem_u32(L.ring);
@@ -497,8 +502,8 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   if (!is_consumer && !is_update && !is_producer) return;            // CTA sized for the widest problem of the launch
 
   const int max_iter = I.max_iter, check_every = I.check_every;
-  const double *pM = I.pstream + (size_t)w0 * (kPR * 32), *pA = I.pstream + I.p_offA + (size_t)w0 * (kPR * 32),
-               *pP = I.pstream + I.p_offP + (size_t)w0 * (kPR * 32);
+  const double *pM = I.pstream + (size_t)w0 * kTileDoubles, *pA = I.pstream + I.p_offA + (size_t)w0 * kTileDoubles,
+               *pP = I.pstream + I.p_offP + (size_t)w0 * kTileDoubles;
 
   // =============================================================== producer warp: mirror of the pass sequence
   if (is_producer) {
@@ -537,27 +542,29 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   // =============================================================== consumers + update warps
   WorkPtrs W;
   {
-    const size_t m8 = (size_t)((m + 7) & ~7);
-    double *p = work + S.tile.work_off + (size_t)rank * panel_work_doubles(np, m, T);   // each CTA of a pair keeps its own copy
+    const size_t m8 = (size_t)((m + kPR - 1) / kPR * kPR);
+    double *p = work + S.tile.work_off + (size_t)rank * panel_work_doubles(np, m);   // each CTA of a pair keeps its own copy
     W.gz = p; p += m8 * T; W.gy = p; p += m8 * T; W.gl = p; p += m8 * T; W.gu = p; p += m8 * T; W.gdy = p; p += m8 * T;
     W.gdx = p; p += (size_t)np * T; W.gpx = p; p += (size_t)np * T; W.gaty = p; p += (size_t)np * T;
-    W.gatd = p; p += (size_t)np * T; W.gpdx = p; p += (size_t)np * T; W.gsx = p;
+    W.gatd = p; p += (size_t)np * T; W.gpdx = p; p += (size_t)np * T; W.gxs = p; p += (size_t)np * T; W.gsx = p;
   }
   const double sigma = I.sigma;
   const int ctid = is_consumer ? tid : NWc * 32 + (tid - nwslots * 32);   // dense index over consumer + update threads
 
   // ---- prologue (node.py:102-105): bounds, warm start (or the saved state of a resumed round)
-  for (int e = ctid; e < m * T; e += nthr_cu) {
+  for (int e = ctid; e < (m + kPR - 1) / kPR * kPR * T; e += nthr_cu) {
     const int i = e / T, t = e - i * T;
-    double lo = -kInfty, up = kInfty, yv = 0.0, zv = 0.0;
-    if (t < nn) {
-      const double *p = in + S.tile.in_off[t];
-      lo = fmax(p[i], -kInfty);
-      up = fmin(p[m + i], kInfty);
-      if (iter_begin == 0) yv = I.c * __ldg(I.Einv + i) * p[2 * (size_t)m + n + i];
-      else { const double *sp = state + S.tile.state_off[t] + n; zv = sp[i]; yv = sp[m + i]; }
+    double lo = -kInfty, up = kInfty, yv = 0.0, zv = 0.0, ei = 1.0;
+    if (i < m) {
+      if (t < nn) {
+        const double *p = in + S.tile.in_off[t];
+        lo = fmax(p[i], -kInfty);
+        up = fmin(p[m + i], kInfty);
+        if (iter_begin == 0) yv = I.c * __ldg(I.Einv + i) * p[2 * (size_t)m + n + i];
+        else { const double *sp = state + S.tile.state_off[t] + n; zv = sp[i]; yv = sp[m + i]; }
+      }
+      ei = __ldg(I.E + i);
     }
-    const double ei = __ldg(I.E + i);
     W.gl[e] = ei * lo; W.gu[e] = ei * up; W.gy[e] = yv; W.gz[e] = zv;
   }
   for (int e = ctid; e < np * T; e += nthr_cu) {
@@ -565,7 +572,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     double xv = 0.0;
     if (j < n && t < nn)
       xv = iter_begin == 0 ? __ldg(I.Dinv + j) * in[S.tile.in_off[t] + 2 * (size_t)m + j] : state[S.tile.state_off[t] + j];
-    L.xs[vidx<T>(j, t)] = xv; L.xts[e] = 0.0;
+    W.gxs[e] = xv;
   }
   named_bar(2, nthr_cu);
 
@@ -626,7 +633,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       const bool bad = !(st == BQP_SOLVED || st == BQP_SOLVED_INACCURATE || st == BQP_MAX_ITER_REACHED);
       double *ox = out + S.tile.out_off[t], *oy = ox + n, *sx = W.gsx + (size_t)t * np;
       for (int j = ctid; j < n; j += nthr_cu) {
-        const double v = bad ? NAN : __ldg(I.D + j) * L.xs[vidx<T>(j, t)];
+        const double v = bad ? NAN : __ldg(I.D + j) * W.gxs[(size_t)j * T + t];
         sx[j] = v;
         if (rank == 0) ox[j] = v;
       }
@@ -641,7 +648,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       for (int t = 0; t < nn; t++) {
         if (S.status[t] != BQP_UNSOLVED) continue;
         double *sp = state + S.tile.state_off[t];
-        for (int j = ctid; j < n; j += nthr_cu) sp[j] = L.xs[vidx<T>(j, t)];
+        for (int j = ctid; j < n; j += nthr_cu) sp[j] = W.gxs[(size_t)j * T + t];
         for (int i = ctid; i < m; i += nthr_cu) { sp[n + i] = W.gz[(size_t)i * T + t]; sp[n + m + i] = W.gy[(size_t)i * T + t]; }
         if (ctid == 0) { NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.pri_res = r.dua_res = r.lower = NAN; ns[S.tile.node[t]] = r; }
       }
@@ -660,33 +667,39 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       }
     }
     named_bar(2, nthr_cu);
-    for (int e = ctid; e < np * T; e += nthr_cu) {
+    for (int e = ctid; e < np * T; e += nthr_cu) {   // the x state is saved: its buffer takes the objective operand
       const int j = e / T, t = e - j * T;
       double v = 0.0;
       if (j < n && t < nn) {
         const int st = S.status[t];
         if (st == BQP_SOLVED || st == BQP_MAX_ITER_REACHED) v = __ldg(I.Dinv + j) * W.gsx[(size_t)t * np + j];
       }
-      L.xs[vidx<T>(j, t)] = v;
+      W.gxs[e] = v;
     }
     named_bar(1, nthr_all);                            // with the producer: epilogue operands ready
   };
 
   if (is_update) {
     // ============================================================= update warps
-    Updater<T, CS> U;
-    U.L = L; U.lane = lane; U.uw = warp - nwslots; U.g = 0; U.gb = 0; U.cls = 0; U.gph = 0; U.active = lane < kPR * T;
+    Updater<CS> U;
+    U.L = L; U.lane = lane; U.uw = warp - nwslots; U.gb = 0; U.cls = 0; U.ph = 0; U.bsel = 0;
     uint32_t ck_ph = 0;
     RowAcc R;
-    auto reset = [&]() { R.pr = R.a1 = R.a2 = R.ndy = R.lhs = R.quad = R.lin = 0.0; R.vu = -INFINITY; R.vl = INFINITY; };
+    auto reset = [&]() {
+#pragma unroll
+      for (int i = 0; i < 2; i++) { R.pr[i] = R.a1[i] = R.a2[i] = R.ndy[i] = R.lhs[i] = R.quad[i] = R.lin[i] = 0.0; R.vu[i] = -INFINITY; R.vl[i] = INFINITY; }
+    };
     // this warp's row-space accumulators -> finp (one value per node)
     auto publish_rows = [&](int cls_sum) {
-      const double v[kFinP] = {reduce_same_node<T, 0>(R.pr), reduce_same_node<T, 0>(R.a1), reduce_same_node<T, 0>(R.a2),
-                               reduce_same_node<T, 0>(R.ndy), reduce_same_node<T, 1>(R.lhs), reduce_same_node<T, 0>(R.vu),
-                               reduce_same_node<T, 2>(R.vl), reduce_same_node<T, 1>(R.quad), reduce_same_node<T, 1>(R.lin)};
-      if (lane < T) {   // maxima / minima: any order; sums (q = 4 lhs, 7 quad, 8 lin): by the class of the pass that made them
 #pragma unroll
-        for (int q = 0; q < kFinP; q++) S.finp[(q == 4 || q == 7 || q == 8) ? cls_sum : U.uw][q][lane] = v[q];
+      for (int i = 0; i < 2; i++) {
+        const double v[kFinP] = {reduce_rows<0>(R.pr[i]), reduce_rows<0>(R.a1[i]), reduce_rows<0>(R.a2[i]), reduce_rows<0>(R.ndy[i]),
+                                 reduce_rows<1>(R.lhs[i]), reduce_rows<0>(R.vu[i]), reduce_rows<2>(R.vl[i]), reduce_rows<1>(R.quad[i]),
+                                 reduce_rows<1>(R.lin[i])};
+        if (lane < 4) {   // maxima / minima: any order; sums (q = 4 lhs, 7 quad, 8 lin): by the class of the pass that made them
+#pragma unroll
+          for (int q = 0; q < kFinP; q++) S.finp[(q == 4 || q == 7 || q == 8) ? cls_sum : U.uw][q][2 * lane + i] = v[q];
+        }
       }
     };
     reset();
@@ -755,75 +768,68 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   }
 
   // =============================================================== consumer warps
-  Consumer<T, LAG, CS> C;
-  C.L = L; C.cw = warp; C.lane = lane; C.rg = lane >> 3; C.cg = lane & 7;
+  Consumer<LAG, CS> C;
+  C.L = L; C.cw = warp; C.lane = lane;
+#ifdef BQP_PANEL_TIMERS
+  for (int i = 0; i < 8; i++) C.tacc[i] = 0;
+  C.tlast = clock64();
+#endif
   C.slot = 0; C.slot2 = 0; C.phase = 0; C.g = 0; C.gb = 0; C.ud_g = 0; C.ud_b = 0; C.ud_ph = 0; C.up_g = 0; C.up_b = 0; C.up_ph = 0;
-  C.writer = T >= 4 ? true : (T == 2 ? (lane & 4) == 0 : (lane & 6) == 0);
   const int wg = w0 + warp;      // this warp's column tile
-  double acc[4][T];
-  // b' = sigma x - q + A'(rho z - y) for this warp's columns, from the pass-2 accumulators, into vs (read back by the
-  // same warp only: the M pass input)
+  const int gq = lane >> 2, tq = lane & 3;
+  const int jcol0 = 32 * w0;     // first column held in xts / vs
+  double acc[4][2];
+  // b' = sigma x - q + A'(rho z - y) for this warp's columns, from the pass-2 accumulators (C fragments), into vs (read
+  // back as B fragments by the same warp only: the M pass input)
   auto finalize_b = [&]() {
-    C.allreduce_rg(acc);
-    if (C.rg == 0) {
-      const int c0 = C.col0();
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int j = c0 + b;
-        const double qj = j < n ? __ldg(I.q + j) : 0.0;
-#pragma unroll
-        for (int t = 0; t < T; t++) L.vs[vidx<T>(j, t)] = j < n ? sigma * L.xs[vidx<T>(j, t)] - qj + acc[b][t] : 0.0;
+    for (int mt = 0; mt < 4; mt++) {
+      const int j = 32 * wg + 8 * mt + gq;
+      double b0 = 0.0, b1 = 0.0;
+      if (j < n) {
+        const double qj = __ldg(I.q + j);
+        const double2 xx = reinterpret_cast<const double2 *>(W.gxs)[j * (T / 2) + tq];
+        b0 = sigma * xx.x - qj + acc[mt][0];
+        b1 = sigma * xx.y - qj + acc[mt][1];
       }
-    }
-    __syncwarp();
-  };
-  // this warp's columns of a workspace vector staged into xts (x~ is dead by then)
-  auto stage_cols = [&](const double *gvec) {
-    if (C.rg == 0) {
-      const int c0 = C.col0();
-#pragma unroll
-      for (int b = 0; b < 4; b++)
-#pragma unroll
-        for (int t = 0; t < T; t++) L.xts[vidx<T>(c0 + b, t)] = gvec[(size_t)(c0 + b) * T + t];
+      reinterpret_cast<double2 *>(L.vs)[(j - jcol0) * (T / 2) + tq] = make_double2(b0, b1);
     }
     __syncwarp();
   };
   auto store_cols = [&](double *gvec) {
-    if (C.rg == 0) {
-      const size_t o = (size_t)C.col0() * T;
 #pragma unroll
-      for (int b = 0; b < 4; b++)
-#pragma unroll
-        for (int t = 0; t < T; t++) gvec[o + b * T + t] = acc[b][t];
+    for (int mt = 0; mt < 4; mt++) {
+      const int j = 32 * wg + 8 * mt + gq;
+      reinterpret_cast<double2 *>(gvec)[j * (T / 2) + tq] = make_double2(acc[mt][0], acc[mt][1]);
     }
     __syncwarp();
   };
-  zero4<T>(acc);
-  C.template pass<true>(npa, L.xs, acc);            // z = A x0 (first round) ; A'(rho z - y)
+  zero4(acc);
+  C.template pass<true>(npa, W.gxs, 0, acc);        // z = A x0 (first round) ; A'(rho z - y)
   finalize_b();
   int iter;
   for (iter = iter_begin + 1; iter <= iter_end; iter++) {
     const bool do_check = (iter % check_every == 0) || iter == max_iter;
-    C.template pass<false>(npm, L.vs, acc);         // x~ = M b  (acc untouched)
+    C.template pass<false>(npm, L.vs, jcol0, acc);  // x~ = M b  (acc untouched)
     C.wait_ud(C.g - 1);                             // every row of x~ is in xts
-    zero4<T>(acc);
-    C.template pass<true>(npa, L.xts, acc);         // z~ = A x~ ; b' += A' w
+    zero4(acc);
+    C.template pass<true>(npa, L.xts, jcol0, acc);  // z~ = A x~ ; b' += A' w
     finalize_b();
     if (!do_check) continue;
 
     // ---- termination check (update_info + check_termination): A x, A'y | A dx, A'dy | P x, P dx   (b' stays in vs)
-    zero4<T>(acc);
-    C.template pass<true>(npa, L.xs, acc);
-    C.allreduce_rg(acc); store_cols(W.gaty);
-    stage_cols(W.gdx); zero4<T>(acc);
-    C.template pass<true>(npa, L.xts, acc);
-    C.allreduce_rg(acc); store_cols(W.gatd);
-    zero4<T>(acc);
-    C.template pass<true>(npm, L.xs, acc);
-    C.allreduce_rg(acc); store_cols(W.gpdx);
+    zero4(acc);
+    C.template pass<true>(npa, W.gxs, 0, acc);
+    store_cols(W.gaty);
+    zero4(acc);
+    C.template pass<true>(npa, W.gdx, 0, acc);
+    store_cols(W.gatd);
+    zero4(acc);
+    C.template pass<true>(npm, W.gxs, 0, acc);
+    store_cols(W.gpdx);
     {
-      // column-space quantities: lane <-> column 32 * (column tile) + lane (the same partition for every tile width).
-      // Everything read here was written by this warp (store_cols) or by update warps whose panels it has waited for.
+      // column-space quantities: lane <-> column 32 * (column tile) + lane.  Everything read here was written by this
+      // warp (store_cols) or by update warps whose panels it has waited for.
       const int j = wg * 32 + lane;
       const bool inr = j < n;
       const double di = inr ? __ldg(I.Dinv + j) : 0.0, dj = inr ? __ldg(I.D + j) : 0.0, qj = inr ? __ldg(I.q + j) : 0.0;
@@ -834,10 +840,9 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
           if constexpr (CS == 2) st_async_remote_f64(L.red_r + 8u * ri, v, L.ck_r);
         }
       };
-#pragma unroll
       for (int t = 0; t < T; t++) {
         const size_t e = (size_t)j * T + t;
-        const double px = inr ? W.gpx[e] : 0.0, aty = inr ? W.gaty[e] : 0.0, xj = inr ? L.xs[vidx<T>(j, t)] : 0.0,
+        const double px = inr ? W.gpx[e] : 0.0, aty = inr ? W.gaty[e] : 0.0, xj = inr ? W.gxs[e] : 0.0,
                      dxj = inr ? W.gdx[e] : 0.0, atd = inr ? W.gatd[e] : 0.0, pdx = inr ? W.gpdx[e] : 0.0;
         put(0, t, reduce_warp<0>(fabs(di * (px + qj + aty))));
         put(1, t, reduce_warp<0>(fabs(di * px)));
@@ -860,28 +865,35 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     if (S.remaining == 0 || iter == iter_end) break;
   }
   finish_common(iter);
-  C.template pass<false>(npm, L.xs, acc);           // P x at the clipped point (sums taken by the update warps)
+  C.template pass<false>(npm, W.gxs, 0, acc);       // P x at the clipped point (sums taken by the update warps)
   C.wait_ud(C.g - 1); C.wait_udp(C.g - 1);   // the update warps of both CTAs are done with our partials: safe to leave the cluster
+#ifdef BQP_PANEL_TIMERS
+  if (lane == 0 && blockIdx.x == 0 && warp < 2) {
+    printf("warp %d panels %d:", warp, C.g);
+    for (int i = 0; i < 8; i++) printf(" t%d=%.0f", i, (double)C.tacc[i] / C.g);
+    printf("\n");
+  }
+#endif
 }
 
 }  // namespace
 
-size_t panel_smem_bytes(int npad, int tt, int nslots, int cs) {
+size_t panel_smem_bytes(int npad, int nslots, int cs) {
   const int nw = npad / 32;
-  const int nwc = cs == 2 ? (nw + 1) / 2 : nw;
+  const int nwh = cs == 2 ? (nw + 1) / 2 : nw;
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
   off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * (size_t)kHB + 1);
   off = (off + 15) & ~size_t(15);
-  off += ((size_t)3 * npad * tt + (size_t)kHB * nw * kPR * tt + (size_t)kHB * kPR * tt + (size_t)kColQ * nw * tt) * 8;
+  off += ((size_t)2 * nwh * 32 * T8 + (size_t)kHB * nw * 64 * kPH + (size_t)kHB * kPR * T8 + (size_t)kColQ * nw * T8) * 8;
   off = (off + 127) & ~size_t(127);
-  return off + (size_t)nslots * nwc * (kPR * 32 * 8);
+  return off + (size_t)nslots * nwh * (kTileDoubles * 8);
 }
 
-template <int T, int LAG, int CS>
+template <int LAG, int CS>
 static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                     const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem,
                     cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<T, LAG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<LAG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return BQP_E_CUDA;
   int prefetch_panels = 0;   // L2 prefetch distance of the producer, in panels (experiment knob)
   if (const char *pk = getenv("BQP_PANEL_PREFETCH")) prefetch_panels = atoi(pk);
@@ -895,24 +907,19 @@ static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, admm_panel_kernel<T, LAG, CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
+  e = cudaLaunchKernelEx(&cfg, admm_panel_kernel<LAG, CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
                          prefetch_panels);
   return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? BQP_OK : BQP_E_CUDA;
 }
 
-// cs = CTAs per tile (1, or 2 = a cluster pair splitting the columns).  Pass 2 runs two panels behind pass 1.
-int launch_admm_panel(int tt, int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+// cs = CTAs per tile (1, or 2 = a cluster pair splitting the columns).  Pass 2 runs one (16-row) panel behind pass 1.
+int launch_admm_panel(int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (nw_max < 1 || nw_max > kPanelMaxWarps || (cs != 1 && cs != 2) || (cs == 1 && nw_max > kPanelCtaWarps)) return BQP_E_ARG;
-#define BQP_PANEL_CASE(TT, CC)                                                                                              \
-  if (tt == TT && cs == CC)                                                                                                  \
-    return launch_p<TT, 2, CC>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  BQP_PANEL_CASE(1, 1) BQP_PANEL_CASE(2, 1) BQP_PANEL_CASE(4, 1)
-  BQP_PANEL_CASE(1, 2) BQP_PANEL_CASE(2, 2) BQP_PANEL_CASE(4, 2)
-#undef BQP_PANEL_CASE
-  return BQP_E_ARG;
+  if (cs == 1) return launch_p<1, 1>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  return launch_p<1, 2>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
 }
 
 }  // namespace bqp

@@ -313,18 +313,18 @@ void build_stream(HostInstance *h, const std::vector<Row> &arows, const std::vec
 namespace {
 
 // X: dense row-major rows x npad (rows beyond `rows` and columns beyond the data are zero) -> panels appended to pn.data
+// position of X[r][c] inside the panel stream of one matrix (bqp_internal.h: fragment-major tiles)
+inline size_t panel_pos(int r, int c, int npad) {
+  const int k = r / kPanelRows, rp = r % kPanelRows, h = rp >> 3, rr = rp & 7, w = c / 32, cc = c % 32;
+  return (size_t)k * kPanelRows * npad + (size_t)w * (kPanelRows * 32) + (size_t)h * 256 + (size_t)(cc >> 2) * 32 + (size_t)rr * 4 + (cc & 3);
+}
+
 void append_panels(HostPanels &pn, const std::vector<double> &X, int rows, int npad) {
-  const int npanels = (rows + kPanelRows - 1) / kPanelRows, nw = npad / 32;
+  const int npanels = (rows + kPanelRows - 1) / kPanelRows;
   const size_t base = pn.data.size();
   pn.data.resize(base + (size_t)npanels * kPanelRows * npad, 0.0);
-  for (int k = 0; k < npanels; k++)
-    for (int w = 0; w < nw; w++)
-      for (int b = 0; b < 4; b++)
-        for (int lane = 0; lane < 32; lane++)
-          for (int a = 0; a < 2; a++) {
-            const int r = k * kPanelRows + 2 * (lane >> 3) + a, c = 32 * w + 4 * (lane & 7) + b;
-            if (r < rows) pn.data[base + (size_t)k * kPanelRows * npad + (((size_t)w * 4 + b) * 32 + lane) * 2 + a] = X[(size_t)r * npad + c];
-          }
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < npad; c++) pn.data[base + panel_pos(r, c, npad)] = X[(size_t)r * npad + c];
 }
 
 // S: column-major npad x npad, unit-lower L22 strictly below the diagonal (after the LDL' above); D2inv its inverse pivots
@@ -694,11 +694,7 @@ int host_panel_kkt_solve(const HostInstance *h, double *rhs) {
   const HostPanels &pn = h->pn;
   if (!pn.built) return BQP_E_UNSUPPORTED;
   const int n = h->n, m = h->m, np_ = h->npad;
-  auto at = [&](long long off, int r, int c) -> double {
-    const int k = r / kPanelRows, rr = r % kPanelRows, w = c / 32, cc = c % 32;
-    const int lane = (rr >> 1) * 8 + (cc >> 2), b = cc & 3, a = rr & 1;
-    return pn.data[(size_t)off + (size_t)k * kPanelRows * np_ + (((size_t)w * 4 + b) * 32 + lane) * 2 + a];
-  };
+  auto at = [&](long long off, int r, int c) -> double { return pn.data[(size_t)off + panel_pos(r, c, np_)]; };
   std::vector<double> b(np_, 0.0), xt(np_, 0.0);
   for (int j = 0; j < n; j++) b[j] = rhs[j];
   for (int i = 0; i < m; i++) {
@@ -725,11 +721,7 @@ int host_panel_matvec_P(const HostInstance *h, const double *in, double *out) {
   const int np_ = h->npad;
   for (int r = 0; r < h->n; r++) {
     double acc = 0;
-    for (int c = 0; c < h->n; c++) {
-      const int k = r / kPanelRows, rr = r % kPanelRows, w = c / 32, cc = c % 32;
-      const int lane = (rr >> 1) * 8 + (cc >> 2), b = cc & 3, a = rr & 1;
-      acc = std::fma(pn.data[(size_t)pn.offP + (size_t)k * kPanelRows * np_ + (((size_t)w * 4 + b) * 32 + lane) * 2 + a], in[c], acc);
-    }
+    for (int c = 0; c < h->n; c++) acc = std::fma(pn.data[(size_t)pn.offP + panel_pos(r, c, np_)], in[c], acc);
     out[r] = acc;
   }
   return BQP_OK;

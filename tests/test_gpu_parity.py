@@ -167,7 +167,7 @@ def test_update_q(oracle_mod):
 
 
 # ---------------------------------------------------------------- fused single-pass panel kernel (bqp_panel.cu)
-@pytest.mark.parametrize("tt", [1, 2, 4])
+@pytest.mark.parametrize("tt", [1, 2, 4, 8])
 def test_panel_kernel_tile_widths(oracle_mod, tt):
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
@@ -195,7 +195,7 @@ def test_panel_kernel_cold_start_and_infeasible(oracle_mod):
     _close(r.y[0], yo[0])
 
 
-@pytest.mark.parametrize("tt", [1, 2, 4])
+@pytest.mark.parametrize("tt", [1, 4, 8])
 def test_panel_kernel_cluster_pair_uneven_split(oracle_mod, tt, monkeypatch):
     """n = 130 has 5 column tiles: forced onto a cluster pair, CTA 0 takes 3 and CTA 1 takes 2 of them"""
     monkeypatch.setenv("BQP_PANEL_CLUSTER", "2")
