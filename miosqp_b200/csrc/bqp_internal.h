@@ -80,7 +80,7 @@ struct HostStream {
 // conflicts).  The tiles of one panel are contiguous in w, so a CTA streaming columns [32 w0, 32 (w0+nwc)) of every
 // panel issues one TMA bulk copy per panel.  Matrices in stream order: M (npad rows), A (m rows padded to 8), P full
 // symmetric (npad rows; termination checks and the final objective only).
-constexpr int kPanelRows = 16;                      // two 8-row mma tiles: one hand-off to the update warps per 16 rows
+constexpr int kPanelRows = 8;                       // one 8-row mma tile per panel (16 also works: two tiles per hand-off)
 constexpr int kPanelT = 8;                          // nodes per tile of the panel kernel (N of the mma)
 constexpr int kPanelMaxWarps = 16;                  // column tiles of 32 (npad <= 512), one consumer warp each
 constexpr int kPanelCtaWarps = 8;                   // consumer warps per CTA; wider problems run as a cluster pair of CTAs

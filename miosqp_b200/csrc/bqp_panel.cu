@@ -45,7 +45,7 @@ constexpr int kPR = kPanelRows;
 constexpr int kColQ = 9;          // column-space reductions per termination check
 constexpr int kFin = 16;
 constexpr int kFinP = 9;          // row-space quantities each update warp accumulates
-constexpr int kHBmul = 1;
+constexpr int kHBmul = 2;
 constexpr int kHB = kHBmul * kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b % kPanelUpdWarps
 constexpr int kPH = kPanelRows / 8;            // 8-row mma tiles per panel
 constexpr int kPanelThreads = (kPanelCtaWarps + kPanelUpdWarps + 1) * 32;
@@ -85,7 +85,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+#ifdef BQP_PANEL_DEBUG
+    if (clock64() - t0 > 400000000LL) {
+      if ((threadIdx.x & 31) == 0) printf("TIMEOUT blk %d warp %d bar %u parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity);
+      __trap();
+    }
+#else
     if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz
+#endif
   }
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
@@ -109,9 +116,20 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 }
 // DSMEM store that signals the peer's mbarrier when it has landed (complete_tx of 8 bytes): data and notification in one
 // asynchronous operation, so the sender needs no cluster-scope fence
+__device__ __forceinline__ void st_remote_u32(uint32_t raddr, uint32_t v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_async_remote_f64(uint32_t raddr, double v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
 }
+// bulk DSMEM copy: `bytes` of this CTA's shared memory into the peer's, completing transaction bytes on the peer's mbarrier.
+// The source was written with ordinary stores: the writers fence the async proxy first (fence_async_smem).
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_remote, uint32_t src_local, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_remote),
+               "r"(src_local), "r"(bytes), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // D (8x8) += A (8x4, row) * B (4x8, col), FP64.  Fragments: A: lane holds A[lane>>2][lane&3]; B: B[lane&3][lane>>2];
 // C/D: rows lane>>2, columns 2*(lane&3), 2*(lane&3)+1.
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -125,40 +143,54 @@ struct PanelShared {
   double finp[kPanelUpdWarps][kFinP][T8];
   int status[T8], iters[T8], newly[T8];
   int remaining;
+  // panels finished by each update warp: [0] of this CTA, [1] of the peer CTA (written there over DSMEM).  The pass-1 warps
+  // poll these with plain shared-memory loads for flow control (a completed mbarrier try_wait costs ~200 cycles)
+  volatile int upd_cnt[2][kPanelUpdWarps];
 };
 
 // everything a role needs to find its way around shared memory (u32 = shared-window addresses; *_r = the same object in
 // the peer CTA of the pair, mapped with mapa)
 struct Lay {
-  uint32_t full, empty, pf, ud, udp, ck; // barrier arrays: [nslots], [nslots], [kHB], [kHB], [kHB], [1]
-  uint32_t pf_r, udp_r, ck_r, part_r, red_r;
+  uint32_t full, empty, pf, ud, udp, uc, ck; // barrier arrays: [nslots], [nslots], [kHB] x4, [1]
+  uint32_t pf_r, udp_r, ck_r, part_r, red_r, part_u32, cnt_r;   // cnt_r: upd_cnt[1] of the peer
+  volatile int *cnt;                                           // upd_cnt[0] of this CTA ([kPanelUpdWarps], then the peer's copy)
   double *xts, *vs;                      // x~ and b for THIS CTA's columns: [32 NWc][8]
   double *part, *ubuf, *red;             // [kHB][NW][32 lanes][2], [kHB][8 rows][8], [kColQ][NW][8]
   unsigned char *ring;
   uint32_t ring_u32;
   int nslots, slot_bytes, nw, nwc, w0, np;    // nw: column tiles of the problem; nwc, w0: this CTA's share
+  int npt, np1;                               // pass-1 warps (= partial sums per panel) of the pair / of this CTA
 };
 
 // LAG = how many panels pass 2 runs behind pass 1 (the update latency it hides), LAG < kHB.  CS = CTAs per tile.
-#ifdef BQP_PANEL_TIMERS
-#define TSTAMP(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+// Consumer warps are specialised by pass, so that the two warps sharing an SM sub-partition (and its FP64 mma pipe) are
+// naturally in different phases of the panel loop:
+//   P1 warps: pass 1 only.  Each owns up to two column tiles; its C fragment (8 rows x 8 nodes per mma tile) sums over
+//             both, so a panel yields one partial per P1 warp.
+//   P2 warps: pass 2 only, following the update warps panel by panel; each owns the accumulators of up to two column tiles.
+// Both walk the same ring of slots (a slot is released when every P1 and every P2 warp has arrived on its empty barrier).
+#ifdef BQP_PANEL_DEBUG
+#define TSTAMP(obj, i) do { const long long now_ = clock64(); (obj).tacc[i] += now_ - (obj).tlast; (obj).tlast = now_; } while (0)
 #else
-#define TSTAMP(i) do { } while (0)
+#define TSTAMP(obj, i) do { } while (0)
 #endif
-template <int LAG, int CS>
-struct Consumer {
-  static_assert(LAG < kHB, "pass 2 may lag at most kHB - 1 panels");
+template <int CS>
+struct ConsumerBase {
   Lay L;
-#ifdef BQP_PANEL_TIMERS
-  long long tacc[8], tlast;
+#ifdef BQP_PANEL_DEBUG
+  long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
 #endif
-  int cw, lane;
-  int slot; uint32_t phase;          // ring position of the next pass-1 panel
-  int slot2;                         // ring position of the next pass-2 panel
+  int lane, ntl, wg0;                // lane; column tiles of this warp (1 or 2) and the first of them (global index)
+  int tl0;                           // first tile, index inside this CTA's slot
+  int slot; uint32_t phase;          // ring position of the next panel
   int g, gb;                         // global panel counter (same sequence in the update warps), g % kHB
   int ud_g, ud_b; uint32_t ud_ph;    // next panel whose "update done" barrier this thread has not observed yet
   int up_g, up_b; uint32_t up_ph;    // the same for the peer CTA's update warps (flow control of the DSMEM partials)
 
+  __device__ __forceinline__ void init(const Lay &lay, int lane_, int tile0_local, int ntiles) {
+    L = lay; lane = lane_; tl0 = tile0_local; ntl = ntiles; wg0 = lay.w0 + tile0_local;
+    slot = 0; phase = 0; g = 0; gb = 0; ud_g = 0; ud_b = 0; ud_ph = 0; up_g = 0; up_b = 0; up_ph = 0;
+  }
   __device__ __forceinline__ void wait_ud(int target) {
     while (ud_g <= target) {
       mbar_wait(L.ud + 8u * ud_b, ud_ph);
@@ -175,97 +207,144 @@ struct Consumer {
       }
     }
   }
-  // one pass over `npanels` panels.  pass 1 multiplies with the column vector src ([column - src_col0][8 nodes]; this
-  // warp's 32 columns are held as 8 B fragments); with PASS2 the per-row values published by the update warps are
-  // multiplied back into acc (C fragments: column 32 wg + 8 mt + (lane >> 2), nodes 2 (lane & 3) + {0, 1}) LAG panels later.
-  template <bool PASS2>
-  __device__ __forceinline__ void pass(int npanels, const double *src, int src_col0, double (&acc)[4][2]) {
-    double acc1[4][2];     // second accumulator set of pass 2 (rows 4..7 of every panel): independent mma chains
+  __device__ __forceinline__ void advance() {
+    if (++slot == L.nslots) { slot = 0; phase ^= 1u; }
+    g++;
+    if (++gb == kHB) gb = 0;
+  }
+  // flow control by the update warps' progress counters: every panel < `upto` has been updated (in both CTAs of a pair)
+  __device__ __forceinline__ void wait_progress(int upto) {
+    if (upto <= 0) return;
+    const long long t0 = clock64();
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) { acc1[mt][0] = 0.0; acc1[mt][1] = 0.0; }
-    const int g0 = g;
-    const int wg = L.w0 + cw, gq = lane >> 2, tq = lane & 3;
-    double bx[8];
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) bx[ks] = src[(size_t)(32 * wg + 4 * ks + tq - src_col0) * T8 + gq];
-    // pass-2 A fragment (A' as the row operand): element (row 4 kk + tq, column 8 mt + gq) of the tile
-    const int a2 = (gq >> 2) * 32 + tq * 4 + (gq & 3);
-    int g2b = gb;
-    slot2 = slot;
-    const int nsteps = npanels + (PASS2 ? LAG : 0);
-    for (int k = 0; k < nsteps; k++) {
-      if (k < npanels) {
-        TSTAMP(7);
-        mbar_wait(L.full + 8u * slot, phase);
-        TSTAMP(0);
-        const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)slot * L.slot_bytes) + cw * kTileDoubles + lane;
-        // independent mma (their latency, not their issue rate, is what a dependent chain would pay), then a fixed tree
-        double c0[kPH][2];
-#pragma unroll
-        for (int h = 0; h < kPH; h++) {
-          double cc[8][2];
-#pragma unroll
-          for (int ks = 0; ks < 8; ks++) { cc[ks][0] = 0.0; cc[ks][1] = 0.0; dmma(cc[ks], sp[h * 256 + ks * 32], bx[ks]); }
-#pragma unroll
-          for (int i = 0; i < 2; i++) c0[h][i] = ((cc[0][i] + cc[1][i]) + (cc[2][i] + cc[3][i])) + ((cc[4][i] + cc[5][i]) + (cc[6][i] + cc[7][i]));
-        }
-        TSTAMP(1);
-        wait_ud(g - kHB); wait_udp(g - kHB);   // the update warps of both CTAs have consumed this partials buffer
-        TSTAMP(2);
-#pragma unroll
-        for (int h = 0; h < kPH; h++) {
-          const int pi = (((gb * L.nw + wg) * kPH + h) * 32 + lane) * 2;
-          *reinterpret_cast<double2 *>(L.part + pi) = make_double2(c0[h][0], c0[h][1]);
-          if constexpr (CS == 2) {
-            st_async_remote_f64(L.part_r + 8u * pi, c0[h][0], L.pf_r + 8u * gb);
-            st_async_remote_f64(L.part_r + 8u * pi + 8u, c0[h][1], L.pf_r + 8u * gb);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) {
-          // pair: the barrier also counts the bytes the peer's consumer warps store into our buffer (posted by warp 0)
-          if (CS == 2 && cw == 0) mbar_expect_tx(L.pf + 8u * gb, (uint32_t)((L.nw - L.nwc) * kPH * 32 * 16));
-          else mbar_arrive(L.pf + 8u * gb);
-          if (!PASS2) mbar_arrive(L.empty + 8u * slot);
-        }
-        if (++slot == L.nslots) { slot = 0; phase ^= 1u; }
-        g++;
-        if (++gb == kHB) gb = 0;
-        TSTAMP(3);
-      }
-      if (PASS2 && k >= LAG) {
-        wait_ud(g0 + k - LAG);
-        TSTAMP(4);
-        const double *up = L.ubuf + g2b * (kPR * T8);
-        const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)slot2 * L.slot_bytes) + cw * kTileDoubles + a2;
-#pragma unroll
-        for (int h = 0; h < kPH; h++) {
-          const double bu0 = up[(h * 8 + tq) * T8 + gq], bu1 = up[(h * 8 + 4 + tq) * T8 + gq];
-#pragma unroll
-          for (int mt = 0; mt < 4; mt++) {
-            dmma(acc[mt], sp[h * 256 + mt * 64], bu0);
-            dmma(acc1[mt], sp[h * 256 + mt * 64 + 16], bu1);
-          }
-        }
-        __syncwarp();
-        TSTAMP(5);
-        if (lane == 0) mbar_arrive(L.empty + 8u * slot2);
-        if (++slot2 == L.nslots) slot2 = 0;
-        if (++g2b == kHB) g2b = 0;
-        TSTAMP(6);
+    for (int u = 0; u < kPanelUpdWarps; u++) {
+      const int need = (upto - u + kPanelUpdWarps - 1) / kPanelUpdWarps;     // panels u, u + KU, ... below upto
+      while (L.cnt[u] < need || (CS == 2 && L.cnt[kPanelUpdWarps + u] < need)) {
+        if (clock64() - t0 > 20000000000LL) __trap();
       }
     }
-    if (PASS2) {
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++) { acc[mt][0] += acc1[mt][0]; acc[mt][1] += acc1[mt][1]; }
+  }
+  // a pass a pass-2 warp has no work in: keep its place in the ring, in the panel sequence and in the barrier phases
+  __device__ __forceinline__ void skip(int npanels) {
+    for (int k = 0; k < npanels; k++) {
+      wait_ud(g);
+      mbar_wait(L.full + 8u * slot, phase);
+      if (lane == 0) { mbar_arrive(L.empty + 8u * slot); mbar_arrive(L.uc + 8u * gb); }
+      advance();
     }
   }
 };
 
-__device__ __forceinline__ void zero4(double (&a)[4][2]) {
+template <int CS>
+struct P1Warp : ConsumerBase<CS> {
+  using B = ConsumerBase<CS>;
+  int pidx;                          // this warp's partial slot (index over the P1 warps of both CTAs)
+  // pass 1 over `npanels` panels with the column vector src ([column - src_col0][8 nodes])
+  __device__ __forceinline__ void pass(int npanels, const double *src, int src_col0) {
+    const Lay &L = B::L;
+    const int lane = B::lane, gq = lane >> 2, tq = lane & 3;
+    double bx[2][8];
 #pragma unroll
-  for (int b = 0; b < 4; b++) { a[b][0] = 0.0; a[b][1] = 0.0; }
-}
+    for (int tl = 0; tl < 2; tl++)
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++)
+        bx[tl][ks] = tl < B::ntl ? src[(size_t)(32 * (B::wg0 + tl) + 4 * ks + tq - src_col0) * T8 + gq] : 0.0;
+    for (int k = 0; k < npanels; k++) {
+      TSTAMP(*this, 5);
+      mbar_wait(L.full + 8u * B::slot, B::phase);
+      TSTAMP(*this, 0);
+      const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)B::slot * L.slot_bytes) + B::tl0 * kTileDoubles + lane;
+      double c0[kPH][2];
+#pragma unroll
+      for (int h = 0; h < kPH; h++) {
+        double cc[8][2];     // independent mma chains (two tiles deep), then a fixed tree
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) { cc[ks][0] = 0.0; cc[ks][1] = 0.0; dmma(cc[ks], sp[h * 256 + ks * 32], bx[0][ks]); }
+        if (B::ntl == 2) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) dmma(cc[ks], sp[kTileDoubles + h * 256 + ks * 32], bx[1][ks]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) c0[h][i] = ((cc[0][i] + cc[1][i]) + (cc[2][i] + cc[3][i])) + ((cc[4][i] + cc[5][i]) + (cc[6][i] + cc[7][i]));
+      }
+      TSTAMP(*this, 1);
+      if (B::g >= kHB) {   // the update warps of both CTAs have consumed this partials buffer (panel g - kHB)
+        const int pg = B::g - kHB, u = pg % kPanelUpdWarps, need = pg / kPanelUpdWarps + 1;
+        const long long t0 = clock64();
+        while (L.cnt[u] < need || (CS == 2 && L.cnt[kPanelUpdWarps + u] < need)) {
+          if (clock64() - t0 > 20000000000LL) __trap();
+        }
+      }
+      TSTAMP(*this, 2);
+      const int pw0 = ((B::gb * L.npt + pidx) * kPH) * 64;     // this warp's partial block (doubles): kPH x 32 lanes x 2
+#pragma unroll
+      for (int h = 0; h < kPH; h++)
+        *reinterpret_cast<double2 *>(L.part + pw0 + (h * 32 + lane) * 2) = make_double2(c0[h][0], c0[h][1]);
+      if constexpr (CS == 2) fence_async_smem();    // the bulk copy below reads these stores through the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        // the same block into the peer CTA's buffer: one bulk DSMEM copy, completing bytes on the peer's barrier
+        if constexpr (CS == 2) dsmem_bulk_copy(L.part_r + 8u * pw0, L.part_u32 + 8u * pw0, (uint32_t)(kPH * 32 * 16), L.pf_r + 8u * B::gb);
+        // pair: the barrier also counts the bytes the peer's P1 warps store into our buffer (posted by P1 warp 0)
+        if (CS == 2 && B::tl0 == 0) mbar_expect_tx(L.pf + 8u * B::gb, (uint32_t)((L.npt - L.np1) * kPH * 32 * 16));
+        else mbar_arrive(L.pf + 8u * B::gb);
+        mbar_arrive(L.empty + 8u * B::slot);
+      }
+      B::advance();
+      TSTAMP(*this, 3);
+    }
+  }
+};
+
+template <int CS>
+struct P2Warp : ConsumerBase<CS> {
+  using B = ConsumerBase<CS>;
+  // pass 2 over `npanels` panels: acc[tile][mt] (C fragments: column 32 wg + 8 mt + (lane >> 2), nodes 2 (lane & 3) + {0, 1})
+  // += A_panel' u, panel by panel as the update warps publish u
+  __device__ __forceinline__ void pass(int npanels, double (&acc)[2][4][2]) {
+    const Lay &L = B::L;
+    const int lane = B::lane, gq = lane >> 2, tq = lane & 3;
+    // A fragment of A' (row operand): element (row 4 kk + tq, column 8 mt + gq) of the tile
+    const int a2 = (gq >> 2) * 32 + tq * 4 + (gq & 3);
+    double acc1[2][4][2];     // second accumulator set (rows 4..7 of every mma tile): independent chains
+#pragma unroll
+    for (int tl = 0; tl < 2; tl++)
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) { acc[tl][mt][0] = acc[tl][mt][1] = 0.0; acc1[tl][mt][0] = acc1[tl][mt][1] = 0.0; }
+    for (int k = 0; k < npanels; k++) {
+      TSTAMP(*this, 5);
+      B::wait_ud(B::g);
+      TSTAMP(*this, 0);
+      mbar_wait(L.full + 8u * B::slot, B::phase);     // long complete: makes the TMA data visible to this warp
+      TSTAMP(*this, 1);
+      const double *up = L.ubuf + B::gb * (kPR * T8);
+      const double *sp = reinterpret_cast<const double *>(L.ring + (size_t)B::slot * L.slot_bytes) + B::tl0 * kTileDoubles + a2;
+#pragma unroll
+      for (int h = 0; h < kPH; h++) {
+        const double bu0 = up[(h * 8 + tq) * T8 + gq], bu1 = up[(h * 8 + 4 + tq) * T8 + gq];
+#pragma unroll
+        for (int tl = 0; tl < 2; tl++) {
+          if (tl < B::ntl) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+              dmma(acc[tl][mt], sp[tl * kTileDoubles + h * 256 + mt * 64], bu0);
+              dmma(acc1[tl][mt], sp[tl * kTileDoubles + h * 256 + mt * 64 + 16], bu1);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      TSTAMP(*this, 2);
+      if (lane == 0) { mbar_arrive(L.empty + 8u * B::slot); mbar_arrive(L.uc + 8u * B::gb); }   // slot and u buffer consumed
+      B::advance();
+      TSTAMP(*this, 3);
+    }
+#pragma unroll
+    for (int tl = 0; tl < 2; tl++)
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) { acc[tl][mt][0] += acc1[tl][mt][0]; acc[tl][mt][1] += acc1[tl][mt][1]; }
+  }
+};
 
 template <int OP>   // OP 0: max, 1: sum, 2: min
 __device__ __forceinline__ double red_op(double v, double w) { return OP == 0 ? fmax(v, w) : (OP == 1 ? v + w : fmin(v, w)); }
@@ -305,7 +384,11 @@ struct Updater {
   int lane, uw;
   int gb, cls;                       // global panel counter % kPanelUpdWarps at the start of the next pass; class of the last pass
   int bsel; uint32_t ph;             // this warp's next hand-off buffer is uw + kPanelUpdWarps * bsel, its phase parity ph
+  int done;                          // panels this warp has finished (published in upd_cnt)
   struct Pre { double2 s0, s1, s2, s3; double rho, rinv, ei; };
+#ifdef BQP_PANEL_DEBUG
+  long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0; int npan = 0;
+#endif
 
   template <int MODE>
   __device__ __forceinline__ void pass(const PanelShared &S, const WorkPtrs &W, int npanels, bool do_check, RowAcc &R) {
@@ -346,7 +429,11 @@ struct Updater {
 #pragma unroll
       for (int h = 0; h < kPH; h++) { cur[h] = nxt[h]; nxt[h] = load_state(k + KU, h); }
       const int hb = uw + KU * bsel;              // hand-off buffer of this panel
+      TSTAMP(*this, 5);
       mbar_wait(L.pf + 8u * hb, ph);
+      TSTAMP(*this, 0);
+      mbar_wait(L.uc + 8u * hb, ph ^ 1u);
+      TSTAMP(*this, 1);   // the pass-2 warps are done with this buffer's previous panel (u values, "update done" phase)
 #pragma unroll
       for (int h = 0; h < kPH; h++) {
         const int row = k * kPR + h * 8 + r;
@@ -355,15 +442,15 @@ struct Updater {
         auto st2 = [&](double *v, double a, double b) { reinterpret_cast<double2 *>(v)[e2] = make_double2(a, b); };
         const double rho = cur[h].rho, rinv = cur[h].rinv, ei = cur[h].ei;
         double sum[2];
-        {   // the NW warp partials in a fixed order: four interleaved chains, then a fixed tree
-          const double2 *pp = reinterpret_cast<const double2 *>(L.part) + (hb * L.nw * kPH + h) * 32 + lane;
+        {   // the pass-1 warps' partials in a fixed order: four interleaved chains, then a fixed tree
+          const double2 *pp = reinterpret_cast<const double2 *>(L.part) + (hb * L.npt * kPH + h) * 32 + lane;
           double2 c0 = make_double2(0, 0), c1 = c0, c2 = c0, c3 = c0;
           int w = 0;
-          for (; w + 4 <= L.nw; w += 4) {
+          for (; w + 4 <= L.npt; w += 4) {
             const double2 p0 = pp[(w + 0) * (kPH * 32)], p1 = pp[(w + 1) * (kPH * 32)], p2 = pp[(w + 2) * (kPH * 32)], p3 = pp[(w + 3) * (kPH * 32)];
             c0.x += p0.x; c0.y += p0.y; c1.x += p1.x; c1.y += p1.y; c2.x += p2.x; c2.y += p2.y; c3.x += p3.x; c3.y += p3.y;
           }
-          for (; w < L.nw; w++) { const double2 p0 = pp[w * (kPH * 32)]; c0.x += p0.x; c0.y += p0.y; }
+          for (; w < L.npt; w++) { const double2 p0 = pp[w * (kPH * 32)]; c0.x += p0.x; c0.y += p0.y; }
           sum[0] = (c0.x + c1.x) + (c2.x + c3.x);
           sum[1] = (c0.y + c1.y) + (c2.y + c3.y);
         }
@@ -428,15 +515,22 @@ struct Updater {
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(L.ud + 8u * hb);
-        if constexpr (CS == 2) mbar_arrive_remote_relaxed(L.udp_r + 8u * hb);
+        __threadfence_block();
+        done++;
+        L.cnt[uw] = done;
+        if constexpr (CS == 2) st_remote_u32(L.cnt_r + 4u * uw, (uint32_t)done);
       }
       if constexpr (kHBmul == 1) { ph ^= 1u; } else { if (bsel) ph ^= 1u; bsel ^= 1; }
+      TSTAMP(*this, 2);
+#ifdef BQP_PANEL_DEBUG
+      npan++;
+#endif
     }
     gb = (gb + npanels) % KU;
   }
 };
 
-template <int LAG, int CS>
+template <int CS>
 __global__ void __launch_bounds__(kPanelThreads, 1)
 admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                   double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
@@ -454,6 +548,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     S.remaining = S.tile.nn;
   }
   if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
+  if (tid < 2 * kPanelUpdWarps) S.upd_cnt[tid / kPanelUpdWarps][tid % kPanelUpdWarps] = 0;
   __syncthreads();
   const DevInstance &I = S.I;
   const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, NW = I.p_nw;
@@ -464,40 +559,50 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   const int w0 = rank == 0 ? 0 : nwh, NWc = rank == 0 ? nwh : NW - nwh;
   const int slot_bytes = NWc * (kTileDoubles * 8);
   const int nwslots = (int)(blockDim.x >> 5) - KU - 1;     // consumer warp slots of this launch
-  const int nthr_cu = (NWc + KU) * 32, nthr_all = (NWc + KU + 1) * 32;
-  const bool is_consumer = warp < NWc, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
+  const int np1 = (NWc + 1) / 2, ncons = 2 * np1;          // pass-1 warps = pass-2 warps of this CTA (two column tiles each)
+  const int np1_r0 = (nwh + 1) / 2, npt = np1_r0 + (CS == 2 ? (NW - nwh + 1) / 2 : 0);
+  const int nthr_cu = (ncons + KU) * 32, nthr_all = (ncons + KU + 1) * 32;
+  const bool is_consumer = warp < ncons, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
 
   Lay L;
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
   L.full = smem_u32(smem_raw + off);
   L.empty = L.full + 8u * nslots; L.pf = L.empty + 8u * nslots; L.ud = L.pf + 8u * kHB; L.udp = L.ud + 8u * kHB;
-  L.ck = L.udp + 8u * kHB;
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * kHB + 1);
+  L.uc = L.udp + 8u * kHB; L.ck = L.uc + 8u * kHB;
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4 * kHB + 1);
   off = (off + 15) & ~size_t(15);
   L.xts = reinterpret_cast<double *>(smem_raw + off);
   L.vs = L.xts + (size_t)nwh * 32 * T;
   L.part = L.vs + (size_t)nwh * 32 * T;
-  L.ubuf = L.part + (size_t)kHB * NW * 64 * kPH;
+  L.ubuf = L.part + (size_t)kHB * npt * 64 * kPH;
   L.red = L.ubuf + (size_t)kHB * kPR * T;
-  off += ((size_t)2 * nwh * 32 * T + (size_t)kHB * NW * 64 * kPH + (size_t)kHB * kPR * T + (size_t)kColQ * NW * T) * 8;
+  off += ((size_t)2 * nwh * 32 * T + (size_t)kHB * npt * 64 * kPH + (size_t)kHB * kPR * T + (size_t)kColQ * NW * T) * 8;
   off = (off + 127) & ~size_t(127);
   L.ring = smem_raw + off;
   L.ring_u32 = smem_u32(L.ring);
-  L.nslots = nslots; L.slot_bytes = slot_bytes; L.nw = NW; L.nwc = NWc; L.w0 = w0; L.np = np;
+  L.nslots = nslots; L.slot_bytes = slot_bytes; L.nw = NW; L.nwc = NWc; L.w0 = w0; L.np = np; L.npt = npt; L.np1 = np1;
   if constexpr (CS == 2) {
     L.pf_r = mapa(L.pf, peer); L.udp_r = mapa(L.udp, peer); L.ck_r = mapa(L.ck, peer);
     L.part_r = mapa(smem_u32(L.part), peer); L.red_r = mapa(smem_u32(L.red), peer);
+    L.part_u32 = smem_u32(L.part);
+    L.cnt_r = mapa(smem_u32(const_cast<int *>(&S.upd_cnt[1][0])), peer);
   } else {
-    L.pf_r = L.udp_r = L.ck_r = L.part_r = L.red_r = 0;
+    L.pf_r = L.udp_r = L.ck_r = L.part_r = L.red_r = L.part_u32 = L.cnt_r = 0;
   }
+  L.cnt = &S.upd_cnt[0][0];
   if (tid == 0) {
-    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, NWc); }
-    // "partials full" / check barriers: one arrival per LOCAL consumer warp; the peer's share arrives as transaction bytes
-    for (int s = 0; s < kHB; s++) { mbar_init(L.pf + 8u * s, NWc); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); }
-    mbar_init(L.ck, NWc);
+    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, ncons); }
+    // "partials full" / check barriers: one arrival per LOCAL pass-1 / pass-2 warp; the peer's share arrives as transaction bytes
+    for (int s = 0; s < kHB; s++) {
+      mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); mbar_init(L.uc + 8u * s, np1);
+    }
+    mbar_init(L.ck, np1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+#ifdef BQP_PANEL_DEBUG
+  if (tid == 0 && blockIdx.x == 0) printf("LAYOUT full %u empty %u pf %u ud %u udp %u ck %u nslots %d np1 %d npt %d ncons %d NWc %d\n", L.full, L.empty, L.pf, L.ud, L.udp, L.ck, nslots, np1, npt, ncons, NWc);
+#endif
   if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs exist before anyone arrives
   if (!is_consumer && !is_update && !is_producer) return;            // CTA sized for the widest problem of the launch
 
@@ -549,7 +654,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     W.gatd = p; p += (size_t)np * T; W.gpdx = p; p += (size_t)np * T; W.gxs = p; p += (size_t)np * T; W.gsx = p;
   }
   const double sigma = I.sigma;
-  const int ctid = is_consumer ? tid : NWc * 32 + (tid - nwslots * 32);   // dense index over consumer + update threads
+  const int ctid = is_consumer ? tid : ncons * 32 + (tid - nwslots * 32);   // dense index over consumer + update threads
 
   // ---- prologue (node.py:102-105): bounds, warm start (or the saved state of a resumed round)
   for (int e = ctid; e < (m + kPR - 1) / kPR * kPR * T; e += nthr_cu) {
@@ -682,7 +787,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   if (is_update) {
     // ============================================================= update warps
     Updater<CS> U;
-    U.L = L; U.lane = lane; U.uw = warp - nwslots; U.gb = 0; U.cls = 0; U.ph = 0; U.bsel = 0;
+    U.L = L; U.lane = lane; U.uw = warp - nwslots; U.gb = 0; U.cls = 0; U.ph = 0; U.bsel = 0; U.done = 0;
     uint32_t ck_ph = 0;
     RowAcc R;
     auto reset = [&]() {
@@ -754,6 +859,11 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     finish_common(iter);
     reset();
     U.template pass<PM_P_OBJ>(S, W, npm, false, R);
+#ifdef BQP_PANEL_DEBUG
+    if (lane == 0 && blockIdx.x == 0 && U.uw == 0)
+      printf("UPD panels %d: pf-wait %.0f uc-wait %.0f compute %.0f loop %.0f\n", U.npan, (double)U.tacc[0] / U.npan, (double)U.tacc[1] / U.npan,
+             (double)U.tacc[2] / U.npan, (double)U.tacc[5] / U.npan);
+#endif
     publish_rows(U.cls);
     named_bar(3, KU * 32);
     if (U.uw == 0 && lane < nn && rank == 0) {
@@ -767,70 +877,102 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     return;
   }
 
-  // =============================================================== consumer warps
-  Consumer<LAG, CS> C;
-  C.L = L; C.cw = warp; C.lane = lane;
-#ifdef BQP_PANEL_TIMERS
-  for (int i = 0; i < 8; i++) C.tacc[i] = 0;
-  C.tlast = clock64();
-#endif
-  C.slot = 0; C.slot2 = 0; C.phase = 0; C.g = 0; C.gb = 0; C.ud_g = 0; C.ud_b = 0; C.ud_ph = 0; C.up_g = 0; C.up_b = 0; C.up_ph = 0;
-  const int wg = w0 + warp;      // this warp's column tile
-  const int gq = lane >> 2, tq = lane & 3;
+  // =============================================================== consumer warps (pass-1 warps, then pass-2 warps)
   const int jcol0 = 32 * w0;     // first column held in xts / vs
-  double acc[4][2];
+  const int gq = lane >> 2, tq = lane & 3;
+  const int ncthr = ncons * 32;
+  int iter;
+  if (warp < np1) {
+    // ------------------------------------------------------------- pass-1 warp
+    P1Warp<CS> C;
+    C.init(L, lane, 2 * warp, min(2, NWc - 2 * warp));
+    C.pidx = (rank == 0 ? 0 : np1_r0) + warp;
+    C.pass(npa, W.gxs, 0);                            // z = A x0 (first round)
+    named_bar(4, ncthr);                              // b' of the pass-2 warps is in vs
+    for (iter = iter_begin + 1; iter <= iter_end; iter++) {
+      const bool do_check = (iter % check_every == 0) || iter == max_iter;
+      C.pass(npm, L.vs, jcol0);                       // x~ = M b
+      C.wait_progress(C.g); __threadfence_block();    // every row of x~ is in xts
+      C.pass(npa, L.xts, jcol0);                      // z~ = A x~
+      named_bar(4, ncthr);
+      if (!do_check) continue;
+      // termination check (update_info + check_termination): A x | A dx | P x
+      C.pass(npa, W.gxs, 0);
+      C.pass(npa, W.gdx, 0);
+      C.pass(npm, W.gxs, 0);
+      named_bar(2, nthr_cu);     // decision made
+      snapshot();
+      named_bar(1, nthr_all);
+      if (S.remaining == 0 || iter == iter_end) break;
+    }
+    finish_common(iter);
+    C.pass(npm, W.gxs, 0);                            // P x at the clipped point (sums taken by the update warps)
+    C.wait_progress(C.g);   // the update warps of both CTAs are done with our partials: safe to leave the cluster
+#ifdef BQP_PANEL_DEBUG
+    if (lane == 0 && blockIdx.x == 0 && warp == 0)
+      printf("P1 panels %d: full %.0f compute %.0f flow %.0f store %.0f loop %.0f\n", C.g, (double)C.tacc[0] / C.g, (double)C.tacc[1] / C.g,
+             (double)C.tacc[2] / C.g, (double)C.tacc[3] / C.g, (double)C.tacc[5] / C.g);
+#endif
+    return;
+  }
+  // --------------------------------------------------------------- pass-2 warp
+  P2Warp<CS> C;
+  const int pw = warp - np1;
+  C.init(L, lane, 2 * pw, min(2, NWc - 2 * pw));
+  double acc[2][4][2];
   // b' = sigma x - q + A'(rho z - y) for this warp's columns, from the pass-2 accumulators (C fragments), into vs (read
-  // back as B fragments by the same warp only: the M pass input)
+  // back as B fragments by the pass-1 warps: the M pass input)
   auto finalize_b = [&]() {
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-      const int j = 32 * wg + 8 * mt + gq;
-      double b0 = 0.0, b1 = 0.0;
-      if (j < n) {
-        const double qj = __ldg(I.q + j);
-        const double2 xx = reinterpret_cast<const double2 *>(W.gxs)[j * (T / 2) + tq];
-        b0 = sigma * xx.x - qj + acc[mt][0];
-        b1 = sigma * xx.y - qj + acc[mt][1];
+    for (int tl = 0; tl < 2; tl++) {
+      if (tl < C.ntl) {
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const int j = 32 * (C.wg0 + tl) + 8 * mt + gq;
+          double b0 = 0.0, b1 = 0.0;
+          if (j < n) {
+            const double qj = __ldg(I.q + j);
+            const double2 xx = reinterpret_cast<const double2 *>(W.gxs)[j * (T / 2) + tq];
+            b0 = sigma * xx.x - qj + acc[tl][mt][0];
+            b1 = sigma * xx.y - qj + acc[tl][mt][1];
+          }
+          reinterpret_cast<double2 *>(L.vs)[(j - jcol0) * (T / 2) + tq] = make_double2(b0, b1);
+        }
       }
-      reinterpret_cast<double2 *>(L.vs)[(j - jcol0) * (T / 2) + tq] = make_double2(b0, b1);
     }
-    __syncwarp();
   };
   auto store_cols = [&](double *gvec) {
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-      const int j = 32 * wg + 8 * mt + gq;
-      reinterpret_cast<double2 *>(gvec)[j * (T / 2) + tq] = make_double2(acc[mt][0], acc[mt][1]);
+    for (int tl = 0; tl < 2; tl++) {
+      if (tl < C.ntl) {
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const int j = 32 * (C.wg0 + tl) + 8 * mt + gq;
+          reinterpret_cast<double2 *>(gvec)[j * (T / 2) + tq] = make_double2(acc[tl][mt][0], acc[tl][mt][1]);
+        }
+      }
     }
     __syncwarp();
   };
-  zero4(acc);
-  C.template pass<true>(npa, W.gxs, 0, acc);        // z = A x0 (first round) ; A'(rho z - y)
+  C.pass(npa, acc);                                   // A'(rho z - y) of the starting point
   finalize_b();
-  int iter;
+  named_bar(4, ncthr);
   for (iter = iter_begin + 1; iter <= iter_end; iter++) {
     const bool do_check = (iter % check_every == 0) || iter == max_iter;
-    C.template pass<false>(npm, L.vs, jcol0, acc);  // x~ = M b  (acc untouched)
-    C.wait_ud(C.g - 1);                             // every row of x~ is in xts
-    zero4(acc);
-    C.template pass<true>(npa, L.xts, jcol0, acc);  // z~ = A x~ ; b' += A' w
+    C.skip(npm);                                      // x~ = M b has no second pass
+    C.pass(npa, acc);                                 // b' += A' w
     finalize_b();
+    named_bar(4, ncthr);
     if (!do_check) continue;
 
-    // ---- termination check (update_info + check_termination): A x, A'y | A dx, A'dy | P x, P dx   (b' stays in vs)
-    zero4(acc);
-    C.template pass<true>(npa, W.gxs, 0, acc);
-    store_cols(W.gaty);
-    zero4(acc);
-    C.template pass<true>(npa, W.gdx, 0, acc);
-    store_cols(W.gatd);
-    zero4(acc);
-    C.template pass<true>(npm, W.gxs, 0, acc);
-    store_cols(W.gpdx);
-    {
+    // ---- termination check: A'y | A'dy | P dx   (b' stays in vs)
+    C.pass(npa, acc); store_cols(W.gaty);
+    C.pass(npa, acc); store_cols(W.gatd);
+    C.pass(npm, acc); store_cols(W.gpdx);
+    for (int tl = 0; tl < C.ntl; tl++) {
       // column-space quantities: lane <-> column 32 * (column tile) + lane.  Everything read here was written by this
       // warp (store_cols) or by update warps whose panels it has waited for.
-      const int j = wg * 32 + lane;
+      const int wg = C.wg0 + tl, j = wg * 32 + lane;
       const bool inr = j < n;
       const double di = inr ? __ldg(I.Dinv + j) : 0.0, dj = inr ? __ldg(I.D + j) : 0.0, qj = inr ? __ldg(I.q + j) : 0.0;
       auto put = [&](int q, int t, double v) {
@@ -854,10 +996,10 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         put(7, t, reduce_warp<0>(fabs(dj * dxj)));
         put(8, t, reduce_warp<1>(qj * dxj));
       }
-      if (lane == 0) {
-        if (CS == 2 && warp == 0) mbar_expect_tx(L.ck, (uint32_t)((NW - NWc) * kColQ * T * 8));
-        else mbar_arrive(L.ck);
-      }
+    }
+    if (lane == 0) {
+      if (CS == 2 && pw == 0) mbar_expect_tx(L.ck, (uint32_t)((NW - NWc) * kColQ * T * 8));
+      else mbar_arrive(L.ck);
     }
     named_bar(2, nthr_cu);     // decision made
     snapshot();
@@ -865,14 +1007,11 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     if (S.remaining == 0 || iter == iter_end) break;
   }
   finish_common(iter);
-  C.template pass<false>(npm, W.gxs, 0, acc);       // P x at the clipped point (sums taken by the update warps)
-  C.wait_ud(C.g - 1); C.wait_udp(C.g - 1);   // the update warps of both CTAs are done with our partials: safe to leave the cluster
-#ifdef BQP_PANEL_TIMERS
-  if (lane == 0 && blockIdx.x == 0 && warp < 2) {
-    printf("warp %d panels %d:", warp, C.g);
-    for (int i = 0; i < 8; i++) printf(" t%d=%.0f", i, (double)C.tacc[i] / C.g);
-    printf("\n");
-  }
+  C.skip(npm);
+#ifdef BQP_PANEL_DEBUG
+  if (lane == 0 && blockIdx.x == 0 && pw == 0)
+    printf("P2 panels %d: ud %.0f full %.0f compute %.0f release %.0f loop %.0f\n", C.g, (double)C.tacc[0] / C.g, (double)C.tacc[1] / C.g,
+           (double)C.tacc[2] / C.g, (double)C.tacc[3] / C.g, (double)C.tacc[5] / C.g);
 #endif
 }
 
@@ -881,45 +1020,46 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
 size_t panel_smem_bytes(int npad, int nslots, int cs) {
   const int nw = npad / 32;
   const int nwh = cs == 2 ? (nw + 1) / 2 : nw;
+  const int npt = (nwh + 1) / 2 + (cs == 2 ? (nw - nwh + 1) / 2 : 0);
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * (size_t)kHB + 1);
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4 * (size_t)kHB + 1);
   off = (off + 15) & ~size_t(15);
-  off += ((size_t)2 * nwh * 32 * T8 + (size_t)kHB * nw * 64 * kPH + (size_t)kHB * kPR * T8 + (size_t)kColQ * nw * T8) * 8;
+  off += ((size_t)2 * nwh * 32 * T8 + (size_t)kHB * npt * 64 * kPH + (size_t)kHB * kPR * T8 + (size_t)kColQ * nw * T8) * 8;
   off = (off + 127) & ~size_t(127);
   return off + (size_t)nslots * nwh * (kTileDoubles * 8);
 }
 
-template <int LAG, int CS>
+template <int CS>
 static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                     const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem,
                     cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<LAG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(admm_panel_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return BQP_E_CUDA;
   int prefetch_panels = 0;   // L2 prefetch distance of the producer, in panels (experiment knob)
   if (const char *pk = getenv("BQP_PANEL_PREFETCH")) prefetch_panels = atoi(pk);
   const int nwc = CS == 2 ? (nw_max + 1) / 2 : nw_max;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ntiles * CS), 1, 1);
-  cfg.blockDim = dim3((unsigned)((nwc + kPanelUpdWarps + 1) * 32), 1, 1);
+  cfg.blockDim = dim3((unsigned)((2 * ((nwc + 1) / 2) + kPanelUpdWarps + 1) * 32), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, admm_panel_kernel<LAG, CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
+  e = cudaLaunchKernelEx(&cfg, admm_panel_kernel<CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
                          prefetch_panels);
   return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? BQP_OK : BQP_E_CUDA;
 }
 
-// cs = CTAs per tile (1, or 2 = a cluster pair splitting the columns).  Pass 2 runs one (16-row) panel behind pass 1.
+// cs = CTAs per tile (1, or 2 = a cluster pair splitting the columns).  
 int launch_admm_panel(int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (nw_max < 1 || nw_max > kPanelMaxWarps || (cs != 1 && cs != 2) || (cs == 1 && nw_max > kPanelCtaWarps)) return BQP_E_ARG;
-  if (cs == 1) return launch_p<1, 1>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  return launch_p<1, 2>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  if (cs == 1) return launch_p<1>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  return launch_p<2>(nw_max, nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
 }
 
 }  // namespace bqp
