@@ -168,13 +168,14 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
     bytes_per_ni = algorithmic_bytes_per_node_iter(inst0, T)
     step_s = dev_s / args.steps
     kernel = {0: "admm_tile_kernel<%d>", 1: "admm_stream_kernel<%d>", 2: "admm_panel_kernel (%d nodes per tile)"}[int(tm.get("kernel", 1))] % tm["tile_nodes"]
-    traffic, traffic_src = None, None
-    try:   # dram__bytes_read+write summed over the launches of ONE step, from the committed ncu capture
+    traffic, traffic_src, traffic_scope = None, None, None
+    try:   # dram__bytes_read+write of the captured launch of this kernel, from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tr = json.load(f)
-        if tr["kernel"] == kernel and tr["launches_per_step"] == tm["launches"]:
+        if tr["kernel"] == kernel:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             traffic_src = tr["source"]
+            traffic_scope = tr.get("scope")
     except (OSError, KeyError, ValueError):
         pass
     achieved = bytes_per_ni * node_iters / step_s / 1e9
@@ -198,7 +199,7 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                     "traffic": traffic, "traffic_source": traffic_src, "traffic_scope": traffic_scope, "kernel": kernel,
                      "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_step": node_iters,
                      "launches_per_step": int(tm["launches"]), "step_kernel_ms": 1e3 * step_s,
                      "note": "one step = %d launches of the same kernel (rounds of ADMM iterations, re-tiled in between); "

@@ -62,11 +62,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// flow-control-only arrive on a peer barrier (no data rides on it): relaxed, so it does not wait for this thread's
-// earlier global stores the way a cluster-scope release would (that compiles to MEMBAR.ALL.GPU)
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t rbar) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
