@@ -203,7 +203,7 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
                      "algorithmic_bytes_per_node_iter": bytes_per_ni, "node_iters_per_step": node_iters,
                      "launches_per_step": int(tm["launches"]), "step_kernel_ms": 1e3 * step_s,
                      "note": "one step = %d launches of the same kernel (rounds of ADMM iterations, re-tiled in between); "
-                             "achieved, traffic and streamed bytes are per step" % int(tm["launches"]),
+                             "achieved and streamed bytes are per step; traffic is the DRAM traffic of the launch named in traffic_scope" % int(tm["launches"]),
                      "streamed_bytes_per_step": int(tm["stream_bytes"]),
                      "streamed_gbs": tm["stream_bytes"] / step_s / 1e9},
         "setup_s": t_setup, "root_iters": root_iters, "wall_s_resident_loop": wall_max,

@@ -523,7 +523,10 @@ int bqp_batch_run(void) {
   g.timing.kernel_ms = ms;
   g.timing.launches = launches;
   g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
-  if (g.use_panel) g.timing.threads = (2 * (((g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max) + 1) / 2) + kPanelUpdWarps + 1) * 32;
+  if (g.use_panel) {
+    const int nwc = g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max;
+    g.timing.threads = ((nwc + kPanelP1Tiles - 1) / kPanelP1Tiles + (nwc + 1) / 2 + kPanelUpdWarps + 1) * 32;
+  }
   g.timing.kernel = g.use_panel ? 2 : (g.use_stream ? 1 : 0);
   g.timing.ring_slots = first_slots;
   g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;

@@ -84,6 +84,7 @@ constexpr int kPanelRows = 8;                       // one 8-row mma tile per pa
 constexpr int kPanelT = 8;                          // nodes per tile of the panel kernel (N of the mma)
 constexpr int kPanelMaxWarps = 16;                  // column tiles of 32 (npad <= 512), one consumer warp each
 constexpr int kPanelCtaWarps = 8;                   // consumer warps per CTA; wider problems run as a cluster pair of CTAs
+constexpr int kPanelP1Tiles = 1;                    // column tiles per pass-1 warp (pass-2 warps own two)
 constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin
 struct HostPanels {
   bool built = false;

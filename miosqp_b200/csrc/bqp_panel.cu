@@ -48,7 +48,8 @@ constexpr int kFinP = 9;          // row-space quantities each update warp accum
 constexpr int kHBmul = 2;
 constexpr int kHB = kHBmul * kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b % kPanelUpdWarps
 constexpr int kPH = kPanelRows / 8;            // 8-row mma tiles per panel
-constexpr int kPanelThreads = (kPanelCtaWarps + kPanelUpdWarps + 1) * 32;
+constexpr int kP1T = kPanelP1Tiles;
+constexpr int kPanelThreads = ((kPanelCtaWarps + kP1T - 1) / kP1T + (kPanelCtaWarps + 1) / 2 + kPanelUpdWarps + 1) * 32;
 constexpr int kTileDoubles = kPR * 32;   // one column tile of one panel
 
 // ------------------------------------------------------------------ mbarrier / TMA / cluster wrappers (PTX)
@@ -243,7 +244,7 @@ struct P1Warp : ConsumerBase<CS> {
     for (int tl = 0; tl < 2; tl++)
 #pragma unroll
       for (int ks = 0; ks < 8; ks++)
-        bx[tl][ks] = tl < B::ntl ? src[(size_t)(32 * (B::wg0 + tl) + 4 * ks + tq - src_col0) * T8 + gq] : 0.0;
+        bx[tl][ks] = (tl < kP1T && tl < B::ntl) ? src[(size_t)(32 * (B::wg0 + tl) + 4 * ks + tq - src_col0) * T8 + gq] : 0.0;
     for (int k = 0; k < npanels; k++) {
       TSTAMP(*this, 5);
       mbar_wait(L.full + 8u * B::slot, B::phase);
@@ -255,7 +256,7 @@ struct P1Warp : ConsumerBase<CS> {
         double cc[8][2];     // independent mma chains (two tiles deep), then a fixed tree
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) { cc[ks][0] = 0.0; cc[ks][1] = 0.0; dmma(cc[ks], sp[h * 256 + ks * 32], bx[0][ks]); }
-        if (B::ntl == 2) {
+        if (kP1T == 2 && B::ntl == 2) {
 #pragma unroll
           for (int ks = 0; ks < 8; ks++) dmma(cc[ks], sp[kTileDoubles + h * 256 + ks * 32], bx[1][ks]);
         }
@@ -416,13 +417,13 @@ struct Updater {
       }
       return p;
     };
-    Pre nxt[kPH];
+    Pre nxt[kPH], nxt2[kPH];     // state of the next two owned panels (two deep: the loads may come from HBM)
 #pragma unroll
-    for (int h = 0; h < kPH; h++) nxt[h] = load_state(cls, h);
+    for (int h = 0; h < kPH; h++) { nxt[h] = load_state(cls, h); nxt2[h] = load_state(cls + KU, h); }
     for (int k = cls; k < npanels; k += KU) {
       Pre cur[kPH];
 #pragma unroll
-      for (int h = 0; h < kPH; h++) { cur[h] = nxt[h]; nxt[h] = load_state(k + KU, h); }
+      for (int h = 0; h < kPH; h++) { cur[h] = nxt[h]; nxt[h] = nxt2[h]; nxt2[h] = load_state(k + 2 * KU, h); }
       const int hb = uw + KU * bsel;              // hand-off buffer of this panel
       TSTAMP(*this, 5);
       mbar_wait(L.pf + 8u * hb, ph);
@@ -554,8 +555,8 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   const int w0 = rank == 0 ? 0 : nwh, NWc = rank == 0 ? nwh : NW - nwh;
   const int slot_bytes = NWc * (kTileDoubles * 8);
   const int nwslots = (int)(blockDim.x >> 5) - KU - 1;     // consumer warp slots of this launch
-  const int np1 = (NWc + 1) / 2, ncons = 2 * np1;          // pass-1 warps = pass-2 warps of this CTA (two column tiles each)
-  const int np1_r0 = (nwh + 1) / 2, npt = np1_r0 + (CS == 2 ? (NW - nwh + 1) / 2 : 0);
+  const int np1 = (NWc + kP1T - 1) / kP1T, np2 = (NWc + 1) / 2, ncons = np1 + np2;   // pass-1 / pass-2 warps of this CTA
+  const int np1_r0 = (nwh + kP1T - 1) / kP1T, npt = np1_r0 + (CS == 2 ? (NW - nwh + kP1T - 1) / kP1T : 0);
   const int nthr_cu = (ncons + KU) * 32, nthr_all = (ncons + KU + 1) * 32;
   const bool is_consumer = warp < ncons, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
 
@@ -589,9 +590,9 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, ncons); }
     // "partials full" / check barriers: one arrival per LOCAL pass-1 / pass-2 warp; the peer's share arrives as transaction bytes
     for (int s = 0; s < kHB; s++) {
-      mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); mbar_init(L.uc + 8u * s, np1);
+      mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); mbar_init(L.uc + 8u * s, np2);
     }
-    mbar_init(L.ck, np1);
+    mbar_init(L.ck, np2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -880,7 +881,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   if (warp < np1) {
     // ------------------------------------------------------------- pass-1 warp
     P1Warp<CS> C;
-    C.init(L, lane, 2 * warp, min(2, NWc - 2 * warp));
+    C.init(L, lane, kP1T * warp, min(kP1T, NWc - kP1T * warp));
     C.pidx = (rank == 0 ? 0 : np1_r0) + warp;
     C.pass(npa, W.gxs, 0);                            // z = A x0 (first round)
     named_bar(4, ncthr);                              // b' of the pass-2 warps is in vs
@@ -1015,7 +1016,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
 size_t panel_smem_bytes(int npad, int nslots, int cs) {
   const int nw = npad / 32;
   const int nwh = cs == 2 ? (nw + 1) / 2 : nw;
-  const int npt = (nwh + 1) / 2 + (cs == 2 ? (nw - nwh + 1) / 2 : 0);
+  const int npt = (nwh + kP1T - 1) / kP1T + (cs == 2 ? (nw - nwh + kP1T - 1) / kP1T : 0);
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
   off += sizeof(uint64_t) * (2 * (size_t)nslots + 4 * (size_t)kHB + 1);
   off = (off + 15) & ~size_t(15);
@@ -1035,7 +1036,7 @@ static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *
   const int nwc = CS == 2 ? (nw_max + 1) / 2 : nw_max;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ntiles * CS), 1, 1);
-  cfg.blockDim = dim3((unsigned)((2 * ((nwc + 1) / 2) + kPanelUpdWarps + 1) * 32), 1, 1);
+  cfg.blockDim = dim3((unsigned)(((nwc + kP1T - 1) / kP1T + (nwc + 1) / 2 + kPanelUpdWarps + 1) * 32), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -22,7 +22,7 @@ def panel_threads(n, cluster=None):
     if cluster is None:
         cluster = 2 if nw > 8 else 1
     nwc = (nw + 1) // 2 if cluster == 2 else nw
-    return (2 * ((nwc + 1) // 2) + 4) * 32     # pass-1 warps + pass-2 warps (two column tiles each) + 3 update + 1 producer
+    return (nwc + (nwc + 1) // 2 + 4) * 32     # pass-1 warps (one column tile each) + pass-2 warps (two each) + 3 update + 1 producer
 
 
 def _close(a, b, tol=TOL):
