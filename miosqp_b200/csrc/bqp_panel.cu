@@ -9,25 +9,32 @@
 //
 // Every matrix is cut into row PANELS (kPanelRows = 8 rows x npad columns, bqp_internal.h), streamed by TMA bulk copies
 // into a ring of shared-memory slots.  While panel k of A sits in shared memory it is used twice:
-//   pass 1   z~_I = A_I x~            consumer warp w owns columns 32w..32w+31; the [8 rows x 32 cols] x [32 cols x 8 nodes]
-//                                     product is 8 FP64 mma.sync.m8n8k4 (the 8 leaves of the tile are the N dimension, so
-//                                     the hardware does the reduction over columns: no shuffles), partial sums go to the
+//   pass 1   z~_I = A_I x~            a PASS-1 WARP owns one column tile (32 columns); the [8 rows x 32 cols] x [32 cols x
+//                                     8 nodes] product is 8 FP64 mma.sync.m8n8k4 (the 8 leaves of the tile are the N
+//                                     dimension, so the hardware does the reduction over columns: no shuffles); the 8x8
+//                                     partial sum of every warp goes to the
 //   update   z_I, y_I, w_I            UPDATE WARPS (one lane per (row, node pair)), which add the warp partials in a fixed
 //                                     order, apply the projection / dual update and publish w_I = rho z_I - y_I;
-//   pass 2   b' += A_I' w_I           same panel read transposed from shared memory: 8 more mma.sync per warp, the
-//                                     [32 cols x 8 nodes] accumulators stay in registers for the whole pass.
-// pass 2 runs LAG panels behind pass 1, so the update latency is hidden.  (FP64 mma.sync issues at the same 64 FMA/clk/SM
-// as DFMA on B200 -- tools/micro/dmma_rate.cu -- but with 1/8 of the instructions; the vector-FMA version of this kernel
-// was instruction-issue bound at a quarter of the HBM roofline.)
+//   pass 2   b' += A_I' w_I           PASS-2 WARPS (two column tiles each) follow the update warps panel by panel and read
+//                                     the same slot transposed: 8 more mma.sync per tile, the [32 cols x 8 nodes]
+//                                     accumulators stay in registers for the whole pass.
+// The consumer warps are specialised by pass so that the warps sharing an SM sub-partition (and its FP64 mma pipe) are in
+// different phases of the panel loop.  (FP64 mma.sync issues at the same 64 FMA/clk/SM as DFMA on B200 --
+// tools/micro/dmma_rate.cu -- but with 1/8 of the instructions; the vector-FMA version of this kernel was
+// instruction-issue bound at a quarter of the HBM roofline.)
 //
 // Problems wider than 8 column tiles run as a CLUSTER OF TWO CTAs (one SM each): CTA r streams and multiplies only
 // its half of the columns of every panel (half the HBM stream, shared-memory traffic and FP64 work per SM), the per-warp
-// partial sums of pass 1 are written into BOTH CTAs' shared memory (st.async over DSMEM, completing transaction bytes on
-// the peer's mbarrier: no cluster-scope fence anywhere in the loop), and both CTAs run the (cheap) row-space update
-// redundantly, so nothing else crosses.
-// Roles per CTA: warps [0, NWc) consumers, kPanelUpdWarps update warps, one TMA producer warp (one lane).
-// Synchronisation inside a pass is mbarrier-only (full/empty per ring slot, "partials full" / "update done" per
-// hand-off buffer); named barriers only at termination checks.
+// partial sums of pass 1 are copied into the peer CTA's shared memory with one bulk DSMEM copy per warp and panel
+// (cp.async.bulk shared::cta -> shared::cluster, completing transaction bytes on the peer's mbarrier: no cluster-scope
+// fence anywhere in the loop -- a release.cluster arrive costs a MEMBAR.ALL.GPU), and both CTAs run the (cheap)
+// row-space update redundantly on identical inputs, so nothing else crosses the pair.
+// Roles per CTA: pass-1 warps, pass-2 warps, kPanelUpdWarps update warps, one TMA producer warp (one lane).
+// Synchronisation inside a pass: mbarriers (full/empty per ring slot; "partials full", "update done", "u consumed" per
+// hand-off buffer, each buffer owned by one update warp so that every barrier is waited on strictly phase by phase) and,
+// for the pass-1 warps' flow control, polled progress counters in shared memory (a completed mbarrier try_wait costs
+// ~200 cycles).  Named barriers only at termination checks and once per iteration between pass-2 and pass-1 warps.
+// Every wait is bounded: a broken protocol traps instead of hanging the GPU.  -DBQP_PANEL_DEBUG adds per-role phase timers.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -147,8 +154,8 @@ struct PanelShared {
 // everything a role needs to find its way around shared memory (u32 = shared-window addresses; *_r = the same object in
 // the peer CTA of the pair, mapped with mapa)
 struct Lay {
-  uint32_t full, empty, pf, ud, udp, uc, ck; // barrier arrays: [nslots], [nslots], [kHB] x4, [1]
-  uint32_t pf_r, udp_r, ck_r, part_r, red_r, part_u32, cnt_r;   // cnt_r: upd_cnt[1] of the peer
+  uint32_t full, empty, pf, ud, uc, ck;      // barrier arrays: [nslots], [nslots], [kHB] x3, [1]
+  uint32_t pf_r, ck_r, part_r, red_r, part_u32, cnt_r;          // cnt_r: upd_cnt[1] of the peer
   volatile int *cnt;                                           // upd_cnt[0] of this CTA ([kPanelUpdWarps], then the peer's copy)
   double *xts, *vs;                      // x~ and b for THIS CTA's columns: [32 NWc][8]
   double *part, *ubuf, *red;             // [kHB][NW][32 lanes][2], [kHB][8 rows][8], [kColQ][NW][8]
@@ -181,26 +188,16 @@ struct ConsumerBase {
   int slot; uint32_t phase;          // ring position of the next panel
   int g, gb;                         // global panel counter (same sequence in the update warps), g % kHB
   int ud_g, ud_b; uint32_t ud_ph;    // next panel whose "update done" barrier this thread has not observed yet
-  int up_g, up_b; uint32_t up_ph;    // the same for the peer CTA's update warps (flow control of the DSMEM partials)
 
   __device__ __forceinline__ void init(const Lay &lay, int lane_, int tile0_local, int ntiles) {
     L = lay; lane = lane_; tl0 = tile0_local; ntl = ntiles; wg0 = lay.w0 + tile0_local;
-    slot = 0; phase = 0; g = 0; gb = 0; ud_g = 0; ud_b = 0; ud_ph = 0; up_g = 0; up_b = 0; up_ph = 0;
+    slot = 0; phase = 0; g = 0; gb = 0; ud_g = 0; ud_b = 0; ud_ph = 0;
   }
   __device__ __forceinline__ void wait_ud(int target) {
     while (ud_g <= target) {
       mbar_wait(L.ud + 8u * ud_b, ud_ph);
       ud_g++;
       if (++ud_b == kHB) { ud_b = 0; ud_ph ^= 1u; }
-    }
-  }
-  __device__ __forceinline__ void wait_udp(int target) {   // the peer's update warp has read our partials of that panel
-    if constexpr (CS == 2) {
-      while (up_g <= target) {
-        mbar_wait(L.udp + 8u * up_b, up_ph);
-        up_g++;
-        if (++up_b == kHB) { up_b = 0; up_ph ^= 1u; }
-      }
     }
   }
   __device__ __forceinline__ void advance() {
@@ -563,9 +560,9 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   Lay L;
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
   L.full = smem_u32(smem_raw + off);
-  L.empty = L.full + 8u * nslots; L.pf = L.empty + 8u * nslots; L.ud = L.pf + 8u * kHB; L.udp = L.ud + 8u * kHB;
-  L.uc = L.udp + 8u * kHB; L.ck = L.uc + 8u * kHB;
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4 * kHB + 1);
+  L.empty = L.full + 8u * nslots; L.pf = L.empty + 8u * nslots; L.ud = L.pf + 8u * kHB; L.uc = L.ud + 8u * kHB;
+  L.ck = L.uc + 8u * kHB;
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * kHB + 1);
   off = (off + 15) & ~size_t(15);
   L.xts = reinterpret_cast<double *>(smem_raw + off);
   L.vs = L.xts + (size_t)nwh * 32 * T;
@@ -578,26 +575,26 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   L.ring_u32 = smem_u32(L.ring);
   L.nslots = nslots; L.slot_bytes = slot_bytes; L.nw = NW; L.nwc = NWc; L.w0 = w0; L.np = np; L.npt = npt; L.np1 = np1;
   if constexpr (CS == 2) {
-    L.pf_r = mapa(L.pf, peer); L.udp_r = mapa(L.udp, peer); L.ck_r = mapa(L.ck, peer);
+    L.pf_r = mapa(L.pf, peer); L.ck_r = mapa(L.ck, peer);
     L.part_r = mapa(smem_u32(L.part), peer); L.red_r = mapa(smem_u32(L.red), peer);
     L.part_u32 = smem_u32(L.part);
     L.cnt_r = mapa(smem_u32(const_cast<int *>(&S.upd_cnt[1][0])), peer);
   } else {
-    L.pf_r = L.udp_r = L.ck_r = L.part_r = L.red_r = L.part_u32 = L.cnt_r = 0;
+    L.pf_r = L.ck_r = L.part_r = L.red_r = L.part_u32 = L.cnt_r = 0;
   }
   L.cnt = &S.upd_cnt[0][0];
   if (tid == 0) {
     for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, ncons); }
     // "partials full" / check barriers: one arrival per LOCAL pass-1 / pass-2 warp; the peer's share arrives as transaction bytes
     for (int s = 0; s < kHB; s++) {
-      mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.udp + 8u * s, 1); mbar_init(L.uc + 8u * s, np2);
+      mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.uc + 8u * s, np2);
     }
     mbar_init(L.ck, np2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
 #ifdef BQP_PANEL_DEBUG
-  if (tid == 0 && blockIdx.x == 0) printf("LAYOUT full %u empty %u pf %u ud %u udp %u ck %u nslots %d np1 %d npt %d ncons %d NWc %d\n", L.full, L.empty, L.pf, L.ud, L.udp, L.ck, nslots, np1, npt, ncons, NWc);
+  if (tid == 0 && blockIdx.x == 0) printf("LAYOUT full %u empty %u pf %u ud %u uc %u ck %u nslots %d np1 %d npt %d ncons %d NWc %d\n", L.full, L.empty, L.pf, L.ud, L.uc, L.ck, nslots, np1, npt, ncons, NWc);
 #endif
   if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs exist before anyone arrives
   if (!is_consumer && !is_update && !is_producer) return;            // CTA sized for the widest problem of the launch
@@ -1018,7 +1015,7 @@ size_t panel_smem_bytes(int npad, int nslots, int cs) {
   const int nwh = cs == 2 ? (nw + 1) / 2 : nw;
   const int npt = (nwh + kP1T - 1) / kP1T + (cs == 2 ? (nw - nwh + kP1T - 1) / kP1T : 0);
   size_t off = (sizeof(PanelShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4 * (size_t)kHB + 1);
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3 * (size_t)kHB + 1);
   off = (off + 15) & ~size_t(15);
   off += ((size_t)2 * nwh * 32 * T8 + (size_t)kHB * npt * 64 * kPH + (size_t)kHB * kPR * T8 + (size_t)kColQ * nw * T8) * 8;
   off = (off + 127) & ~size_t(127);
