@@ -253,7 +253,8 @@ int bqp_set_tuning(int tile_nodes, int threads) {
 // the tile table.  Nodes are grouped by (problem, iterations done so far); groups with the least progress go first, and
 // when more tiles exist than the GPU holds at once (`capacity`) the rest wait for the next launch -- so every launch is
 // one full wave, and stragglers are re-tiled ever narrower as the frontier drains.  `scheduled` returns the chosen nodes.
-static int plan_round(const std::vector<int> &alive, const std::vector<int> &progress, std::vector<int> *scheduled) {
+static int plan_round(const std::vector<int> &alive, const std::vector<int> &progress, const std::vector<double> &remaining,
+                      std::vector<int> *scheduled) {
   int ndev_sms = 148;
   cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
   const bool use_stream = g.use_stream, use_panel = g.use_panel, w_in_stage = g.w_in_stage;
@@ -281,6 +282,19 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   {
     std::vector<int> order(alive);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return progress[a] < progress[b]; });
+    if (rounds) {
+      // critical path first: a group's priority is the largest predicted number of remaining iterations of its nodes
+      // (extrapolated from the decay of their residuals, `remaining`; unknown = infinite), least progress breaking ties
+      std::map<std::pair<int, bqp_instance *>, double> prio;
+      for (int b : order) {
+        auto key = std::make_pair(progress[b], g.node_inst[b]);
+        auto it = prio.find(key);
+        if (it == prio.end()) prio[key] = remaining[b]; else it->second = std::max(it->second, remaining[b]);
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return prio[std::make_pair(progress[a], g.node_inst[a])] > prio[std::make_pair(progress[b], g.node_inst[b])];
+      });
+    }
     for (int b : order) {
       bqp_instance *h = g.node_inst[b];
       auto key = std::make_pair(progress[b], h);
@@ -321,7 +335,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     for (auto *inst : uniq) while (tt > 1 && stream_slots(inst->h, tt) < 2) tt >>= 1;
   if (!g_tune_tt) {   // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small
     auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
-    while (tt > 1 && count_tiles(tt / 2) <= ndev_sms) tt >>= 1;
+    while (tt > 1 && count_tiles(tt / 2) <= std::min(capacity, ndev_sms)) tt >>= 1;
   }
   if (use_panel) {
     nslots = 16;
@@ -473,13 +487,18 @@ int bqp_batch_run(void) {
   if (!g.resident) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
   std::vector<int> alive(g.B), progress(g.B, 0), scheduled;
+  // scheduling hint per running node: distance to the tolerance at its last check (reported by the panel kernel) and the
+  // number of iterations it is predicted to need still, from the geometric decay of that distance between two rounds
+  const double kUnknown = 1e30;
+  std::vector<double> dist(g.B, NAN), remaining(g.B, kUnknown);
+  const bool predict = std::getenv("BQP_NO_PREDICT") == nullptr;
   for (int b = 0; b < g.B; b++) alive[b] = b;
   long long tile_iters = 0, bytes = 0, h2d_extra = 0;
   int launches = 0, first_tiles = 0, first_tt = 0, first_slots = 0;
   long long first_smem = 0;
   CK(cudaEventRecord(g.ev[1], g.stream));
   while (!alive.empty()) {
-    int rc = plan_round(alive, progress, &scheduled);
+    int rc = plan_round(alive, progress, remaining, &scheduled);
     if (rc) return rc;
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
@@ -508,8 +527,17 @@ int bqp_batch_run(void) {
     }
     std::vector<char> done(g.B, 0);
     for (int b : scheduled) {
-      if (hs[b].status == BQP_UNSOLVED) progress[b] = hs[b].iters;   // iterations completed so far (its tile's iter_end)
-      else done[b] = 1;
+      if (hs[b].status == BQP_UNSOLVED) {
+        const int before = progress[b];
+        progress[b] = hs[b].iters;   // iterations completed so far (its tile's iter_end)
+        const double d = hs[b].pri_res;
+        if (predict && d == d && d > 0) {
+          if (dist[b] == dist[b] && dist[b] > d && d > 1.0 && progress[b] > before)
+            remaining[b] = std::log(d) / std::log(dist[b] / d) * (progress[b] - before);
+          else if (dist[b] == dist[b]) remaining[b] = kUnknown * 0.5;   // not converging yet: behind the unknown ones only
+          dist[b] = d;
+        }
+      } else done[b] = 1;
     }
     std::vector<int> next;
     for (int b : alive) if (!done[b]) next.push_back(b);

@@ -145,6 +145,7 @@ struct PanelShared {
   double fin[kFin][T8];
   double finp[kPanelUpdWarps][kFinP][T8];
   int status[T8], iters[T8], newly[T8];
+  double dist[T8];          // max(pri_res / eps_prim, dua_res / eps_dual) at the last check: how far a running node is from done
   int remaining;
   // panels finished by each update warp: [0] of this CTA, [1] of the peer CTA (written there over DSMEM).  The pass-1 warps
   // poll these with plain shared-memory loads for flow control (a completed mbarrier try_wait costs ~200 cycles)
@@ -540,7 +541,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     S.I = insts[S.tile.inst];
     S.remaining = S.tile.nn;
   }
-  if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
+  if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; S.dist[tid] = NAN; }
   if (tid < 2 * kPanelUpdWarps) S.upd_cnt[tid / kPanelUpdWarps][tid % kPanelUpdWarps] = 0;
   __syncthreads();
   const DevInstance &I = S.I;
@@ -710,6 +711,10 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       else if (dinf) status = pass ? BQP_DUAL_INFEASIBLE_INACCURATE : BQP_DUAL_INFEASIBLE;
     }
     if (status == BQP_UNSOLVED && iter == max_iter) status = BQP_MAX_ITER_REACHED;
+    if (status == BQP_UNSOLVED) {   // still running: distance to the (first-pass) tolerances, a scheduling hint for the host
+      const double eps_prim = I.eps_abs + I.eps_rel * fmax(nAx, nz), eps_dual = I.eps_abs + I.eps_rel * fmax(fmax(nPx, nAty), nq);
+      S.dist[t] = fmax(pri / eps_prim, dua / eps_dual);
+    }
     if (status != BQP_UNSOLVED) {
       S.status[t] = status; S.iters[t] = iter; S.newly[t] = 1;
       NodeScalars r;
@@ -748,7 +753,10 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         double *sp = state + S.tile.state_off[t];
         for (int j = ctid; j < n; j += nthr_cu) sp[j] = W.gxs[(size_t)j * T + t];
         for (int i = ctid; i < m; i += nthr_cu) { sp[n + i] = W.gz[(size_t)i * T + t]; sp[n + m + i] = W.gy[(size_t)i * T + t]; }
-        if (ctid == 0) { NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.pri_res = r.dua_res = r.lower = NAN; ns[S.tile.node[t]] = r; }
+        if (ctid == 0) {   // pri_res of a node that is still running carries its distance to the tolerance (scheduling hint)
+          NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.dua_res = r.lower = NAN; r.pri_res = S.dist[t];
+          ns[S.tile.node[t]] = r;
+        }
       }
     }
     // epilogue (node.py:128-143): clip integer entries, lower = 1/2 x'Px + q'x at the clipped point
