@@ -333,7 +333,10 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   int tt = g_tune_tt ? std::min(g_tune_tt, use_panel ? tt_cap : (use_stream ? kMaxTT : tt_cap)) : std::min(tt_cap, pow2ceil(widest));
   if (g_tune_tt && use_stream)
     for (auto *inst : uniq) while (tt > 1 && stream_slots(inst->h, tt) < 2) tt >>= 1;
-  if (!g_tune_tt) {   // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small
+  // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small.  Not for the panel
+  // kernel: a tile-iteration costs the same for 1..8 nodes there (the nodes are the N dimension of the mma), so splitting
+  // an instance's nodes over two tiles only doubles its HBM stream
+  if (!g_tune_tt && !use_panel) {
     auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
     while (tt > 1 && count_tiles(tt / 2) <= std::min(capacity, ndev_sms)) tt >>= 1;
   }
