@@ -47,6 +47,7 @@ class Node(object):
         self.nextvar_idx = None
         self.constr_idx = None
         self.cached = None          # (status, iters, seconds, x, y) of a batch solve not yet consumed
+        self.shadow = None          # speculation: (left, right) children solved ahead of the replay, () if none can exist
 
     def solve(self):
         """Consume the cached batch result (solving this node alone first if nobody batched it)."""
@@ -77,6 +78,8 @@ class Workspace(object):
         self.setup_time = self.solve_time = self.run_time = 0.
         self.batches = 0            # kernel launches issued for this workspace
         self.batched_nodes = 0      # nodes solved in them (>= consumed nodes: speculation)
+        self.spec_nodes = 0         # of those, nodes solved ahead of the replay (settings['speculation'])
+        self.spec_hits = 0          # speculative results the replay went on to consume
         self.reset()
 
     def reset(self):
@@ -111,6 +114,11 @@ class Workspace(object):
         nodes = self.pending()
         if not nodes:
             return 0
+        budget = int(self.settings.get('speculation', 0) or 0)
+        if budget > 0:
+            ahead = self.speculate(budget)
+            self.spec_nodes += len(ahead)
+            nodes = nodes + ahead
         t0 = perf_counter()
         if dist_ctx is None:
             mine = list(range(len(nodes)))
@@ -137,6 +145,65 @@ class Workspace(object):
         self.batched_nodes += len(nodes)
         return len(nodes)
 
+    # ------------------------------------------------------------------ speculation (host-side look-ahead)
+    def prospect(self, node):
+        """The two children branch() WOULD create from `node` once the replay consumes its cached result, as
+        unsolved shadow nodes (not in `leaves`); () when it cannot branch.  This is node.py:128-143 followed by
+        workspace.py:245-264,205-230,157-203 evaluated on a copy: it depends on the node's own result only, never on
+        the incumbent, which is what makes solving the children early legal.  Nothing visible changes."""
+        st, _, _, x, y = node.cached
+        if st != OSQP_SOLVED and st != OSQP_MAX_ITER_REACHED:
+            return ()
+        k, idx = self.data.n_int, self.data.i_idx
+        xc = np.copy(x)
+        xc[idx] = np.minimum(np.maximum(xc[idx], node.l[-k:]), node.u[-k:])
+        x_int = xc[idx]
+        dist = abs(x_int - np.round(x_int))
+        frac = np.where(dist > self.settings['eps_int_feas'])[0]
+        if len(frac) == 0:
+            return ()
+        nextvar = frac[int(np.argmax(dist[frac]))]
+        row, var = self.data.m + nextvar, idx[nextvar]
+        lower = self.data.compute_obj_val(xc)
+        if lower > self.upper_glob:
+            return ()                                   # the replay will drop it (workspace.py:299-300)
+        kids = []
+        for side in (0, 1):
+            l, u = np.copy(node.l), np.copy(node.u)
+            if side == 0:
+                u[row] = np.floor(xc[var])
+            else:
+                l[row] = np.ceil(xc[var])
+            if l[row] > u[row]:
+                return ()                               # the engine would reject the whole launch; leave it to the replay
+            kids.append(Node(self.data, l, u, self.solver, depth=node.depth + 1, lower=lower, x0=xc, y0=y))
+        return tuple(kids)
+
+    def speculate(self, budget):
+        """Up to `budget` shadow nodes for this launch: children of solved-but-unconsumed nodes (open leaves and
+        earlier shadows), the ones the exploration rule would reach first going first."""
+        cands, stack = [], list(self.leaves)
+        while stack:
+            nd = stack.pop()
+            if nd.cached is None:
+                continue
+            if nd.shadow is None:
+                cands.append(nd)
+            else:
+                stack.extend(nd.shadow)
+        rule = self.settings['tree_explor_rule']
+        if rule == 0 or np.isinf(self.upper_glob):
+            cands.sort(key=lambda nd: -nd.depth)
+        else:
+            cands.sort(key=lambda nd: -nd.lower)        # visible lower = the bound the "best bound" rule compares
+        ahead = []
+        for nd in cands:
+            if len(ahead) + 2 > budget:
+                break
+            nd.shadow = self.prospect(nd)
+            ahead.extend(nd.shadow)
+        return ahead
+
     # ------------------------------------------------------------------ reference logic, replayed
     def set_x0(self, x0):
         root = self.leaves[0]
@@ -161,21 +228,28 @@ class Workspace(object):
             raise ValueError('Tree exploring strategy not recognized')
         return self.leaves.pop(pick)
 
-    def _child(self, leaf, l, u):
+    def _child(self, leaf, l, u, side):
         # children warm-start from (and share) the parent's solution arrays (workspace.py:174-176)
         child = Node(self.data, l, u, self.solver, depth=leaf.depth + 1, lower=leaf.lower, x0=leaf.x, y0=leaf.y)
         child.parent_iters = leaf.num_iter      # scheduling hint only (longest-first submission)
+        if leaf.shadow:
+            # a result solved ahead of the replay is adopted only if it was computed from exactly these inputs
+            sh = leaf.shadow[side]
+            if sh.cached is not None and np.array_equal(sh.l, l) and np.array_equal(sh.u, u) \
+                    and np.array_equal(sh.x, leaf.x) and np.array_equal(sh.y, leaf.y):
+                child.cached, child.shadow = sh.cached, sh.shadow
+                self.spec_hits += 1
         self.leaves.append(child)
 
     def add_left(self, leaf):
         l, u = np.copy(leaf.l), np.copy(leaf.u)
         u[leaf.constr_idx] = np.floor(leaf.x[leaf.nextvar_idx])
-        self._child(leaf, l, u)
+        self._child(leaf, l, u, 0)
 
     def add_right(self, leaf):
         l, u = np.copy(leaf.l), np.copy(leaf.u)
         l[leaf.constr_idx] = np.ceil(leaf.x[leaf.nextvar_idx])
-        self._child(leaf, l, u)
+        self._child(leaf, l, u, 1)
 
     def pick_nextvar(self, leaf):
         if self.settings['branching_rule'] != 0:

@@ -26,6 +26,9 @@ class FakeBatchedQP(object):
     def update_q(self, q):
         self.o.update(q=q)
 
+    def free(self):
+        self.o = None
+
     def solve_batch(self, l, u, x0, y0):
         x, y, st, it, extra = self.o.solve_batch(np.atleast_2d(l), np.atleast_2d(u), np.atleast_2d(x0), np.atleast_2d(y0))
         r = Scalars()

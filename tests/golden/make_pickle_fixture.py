@@ -11,58 +11,16 @@ dtypes and scipy CSC containers.
 """
 import json
 import os
-import pickle
+import sys
 
 import numpy as np
-import scipy.sparse as spa
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 SRC = "/root/reference/max_iter_examples"
 
 
-class _Obj(object):
-    """Placeholder for copy_reg._reconstructor targets (scipy.sparse.csc.csc_matrix instances)."""
-
-
-def _reconstructor(cls, base, state):
-    return _Obj()
-
-
-class SafeUnpickler(pickle.Unpickler):
-    ALLOWED = {
-        ("copy_reg", "_reconstructor"): _reconstructor,
-        ("__builtin__", "object"): object,
-        ("scipy.sparse.csc", "csc_matrix"): _Obj,
-        ("numpy.core.multiarray", "_reconstruct"): None,     # resolved lazily in find_class (numpy._core on numpy 2)
-        ("numpy", "ndarray"): np.ndarray,
-        ("numpy", "dtype"): np.dtype,
-        ("numpy.core.multiarray", "scalar"): None,
-    }
-
-    def find_class(self, module, name):
-        key = (module, name)
-        if key == ("numpy.core.multiarray", "_reconstruct"):
-            from numpy._core import multiarray
-            return multiarray._reconstruct
-        if key == ("numpy.core.multiarray", "scalar"):
-            from numpy._core import multiarray
-            return multiarray.scalar
-        if key in self.ALLOWED and self.ALLOWED[key] is not None:
-            return self.ALLOWED[key]
-        raise pickle.UnpicklingError("blocked global %s.%s" % key)
-
-
-def load(path):
-    with open(path, "rb") as f:
-        d = SafeUnpickler(f, encoding="latin1").load()
-    out = {}
-    for k, v in d.items():
-        if isinstance(v, _Obj):
-            st = v.__dict__
-            shape = tuple(int(s) for s in st["_shape"])
-            v = spa.csc_matrix((st["data"], st["indices"], st["indptr"]), shape=shape)
-        out[k] = v
-    return out
+from miosqp_b200.maxiter_problems import load_pickle as load   # whitelisting Unpickler lives in the package
 
 
 def main():
@@ -75,7 +33,7 @@ def main():
         for v in ("q", "l", "u"):
             arrays["%s_%d" % (v, k)] = np.asarray(p[v], dtype=np.float64)
         arrays["i_idx_%d" % k] = np.asarray(p["i_idx"], dtype=np.int64)
-        settings[str(k)] = {kk: (vv.item() if hasattr(vv, "item") else vv) for kk, vv in p["settings"].items()}
+        settings[str(k)] = p["settings"]
     arrays["names"] = np.array(names)
     arrays["settings_json"] = np.array(json.dumps(settings))
     out = os.path.join(HERE, "max_iter_examples.npz")

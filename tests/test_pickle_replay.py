@@ -4,27 +4,19 @@ only -- the reference holds no expected outputs for them), replayed as ONE batch
 compared with the CPU oracle: same status and iteration count, iterates and residuals to 1e-9 relative.
 The fixture tests/golden/max_iter_examples.npz is produced by tests/golden/make_pickle_fixture.py.
 """
-import json
 import os
 
 import numpy as np
 import pytest
 import scipy.sparse as spa
 
-from miosqp_b200 import engine
+from miosqp_b200 import engine, maxiter_problems
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def load_problems():
-    z = np.load(os.path.join(HERE, "golden", "max_iter_examples.npz"))
-    settings = json.loads(str(z["settings_json"]))
-    probs = []
-    for k in z["names"]:
-        k = int(k)
-        probs.append(dict(name=k, P=spa.csc_matrix(z["P_%d" % k]), A=spa.csc_matrix(z["A_%d" % k]), q=z["q_%d" % k],
-                          l=z["l_%d" % k], u=z["u_%d" % k], i_idx=z["i_idx_%d" % k], settings=settings[str(k)]))
-    return probs
+    return maxiter_problems.load_npz(os.path.join(HERE, "golden", "max_iter_examples.npz"))
 
 
 def test_fixture_shape_and_settings():
