@@ -816,6 +816,11 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       U.template pass<PM_M>(S, W, npm, do_check, R);
       U.template pass<PM_A_ITER>(S, W, npa, do_check, R);
       if (!do_check) continue;
+      // CHK1 prefetches z, y of its first 2 KU panels before it waits for anything, and the panel -> warp ownership shifts from
+      // pass to pass: those rows were written in the A pass just finished, possibly by a warp that is still up to kHB panels
+      // behind.  With fewer than 2 KU + kHB + KU - 1 = 14 panels in A that prefetch read stale rows (found at m = 60: dual
+      // residual and termination decision depended on timing).  Join the update warps first; once per check, so free.
+      named_bar(3, KU * 32);
       reset();
       U.template pass<PM_A_CHK1>(S, W, npa, true, R);
       U.template pass<PM_A_CHK2>(S, W, npa, true, R);
