@@ -260,7 +260,7 @@ class Workspace(object):
         leaf.nextvar_idx = self.data.i_idx[nextvar]
 
     def satisfies_lin_constraints(self, x, l, u):
-        z = self.data.A.dot(x)
+        z = self.data.A_op.dot(x)
         eps = self.qp_settings['eps_abs']       # reference quirk: KeyError when qp_settings lacks eps_abs
         return not (np.any(z < l - eps) or np.any(z > u + eps))
 
