@@ -28,12 +28,12 @@ def _worker(rank, world, port, mode, out_dir):
     golden = json.load(open(os.path.join(HERE, "golden", "bnb_random_miqp.json")))
     names = sorted(golden)
 
-    def build(name):
+    def build(name, speculation=0):
         c = golden[name]["case"]
         pr = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"])[0]
         m = miosqp_b200.MIOSQP()
         m.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
-                dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+                dict(problems.RANDOM_MIQP_SETTINGS, speculation=speculation), dict(problems.RANDOM_MIQP_QP_SETTINGS))
         return m
 
     if mode == "instances":
@@ -44,19 +44,22 @@ def _worker(rank, world, port, mode, out_dir):
                  for n, m, r in zip(names[lo:hi], mine, res)]
         allres = sharding.gather_results(local)
     else:
-        m = build("small_seed5")
+        # "frontier+lookahead": the batch every rank splits also carries look-ahead nodes (settings['speculation']):
+        # this is what gives a single-instance frontier (2 real nodes per B&B step) enough nodes to spread over GPUs
+        m = build("small_seed5", speculation=0 if mode == "frontier" else 16)
         r = m.solve(dist_ctx=(rank, world, None))
-        allres = [("small_seed5", r.status, float(r.upper_glob), [list(d) for d in m.work.decisions], m.work.batched_nodes)]
+        allres = [("small_seed5", r.status, float(r.upper_glob), [list(d) for d in m.work.decisions], m.work.batched_nodes,
+                   m.work.batches, m.work.spec_hits)]
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
         json.dump(allres, f)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["instances", "frontier"])
+@pytest.mark.parametrize("mode", ["instances", "frontier", "frontier+lookahead"])
 def test_two_rank_gloo(tmp_path, mode):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 2000) + (0 if mode == "instances" else 1)
+    port = 29500 + (os.getpid() % 2000) + ["instances", "frontier", "frontier+lookahead"].index(mode)
     mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
     golden = json.load(open(os.path.join(HERE, "golden", "bnb_random_miqp.json")))
     outs = [json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r))) for r in range(2)]
@@ -68,6 +71,9 @@ def test_two_rank_gloo(tmp_path, mode):
         assert rec[3] == [list(d) for d in g["decisions"]]
     if mode == "instances":
         assert [rec[0] for rec in outs[0]] == sorted(golden)
+    if mode == "frontier+lookahead":
+        g = golden["small_seed5"]["result"]
+        assert outs[0][0][6] > 0 and outs[0][0][4] >= g["iter_num"] - 1 and outs[0][0][5] < g["iter_num"] - 1
 
 
 def test_shard_helpers():
