@@ -56,6 +56,13 @@ def test_replay_maxiter_example_cpu(cpu_engine, capsys):
     assert "2 problems in one launch" in out and "summary:" in out
 
 
+def test_frontier_split_example_single_process_cpu(cpu_engine, capsys):
+    import frontier_split
+    frontier_split.main(["--n", "40", "--m", "40", "--p", "20", "--density", "0.7", "--seed", "3", "--speculation", "32"])
+    rec = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rec["status"] == "Solved" and rec["nodes"] >= 100 and rec["launches"] * 3 < rec["nodes"]
+
+
 def _bnb(speculation, rule=1):
     import miosqp_b200
     from miosqp_b200 import problems
