@@ -150,3 +150,79 @@ def test_bounds_validation():
     bad = l.copy(); bad[0] = u[0] + 1
     with pytest.raises(ValueError):
         o.update(l=bad, u=u)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_against_an_independent_solver(seed):
+    """Cross-solver check: the oracle at tight tolerance against scipy's SLSQP (a sequential-QP active-set method that
+    shares nothing with ADMM) on random strictly convex QPs with two-sided, one-sided and equality rows."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(seed)
+    n, m = 8, 12
+    M = rng.standard_normal((n, n)); P = M @ M.T + 0.1 * np.eye(n); q = rng.standard_normal(n)
+    A = rng.standard_normal((m, n))
+    xf = rng.standard_normal(n); z = A @ xf                       # a feasible point keeps the problem feasible
+    l = z - rng.uniform(0.1, 1.0, m); u = z + rng.uniform(0.1, 1.0, m)
+    l[:3] = -np.inf; u[3:5] = np.inf; l[5] = u[5] = z[5]
+    o, r = _solve(P, q, A, l, u)
+    assert r.info.status_val == 1
+    cons = []
+    for i in range(m):
+        if l[i] == u[i]:
+            cons.append({"type": "eq", "fun": lambda x, i=i: A[i] @ x - u[i], "jac": lambda x, i=i: A[i]})
+            continue
+        if np.isfinite(u[i]):
+            cons.append({"type": "ineq", "fun": lambda x, i=i: u[i] - A[i] @ x, "jac": lambda x, i=i: -A[i]})
+        if np.isfinite(l[i]):
+            cons.append({"type": "ineq", "fun": lambda x, i=i: A[i] @ x - l[i], "jac": lambda x, i=i: A[i]})
+    ref = minimize(lambda x: 0.5 * x @ P @ x + q @ x, xf, jac=lambda x: P @ x + q, constraints=cons, method="SLSQP",
+                   options={"ftol": 1e-14, "maxiter": 500})
+    assert ref.success
+    f_or = 0.5 * r.x @ P @ r.x + q @ r.x
+    assert abs(f_or - ref.fun) <= 1e-7 * (1 + abs(ref.fun))
+    assert np.abs(r.x - ref.x).max() <= 1e-5 * (1 + np.abs(ref.x).max())
+    # dual sign convention (OSQP): y_i > 0 only at the upper bound, y_i < 0 only at the lower bound
+    Ax = A @ r.x
+    assert np.all(r.y[Ax < u - 1e-5] <= 1e-6) and np.all(r.y[Ax > l + 1e-5] >= -1e-6)
+
+
+def test_miqp_optimum_by_enumeration_small():
+    """A second reference-independent MIQP answer (besides BASELINE config 1): every 0/1 assignment of 6 integer
+    variables solved as a QP by SLSQP; the B&B on the oracle must return that assignment and objective (1e-3, the
+    example tolerances)."""
+    import itertools
+    from scipy.optimize import minimize
+    import fake_engine
+    import miosqp_b200
+    from miosqp_b200 import engine
+    pr = problems.random_miqp(10, 14, 6, 0.7, seed=11)[0]
+    P = pr['P'].toarray(); A = pr['A'].toarray(); q, l, u, idx = pr['q'], pr['l'], pr['u'], pr['i_idx']
+    free = np.setdiff1d(np.arange(10), idx)
+    best = (np.inf, None)
+    for bits in itertools.product((0.0, 1.0), repeat=6):
+        xb = np.zeros(10); xb[idx] = bits
+        # reduced QP in the 4 continuous variables
+        Pf = P[np.ix_(free, free)]; qf = q[free] + P[np.ix_(free, idx)] @ np.array(bits); Af = A[:, free]; off = A[:, idx] @ np.array(bits)
+        cons = [{"type": "ineq", "fun": lambda x: u - off - Af @ x, "jac": lambda x: -Af},
+                {"type": "ineq", "fun": lambda x: Af @ x + off - l, "jac": lambda x: Af}]
+        ref = minimize(lambda x: 0.5 * x @ Pf @ x + qf @ x, np.zeros(4), jac=lambda x: Pf @ x + qf, constraints=cons, method="SLSQP",
+                       options={"ftol": 1e-13, "maxiter": 300})
+        if not ref.success or np.any(Af @ ref.x + off > u + 1e-7) or np.any(Af @ ref.x + off < l - 1e-7):
+            continue
+        xb[free] = ref.x
+        f = 0.5 * xb @ P @ xb + q @ xb
+        if f < best[0]:
+            best = (f, np.array(bits))
+    assert best[1] is not None
+    saved = engine.BatchedQP, engine.solve_multi
+    engine.BatchedQP, engine.solve_multi = fake_engine.FakeBatchedQP, fake_engine.solve_multi
+    try:
+        s = miosqp_b200.MIOSQP()
+        s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+        r = s.solve()
+    finally:
+        engine.BatchedQP, engine.solve_multi = saved
+    assert r.status == 'Solved'
+    assert np.array_equal(r.x[idx], best[1])
+    assert abs(r.upper_glob - best[0]) <= 5e-3 * (1 + abs(best[0]))
