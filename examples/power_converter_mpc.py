@@ -6,7 +6,7 @@ arm, THD figures and plots (/root/reference/examples/power_converter/run_example
 power_converter.py:589-675).  Prints the reference's timing table (avg/std/min/max solve time per MPC step, OSQP share,
 average ADMM iterations) per horizon, plus B&B nodes, engine launches and the switching frequency, and one JSON line.
 
-    python examples/power_converter_mpc.py --horizons 10 --steps 1000 --speculation 256      # BASELINE config 3
+    python examples/power_converter_mpc.py --horizons 10 --steps 1000 --speculation 32       # BASELINE config 3
     python examples/power_converter_mpc.py --horizons 1,2,3,4,5                              # the reference's sweep
 """
 import argparse
@@ -23,7 +23,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--horizons", default="1,2,3,4,5")
     ap.add_argument("--steps", type=int, default=None, help="sampling instants (default: the reference's 3 periods = 2400)")
-    ap.add_argument("--speculation", type=int, default=256, help="nodes solved ahead of the replay per launch (0 = off)")
+    ap.add_argument("--speculation", type=int, default=32, help="nodes solved ahead of the replay per launch (0 = off)")
     ap.add_argument("--tail", default="delta_550")
     ap.add_argument("--csv", default=None)
     args = ap.parse_args(argv)

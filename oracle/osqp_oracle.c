@@ -523,6 +523,30 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
     double li = l_in[i] < -OSQP_INFTY ? -OSQP_INFTY : l_in[i], ui = u_in[i] > OSQP_INFTY ? OSQP_INFTY : u_in[i];
     l[i] = w->E[i] * li; u[i] = w->E[i] * ui;
   }
+  /* eq_rho == 2: what osqp >= 0.4 does in update_bounds -- re-type every row from THIS node's scaled
+   * bounds and, if any type changed against the factor at hand, rebuild rho_vec and refactor numerically.  Not the
+   * engine's parity contract (eq_rho == 1: typed once at setup); kept to measure what that contract costs (section 8f2). */
+  OracleWork tw; double *rv = NULL, *ri = NULL; int refactored = 0;
+  if (S->eq_rho == 2 && m > 0) {
+    rv = malloc(8 * (size_t)m); ri = malloc(8 * (size_t)m);
+    int changed = 0;
+    for (int i = 0; i < m; i++) {
+      double r = S->rho;
+      if (l[i] < -OSQP_INFTY * MIN_SCALING && u[i] > OSQP_INFTY * MIN_SCALING) r = RHO_MIN;
+      else if (u[i] - l[i] < RHO_TOL) r = RHO_EQ_OVER_RHO_INEQ * S->rho;
+      rv[i] = r; ri[i] = 1.0 / r;
+      if (r != w->rho_vec[i]) changed = 1;
+    }
+    if (changed) {
+      tw = *w; tw.rho_vec = rv; tw.rho_inv_vec = ri;
+      tw.perm = NULL; tw.Lp = NULL; tw.Li = NULL; tw.Lx = NULL; tw.Dd = NULL; tw.Ddinv = NULL; tw.etree = NULL;
+      if (factor_kkt(&tw) != 0) {
+        free(tw.perm); free(tw.Lp); free(tw.Li); free(tw.Lx); free(tw.Dd); free(tw.Ddinv); free(tw.etree);
+        free(rv); free(ri); free(l); free(u); return 2;
+      }
+      w = &tw; S = &w->s; refactored = 1;
+    }
+  }
   for (int j = 0; j < n; j++) s->x[j] = w->Dinv[j] * x0[j];
   for (int i = 0; i < m; i++) s->y[i] = w->c * w->Einv[i] * y0[i];
   mat_vec_A(w, s->x, s->z);
@@ -570,6 +594,8 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
   for (int j = 0; j < n; j++) x_out[j] = infeas ? NAN : w->D[j] * s->x[j];
   for (int i = 0; i < m; i++) y_out[i] = infeas ? NAN : w->cinv * w->E[i] * s->y[i];
   free(l); free(u);
+  if (refactored) { free(tw.perm); free(tw.Lp); free(tw.Li); free(tw.Lx); free(tw.Dd); free(tw.Ddinv); free(tw.etree); }
+  free(rv); free(ri);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   info->solve_time = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
   return 0;

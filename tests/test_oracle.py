@@ -226,3 +226,27 @@ def test_miqp_optimum_by_enumeration_small():
     assert r.status == 'Solved'
     assert np.array_equal(r.x[idx], best[1])
     assert abs(r.upper_glob - best[0]) <= 5e-3 * (1 + abs(best[0]))
+
+
+def test_per_node_rho_retyping_option():
+    """eq_rho = 2 (test infrastructure for SURVEY section 8f2): what osqp >= 0.4 does in update_bounds -- rows whose bounds
+    became equalities in a B&B child get rho x 1e3 and the KKT matrix is refactored.  At the root it is the contract
+    (eq_rho = 1) bit for bit; in a child with fixed binaries it reaches the same optimum, normally in fewer iterations."""
+    pr = problems.random_miqp(30, 60, 10, 0.7, seed=1)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    s = dict(eps_abs=1e-6, eps_rel=1e-6, max_iter=20000)
+    o1 = oracle.OSQP(); o1.setup(P, q, A, l, u, eq_rho=1, **s)
+    o2 = oracle.OSQP(); o2.setup(P, q, A, l, u, eq_rho=2, **s)
+    x0 = np.zeros(30); y0 = np.zeros(70)
+    r1 = o1.solve_node(l, u, x0, y0); r2 = o2.solve_node(l, u, x0, y0)
+    assert r1.info.iter == r2.info.iter and np.array_equal(r1.x, r2.x) and np.array_equal(r1.y, r2.y)
+    lc, uc = l.copy(), u.copy()
+    uc[-10:-5] = 0.0; lc[-5:-2] = 1.0                  # five binaries fixed to 0, three to 1: eight equality rows
+    c1 = o1.solve_node(lc, uc, x0, y0); c2 = o2.solve_node(lc, uc, x0, y0)
+    assert c1.info.status_val == c2.info.status_val == 1
+    assert np.abs(c1.x - c2.x).max() <= 1e-4 * (1 + np.abs(c1.x).max())
+    assert np.abs(c2.x[i_idx[:5]]).max() <= 1e-5 and np.abs(c2.x[i_idx[5:8]] - 1).max() <= 1e-5
+    assert c2.info.iter != c1.info.iter                 # a different rho vector is a different ADMM trajectory
+    # stateless: the retyped factor is private to the call
+    r1b = o2.solve_node(l, u, x0, y0)
+    assert r1b.info.iter == r1.info.iter and np.array_equal(r1b.x, r1.x)
