@@ -171,11 +171,11 @@ class ClosedLoopResult(object):
 
 
 def closed_loop(steps, N=10, make_solver=None, drive=None, fsw_des=300, delta=5.5, gamma=0.95, tail="delta_550",
-                on_step=None, speculation=0):
+                on_step=None, speculation=0, qp_settings=None):
     """First `steps` sampling instants of the reference's closed loop (power_converter.py:589-649): at every instant
     build (q,l,u) from the state, warm start from the shifted previous plan, solve the MIQP, apply the first input.
     `make_solver()` returns an object with the MIOSQP interface (default: miosqp_b200.MIOSQP on the CUDA engine).
-    `speculation` > 0 lets every launch also solve up to that many nodes ahead of the replay (tree.py `speculate`):
+    `qp_settings` overrides entries of the reference's OSQP settings.  `speculation` > 0 lets every launch also solve up to that many nodes ahead of the replay (tree.py `speculate`):
     same answers, far fewer host round trips on this workload's deep, narrow trees.
     Returns the trajectories and the per-step B&B statistics."""
     if make_solver is None:
@@ -197,7 +197,7 @@ def closed_loop(steps, N=10, make_solver=None, drive=None, fsw_des=300, delta=5.
         if solver is None:
             solver = make_solver()
             solver.setup(prog.P, q, prog.A, l, u, prog.i_idx, prog.i_l, prog.i_u,
-                         dict(MPC_SETTINGS, speculation=speculation), dict(MPC_QP_SETTINGS))
+                         dict(MPC_SETTINGS, speculation=speculation), dict(MPC_QP_SETTINGS, **(qp_settings or {})))
         else:
             solver.update_vectors(q, l, u)
         solver.set_x0(plan)

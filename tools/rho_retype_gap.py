@@ -37,18 +37,15 @@ def main():
         pr = problems.random_miqp(n, m, p, 0.7, seed=seed)[0]
         a, b = bnb(pr, 1), bnb(pr, 2)
         rows.append(dict(workload="random_miqp n=%d m=%d p=%d seed=%d" % (n, m, p, seed), setup_typing=a, per_node_typing=b))
-    saved = dict(pc.MPC_QP_SETTINGS)
     for N in (3, 10):
         out = {}
         for eq in (1, 2):
-            pc.MPC_QP_SETTINGS.clear(); pc.MPC_QP_SETTINGS.update(saved, eq_rho=eq)
-            r = pc.closed_loop(10, N=N, speculation=32)
+            r = pc.closed_loop(10, N=N, speculation=32, qp_settings=dict(eq_rho=eq))
             out[eq] = dict(nodes=int(r.nodes.sum()), admm_iters=int(r.admm_iters.sum()), node_limit_steps=sum(s != 'Solved' for s in r.status),
                            obj_sum=float(r.obj.sum()), inputs_equal_to_setup_typing=None)
             out[eq]["U"] = r.U
         out[2]["inputs_equal_to_setup_typing"] = bool(np.array_equal(out[1].pop("U"), out[2].pop("U")))
         rows.append(dict(workload="power_converter MPC N=%d, first 10 steps" % N, setup_typing=out[1], per_node_typing=out[2]))
-    pc.MPC_QP_SETTINGS.clear(); pc.MPC_QP_SETTINGS.update(saved)
     for r in rows:
         print(json.dumps(r))
 
