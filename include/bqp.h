@@ -38,7 +38,9 @@ typedef enum {
   BQP_E_NONCONVEX = -3,  /* reduced KKT matrix not positive definite */
   BQP_E_CUDA = -4,       /* CUDA runtime error or no usable device */
   BQP_E_ALLOC = -5,      /* out of host or device memory */
-  BQP_E_UNSUPPORTED = -6 /* setting outside the parity contract (e.g. adaptive_rho) or problem too large for one CTA */
+  BQP_E_UNSUPPORTED = -6, /* setting outside the parity contract (e.g. adaptive_rho) or problem too large for one CTA */
+  BQP_BNB_E_EXPLOR_RULE = -7, /* bqp_bnb_solve: 'Tree exploring strategy not recognized'   workspace.py:147 */
+  BQP_BNB_E_BRANCH_RULE = -8  /* bqp_bnb_solve: 'No variable selection rule recognized!'   workspace.py:224 */
 } bqp_error;
 
 /* OSQP status codes written to status[] (osqp.constant values) */
@@ -110,6 +112,40 @@ int bqp_batch_run(void);
 int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *out);
 int bqp_last_timing(bqp_timing *t);
 int bqp_free(bqp_handle h);
+
+/* ---- native branch-and-bound replay (miosqp_b200/csrc/bqp_bnb.cpp) ------------------------------------------------
+ * bqp_bnb_solve <- MIOSQP.solve(): the while-loop of solver.py:85-123 with workspace.py:128-384 and node.py:96-143,
+ * every open leaf solved by the batched engine (one bqp_solve_multi per B&B step, plus `speculation` look-ahead nodes).
+ * Same decisions as the reference's sequential loop; statuses are the strings of constants.py:2-7 by index. */
+enum { BQP_MI_UNSOLVED = 0, BQP_MI_SOLVED = 1, BQP_MI_PRIMAL_INFEASIBLE = 2, BQP_MI_DUAL_INFEASIBLE = 3,
+       BQP_MI_MAX_ITER_FEASIBLE = 4, BQP_MI_MAX_ITER_UNSOLVED = 5 };
+typedef struct {
+  double eps_int_feas;     /* settings['eps_int_feas']                                   workspace.py:257 */
+  int max_iter_bb;         /* settings['max_iter_bb']                                    workspace.py:113-126 */
+  int tree_explor_rule;    /* 0 depth first, 1 two-phase                                 workspace.py:128-155 */
+  int branching_rule;      /* 0 most fractional                                          workspace.py:205-230 */
+  int speculation;         /* look-ahead nodes per launch (0 = the reference's two nodes per step) */
+  double eps_abs;          /* qp_settings['eps_abs']: feasibility slack of the rounding heuristic   workspace.py:238 */
+} bqp_bnb_settings;
+typedef struct {
+  int status;              /* BQP_MI_* */
+  int iter_num;            /* starts at 1, as the reference's counter */
+  long long osqp_iter;     /* ADMM iterations of the consumed nodes */
+  double osqp_solve_time, upper_glob, lower_glob;
+  int batches;             /* launches */
+  long long batched_nodes, spec_nodes, spec_hits;
+  int n_decisions, open_leaves;
+} bqp_bnb_result;
+/* batch solver used instead of the engine (tests): same contract as bqp_solve_multi with one problem, returns 0 or a bqp_error */
+typedef int (*bqp_solve_fn)(void *ctx, int B, const double *const *l, const double *const *u, const double *const *x0,
+                            const double *const *y0, double *const *x, double *const *y, int *status, int *iters);
+/* p: the UNSCALED problem as Data holds it (P as the caller passed it -- full symmetric for the reference's examples --,
+ * q, extended A, root l/u, i_idx).  x_incumbent/upper_incumbent: what set_x0 accepted (NULL / +inf: none).
+ * fn == NULL: nodes are solved on the device through h.  x[n]: the returned solution (integer entries rounded).
+ * decisions: up to decisions_cap (constr_idx, nextvar_idx) pairs. */
+int bqp_bnb_solve(bqp_handle h, const bqp_problem *p, const bqp_bnb_settings *s, const double *x_incumbent,
+                  double upper_incumbent, bqp_solve_fn fn, void *ctx, double *x, bqp_bnb_result *res,
+                  int *decisions, int decisions_cap);
 
 /* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
 int bqp_set_tuning(int tile_nodes, int threads);

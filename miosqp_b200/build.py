@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbqp.so")
-SOURCES = ["bqp_setup.cpp", "bqp_kernels.cu", "bqp_stream.cu", "bqp_panel.cu", "bqp_api.cu"]
+SOURCES = ["bqp_setup.cpp", "bqp_bnb.cpp", "bqp_kernels.cu", "bqp_stream.cu", "bqp_panel.cu", "bqp_api.cu"]
 HEADERS = ["bqp_internal.h", os.path.join("..", "..", "include", "bqp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-Xptxas", "-v"]

@@ -666,6 +666,8 @@ const char *bqp_strerror(int code) {
       return buf;
     case BQP_E_ALLOC: return "out of memory";
     case BQP_E_UNSUPPORTED: return "unsupported setting or problem too large for one CTA's shared memory";
+    case BQP_BNB_E_EXPLOR_RULE: return "Tree exploring strategy not recognized";
+    case BQP_BNB_E_BRANCH_RULE: return "No variable selection rule recognized!";
   }
   return "unknown error";
 }

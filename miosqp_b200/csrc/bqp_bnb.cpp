@@ -1,0 +1,292 @@
+// bqp_bnb.cpp -- native branch-and-bound replay with look-ahead (bqp_bnb_solve, include/bqp.h).
+//
+// The reference runs its B&B loop in Python, one node per iteration (/root/reference/miosqp/solver.py:85-123,
+// workspace.py:128-384, node.py:96-143).  miosqp_b200/tree.py replays that logic over batched results; at BASELINE
+// config 3 (hundreds of tiny nodes per MPC step) its ~90 us of interpreter time per node is what remains once the
+// look-ahead has removed the host round trips.  This file is the same replay, statement for
+// statement, in C++: frontier, leaf selection, clip + objective, integer-feasibility test, rounding heuristic against
+// the ROOT bounds, most-fractional branching, the reference's prune()/iter_num/"largest lower bound" quirks, and the
+// look-ahead of tree.py (shadow children adopted only when computed from exactly the replay's inputs).
+// It talks to the engine only through the public entry point bqp_solve_multi -- or through a caller-supplied solve
+// function (CPU tests drive it with the oracle; nothing here links to oracle/).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "../../include/bqp.h"
+
+namespace {
+
+using Vec = std::vector<double>;
+using VecP = std::shared_ptr<Vec>;
+constexpr double kInf = std::numeric_limits<double>::infinity();
+
+struct Node;
+using NodeP = std::shared_ptr<Node>;
+
+struct Node {
+  Vec l, u;                 // extended bounds of this node
+  VecP x, y;                // warm start before solve(), solution after (children share the parent's arrays)
+  int depth = 0;
+  double lower = -kInf;
+  int status = BQP_UNSOLVED, num_iter = 0;
+  double seconds = 0.0;
+  // result of a launch not yet consumed by the replay (cache isolation: nothing above changes until solve())
+  bool has_cached = false;
+  int c_status = BQP_UNSOLVED, c_iters = 0; double c_seconds = 0.0; VecP cx, cy;
+  // look-ahead: 0 = not examined, 1 = cannot branch, 2 = sh[0], sh[1] exist
+  int shadow_state = 0;
+  NodeP sh[2];
+  std::vector<int> frac_idx;
+  int constr_idx = -1, nextvar_idx = -1;
+};
+
+struct Csc { int rows = 0, cols = 0; const int *p = nullptr, *i = nullptr; const double *x = nullptr; };
+
+struct Tree {
+  int n = 0, m = 0, n_int = 0, m_ext = 0;       // m = ORIGINAL rows, m_ext = m + n_int
+  Csc P, A;
+  const double *q = nullptr; const int *i_idx = nullptr;
+  Vec l_root, u_root;
+  bqp_bnb_settings s;
+  std::vector<NodeP> leaves;
+  int iter_num = 1;                              // reference quirk: counts from 1 (solver.py:130 divides by nodes + 1)
+  long long osqp_iter = 0; double osqp_solve_time = 0.0;
+  double upper_glob = kInf, lower_glob = -kInf;
+  Vec x_best;
+  std::vector<int> decisions;
+  int batches = 0; long long batched_nodes = 0, spec_nodes = 0, spec_hits = 0;
+  bqp_handle h = nullptr; bqp_solve_fn fn = nullptr; void *ctx = nullptr;
+  Vec tmp;
+
+  // y = M x in CSC column order: the loop scipy's csc_matvec runs
+  static void matvec(const Csc &M, const double *x, double *y) {
+    for (int r = 0; r < M.rows; r++) y[r] = 0.0;
+    for (int j = 0; j < M.cols; j++) { const double xj = x[j]; for (int k = M.p[j]; k < M.p[j + 1]; k++) y[M.i[k]] += M.x[k] * xj; }
+  }
+  double obj(const Vec &x) {                     // data.py:99-103
+    tmp.resize(std::max(n, m_ext));
+    matvec(P, x.data(), tmp.data());
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < n; j++) { a += x[j] * tmp[j]; b += q[j] * x[j]; }
+    return .5 * a + b;
+  }
+  bool satisfies_lin(const Vec &x, const Vec &l, const Vec &u) {      // workspace.py:232-243
+    tmp.resize(std::max(n, m_ext));
+    matvec(A, x.data(), tmp.data());
+    for (int r = 0; r < m_ext; r++) if (tmp[r] < l[r] - s.eps_abs || tmp[r] > u[r] + s.eps_abs) return false;
+    return true;
+  }
+  // fractional integer entries of x (workspace.py:245-264); returns true when there are none
+  bool int_feas(const Vec &x, std::vector<int> &frac) const {
+    frac.clear();
+    for (int k = 0; k < n_int; k++) { const double v = x[i_idx[k]]; if (std::fabs(v - std::nearbyint(v)) > s.eps_int_feas) frac.push_back(k); }
+    return frac.empty();
+  }
+  int most_fractional(const Vec &x, const std::vector<int> &frac) const {   // workspace.py:205-230, first maximum wins
+    int best = frac[0]; double bd = -1.0;
+    for (int k : frac) { const double v = x[i_idx[k]], d = std::fabs(v - std::nearbyint(v)); if (d > bd) { bd = d; best = k; } }
+    return best;
+  }
+  void clip_int(Vec &x, const Vec &l, const Vec &u) const {                  // node.py:131-136
+    for (int k = 0; k < n_int; k++) { double &v = x[i_idx[k]]; v = std::fmin(std::fmax(v, l[m + k]), u[m + k]); }
+  }
+
+  static bool unsolved(const Node &nd) { return !nd.has_cached && nd.status == BQP_UNSOLVED; }
+
+  // ---- look-ahead (tree.py prospect / speculate)
+  void prospect(Node &nd) {
+    nd.shadow_state = 1;
+    if (nd.c_status != BQP_SOLVED && nd.c_status != BQP_MAX_ITER_REACHED) return;
+    auto xc = std::make_shared<Vec>(*nd.cx);
+    clip_int(*xc, nd.l, nd.u);
+    std::vector<int> frac;
+    if (int_feas(*xc, frac)) return;
+    const int nextvar = most_fractional(*xc, frac), row = m + nextvar, var = i_idx[nextvar];
+    const double lower = obj(*xc);
+    if (lower > upper_glob) return;                           // the replay will drop it (workspace.py:299-300)
+    NodeP kids[2];
+    for (int side = 0; side < 2; side++) {
+      auto c = std::make_shared<Node>();
+      c->l = nd.l; c->u = nd.u;
+      if (side == 0) c->u[row] = std::floor((*xc)[var]); else c->l[row] = std::ceil((*xc)[var]);
+      if (c->l[row] > c->u[row]) return;                      // the engine would reject the whole launch
+      c->x = xc; c->y = nd.cy; c->depth = nd.depth + 1; c->lower = lower;
+      kids[side] = c;
+    }
+    nd.sh[0] = kids[0]; nd.sh[1] = kids[1]; nd.shadow_state = 2;
+  }
+  void speculate(int budget, std::vector<Node *> &batch) {
+    std::vector<Node *> cands, stack;
+    for (auto &lf : leaves) stack.push_back(lf.get());
+    while (!stack.empty()) {
+      Node *nd = stack.back(); stack.pop_back();
+      if (!nd->has_cached) continue;
+      if (nd->shadow_state == 0) cands.push_back(nd);
+      else if (nd->shadow_state == 2) { stack.push_back(nd->sh[0].get()); stack.push_back(nd->sh[1].get()); }
+    }
+    const bool depth_first = s.tree_explor_rule == 0 || std::isinf(upper_glob);
+    std::stable_sort(cands.begin(), cands.end(), [&](const Node *a, const Node *b) {
+      return depth_first ? a->depth > b->depth : a->lower > b->lower; });
+    int added = 0;
+    for (Node *nd : cands) {
+      if (added + 2 > budget) break;
+      prospect(*nd);
+      if (nd->shadow_state == 2) { batch.push_back(nd->sh[0].get()); batch.push_back(nd->sh[1].get()); added += 2; }
+    }
+    spec_nodes += added;
+  }
+
+  // ---- one launch over every unsolved open leaf (+ look-ahead)
+  int launch() {
+    std::vector<Node *> batch;
+    for (auto &lf : leaves) if (unsolved(*lf)) batch.push_back(lf.get());
+    if (batch.empty()) return BQP_OK;
+    if (s.speculation > 0) speculate(s.speculation, batch);
+    const int B = (int)batch.size();
+    std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
+    std::vector<double *> px(B), py(B);
+    std::vector<int> status(B), iters(B);
+    for (int b = 0; b < B; b++) {
+      Node &nd = *batch[b];
+      nd.cx = std::make_shared<Vec>(n); nd.cy = std::make_shared<Vec>(m_ext);
+      pl[b] = nd.l.data(); pu[b] = nd.u.data(); px0[b] = nd.x->data(); py0[b] = nd.y->data();
+      px[b] = nd.cx->data(); py[b] = nd.cy->data();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc;
+    if (fn) rc = fn(ctx, B, pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), status.data(), iters.data());
+    else {
+      std::vector<bqp_handle> hs(B, h);
+      bqp_node_out out; std::memset(&out, 0, sizeof(out));
+      out.status = status.data(); out.iters = iters.data();
+      rc = bqp_solve_multi(B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), &out);
+    }
+    if (rc) return rc;
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    long long total = 0; for (int b = 0; b < B; b++) total += iters[b];
+    if (total < 1) total = 1;
+    for (int b = 0; b < B; b++) {
+      Node &nd = *batch[b];
+      nd.has_cached = true; nd.c_status = status[b]; nd.c_iters = iters[b]; nd.c_seconds = dt * (double)iters[b] / (double)total;
+    }
+    batches++; batched_nodes += B;
+    return BQP_OK;
+  }
+
+  // ---- reference logic, replayed
+  int choose_leaf(NodeP &out) {                                           // workspace.py:128-155
+    size_t pick = 0;
+    if (s.tree_explor_rule == 0 || (s.tree_explor_rule == 1 && std::isinf(upper_glob))) {
+      for (size_t k = 1; k < leaves.size(); k++) if (leaves[k]->depth > leaves[pick]->depth) pick = k;
+    } else if (s.tree_explor_rule == 1) {
+      // reference quirk: the "best bound" phase takes the LARGEST lower bound (workspace.py:145)
+      for (size_t k = 1; k < leaves.size(); k++) if (leaves[k]->lower > leaves[pick]->lower) pick = k;
+    } else return BQP_BNB_E_EXPLOR_RULE;
+    out = leaves[pick];
+    leaves.erase(leaves.begin() + (long)pick);
+    return BQP_OK;
+  }
+  void solve_node(Node &nd) {                                             // node.py:96-143 over the cached result
+    nd.status = nd.c_status; nd.num_iter = nd.c_iters; nd.seconds = nd.c_seconds; nd.x = nd.cx; nd.y = nd.cy;
+    nd.has_cached = false;
+    if (nd.status == BQP_SOLVED || nd.status == BQP_MAX_ITER_REACHED) { clip_int(*nd.x, nd.l, nd.u); nd.lower = obj(*nd.x); }
+  }
+  void prune() {
+    // reference quirk (workspace.py:274-280): the list is mutated while iterated, so the element that slides into a
+    // removed slot is not examined in this pass
+    for (size_t k = 0; k < leaves.size(); k++) if (leaves[k]->lower > upper_glob) leaves.erase(leaves.begin() + (long)k);
+  }
+  void add_child(Node &leaf, int side) {                                  // workspace.py:157-203
+    auto c = std::make_shared<Node>();
+    c->l = leaf.l; c->u = leaf.u;
+    if (side == 0) c->u[leaf.constr_idx] = std::floor((*leaf.x)[leaf.nextvar_idx]);
+    else c->l[leaf.constr_idx] = std::ceil((*leaf.x)[leaf.nextvar_idx]);
+    c->x = leaf.x; c->y = leaf.y; c->depth = leaf.depth + 1; c->lower = leaf.lower;
+    if (leaf.shadow_state == 2) {
+      const Node &sh = *leaf.sh[side];
+      // adopt a result solved ahead of the replay only if it was computed from exactly these inputs
+      if (sh.has_cached && sh.l == c->l && sh.u == c->u && *sh.x == *c->x && *sh.y == *c->y) {
+        c->has_cached = true; c->c_status = sh.c_status; c->c_iters = sh.c_iters; c->c_seconds = sh.c_seconds; c->cx = sh.cx; c->cy = sh.cy;
+        c->shadow_state = sh.shadow_state; c->sh[0] = sh.sh[0]; c->sh[1] = sh.sh[1];
+        spec_hits++;
+      }
+    }
+    leaves.push_back(c);
+  }
+  int bound_and_branch(Node &leaf) {                                      // workspace.py:282-334
+    osqp_iter += leaf.num_iter; osqp_solve_time += leaf.seconds;
+    if (leaf.status == BQP_PRIMAL_INFEASIBLE || leaf.status == BQP_DUAL_INFEASIBLE) return BQP_OK;
+    if (leaf.lower > upper_glob) return BQP_OK;
+    if (int_feas(*leaf.x, leaf.frac_idx)) { x_best = *leaf.x; upper_glob = leaf.lower; prune(); return BQP_OK; }
+    Vec x_int = *leaf.x;                                                  // rounding heuristic against the ROOT bounds
+    for (int k = 0; k < n_int; k++) x_int[i_idx[k]] = std::nearbyint(x_int[i_idx[k]]);
+    if (satisfies_lin(x_int, l_root, u_root)) {
+      const double o = obj(x_int);
+      if (o < upper_glob) { upper_glob = o; x_best = x_int; prune(); }
+    }
+    if (s.branching_rule != 0) return BQP_BNB_E_BRANCH_RULE;
+    const int nextvar = most_fractional(*leaf.x, leaf.frac_idx);
+    leaf.constr_idx = m + nextvar; leaf.nextvar_idx = i_idx[nextvar];
+    decisions.push_back(leaf.constr_idx); decisions.push_back(leaf.nextvar_idx);
+    add_child(leaf, 0); add_child(leaf, 1);
+    lower_glob = kInf;
+    for (auto &lf : leaves) lower_glob = std::fmin(lower_glob, lf->lower);
+    return BQP_OK;
+  }
+  int run() {
+    while (!leaves.empty() && iter_num < s.max_iter_bb) {
+      bool pending = false;
+      for (auto &lf : leaves) if (unsolved(*lf)) { pending = true; break; }
+      if (pending) { const int rc = launch(); if (rc) return rc; continue; }
+      NodeP leaf;
+      int rc = choose_leaf(leaf); if (rc) return rc;
+      solve_node(*leaf);
+      rc = bound_and_branch(*leaf); if (rc) return rc;
+      iter_num++;
+    }
+    return BQP_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" int bqp_bnb_solve(bqp_handle h, const bqp_problem *p, const bqp_bnb_settings *s, const double *x_incumbent,
+                             double upper_incumbent, bqp_solve_fn fn, void *ctx, double *x, bqp_bnb_result *res,
+                             int *decisions, int decisions_cap) {
+  if (!p || !s || !x || !res || (!h && !fn) || p->n <= 0 || p->m < p->n_int || p->n_int < 0) return BQP_E_ARG;
+  if (!p->Pp || !p->Pi || !p->Px || !p->Ap || !p->Ai || !p->Ax || !p->q || !p->l || !p->u || (p->n_int && !p->i_idx)) return BQP_E_ARG;
+  Tree t;
+  t.n = p->n; t.m_ext = p->m; t.n_int = p->n_int; t.m = p->m - p->n_int;
+  t.P.rows = t.P.cols = p->n; t.P.p = p->Pp; t.P.i = p->Pi; t.P.x = p->Px;
+  t.A.rows = p->m; t.A.cols = p->n; t.A.p = p->Ap; t.A.i = p->Ai; t.A.x = p->Ax;
+  t.q = p->q; t.i_idx = p->i_idx; t.s = *s; t.h = h; t.fn = fn; t.ctx = ctx;
+  t.l_root.assign(p->l, p->l + p->m); t.u_root.assign(p->u, p->u + p->m);
+  auto root = std::make_shared<Node>();
+  root->l = t.l_root; root->u = t.u_root;
+  root->x = std::make_shared<Vec>(p->n, 0.0); root->y = std::make_shared<Vec>(p->m, 0.0);
+  t.leaves.push_back(root);
+  t.x_best.assign(p->n, 0.0);
+  if (x_incumbent && std::isfinite(upper_incumbent)) { t.x_best.assign(x_incumbent, x_incumbent + p->n); t.upper_glob = upper_incumbent; }
+  const int rc = t.run();
+  std::memset(res, 0, sizeof(*res));
+  res->iter_num = t.iter_num; res->osqp_iter = t.osqp_iter; res->osqp_solve_time = t.osqp_solve_time;
+  res->upper_glob = t.upper_glob; res->lower_glob = t.lower_glob;
+  res->batches = t.batches; res->batched_nodes = t.batched_nodes; res->spec_nodes = t.spec_nodes; res->spec_hits = t.spec_hits;
+  res->n_decisions = (int)(t.decisions.size() / 2);
+  res->open_leaves = (int)t.leaves.size();
+  if (decisions) std::memcpy(decisions, t.decisions.data(), sizeof(int) * std::min<size_t>(t.decisions.size(), 2 * (size_t)std::max(0, decisions_cap)));
+  // workspace.py:352-384
+  const bool finished = t.iter_num < s->max_iter_bb;
+  if (t.upper_glob != kInf) res->status = finished ? BQP_MI_SOLVED : BQP_MI_MAX_ITER_FEASIBLE;
+  else if (t.upper_glob >= 0) res->status = finished ? BQP_MI_PRIMAL_INFEASIBLE : BQP_MI_MAX_ITER_UNSOLVED;
+  else res->status = BQP_MI_DUAL_INFEASIBLE;
+  if (res->status == BQP_MI_SOLVED || res->status == BQP_MI_MAX_ITER_FEASIBLE)
+    for (int k = 0; k < t.n_int; k++) t.x_best[p->i_idx[k]] = std::nearbyint(t.x_best[p->i_idx[k]]);
+  std::memcpy(x, t.x_best.data(), sizeof(double) * (size_t)p->n);
+  return rc;
+}

@@ -59,6 +59,23 @@ class _Problem(C.Structure):
                 ("n_int", C.c_int), ("i_idx", _ip)]
 
 
+class _BnbSettings(C.Structure):
+    _fields_ = [("eps_int_feas", C.c_double), ("max_iter_bb", C.c_int), ("tree_explor_rule", C.c_int),
+                ("branching_rule", C.c_int), ("speculation", C.c_int), ("eps_abs", C.c_double)]
+
+
+class _BnbResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("iter_num", C.c_int), ("osqp_iter", C.c_longlong),
+                ("osqp_solve_time", C.c_double), ("upper_glob", C.c_double), ("lower_glob", C.c_double),
+                ("batches", C.c_int), ("batched_nodes", C.c_longlong), ("spec_nodes", C.c_longlong),
+                ("spec_hits", C.c_longlong), ("n_decisions", C.c_int), ("open_leaves", C.c_int)]
+
+
+_pp_d = C.POINTER(C.POINTER(C.c_double))
+# bqp_solve_fn of include/bqp.h: a batch solver that stands in for the engine (CPU tests drive the native replay with the oracle)
+SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _pp_d, _pp_d, _pp_d, _pp_d, _pp_d, _pp_d, C.POINTER(C.c_int), C.POINTER(C.c_int))
+
+
 class _NodeOut(C.Structure):
     _fields_ = [("status", _ip), ("iters", _ip), ("obj", _dp), ("pri_res", _dp), ("dua_res", _dp), ("lower", _dp)]
 
@@ -79,7 +96,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
            "bqp_debug_host_panel_kkt_solve",
-           "bqp_debug_host_matvec"]
+           "bqp_debug_host_matvec", "bqp_bnb_solve"]
 
 _lib = None
 
@@ -113,6 +130,8 @@ def lib():
         L.bqp_debug_host_stream_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_panel_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
+        L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
+                                    C.POINTER(_BnbResult), _ip, C.c_int]
         _lib = L
     return _lib
 
@@ -121,7 +140,7 @@ def _check(rc):
     if rc == 0:
         return
     msg = lib().bqp_strerror(rc).decode()
-    if rc in (-1, -2, -3, -6):     # osqp raises ValueError for bad data / l > u / non-convex
+    if rc in (-1, -2, -3, -6, -7, -8):     # osqp / miosqp raise ValueError for bad data, l > u, non-convex, unknown rules
         raise ValueError(msg)
     raise BqpError(msg)
 
@@ -222,6 +241,10 @@ class BatchedQP(object):
         self.n_int = int(idx.size)
         return self
 
+    def native_solve_fn(self):
+        """None: the native B&B replay solves its nodes on the device through this handle."""
+        return None
+
     def update_q(self, q):
         q = _f64(q)
         if q.shape != (self.n,):
@@ -272,6 +295,38 @@ class BatchedQP(object):
         out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n, 4: self.n}[which])
         _check(lib().bqp_debug_host_matvec(self._h, which, _d(v), _d(out)))
         return out
+
+
+def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.inf):
+    """The native B&B replay (include/bqp.h bqp_bnb_solve, csrc/bqp_bnb.cpp) on one set-up problem.
+    `qp` is the BatchedQP holding the factor (or a stand-in exposing `native_solve_fn()`, CPU tests);
+    `data` the MIQP's problem_data.Data; `settings` the reference's MIOSQP settings dict (+ 'speculation').
+    Returns (x, result dict, decisions)."""
+    fixed = getattr(data, "_native_csc", None)          # P, A never change after setup: convert once per Data
+    if fixed is None:
+        P = spa.csc_matrix(data.P); A = spa.csc_matrix(data.A)
+        fixed = (A.shape, P.indptr.astype(np.int32), P.indices.astype(np.int32), _f64(P.data),
+                 A.indptr.astype(np.int32), A.indices.astype(np.int32), _f64(A.data),
+                 np.ascontiguousarray(np.asarray(data.i_idx, dtype=np.int32)))
+        data._native_csc = fixed
+    m_ext, n = fixed[0]
+    keep = list(fixed[1:7]) + [_f64(data.q), _f64(data.l), _f64(data.u), fixed[7]]
+    prob = _Problem(n, m_ext, _i(keep[0]), _i(keep[1]), _d(keep[2]), _i(keep[3]), _i(keep[4]), _d(keep[5]),
+                    _d(keep[6]), _d(keep[7]), _d(keep[8]), int(keep[9].size), _i(keep[9]))
+    st = _BnbSettings(float(settings['eps_int_feas']), int(settings['max_iter_bb']), int(settings['tree_explor_rule']),
+                      int(settings['branching_rule']), int(settings.get('speculation', 0) or 0), float(eps_abs))
+    fn = qp.native_solve_fn()
+    handle = getattr(qp, "_h", None) if fn is None else None
+    x = np.empty(n); res = _BnbResult()
+    cap = max(1, int(settings['max_iter_bb']))
+    dec = np.zeros(2 * cap, dtype=np.int32)
+    xin = _f64(x_incumbent) if x_incumbent is not None and np.isfinite(upper_incumbent) else None
+    rc = lib().bqp_bnb_solve(handle, C.byref(prob), C.byref(st), _d(xin) if xin is not None else None, float(upper_incumbent),
+                             C.cast(fn, C.c_void_p) if fn is not None else None, None, _d(x), C.byref(res), _i(dec), cap)
+    _check(rc)
+    out = {k: getattr(res, k) for k, _ in _BnbResult._fields_}
+    decisions = [(int(dec[2 * k]), int(dec[2 * k + 1])) for k in range(min(res.n_decisions, cap))]
+    return x, out, decisions
 
 
 def _alloc_result(B, n, m):

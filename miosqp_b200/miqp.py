@@ -71,10 +71,39 @@ class MIOSQP(object):
             print("Elapsed time: %.4es" % work.run_time)
         return Results(work.x, work.upper_glob, work.run_time, work.status, work.osqp_solve_time, work.osqp_iter_avg)
 
+    def _solve_native(self):
+        """settings['replay'] = 'native': the same loop in C++ (csrc/bqp_bnb.cpp, bqp_bnb_solve) -- no interpreter time
+        per node; one call in, the reference's Results out.  Leaves `work` as the Python replay would."""
+        from .constants import (MI_UNSOLVED, MI_SOLVED, MI_PRIMAL_INFEASIBLE, MI_DUAL_INFEASIBLE,
+                                MI_MAX_ITER_FEASIBLE, MI_MAX_ITER_UNSOLVED)
+        work = self.work
+        x, r, decisions = engine.bnb_solve(work.solver, work.data, work.settings, work.qp_settings['eps_abs'],
+                                           work.x if np.isfinite(work.upper_glob) else None, work.upper_glob)
+        work.x, work.upper_glob, work.lower_glob = x, r["upper_glob"], r["lower_glob"]
+        work.iter_num, work.osqp_iter, work.osqp_solve_time = r["iter_num"], r["osqp_iter"], r["osqp_solve_time"]
+        work.batches += r["batches"]; work.batched_nodes += r["batched_nodes"]
+        work.spec_nodes += r["spec_nodes"]; work.spec_hits += r["spec_hits"]
+        work.decisions = decisions
+        work.leaves = []                       # the native tree is not materialised on the Python side
+        work.osqp_iter_avg = work.osqp_iter / work.iter_num
+        work.status = (MI_UNSOLVED, MI_SOLVED, MI_PRIMAL_INFEASIBLE, MI_DUAL_INFEASIBLE, MI_MAX_ITER_FEASIBLE,
+                       MI_MAX_ITER_UNSOLVED)[r["status"]]
+        if work.settings['verbose']:
+            work.print_footer()
+        work.solve_time = time() - self._t0
+        if work.first_run:
+            work.first_run = 0
+            work.run_time = work.setup_time + work.solve_time
+        else:
+            work.run_time = work.solve_time
+        return Results(work.x, work.upper_glob, work.run_time, work.status, work.osqp_solve_time, work.osqp_iter_avg)
+
     def solve(self, dist_ctx=None):
         """dist_ctx = (rank, world, group): split every frontier batch across the ranks' GPUs (config 4); all ranks
         replay the same tree and agree on the incumbent with one all-reduce(MIN) per B&B step."""
         self._begin()
+        if self.work.settings.get('replay') == 'native' and dist_ctx is None:
+            return self._solve_native()
         while self._replay():
             self.work.solve_pending(dist_ctx)
             if dist_ctx is not None:

@@ -171,11 +171,12 @@ class ClosedLoopResult(object):
 
 
 def closed_loop(steps, N=10, make_solver=None, drive=None, fsw_des=300, delta=5.5, gamma=0.95, tail="delta_550",
-                on_step=None, speculation=0, qp_settings=None):
+                on_step=None, speculation=0, qp_settings=None, replay=None):
     """First `steps` sampling instants of the reference's closed loop (power_converter.py:589-649): at every instant
     build (q,l,u) from the state, warm start from the shifted previous plan, solve the MIQP, apply the first input.
     `make_solver()` returns an object with the MIOSQP interface (default: miosqp_b200.MIOSQP on the CUDA engine).
-    `qp_settings` overrides entries of the reference's OSQP settings.  `speculation` > 0 lets every launch also solve up to that many nodes ahead of the replay (tree.py `speculate`):
+    `replay='native'` runs the B&B loop in C++ (csrc/bqp_bnb.cpp) instead of tree.py: same decisions, no interpreter time
+    per node.  `qp_settings` overrides entries of the reference's OSQP settings.  `speculation` > 0 lets every launch also solve up to that many nodes ahead of the replay (tree.py `speculate`):
     same answers, far fewer host round trips on this workload's deep, narrow trees.
     Returns the trajectories and the per-step B&B statistics."""
     if make_solver is None:
@@ -197,7 +198,7 @@ def closed_loop(steps, N=10, make_solver=None, drive=None, fsw_des=300, delta=5.
         if solver is None:
             solver = make_solver()
             solver.setup(prog.P, q, prog.A, l, u, prog.i_idx, prog.i_l, prog.i_u,
-                         dict(MPC_SETTINGS, speculation=speculation), dict(MPC_QP_SETTINGS, **(qp_settings or {})))
+                         dict(MPC_SETTINGS, speculation=speculation, replay=replay), dict(MPC_QP_SETTINGS, **(qp_settings or {})))
         else:
             solver.update_vectors(q, l, u)
         solver.set_x0(plan)

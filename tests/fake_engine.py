@@ -29,6 +29,28 @@ class FakeBatchedQP(object):
     def free(self):
         self.o = None
 
+    def native_solve_fn(self):
+        """bqp_solve_fn (include/bqp.h) backed by the oracle: lets the C++ B&B replay run where there is no GPU."""
+        import ctypes as C
+        from miosqp_b200 import engine
+        n, m, o = self.n, self.m, self.o
+
+        def fn(ctx, B, l, u, x0, y0, x, y, status, iters):
+            try:
+                arr = lambda pp, k, size: np.ctypeslib.as_array(pp[k], shape=(size,))
+                L = np.array([arr(l, b, m) for b in range(B)]); U = np.array([arr(u, b, m) for b in range(B)])
+                X0 = np.array([arr(x0, b, n) for b in range(B)]); Y0 = np.array([arr(y0, b, m) for b in range(B)])
+                xs, ys, st, it, _ = o.solve_batch(L, U, X0, Y0, threads=4)
+                for b in range(B):
+                    arr(x, b, n)[:] = xs[b]; arr(y, b, m)[:] = ys[b]; status[b] = int(st[b]); iters[b] = int(it[b])
+                return 0
+            except Exception:           # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+        self._native_fn = engine.SOLVE_FN(fn)      # keep the callback object alive
+        return self._native_fn
+
     def solve_batch(self, l, u, x0, y0):
         x, y, st, it, extra = self.o.solve_batch(np.atleast_2d(l), np.atleast_2d(u), np.atleast_2d(x0), np.atleast_2d(y0))
         r = Scalars()
