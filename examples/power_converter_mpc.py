@@ -24,6 +24,8 @@ def main(argv=None):
     ap.add_argument("--horizons", default="1,2,3,4,5")
     ap.add_argument("--steps", type=int, default=None, help="sampling instants (default: the reference's 3 periods = 2400)")
     ap.add_argument("--speculation", type=int, default=32, help="nodes solved ahead of the replay per launch (0 = off)")
+    ap.add_argument("--replay", default="python", choices=("python", "native"),
+                    help="B&B loop in miosqp_b200/tree.py (python) or in csrc/bqp_bnb.cpp (native): same decisions")
     ap.add_argument("--tail", default="delta_550")
     ap.add_argument("--csv", default=None)
     args = ap.parse_args(argv)
@@ -35,7 +37,8 @@ def main(argv=None):
     rows = []
     for N in [int(v) for v in args.horizons.split(",")]:
         t0 = time.perf_counter()
-        r = pc.closed_loop(steps, N=N, drive=drive, tail=args.tail, speculation=args.speculation)
+        r = pc.closed_loop(steps, N=N, drive=drive, tail=args.tail, speculation=args.speculation,
+                           replay='native' if args.replay == 'native' else None)
         wall = time.perf_counter() - t0
         w = r.solver.work
         t = r.run_time
@@ -48,11 +51,11 @@ def main(argv=None):
                          qp_per_s=float(r.nodes.sum()) / wall, wall_s=wall))
         r.solver.work.solver.free()
     table = pd.DataFrame(rows)
-    print("backend:", backend, "| speculation", args.speculation)
+    print("backend:", backend, "| speculation", args.speculation, "| replay", args.replay)
     print(table.to_string(index=False, float_format=lambda v: "%.4g" % v))
     if args.csv:
         table.to_csv(args.csv, index=False)
-    print(json.dumps({"workload": "power_converter MPC closed loop", "backend": backend, "speculation": args.speculation, "rows": rows}))
+    print(json.dumps({"workload": "power_converter MPC closed loop", "backend": backend, "speculation": args.speculation, "replay": args.replay, "rows": rows}))
 
 
 if __name__ == "__main__":

@@ -31,6 +31,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--together", action="store_true", help="solve the instances of one size in lock-step (solve_many)")
     ap.add_argument("--speculation", type=int, default=0, help="nodes solved ahead of the replay per launch")
+    ap.add_argument("--replay", default="python", choices=("python", "native"), help="B&B loop in Python or in C++ (not with --together)")
     ap.add_argument("--csv", default=None)
     args = ap.parse_args(argv)
     backend = _common.BACKEND
@@ -53,7 +54,9 @@ def main(argv=None):
             pr = problems.random_miqp_draw(n, m, p, args.density)
             s = miosqp_b200.MIOSQP()
             s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
-                    dict(problems.RANDOM_MIQP_SETTINGS, speculation=args.speculation), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+                    dict(problems.RANDOM_MIQP_SETTINGS, speculation=args.speculation,
+                         replay='native' if args.replay == 'native' and not args.together else None),
+                    dict(problems.RANDOM_MIQP_QP_SETTINGS))
             solvers.append(s)
         t_setup = time.perf_counter() - t_setup
         t0 = time.perf_counter()

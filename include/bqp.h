@@ -11,6 +11,7 @@
  *                            for B nodes of one problem at once              node.py:96-143
  *   bqp_solve_multi       <- the same for nodes of several set-up problems in ONE launch
  *                            (frontier of many MIQP instances, BASELINE cfg 2)
+ *   bqp_bnb_solve         <- MIOSQP.solve(): the B&B while-loop itself, natively  solver.py:85-172
  *   BQP_* status codes    <- osqp.constant('OSQP_*')                        node.py:88,128-129
  *   bqp_free              <- garbage collection of the osqp object
  *

@@ -40,8 +40,18 @@ def test_power_converter_example_cpu(cpu_engine, capsys):
     _check_mpc_rows(_mpc(capsys, ["--horizons", "1,3", "--steps", "40", "--speculation", "64"]))
 
 
+def test_power_converter_example_native_replay_cpu(cpu_engine, capsys):
+    a = _mpc(capsys, ["--horizons", "1,3", "--steps", "25", "--speculation", "16"])
+    b = _mpc(capsys, ["--horizons", "1,3", "--steps", "25", "--speculation", "16", "--replay", "native"])
+    for ra, rb in zip(a, b):
+        for key in ("nodes_per_step", "admm_iters_per_step", "launches_per_step", "solved_nodes_per_step", "fsw_hz", "node_limit_steps"):
+            assert ra[key] == rb[key], key
+
+
 def test_random_miqp_example_cpu(cpu_engine, capsys):
     import random_miqp
+    random_miqp.main(["--sizes", "10,5,2;50,25,5", "--repeat", "3", "--replay", "native"])
+    assert "t_osqp_avg" in capsys.readouterr().out
     random_miqp.main(["--sizes", "10,5,2;50,25,5", "--repeat", "3"])
     out = capsys.readouterr().out
     assert "t_osqp_avg" in out and "one instance at a time" in out

@@ -20,18 +20,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--horizon", type=int, default=10)
     ap.add_argument("--budgets", default="0,32,256")
+    ap.add_argument("--replay", default="python", choices=("python", "native"))
+    ap.add_argument("--warm", action="store_true", help="run 2 untimed steps first (CUDA context, first-launch costs)")
     args = ap.parse_args()
     from miosqp_b200 import power_converter as pc
     ref = None
+    replay = 'native' if args.replay == 'native' else None
+    if args.warm:
+        pc.closed_loop(2, N=args.horizon, speculation=0, replay=replay).solver.work.solver.free()
     for b in [int(v) for v in args.budgets.split(",")]:
         t0 = time.perf_counter()
-        r = pc.closed_loop(args.steps, N=args.horizon, speculation=b)
+        r = pc.closed_loop(args.steps, N=args.horizon, speculation=b, replay=replay)
         wall = time.perf_counter() - t0
         w = r.solver.work
         same = None if ref is None else bool((ref.U == r.U).all() and (ref.nodes == r.nodes).all() and (ref.admm_iters == r.admm_iters).all())
         if ref is None:
             ref = r
-        print(json.dumps({"workload": "power_converter MPC N=%d, %d steps" % (args.horizon, args.steps), "speculation": b,
+        print(json.dumps({"workload": "power_converter MPC N=%d, %d steps" % (args.horizon, args.steps), "speculation": b, "replay": args.replay,
                           "ms_per_mpc_step": 1e3 * wall / args.steps, "launches_per_step": w.batches / float(args.steps),
                           "nodes_per_step": float(r.nodes.mean()), "solved_nodes_per_step": w.batched_nodes / float(args.steps),
                           "qp_per_s_consumed": float(r.nodes.sum()) / wall, "qp_per_s_solved": w.batched_nodes / wall,
