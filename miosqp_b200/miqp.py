@@ -138,8 +138,15 @@ def solve_many(solvers, on_batch=None):
         active = [s for s in active if s._replay()]
         nodes, owners = [], []
         for s in active:
-            for nd in s.work.pending():
-                nodes.append(nd); owners.append(s.work)
+            w = s.work
+            mine = w.pending()
+            budget = int(w.settings.get('speculation', 0) or 0)
+            if mine and budget > 0:              # look-ahead nodes of this instance ride along (tree.py speculate)
+                ahead = w.speculate(budget)
+                w.spec_nodes += len(ahead)
+                mine = mine + ahead
+            for nd in mine:
+                nodes.append(nd); owners.append(w)
         if not nodes:
             continue
         # longest-first submission: children of slow-converging parents go first (tile order = submission order)

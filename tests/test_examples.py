@@ -141,3 +141,26 @@ def test_replay_maxiter_example_engine(capsys):
     import replay_maxiter
     replay_maxiter.main([])
     assert "49 problems in one launch" in capsys.readouterr().out
+
+
+def test_solve_many_with_lookahead_cpu(cpu_engine):
+    """Lock-step over several MIQPs with per-instance look-ahead: same B&B per instance, fewer launches."""
+    import miosqp_b200
+    from miosqp_b200 import problems
+
+    def build(spec):
+        out = []
+        for seed in (3, 4, 5):
+            pr = problems.random_miqp(40, 40, 20, 0.7, seed=seed)[0]
+            s = miosqp_b200.MIOSQP()
+            s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                    dict(problems.RANDOM_MIQP_SETTINGS, speculation=spec), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+            out.append(s)
+        return out
+    a, b = build(0), build(16)
+    ra, rb = miosqp_b200.solve_many(a), miosqp_b200.solve_many(b)
+    for sa, sb, xa, xb in zip(a, b, ra, rb):
+        assert sa.work.decisions == sb.work.decisions and sa.work.osqp_iter == sb.work.osqp_iter
+        assert xa.status == xb.status and xa.upper_glob == xb.upper_glob and np.array_equal(xa.x, xb.x)
+        assert sb.work.spec_hits > 0
+    assert max(s.work.batches for s in b) * 2 < max(s.work.batches for s in a)
