@@ -135,3 +135,23 @@ def test_native_replay_on_engine(name):
 @pytest.mark.gpu
 def test_native_mpc_closed_loop_on_engine():
     _mpc_closed_loop(8, 1e-9, 32)
+
+
+def test_native_replay_under_sanitizers(tmp_path):
+    """csrc/bqp_bnb.cpp compiled with -fsanitize=address,undefined against a fake solve function (separable QPs whose
+    relaxation is a clip, so every optimum is known): 200 random MIQPs x look-ahead budgets x rules x node limits."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "harness")
+    cmd = ["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+           "-I", os.path.join(root, "include"), os.path.join(HERE, "native", "bnb_asan_harness.cpp"),
+           os.path.join(root, "miosqp_b200", "csrc", "bqp_bnb.cpp"), "-o", exe]
+    build = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if build.returncode != 0 and "sanitize" in build.stdout:
+        pytest.skip("sanitizer runtime not installed")
+    assert build.returncode == 0, build.stdout
+    run = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert run.returncode == 0 and "asan harness ok" in run.stdout, run.stdout[-2000:]
