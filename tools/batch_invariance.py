@@ -16,9 +16,22 @@ from miosqp_b200 import engine, problems            # noqa: E402
 from oracle import oracle                           # noqa: E402
 
 
+SWEEP = [(34, 30, 8, 0.7, 1), (40, 40, 20, 0.7, 3), (64, 40, 10, 0.7, 2), (50, 100, 5, 0.7, 1), (96, 60, 12, 0.7, 4),
+         (70, 150, 10, 0.1, 5), (130, 60, 10, 0.7, 6), (33, 96, 6, 0.5, 7)]      # (n, m, p, density, seed): A passes of 5..20 row panels
+
+
 def main():
+    if "--sweep" in sys.argv:
+        for n, m, p, d, seed in SWEEP:
+            print("==== n=%d m=%d p=%d density=%g seed=%d" % (n, m, p, d, seed), flush=True)
+            one(n, m, p, d, seed)
+        return
     n, m, p, seed = (int(v) for v in (sys.argv[1:5] + [40, 40, 20, 3][len(sys.argv) - 1:]))
-    pr = problems.random_miqp(n, m, p, 0.7, seed=seed)[0]
+    one(n, m, p, 0.7, seed)
+
+
+def one(n, m, p, density, seed):
+    pr = problems.random_miqp(n, m, p, density, seed=seed)[0]
     rec = []
     real = engine.solve_multi
 

@@ -10,6 +10,6 @@ timeout 120 python tools/mpc_bench.py --steps 20 --horizon 10 --budgets 0,32,128
 timeout 120 python tools/mpc_bench.py --steps 20 --horizon 10 --budgets 0,32,128 --warm --replay native > gpurun_out/n1_mpc_native.jsonl 2>&1
 cat gpurun_out/n1_mpc_python.jsonl gpurun_out/n1_mpc_native.jsonl | cut -c1-400
 # launch invariance of all three kernels on a small problem (the race fixed in round 1)
-timeout 60 python tools/batch_invariance.py > gpurun_out/n1_invariance.log 2>&1; grep -E "^(panel|stream|direct)" gpurun_out/n1_invariance.log | cut -c1-300
+timeout 180 python tools/batch_invariance.py --sweep > gpurun_out/n1_invariance.log 2>&1; grep -E "^(====|panel|stream|direct|   node)" gpurun_out/n1_invariance.log | cut -c1-300
 # the bench line after the barrier added to the panel kernel (expected: unchanged, 431 ms per step)
 timeout 400 python bench.py > gpurun_out/n1_bench.json 2> gpurun_out/n1_bench.err; cut -c1-600 gpurun_out/n1_bench.json
