@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--parallel-setup", action="store_true", help="bqp_setup_many: factorise the instances on all host threads")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -247,8 +248,11 @@ def main():
     # ---- setup (untimed): instances, device-resident factors, root relaxations, leaf batch
     t_setup = time.perf_counter()
     insts = make_instances(args.instances, seed=1 + rank)
-    qps = [engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, device=local_rank, **QP_SETTINGS)
-           for (P, q, A, l, u, i_idx) in insts]
+    if args.parallel_setup:     # host halves of the 100 factorisations on all host threads (untimed either way)
+        qps = engine.setup_many(insts, device=local_rank, **QP_SETTINGS)
+    else:
+        qps = [engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, device=local_rank, **QP_SETTINGS)
+               for (P, q, A, l, u, i_idx) in insts]
     n, m = N_VAR, M_CON + P_INT
     xs, ys, sc = engine.solve_multi(qps, [i[3] for i in insts], [i[4] for i in insts],
                                     [np.zeros(n)] * len(insts), [np.zeros(m)] * len(insts))

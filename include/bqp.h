@@ -97,6 +97,10 @@ typedef struct {
 
 void bqp_default_settings(bqp_settings *s);
 int bqp_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out);
+/* bqp_setup for `count` problems sharing one settings struct: host halves on `threads` host threads (0 = all), device
+ * uploads one by one.  out[count].  All or nothing: on any error every handle is freed and out[] is all NULL.
+ * host_only != 0 is the layout-test variant of bqp_debug_host_setup (no device touched). */
+int bqp_setup_many(int count, const bqp_problem *const *p, const bqp_settings *s, bqp_handle *out, int threads, int host_only);
 int bqp_update_q(bqp_handle h, const double *q);
 int bqp_solve_batch(bqp_handle h, int B, const double *l, const double *u, const double *x0, const double *y0,
                     double *x, double *y, const bqp_node_out *out);

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "bqp_internal.h"
@@ -215,6 +217,41 @@ int bqp_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out) {
   if (max_tile_nodes((*out)->h, 64) == 0) { bqp_free(*out); *out = nullptr; return BQP_E_UNSUPPORTED; }
   rc = to_device(*out);
   if (rc) { bqp_free(*out); *out = nullptr; }
+  return rc;
+}
+
+// Many problems at once (100 instances of BASELINE config 2): the host halves -- scaling, LDL', explicit reduced inverse,
+// streamed layouts; ~0.2 s each at n = 500 and independent of one another -- run on `threads` host threads (0 = hardware
+// concurrency); the device uploads then go one by one through the same to_device() as bqp_setup.  All or nothing.
+int bqp_setup_many(int count, const bqp_problem *const *p, const bqp_settings *s, bqp_handle *out, int threads, int host_only) {
+  if (count <= 0 || !p || !s || !out) return BQP_E_ARG;
+  for (int k = 0; k < count; k++) out[k] = nullptr;
+  if (!host_only) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return BQP_E_CUDA;
+  }
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, count));
+  std::vector<int> rcs((size_t)count, BQP_OK);
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int k = next.fetch_add(1);
+      if (k >= count) break;
+      rcs[(size_t)k] = bqp_debug_host_setup(p[k], s, &out[k]);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+  worker();
+  for (auto &th : pool) th.join();
+  int rc = BQP_OK;
+  for (int k = 0; k < count && !rc; k++) rc = rcs[(size_t)k];
+  for (int k = 0; k < count && !rc && !host_only; k++) {
+    if (max_tile_nodes(out[k]->h, 64) == 0) rc = BQP_E_UNSUPPORTED;
+    else rc = to_device(out[k]);
+  }
+  if (rc) for (int k = 0; k < count; k++) { bqp_free(out[k]); out[k] = nullptr; }
   return rc;
 }
 

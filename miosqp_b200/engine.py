@@ -96,7 +96,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
            "bqp_debug_host_panel_kkt_solve",
-           "bqp_debug_host_matvec", "bqp_bnb_solve"]
+           "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_setup_many"]
 
 _lib = None
 
@@ -130,6 +130,7 @@ def lib():
         L.bqp_debug_host_stream_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_panel_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
+        L.bqp_setup_many.argtypes = [C.c_int, C.POINTER(C.POINTER(_Problem)), C.POINTER(_Settings), pp, C.c_int, C.c_int]
         L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
                                     C.POINTER(_BnbResult), _ip, C.c_int]
         _lib = L
@@ -295,6 +296,41 @@ class BatchedQP(object):
         out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n, 4: self.n}[which])
         _check(lib().bqp_debug_host_matvec(self._h, which, _d(v), _d(out)))
         return out
+
+
+def setup_many(items, host_only=False, threads=0, **settings):
+    """`BatchedQP().setup(...)` for many problems that share their OSQP settings (include/bqp.h bqp_setup_many): the host
+    halves (scaling, factorisation, layouts) run on `threads` host threads (0 = all), the device uploads one by one.
+    items: sequence of (P, q, A, l, u, i_idx or None).  Returns the list of set-up BatchedQP objects."""
+    s = normalize_settings(settings)
+    probs, keep, qps = [], [], []
+    for (P, q, A, l, u, i_idx) in items:
+        P = spa.triu(spa.csc_matrix(P), format="csc"); A = spa.csc_matrix(A)
+        P.sort_indices(); A.sort_indices()
+        n, m = A.shape[1], A.shape[0]
+        if P.shape != (n, n):
+            raise ValueError("P must be n x n")
+        q = _f64(q); l = _f64(l); u = _f64(u)
+        if q.shape != (n,) or l.shape != (m,) or u.shape != (m,):
+            raise ValueError("q, l, u have inconsistent dimensions")
+        idx = np.ascontiguousarray(np.asarray(i_idx if i_idx is not None else [], dtype=np.int32))
+        arrs = [P.indptr.astype(np.int32), P.indices.astype(np.int32), _f64(P.data),
+                A.indptr.astype(np.int32), A.indices.astype(np.int32), _f64(A.data), q, l, u, idx]
+        keep.append(arrs)
+        probs.append(_Problem(n, m, _i(arrs[0]), _i(arrs[1]), _d(arrs[2]), _i(arrs[3]), _i(arrs[4]), _d(arrs[5]),
+                              _d(q), _d(l), _d(u), int(idx.size), _i(idx)))
+        qp = BatchedQP(); qp.settings = s; qp.n, qp.m, qp.n_int = n, m, int(idx.size)
+        qps.append(qp)
+    count = len(probs)
+    if count == 0:
+        return []
+    pptr = (C.POINTER(_Problem) * count)(*[C.pointer(p) for p in probs])
+    handles = (C.c_void_p * count)()
+    st = _Settings(**{k: s[k] for k, _ in _Settings._fields_})
+    _check(lib().bqp_setup_many(count, pptr, C.byref(st), handles, int(threads), 1 if host_only else 0))
+    for qp, h in zip(qps, handles):
+        qp._h = C.c_void_p(h)
+    return qps
 
 
 def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.inf):

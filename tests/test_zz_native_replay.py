@@ -155,3 +155,22 @@ def test_native_replay_under_sanitizers(tmp_path):
     assert build.returncode == 0, build.stdout
     run = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert run.returncode == 0 and "asan harness ok" in run.stdout, run.stdout[-2000:]
+
+
+@pytest.mark.gpu
+def test_setup_many_on_device_equals_one_by_one():
+    """bqp_setup_many (parallel host halves, sequential uploads) then one launch over all problems: same results as
+    problems set up one by one."""
+    from miosqp_b200 import engine
+    shapes = [(130, 200, 10, 0.7, 4), (50, 100, 5, 0.7, 1), (130, 200, 10, 0.7, 5)]
+    items = [problems.extend(problems.random_miqp(n, m, p, d, seed=seed)[0]) for (n, m, p, d, seed) in shapes]
+    qp = dict(problems.RANDOM_MIQP_QP_SETTINGS)
+    many = engine.setup_many(items, **qp)
+    single = [engine.BatchedQP().setup(P, q, A, l, u, i_idx=i, **qp) for (P, q, A, l, u, i) in items]
+    L = [it[3] for it in items]; U = [it[4] for it in items]
+    X0 = [np.zeros(it[2].shape[1]) for it in items]; Y0 = [np.zeros(it[2].shape[0]) for it in items]
+    xa, ya, sa = engine.solve_multi(many, L, U, X0, Y0)
+    xb, yb, sb = engine.solve_multi(single, L, U, X0, Y0)
+    assert list(sa.status) == list(sb.status) and list(sa.iters) == list(sb.iters)
+    for a, b in zip(xa, xb):
+        assert np.array_equal(a, b, equal_nan=True)

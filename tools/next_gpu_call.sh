@@ -13,3 +13,5 @@ cat gpurun_out/n1_mpc_python.jsonl gpurun_out/n1_mpc_native.jsonl | cut -c1-400
 timeout 180 python tools/batch_invariance.py --sweep > gpurun_out/n1_invariance.log 2>&1; grep -E "^(====|panel|stream|direct|   node)" gpurun_out/n1_invariance.log | cut -c1-300
 # the bench line after the barrier added to the panel kernel (expected: unchanged, 431 ms per step)
 timeout 400 python bench.py > gpurun_out/n1_bench.json 2> gpurun_out/n1_bench.err; cut -c1-600 gpurun_out/n1_bench.json
+# parallel host setup path (bqp_setup_many): same bench line, shorter untimed setup
+timeout 400 python bench.py --parallel-setup --no-cpu-baseline > gpurun_out/n1_bench_parallel_setup.json 2>> gpurun_out/n1_bench.err; cut -c1-300 gpurun_out/n1_bench_parallel_setup.json
