@@ -6,9 +6,9 @@ look-ahead nodes, which is what gives a single instance more than two nodes per 
 to the ranks, solved on the local GPU, exchanged with one all-gather, and the incumbent agreed with one
 all-reduce(MIN).  Rank 0 prints one JSON line.
 
-    python examples/frontier_split.py --n 500 --m 1000 --p 50 --density 0.7 --speculation 64          # 1 GPU
+    python examples/frontier_split.py --vars 500 --rows 1000 --ints 50 --density 0.7 --speculation 64          # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \\
-        examples/frontier_split.py --n 2000 --m 4000 --p 200 --density 0.05 --speculation 512           # config 4
+        examples/frontier_split.py --vars 2000 --rows 4000 --ints 200 --density 0.05 --speculation 512           # config 4
 """
 import argparse
 import json
@@ -20,13 +20,15 @@ import _common  # noqa: F401
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--n", type=int, default=2000)
-    ap.add_argument("--m", type=int, default=4000)
-    ap.add_argument("--p", type=int, default=200)
+    ap.add_argument("--vars", dest="n", type=int, default=2000, help="n (torchrun claims every prefix of --n...)")
+    ap.add_argument("--rows", dest="m", type=int, default=4000, help="m")
+    ap.add_argument("--ints", dest="p", type=int, default=200, help="|i_idx|")
     ap.add_argument("--density", type=float, default=0.05)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--speculation", type=int, default=64)
     ap.add_argument("--max-nodes", type=int, default=1000, help="max_iter_bb of the reference's settings")
+    ap.add_argument("--dist-backend", default="nccl", choices=("nccl", "gloo"),
+                    help="torch.distributed backend for the node-result exchange (gloo: host-side exchange, used by the CPU tests)")
     args = ap.parse_args(argv)
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -34,9 +36,13 @@ def main(argv=None):
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ctx = (rank, world, None, torch.device("cuda", local))
+        if args.dist_backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            ctx = (rank, world, None, torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+            ctx = (rank, world, None)
     import miosqp_b200
     from miosqp_b200 import problems
 

@@ -68,7 +68,7 @@ def test_replay_maxiter_example_cpu(cpu_engine, capsys):
 
 def test_frontier_split_example_single_process_cpu(cpu_engine, capsys):
     import frontier_split
-    frontier_split.main(["--n", "40", "--m", "40", "--p", "20", "--density", "0.7", "--seed", "3", "--speculation", "32"])
+    frontier_split.main(["--vars", "40", "--rows", "40", "--ints", "20", "--density", "0.7", "--seed", "3", "--speculation", "32"])
     rec = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert rec["status"] == "Solved" and rec["nodes"] >= 100 and rec["launches"] * 3 < rec["nodes"]
 
@@ -164,3 +164,26 @@ def test_solve_many_with_lookahead_cpu(cpu_engine):
         assert xa.status == xb.status and xa.upper_glob == xb.upper_glob and np.array_equal(xa.x, xb.x)
         assert sb.work.spec_hits > 0
     assert max(s.work.batches for s in b) * 2 < max(s.work.batches for s in a)
+
+
+def test_frontier_split_example_two_ranks_gloo(tmp_path):
+    """examples/frontier_split.py under torch.distributed.run with 2 ranks (gloo, stand-in engine): the replicated replays
+    agree, rank 0 reports the same B&B as the single-process run, and each rank solved about half of every batch."""
+    import subprocess
+    args = ["--vars", "40", "--rows", "40", "--ints", "20", "--density", "0.7", "--seed", "3", "--speculation", "16"]
+    port = 29700 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "_frontier_split_worker.py")] + args + ["--dist-backend", "gloo"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                     # rank 0 only
+    two = json.loads(lines[0])
+    one = subprocess.run([sys.executable, os.path.join(HERE, "_frontier_split_worker.py")] + args, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=240, env=env)
+    assert one.returncode == 0, one.stderr[-2000:]
+    single = json.loads([ln for ln in one.stdout.splitlines() if ln.startswith("{")][0])
+    for key in ("status", "upper_glob", "nodes", "admm_iters", "launches", "solved_nodes"):
+        assert two[key] == single[key], key
+    assert "2 GPU(s)" in two["workload"]
