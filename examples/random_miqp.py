@@ -31,7 +31,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--together", action="store_true", help="solve the instances of one size in lock-step (solve_many)")
     ap.add_argument("--speculation", type=int, default=0, help="nodes solved ahead of the replay per launch")
-    ap.add_argument("--replay", default="python", choices=("python", "native"), help="B&B loop in Python or in C++ (not with --together)")
+    ap.add_argument("--replay", default="python", choices=("python", "native"), help="B&B loop in Python (tree.py) or in C++ (bqp_bnb_solve / bqp_bnb_solve_many)")
     ap.add_argument("--csv", default=None)
     args = ap.parse_args(argv)
     backend = _common.BACKEND
@@ -55,7 +55,7 @@ def main(argv=None):
             s = miosqp_b200.MIOSQP()
             s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
                     dict(problems.RANDOM_MIQP_SETTINGS, speculation=args.speculation,
-                         replay='native' if args.replay == 'native' and not args.together else None),
+                         replay='native' if args.replay == 'native' else None),
                     dict(problems.RANDOM_MIQP_QP_SETTINGS))
             solvers.append(s)
         t_setup = time.perf_counter() - t_setup

@@ -152,6 +152,16 @@ int bqp_bnb_solve(bqp_handle h, const bqp_problem *p, const bqp_bnb_settings *s,
                   double upper_incumbent, bqp_solve_fn fn, void *ctx, double *x, bqp_bnb_result *res,
                   int *decisions, int decisions_cap);
 
+/* lock-step variant over `count` MIQPs (miqp.py solve_many): one launch per B&B step covers every tree's unsolved leaves
+ * (+ per-tree look-ahead); s, res: [count]; x, decisions, x_incumbent: [count] pointers; h: [count] handles (NULL with fn).
+ * fn additionally receives, per node, the index of the problem it belongs to. */
+typedef int (*bqp_solve_many_fn)(void *ctx, int B, const int *owner, const double *const *l, const double *const *u,
+                                 const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                                 int *status, int *iters);
+int bqp_bnb_solve_many(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                       const double *const *x_incumbent, const double *upper_incumbent, bqp_solve_many_fn fn, void *ctx,
+                       double *const *x, bqp_bnb_result *res, int *const *decisions, int decisions_cap);
+
 /* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
 int bqp_set_tuning(int tile_nodes, int threads);
 

@@ -43,6 +43,7 @@ struct Node {
   NodeP sh[2];
   std::vector<int> frac_idx;
   int constr_idx = -1, nextvar_idx = -1;
+  int parent_iters = 0;     // scheduling hint only: longest-first submission in the lock-step driver
 };
 
 struct Csc { int rows = 0, cols = 0; const int *p = nullptr, *i = nullptr; const double *x = nullptr; };
@@ -115,7 +116,7 @@ struct Tree {
       c->l = nd.l; c->u = nd.u;
       if (side == 0) c->u[row] = std::floor((*xc)[var]); else c->l[row] = std::ceil((*xc)[var]);
       if (c->l[row] > c->u[row]) return;                      // the engine would reject the whole launch
-      c->x = xc; c->y = nd.cy; c->depth = nd.depth + 1; c->lower = lower;
+      c->x = xc; c->y = nd.cy; c->depth = nd.depth + 1; c->lower = lower; c->parent_iters = nd.c_iters;
       kids[side] = c;
     }
     nd.sh[0] = kids[0]; nd.sh[1] = kids[1]; nd.shadow_state = 2;
@@ -142,18 +143,26 @@ struct Tree {
   }
 
   // ---- one launch over every unsolved open leaf (+ look-ahead)
+  void collect(std::vector<Node *> &batch) {
+    const size_t first = batch.size();
+    for (auto &lf : leaves) if (unsolved(*lf)) batch.push_back(lf.get());
+    if (batch.size() == first) return;
+    if (s.speculation > 0) speculate(s.speculation, batch);
+    for (size_t b = first; b < batch.size(); b++) { batch[b]->cx = std::make_shared<Vec>(n); batch[b]->cy = std::make_shared<Vec>(m_ext); }
+  }
+  static void absorb(Node &nd, int status, int iters, double seconds) {
+    nd.has_cached = true; nd.c_status = status; nd.c_iters = iters; nd.c_seconds = seconds;
+  }
   int launch() {
     std::vector<Node *> batch;
-    for (auto &lf : leaves) if (unsolved(*lf)) batch.push_back(lf.get());
+    collect(batch);
     if (batch.empty()) return BQP_OK;
-    if (s.speculation > 0) speculate(s.speculation, batch);
     const int B = (int)batch.size();
     std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
     std::vector<double *> px(B), py(B);
     std::vector<int> status(B), iters(B);
     for (int b = 0; b < B; b++) {
       Node &nd = *batch[b];
-      nd.cx = std::make_shared<Vec>(n); nd.cy = std::make_shared<Vec>(m_ext);
       pl[b] = nd.l.data(); pu[b] = nd.u.data(); px0[b] = nd.x->data(); py0[b] = nd.y->data();
       px[b] = nd.cx->data(); py[b] = nd.cy->data();
     }
@@ -170,10 +179,7 @@ struct Tree {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     long long total = 0; for (int b = 0; b < B; b++) total += iters[b];
     if (total < 1) total = 1;
-    for (int b = 0; b < B; b++) {
-      Node &nd = *batch[b];
-      nd.has_cached = true; nd.c_status = status[b]; nd.c_iters = iters[b]; nd.c_seconds = dt * (double)iters[b] / (double)total;
-    }
+    for (int b = 0; b < B; b++) absorb(*batch[b], status[b], iters[b], dt * (double)iters[b] / (double)total);
     batches++; batched_nodes += B;
     return BQP_OK;
   }
@@ -206,7 +212,7 @@ struct Tree {
     c->l = leaf.l; c->u = leaf.u;
     if (side == 0) c->u[leaf.constr_idx] = std::floor((*leaf.x)[leaf.nextvar_idx]);
     else c->l[leaf.constr_idx] = std::ceil((*leaf.x)[leaf.nextvar_idx]);
-    c->x = leaf.x; c->y = leaf.y; c->depth = leaf.depth + 1; c->lower = leaf.lower;
+    c->x = leaf.x; c->y = leaf.y; c->depth = leaf.depth + 1; c->lower = leaf.lower; c->parent_iters = leaf.num_iter;
     if (leaf.shadow_state == 2) {
       const Node &sh = *leaf.sh[side];
       // adopt a result solved ahead of the replay only if it was computed from exactly these inputs
@@ -238,55 +244,136 @@ struct Tree {
     for (auto &lf : leaves) lower_glob = std::fmin(lower_glob, lf->lower);
     return BQP_OK;
   }
-  int run() {
+  // replay until the frontier holds an unsolved leaf (returns 1), or the tree is finished (returns 0); < 0: error
+  int advance() {
     while (!leaves.empty() && iter_num < s.max_iter_bb) {
-      bool pending = false;
-      for (auto &lf : leaves) if (unsolved(*lf)) { pending = true; break; }
-      if (pending) { const int rc = launch(); if (rc) return rc; continue; }
+      for (auto &lf : leaves) if (unsolved(*lf)) return 1;
       NodeP leaf;
       int rc = choose_leaf(leaf); if (rc) return rc;
       solve_node(*leaf);
       rc = bound_and_branch(*leaf); if (rc) return rc;
       iter_num++;
     }
-    return BQP_OK;
+    return 0;
+  }
+  int run() {
+    for (;;) {
+      const int a = advance();
+      if (a <= 0) return a;
+      const int rc = launch(); if (rc) return rc;
+    }
+  }
+  void init(bqp_handle h_, const bqp_problem *p, const bqp_bnb_settings *s_, const double *x_incumbent, double upper_incumbent) {
+    n = p->n; m_ext = p->m; n_int = p->n_int; m = p->m - p->n_int;
+    P.rows = P.cols = p->n; P.p = p->Pp; P.i = p->Pi; P.x = p->Px;
+    A.rows = p->m; A.cols = p->n; A.p = p->Ap; A.i = p->Ai; A.x = p->Ax;
+    q = p->q; i_idx = p->i_idx; s = *s_; h = h_;
+    l_root.assign(p->l, p->l + p->m); u_root.assign(p->u, p->u + p->m);
+    auto root = std::make_shared<Node>();
+    root->l = l_root; root->u = u_root;
+    root->x = std::make_shared<Vec>(p->n, 0.0); root->y = std::make_shared<Vec>(p->m, 0.0);
+    leaves.push_back(root);
+    x_best.assign(p->n, 0.0);
+    if (x_incumbent && std::isfinite(upper_incumbent)) { x_best.assign(x_incumbent, x_incumbent + p->n); upper_glob = upper_incumbent; }
+  }
+  void finish(const bqp_problem *p, double *x, bqp_bnb_result *res, int *dec, int decisions_cap) {
+    std::memset(res, 0, sizeof(*res));
+    res->iter_num = iter_num; res->osqp_iter = osqp_iter; res->osqp_solve_time = osqp_solve_time;
+    res->upper_glob = upper_glob; res->lower_glob = lower_glob;
+    res->batches = batches; res->batched_nodes = batched_nodes; res->spec_nodes = spec_nodes; res->spec_hits = spec_hits;
+    res->n_decisions = (int)(decisions.size() / 2);
+    res->open_leaves = (int)leaves.size();
+    if (dec) std::memcpy(dec, decisions.data(), sizeof(int) * std::min<size_t>(decisions.size(), 2 * (size_t)std::max(0, decisions_cap)));
+    // workspace.py:352-384
+    const bool finished = iter_num < s.max_iter_bb;
+    if (upper_glob != kInf) res->status = finished ? BQP_MI_SOLVED : BQP_MI_MAX_ITER_FEASIBLE;
+    else if (upper_glob >= 0) res->status = finished ? BQP_MI_PRIMAL_INFEASIBLE : BQP_MI_MAX_ITER_UNSOLVED;
+    else res->status = BQP_MI_DUAL_INFEASIBLE;
+    if (res->status == BQP_MI_SOLVED || res->status == BQP_MI_MAX_ITER_FEASIBLE)
+      for (int k = 0; k < n_int; k++) x_best[p->i_idx[k]] = std::nearbyint(x_best[p->i_idx[k]]);
+    std::memcpy(x, x_best.data(), sizeof(double) * (size_t)p->n);
   }
 };
 
 }  // namespace
 
+static bool problem_ok(const bqp_problem *p) {
+  return p && p->n > 0 && p->m >= p->n_int && p->n_int >= 0 && p->Pp && p->Pi && p->Px && p->Ap && p->Ai && p->Ax && p->q && p->l &&
+         p->u && (!p->n_int || p->i_idx);
+}
+
 extern "C" int bqp_bnb_solve(bqp_handle h, const bqp_problem *p, const bqp_bnb_settings *s, const double *x_incumbent,
                              double upper_incumbent, bqp_solve_fn fn, void *ctx, double *x, bqp_bnb_result *res,
                              int *decisions, int decisions_cap) {
-  if (!p || !s || !x || !res || (!h && !fn) || p->n <= 0 || p->m < p->n_int || p->n_int < 0) return BQP_E_ARG;
-  if (!p->Pp || !p->Pi || !p->Px || !p->Ap || !p->Ai || !p->Ax || !p->q || !p->l || !p->u || (p->n_int && !p->i_idx)) return BQP_E_ARG;
+  if (!s || !x || !res || (!h && !fn) || !problem_ok(p)) return BQP_E_ARG;
   Tree t;
-  t.n = p->n; t.m_ext = p->m; t.n_int = p->n_int; t.m = p->m - p->n_int;
-  t.P.rows = t.P.cols = p->n; t.P.p = p->Pp; t.P.i = p->Pi; t.P.x = p->Px;
-  t.A.rows = p->m; t.A.cols = p->n; t.A.p = p->Ap; t.A.i = p->Ai; t.A.x = p->Ax;
-  t.q = p->q; t.i_idx = p->i_idx; t.s = *s; t.h = h; t.fn = fn; t.ctx = ctx;
-  t.l_root.assign(p->l, p->l + p->m); t.u_root.assign(p->u, p->u + p->m);
-  auto root = std::make_shared<Node>();
-  root->l = t.l_root; root->u = t.u_root;
-  root->x = std::make_shared<Vec>(p->n, 0.0); root->y = std::make_shared<Vec>(p->m, 0.0);
-  t.leaves.push_back(root);
-  t.x_best.assign(p->n, 0.0);
-  if (x_incumbent && std::isfinite(upper_incumbent)) { t.x_best.assign(x_incumbent, x_incumbent + p->n); t.upper_glob = upper_incumbent; }
+  t.init(h, p, s, x_incumbent, upper_incumbent);
+  t.fn = fn; t.ctx = ctx;
   const int rc = t.run();
-  std::memset(res, 0, sizeof(*res));
-  res->iter_num = t.iter_num; res->osqp_iter = t.osqp_iter; res->osqp_solve_time = t.osqp_solve_time;
-  res->upper_glob = t.upper_glob; res->lower_glob = t.lower_glob;
-  res->batches = t.batches; res->batched_nodes = t.batched_nodes; res->spec_nodes = t.spec_nodes; res->spec_hits = t.spec_hits;
-  res->n_decisions = (int)(t.decisions.size() / 2);
-  res->open_leaves = (int)t.leaves.size();
-  if (decisions) std::memcpy(decisions, t.decisions.data(), sizeof(int) * std::min<size_t>(t.decisions.size(), 2 * (size_t)std::max(0, decisions_cap)));
-  // workspace.py:352-384
-  const bool finished = t.iter_num < s->max_iter_bb;
-  if (t.upper_glob != kInf) res->status = finished ? BQP_MI_SOLVED : BQP_MI_MAX_ITER_FEASIBLE;
-  else if (t.upper_glob >= 0) res->status = finished ? BQP_MI_PRIMAL_INFEASIBLE : BQP_MI_MAX_ITER_UNSOLVED;
-  else res->status = BQP_MI_DUAL_INFEASIBLE;
-  if (res->status == BQP_MI_SOLVED || res->status == BQP_MI_MAX_ITER_FEASIBLE)
-    for (int k = 0; k < t.n_int; k++) t.x_best[p->i_idx[k]] = std::nearbyint(t.x_best[p->i_idx[k]]);
-  std::memcpy(x, t.x_best.data(), sizeof(double) * (size_t)p->n);
+  t.finish(p, x, res, decisions, decisions_cap);
+  return rc;
+}
+
+// Lock-step over several MIQPs (miqp.py solve_many; BASELINE config 2): every step replays each tree up to its next
+// unsolved leaves, flattens all of them (+ per-tree look-ahead) into ONE launch, longest-first by the parent's iteration
+// count, and shares the launch time by iteration count.  Each tree's result equals its own bqp_bnb_solve.
+extern "C" int bqp_bnb_solve_many(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                                  const double *const *x_incumbent, const double *upper_incumbent, bqp_solve_many_fn fn,
+                                  void *ctx, double *const *x, bqp_bnb_result *res, int *const *decisions, int decisions_cap) {
+  if (count <= 0 || !p || !s || !x || !res || (!h && !fn)) return BQP_E_ARG;
+  for (int k = 0; k < count; k++) if (!problem_ok(p[k]) || !x[k] || (!fn && !h[k])) return BQP_E_ARG;
+  std::vector<std::unique_ptr<Tree>> trees;
+  for (int k = 0; k < count; k++) {
+    trees.emplace_back(new Tree());
+    trees.back()->init(h ? h[k] : nullptr, p[k], &s[k], x_incumbent ? x_incumbent[k] : nullptr, upper_incumbent ? upper_incumbent[k] : kInf);
+  }
+  std::vector<char> active((size_t)count, 1);
+  int rc = BQP_OK;
+  for (;;) {
+    std::vector<Node *> batch; std::vector<int> owner;
+    for (int k = 0; k < count && !rc; k++) {
+      if (!active[(size_t)k]) continue;
+      const int a = trees[(size_t)k]->advance();
+      if (a < 0) { rc = a; break; }
+      if (a == 0) { active[(size_t)k] = 0; continue; }
+      const size_t first = batch.size();
+      trees[(size_t)k]->collect(batch);
+      owner.insert(owner.end(), batch.size() - first, k);
+    }
+    if (rc || batch.empty()) break;
+    const int B = (int)batch.size();
+    std::vector<int> order((size_t)B);
+    for (int b = 0; b < B; b++) order[(size_t)b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return batch[(size_t)a]->parent_iters > batch[(size_t)b]->parent_iters; });
+    std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
+    std::vector<double *> px(B), py(B);
+    std::vector<int> status(B), iters(B), own(B);
+    std::vector<bqp_handle> hs(B);
+    for (int j = 0; j < B; j++) {
+      Node &nd = *batch[(size_t)order[(size_t)j]];
+      own[j] = owner[(size_t)order[(size_t)j]];
+      hs[j] = h ? h[own[j]] : nullptr;
+      pl[j] = nd.l.data(); pu[j] = nd.u.data(); px0[j] = nd.x->data(); py0[j] = nd.y->data(); px[j] = nd.cx->data(); py[j] = nd.cy->data();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    if (fn) rc = fn(ctx, B, own.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), status.data(), iters.data());
+    else {
+      bqp_node_out out; std::memset(&out, 0, sizeof(out));
+      out.status = status.data(); out.iters = iters.data();
+      rc = bqp_solve_multi(B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), &out);
+    }
+    if (rc) break;
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    long long total = 0; for (int j = 0; j < B; j++) total += iters[j];
+    if (total < 1) total = 1;
+    std::vector<char> seen((size_t)count, 0);
+    for (int j = 0; j < B; j++) {
+      Tree::absorb(*batch[(size_t)order[(size_t)j]], status[j], iters[j], dt * (double)iters[j] / (double)total);
+      Tree &t = *trees[(size_t)own[j]];
+      t.batched_nodes++;
+      if (!seen[(size_t)own[j]]) { seen[(size_t)own[j]] = 1; t.batches++; }
+    }
+  }
+  for (int k = 0; k < count; k++) trees[(size_t)k]->finish(p[k], x[k], &res[k], decisions ? decisions[k] : nullptr, decisions_cap);
   return rc;
 }

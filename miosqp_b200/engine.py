@@ -76,6 +76,10 @@ _pp_d = C.POINTER(C.POINTER(C.c_double))
 SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _pp_d, _pp_d, _pp_d, _pp_d, _pp_d, _pp_d, C.POINTER(C.c_int), C.POINTER(C.c_int))
 
 
+SOLVE_MANY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), _pp_d, _pp_d, _pp_d, _pp_d, _pp_d, _pp_d,
+                            C.POINTER(C.c_int), C.POINTER(C.c_int))
+
+
 class _NodeOut(C.Structure):
     _fields_ = [("status", _ip), ("iters", _ip), ("obj", _dp), ("pri_res", _dp), ("dua_res", _dp), ("lower", _dp)]
 
@@ -96,7 +100,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
            "bqp_debug_host_panel_kkt_solve",
-           "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_setup_many"]
+           "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many"]
 
 _lib = None
 
@@ -131,6 +135,8 @@ def lib():
         L.bqp_debug_host_panel_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
         L.bqp_setup_many.argtypes = [C.c_int, C.POINTER(C.POINTER(_Problem)), C.POINTER(_Settings), pp, C.c_int, C.c_int]
+        L.bqp_bnb_solve_many.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp, C.c_void_p, vp,
+                                         _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int]
         L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
                                     C.POINTER(_BnbResult), _ip, C.c_int]
         _lib = L
@@ -333,11 +339,14 @@ def setup_many(items, host_only=False, threads=0, **settings):
     return qps
 
 
-def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.inf):
-    """The native B&B replay (include/bqp.h bqp_bnb_solve, csrc/bqp_bnb.cpp) on one set-up problem.
-    `qp` is the BatchedQP holding the factor (or a stand-in exposing `native_solve_fn()`, CPU tests);
-    `data` the MIQP's problem_data.Data; `settings` the reference's MIOSQP settings dict (+ 'speculation').
-    Returns (x, result dict, decisions)."""
+def native_solve_many_fn(qps):
+    """None: the lock-step native replay solves its nodes on the device through the handles of `qps`
+    (the CPU tests replace this hook with an oracle-backed bqp_solve_many_fn)."""
+    return None
+
+
+def _bnb_problem(data):
+    """(bqp_problem, keep-alive arrays) of a problem_data.Data: the UNSCALED problem the replay evaluates objectives on."""
     fixed = getattr(data, "_native_csc", None)          # P, A never change after setup: convert once per Data
     if fixed is None:
         P = spa.csc_matrix(data.P); A = spa.csc_matrix(data.A)
@@ -349,11 +358,24 @@ def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.
     keep = list(fixed[1:7]) + [_f64(data.q), _f64(data.l), _f64(data.u), fixed[7]]
     prob = _Problem(n, m_ext, _i(keep[0]), _i(keep[1]), _d(keep[2]), _i(keep[3]), _i(keep[4]), _d(keep[5]),
                     _d(keep[6]), _d(keep[7]), _d(keep[8]), int(keep[9].size), _i(keep[9]))
-    st = _BnbSettings(float(settings['eps_int_feas']), int(settings['max_iter_bb']), int(settings['tree_explor_rule']),
-                      int(settings['branching_rule']), int(settings.get('speculation', 0) or 0), float(eps_abs))
+    return prob, keep
+
+
+def _bnb_settings(settings, eps_abs):
+    return _BnbSettings(float(settings['eps_int_feas']), int(settings['max_iter_bb']), int(settings['tree_explor_rule']),
+                        int(settings['branching_rule']), int(settings.get('speculation', 0) or 0), float(eps_abs))
+
+
+def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.inf):
+    """The native B&B replay (include/bqp.h bqp_bnb_solve, csrc/bqp_bnb.cpp) on one set-up problem.
+    `qp` is the BatchedQP holding the factor (or a stand-in exposing `native_solve_fn()`, CPU tests);
+    `data` the MIQP's problem_data.Data; `settings` the reference's MIOSQP settings dict (+ 'speculation').
+    Returns (x, result dict, decisions)."""
+    prob, keep = _bnb_problem(data)
+    st = _bnb_settings(settings, eps_abs)
     fn = qp.native_solve_fn()
     handle = getattr(qp, "_h", None) if fn is None else None
-    x = np.empty(n); res = _BnbResult()
+    x = np.empty(prob.n); res = _BnbResult()
     cap = max(1, int(settings['max_iter_bb']))
     dec = np.zeros(2 * cap, dtype=np.int32)
     xin = _f64(x_incumbent) if x_incumbent is not None and np.isfinite(upper_incumbent) else None
@@ -363,6 +385,34 @@ def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.
     out = {k: getattr(res, k) for k, _ in _BnbResult._fields_}
     decisions = [(int(dec[2 * k]), int(dec[2 * k + 1])) for k in range(min(res.n_decisions, cap))]
     return x, out, decisions
+
+
+def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None):
+    """Lock-step native replay over several set-up problems (bqp_bnb_solve_many): one launch per B&B step covers all
+    their frontiers.  Arguments are sequences of equal length; `many_fn` (tests) replaces the engine.
+    Returns a list of (x, result dict, decisions)."""
+    count = len(qps)
+    built = [_bnb_problem(d) for d in datas]
+    pptr = (C.POINTER(_Problem) * count)(*[C.pointer(b[0]) for b in built])
+    sts = (_BnbSettings * count)(*[_bnb_settings(s, e) for s, e in zip(settings, eps_abs)])
+    cap = max(1, max(int(s['max_iter_bb']) for s in settings))
+    xs = [np.empty(b[0].n) for b in built]
+    decs = [np.zeros(2 * cap, dtype=np.int32) for _ in range(count)]
+    res = (_BnbResult * count)()
+    xins = [(_f64(x) if x is not None and np.isfinite(u) else None) for x, u in zip(x_incumbents, upper_incumbents)]
+    xin_ptrs = (_dp * count)(*[(_d(x) if x is not None else None) for x in xins])
+    uppers = _f64(np.asarray(upper_incumbents, dtype=np.float64))
+    handles = None if many_fn is not None else (C.c_void_p * count)(*[q._h.value for q in qps])
+    x_ptrs = (_dp * count)(*[_d(x) for x in xs])
+    dec_ptrs = (_ip * count)(*[_i(d) for d in decs])
+    rc = lib().bqp_bnb_solve_many(count, handles, pptr, sts, xin_ptrs, _d(uppers),
+                                  C.cast(many_fn, C.c_void_p) if many_fn is not None else None, None, x_ptrs, res, dec_ptrs, cap)
+    _check(rc)
+    out = []
+    for k in range(count):
+        r = {name: getattr(res[k], name) for name, _ in _BnbResult._fields_}
+        out.append((xs[k], r, [(int(decs[k][2 * j]), int(decs[k][2 * j + 1])) for j in range(min(r["n_decisions"], cap))]))
+    return out
 
 
 def _alloc_result(B, n, m):

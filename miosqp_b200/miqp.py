@@ -74,11 +74,15 @@ class MIOSQP(object):
     def _solve_native(self):
         """settings['replay'] = 'native': the same loop in C++ (csrc/bqp_bnb.cpp, bqp_bnb_solve) -- no interpreter time
         per node; one call in, the reference's Results out.  Leaves `work` as the Python replay would."""
-        from .constants import (MI_UNSOLVED, MI_SOLVED, MI_PRIMAL_INFEASIBLE, MI_DUAL_INFEASIBLE,
-                                MI_MAX_ITER_FEASIBLE, MI_MAX_ITER_UNSOLVED)
         work = self.work
         x, r, decisions = engine.bnb_solve(work.solver, work.data, work.settings, work.qp_settings['eps_abs'],
                                            work.x if np.isfinite(work.upper_glob) else None, work.upper_glob)
+        return self._absorb_native(x, r, decisions)
+
+    def _absorb_native(self, x, r, decisions):
+        from .constants import (MI_UNSOLVED, MI_SOLVED, MI_PRIMAL_INFEASIBLE, MI_DUAL_INFEASIBLE,
+                                MI_MAX_ITER_FEASIBLE, MI_MAX_ITER_UNSOLVED)
+        work = self.work
         work.x, work.upper_glob, work.lower_glob = x, r["upper_glob"], r["lower_glob"]
         work.iter_num, work.osqp_iter, work.osqp_solve_time = r["iter_num"], r["osqp_iter"], r["osqp_solve_time"]
         work.batches += r["batches"]; work.batched_nodes += r["batched_nodes"]
@@ -133,6 +137,15 @@ def solve_many(solvers, on_batch=None):
     `on_batch(n_nodes, seconds)` is called after every launch (benchmarks)."""
     for s in solvers:
         s._begin()
+    if solvers and all(s.work.settings.get('replay') == 'native' for s in solvers):
+        # the lock-step loop itself in C++ (bqp_bnb_solve_many): same launches, no interpreter time per node
+        works = [s.work for s in solvers]
+        many_fn = engine.native_solve_many_fn([w.solver for w in works])
+        outs = engine.bnb_solve_many([w.solver for w in works], [w.data for w in works], [w.settings for w in works],
+                                     [w.qp_settings['eps_abs'] for w in works],
+                                     [(w.x if np.isfinite(w.upper_glob) else None) for w in works],
+                                     [w.upper_glob for w in works], many_fn=many_fn)
+        return [s._absorb_native(x, r, d) for s, (x, r, d) in zip(solvers, outs)]
     active = list(solvers)
     while active:
         active = [s for s in active if s._replay()]

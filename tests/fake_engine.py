@@ -64,3 +64,28 @@ def solve_multi(qps, l, u, x0, y0):
     sc = Scalars()
     sc.status = np.array(st); sc.iters = np.array(it)
     return xs, ys, sc
+
+
+def native_solve_many_fn(qps):
+    """bqp_solve_many_fn (include/bqp.h) backed by the oracle: node b belongs to problem owner[b]."""
+    from miosqp_b200 import engine
+    oracles = [q.o for q in qps]
+
+    def fn(ctx, B, owner, l, u, x0, y0, x, y, status, iters):
+        try:
+            own = [int(owner[b]) for b in range(B)]
+            arr = lambda pp, b, size: np.ctypeslib.as_array(pp[b], shape=(size,))
+            os_ = [oracles[k] for k in own]
+            L = [np.array(arr(l, b, os_[b].m)) for b in range(B)]; U = [np.array(arr(u, b, os_[b].m)) for b in range(B)]
+            X0 = [np.array(arr(x0, b, os_[b].n)) for b in range(B)]; Y0 = [np.array(arr(y0, b, os_[b].m)) for b in range(B)]
+            xs, ys, st, it, _ = oracle.solve_multi(os_, L, U, X0, Y0, threads=4)
+            for b in range(B):
+                arr(x, b, os_[b].n)[:] = xs[b]; arr(y, b, os_[b].m)[:] = ys[b]; status[b] = int(st[b]); iters[b] = int(it[b])
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return -1
+    keep = engine.SOLVE_MANY_FN(fn)
+    qps[0]._native_many_fn = keep          # keep the callback object alive
+    return keep

@@ -174,3 +174,44 @@ def test_setup_many_on_device_equals_one_by_one():
     assert list(sa.status) == list(sb.status) and list(sa.iters) == list(sb.iters)
     for a, b in zip(xa, xb):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def _many(replay, speculation, seeds=(3, 4, 5)):
+    import miosqp_b200
+    solvers = []
+    for seed in seeds:
+        pr = problems.random_miqp(40, 40, 20, 0.7, seed=seed)[0]
+        s = miosqp_b200.MIOSQP()
+        s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                dict(problems.RANDOM_MIQP_SETTINGS, speculation=speculation, replay=replay), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+        solvers.append(s)
+    return solvers, miosqp_b200.solve_many(solvers)
+
+
+def _same_many(a, b, tol, counts=True):
+    (sa, ra), (sb, rb) = a, b
+    for s1, s2, r1, r2 in zip(sa, sb, ra, rb):
+        assert [tuple(d) for d in s1.work.decisions] == [tuple(d) for d in s2.work.decisions]
+        assert (r1.status, s1.work.iter_num, s1.work.osqp_iter) == (r2.status, s2.work.iter_num, s2.work.osqp_iter)
+        if counts:
+            assert (s1.work.batches, s1.work.batched_nodes, s1.work.spec_hits) == (s2.work.batches, s2.work.batched_nodes, s2.work.spec_hits)
+        assert abs(r1.upper_glob - r2.upper_glob) <= tol * (1 + abs(r1.upper_glob)) and np.abs(r1.x - r2.x).max() <= tol
+
+
+@pytest.mark.parametrize("speculation", [0, 16])
+def test_native_lock_step_equals_python_solve_many_cpu(cpu_engine, monkeypatch, speculation):
+    """bqp_bnb_solve_many against miqp.solve_many: same per-instance B&B, same launches, same look-ahead adoptions; and
+    each instance equals its own single solve."""
+    import fake_engine
+    from miosqp_b200 import engine
+    monkeypatch.setattr(engine, "native_solve_many_fn", fake_engine.native_solve_many_fn)
+    py = _many(None, speculation); nat = _many('native', speculation)
+    _same_many(py, nat, 1e-12)
+    pr = problems.random_miqp(40, 40, 20, 0.7, seed=4)[0]
+    r1, w1 = _solve(pr, replay='native', speculation=speculation)
+    assert [tuple(d) for d in w1.decisions] == [tuple(d) for d in nat[0][1].work.decisions] and r1.upper_glob == nat[1][1].upper_glob
+
+
+@pytest.mark.gpu
+def test_native_lock_step_on_engine():
+    _same_many(_many(None, 8), _many('native', 8), 1e-9, counts=False)
