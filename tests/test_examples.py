@@ -20,6 +20,7 @@ def cpu_engine(monkeypatch):
     from miosqp_b200 import engine
     monkeypatch.setattr(engine, "BatchedQP", fake_engine.FakeBatchedQP)
     monkeypatch.setattr(engine, "solve_multi", fake_engine.solve_multi)
+    monkeypatch.setattr(engine, "native_solve_many_fn", fake_engine.native_solve_many_fn)
 
 
 def _mpc(capsys, argv):
@@ -56,6 +57,8 @@ def test_random_miqp_example_cpu(cpu_engine, capsys):
     out = capsys.readouterr().out
     assert "t_osqp_avg" in out and "one instance at a time" in out
     random_miqp.main(["--sizes", "50,25,5", "--repeat", "3", "--together", "--speculation", "8"])
+    assert "lock-step" in capsys.readouterr().out
+    random_miqp.main(["--sizes", "50,25,5", "--repeat", "3", "--together", "--speculation", "8", "--replay", "native"])
     assert "lock-step" in capsys.readouterr().out
 
 
