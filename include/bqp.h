@@ -12,6 +12,8 @@
  *   bqp_solve_multi       <- the same for nodes of several set-up problems in ONE launch
  *                            (frontier of many MIQP instances, BASELINE cfg 2)
  *   bqp_bnb_solve         <- MIOSQP.solve(): the B&B while-loop itself, natively  solver.py:85-172
+ *   bqp_bnb_solve_many    <- the same for several MIQPs in lock-step (one launch per B&B step over all frontiers)
+ *   bqp_setup_many        <- setup of many problems, host halves on all host threads
  *   BQP_* status codes    <- osqp.constant('OSQP_*')                        node.py:88,128-129
  *   bqp_free              <- garbage collection of the osqp object
  *
