@@ -4,7 +4,7 @@
 # Writes logs under gpurun_out/; copy what is worth keeping into profiles/.
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q > gpurun_out/n1_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/n1_tests.log
+timeout 400 python -m pytest tests -m "gpu or gpu_next" -q > gpurun_out/n1_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/n1_tests.log
 # config 3: Python vs native replay, look-ahead 0 / 32 / 128, warmed up
 timeout 120 python tools/mpc_bench.py --steps 20 --horizon 10 --budgets 0,32,128 --warm > gpurun_out/n1_mpc_python.jsonl 2>&1
 timeout 120 python tools/mpc_bench.py --steps 20 --horizon 10 --budgets 0,32,128 --warm --replay native > gpurun_out/n1_mpc_native.jsonl 2>&1
