@@ -329,6 +329,13 @@ def main():
                                    "sample": "first %d leaves of the step's batch, CPU oracle (oracle/osqp_oracle.c), %d threads, %.1f s" % (
                                        nodes, cores, secs),
                                    "admm_node_iters_per_s": its / secs}
+            try:    # the reference's own execution model: one node at a time on one core (SURVEY 8d asks for both figures)
+                s1, n1, i1 = run_oracle_sample(sample[:8], 1)
+                out["cpu_baseline"]["single_core"] = {"value": n1 / s1, "unit": "QP/s", "cores": 1,
+                                                      "sample": "first %d leaves of the step's batch, one thread, %.1f s" % (n1, s1),
+                                                      "admm_node_iters_per_s": i1 / s1}
+            except Exception as e:      # never lose the bench line over an extra figure
+                out["cpu_baseline"]["single_core"] = {"error": repr(e)}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
