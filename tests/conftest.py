@@ -11,9 +11,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "gpu_next: needs a B200 and was written AFTER the round's GPU budget was spent, so it has never "
-                                       "run on one; deliberately outside `-m gpu` until it has (tools/next_gpu_call.sh runs "
-                                       "`-m \"gpu or gpu_next\"` first thing next round, then the marker becomes `gpu`)")
 
 
 @pytest.fixture(scope="session")
@@ -32,11 +29,11 @@ def _have_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    """`gpu_next` tests are not `gpu`, so `-m "not gpu"` selects them: skip them where there is no device."""
+    """A plain `pytest` run on a machine without a device skips the `gpu` tests instead of failing them."""
     have = None
     for item in items:
-        if item.get_closest_marker("gpu_next") is not None:
+        if item.get_closest_marker("gpu") is not None:
             if have is None:
                 have = _have_gpu()
             if not have:
-                item.add_marker(pytest.mark.skip(reason="gpu_next: needs a B200 (never run on one yet)"))
+                item.add_marker(pytest.mark.skip(reason="needs a B200"))

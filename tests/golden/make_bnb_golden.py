@@ -73,9 +73,45 @@ def main_cfg4():
     print("cfg4", r["status"], r["upper_glob"], "nodes", r["iter_num"] - 1, "admm", r["osqp_iter"], "branchings", len(r["decisions"]))
 
 
+# BASELINE config 2 (n=500, m=1000, |i_idx|=50, density 0.7): the first draws of the 100-instance workload, to completion.
+# Also records, per consumed node in consumption order, (status, ADMM iterations): the workload shape bench.py --mode bnb
+# is judged on.  x is kept (500 doubles per instance).
+CFG2 = dict(n=500, m=1000, p=50, density=0.7, seed=1)
+
+
+def main_cfg2(count):
+    c = CFG2
+    prs = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"], count=count)
+    path = os.path.join(HERE, "bnb_cfg2.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    from miosqp import node as ref_node
+    for k, pr in enumerate(prs):
+        name = "cfg2_inst%d" % k
+        if name in out:
+            continue
+        trace = []
+        orig_solve = ref_node.Node.solve
+
+        def solve(self, _o=orig_solve):
+            _o(self)
+            trace.append((int(self.status), int(self.num_iter), int(self.depth)))
+        ref_node.Node.solve = solve
+        try:
+            r = run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+        finally:
+            ref_node.Node.solve = orig_solve
+        r["node_trace"] = trace
+        out[name] = dict(case=dict(c, instance=k), result=r)
+        print(name, r["status"], r["upper_glob"], "nodes", r["iter_num"] - 1, "admm", r["osqp_iter"], "branchings", len(r["decisions"]), flush=True)
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+
+
 def main():
     if "--cfg4" in sys.argv:
         return main_cfg4()
+    if "--cfg2" in sys.argv:
+        return main_cfg2(int(sys.argv[sys.argv.index("--cfg2") + 1]))
     out = {}
     for name, c in CASES.items():
         pr = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"])[0]

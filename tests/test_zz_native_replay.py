@@ -126,13 +126,13 @@ def test_abi_argument_checks():
 
 
 # ------------------------------------------------------------------ the real engine
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(GOLDEN))
 def test_native_replay_on_engine(name):
     _golden_case(name, 1e-9, speculation=16)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_native_mpc_closed_loop_on_engine():
     _mpc_closed_loop(8, 1e-9, 32)
 
@@ -157,7 +157,7 @@ def test_native_replay_under_sanitizers(tmp_path):
     assert run.returncode == 0 and "asan harness ok" in run.stdout, run.stdout[-2000:]
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_setup_many_on_device_equals_one_by_one():
     """bqp_setup_many (parallel host halves, sequential uploads) then one launch over all problems: same results as
     problems set up one by one."""
@@ -212,6 +212,6 @@ def test_native_lock_step_equals_python_solve_many_cpu(cpu_engine, monkeypatch, 
     assert [tuple(d) for d in w1.decisions] == [tuple(d) for d in nat[0][1].work.decisions] and r1.upper_glob == nat[1][1].upper_glob
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_native_lock_step_on_engine():
     _same_many(_many(None, 8), _many('native', 8), 1e-9, counts=False)

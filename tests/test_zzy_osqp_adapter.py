@@ -94,7 +94,7 @@ def test_adapter_call_sequence_cpu(monkeypatch):
         assert np.abs(ra.x - rb.x).max() <= 1e-12 * (1 + np.abs(rb.x).max())
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_adapter_call_sequence_engine():
     from miosqp_b200 import osqp_compat
     from oracle import oracle

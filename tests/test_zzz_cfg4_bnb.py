@@ -42,7 +42,7 @@ def test_cfg4_node_limited_bnb_cpu(monkeypatch):
     assert w.spec_nodes > 0          # look-ahead nodes rode along (a 9-node dive never returns to them: no adoption expected)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_cfg4_node_limited_bnb_engine():
     from miosqp_b200 import engine
     w = _run(speculation=4)
