@@ -167,7 +167,8 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
     T = 1 << LEAF_DEPTH
     bytes_per_ni = algorithmic_bytes_per_node_iter(inst0, T)
     step_s = dev_s / args.steps
-    kernel = {0: "admm_tile_kernel<%d>", 1: "admm_stream_kernel<%d>", 2: "admm_panel_kernel (%d nodes per tile)"}[int(tm.get("kernel", 1))] % tm["tile_nodes"]
+    kernel = {0: "admm_tile_kernel<%d>", 1: "admm_stream_kernel<%d>", 2: "admm_panel_kernel (%d nodes per tile)",
+              3: "admm_rows_kernel (%d nodes per tile)"}[int(tm.get("kernel", 1))] % tm["tile_nodes"]
     traffic, traffic_src, traffic_scope = None, None, None
     try:   # dram__bytes_read+write of the captured launch of this kernel, from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:

@@ -93,7 +93,7 @@ typedef struct {
   long long node_iters;     /* sum over nodes of ADMM iterations executed until that node terminated */
   long long tile_iters;     /* sum over tiles of iterations the tile ran (= max over its nodes) */
   long long stream_bytes;   /* matrix/factor bytes the kernel streamed: sum over tiles of iterations x per-iteration panel bytes (+ checks) */
-  int kernel;               /* which kernel ran: 0 direct-load tile kernel, 1 TMA-streamed two-pass kernel, 2 fused single-pass panel kernel */
+  int kernel;               /* which kernel ran: 0 direct-load tile kernel, 1 TMA-streamed two-pass kernel, 2 fused single-pass panel kernel (column-split pair), 3 row-split cluster kernel */
   int ring_slots;           /* shared-memory ring depth (TMA stages / panels in flight) of the first launch */
 } bqp_timing;
 

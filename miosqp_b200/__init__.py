@@ -7,4 +7,4 @@ miosqp_b200 -- Blackwell-native batched QP-relaxation engine behind miOSQP's API
 from .constants import *          # noqa: F401,F403
 from .problem_data import Data, add_bounds          # noqa: F401
 from .results import Results      # noqa: F401
-from .miqp import MIOSQP, solve_many                # noqa: F401
+from .miqp import MIOSQP, solve_many, setup_many                # noqa: F401

@@ -87,7 +87,7 @@ struct BatchCtx {
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
-  bool use_stream = false, use_panel = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
+  bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
   int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
   std::vector<long long> in_off, state_off;
   Buf d_state;
@@ -298,13 +298,28 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   const bool rounds = (use_stream || use_panel) && g.round_iters > 0;
   // panel kernel: problems wider than one CTA's consumer warps run as cluster pairs (2 SMs per tile)
   int cs = 1;
-  if (use_panel) {
+  const bool use_rows = use_panel && g.use_rows;
+  if (use_rows) {
+    // rows kernel: CTA r of a cluster owns the row panels k = r (mod cs); the column chunks of the per-iteration exchange need
+    // cs | nw.  The cluster size is a function of the problems only (never of the batch size): a node's result must not depend
+    // on what else is in the launch
+    bool wide = false, even = true, quad = true;
+    for (int b : alive) { const int nw = g.node_inst[b]->h.pn.nw; wide = wide || nw > kPanelCtaWarps; even = even && nw % 2 == 0; quad = quad && nw % 4 == 0; }
+    cs = (wide && even) ? 2 : 1;
+    if (const char *e = std::getenv("BQP_ROWS_CLUSTER")) { const int v = std::atoi(e); if (v == 1 || (v == 2 && even) || (v == 4 && quad)) cs = v; }
+  } else if (use_panel) {
     for (int b : alive) if (g.node_inst[b]->h.pn.nw > kPanelCtaWarps) cs = 2;
     if (const char *e = std::getenv("BQP_PANEL_CLUSTER")) { const int v = std::atoi(e); if (v == 2 || (v == 1 && cs == 1)) cs = v; }
   }
   g.cs = cs;
   const int capacity = rounds ? ndev_sms / cs : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
   auto panel_slots = [&](const HostInstance &h) {   // ring slots (this CTA's share of one panel each) beside the vectors
+    if (use_rows) {   // full-width panels
+      const long long fixed = (long long)rows_smem_bytes(h.npad, 0, cs) + 256, sb = (long long)h.pn.nw * kPanelRows * 32 * 8;
+      long long cap = 8;
+      if (const char *e = std::getenv("BQP_ROWS_SLOTS")) cap = std::max(2, std::atoi(e));
+      return (int)std::min<long long>(cap, ((long long)kMaxSmem - fixed) / sb);
+    }
     const long long fixed = (long long)panel_smem_bytes(h.npad, 0, cs) + 256;
     const long long sb = (long long)(cs == 2 ? (h.pn.nw + 1) / 2 : h.pn.nw) * kPanelRows * 32 * 8;
     long long cap = 16;
@@ -341,7 +356,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     }
   }
   const int slot_bytes = g.stage_bytes;
-  if (use_panel && cs == 1)
+  if (use_panel && !use_rows && cs == 1)
     for (int b : alive) if (g.node_inst[b]->h.pn.nw > kPanelCtaWarps) return BQP_E_UNSUPPORTED;
   auto slot_size = [&](int t) { return slot_bytes + (w_in_stage ? kKC * t * 8 : 0); };
   auto stream_slots = [&](const HostInstance &h, int t) {   // slots PER QUAD (one ring per quad of consumer warps)
@@ -353,7 +368,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   for (auto *inst : uniq) {
     int t = 0;
     if (use_panel) {
-      t = panel_slots(inst->h) >= 4 ? kPanelT : 0;   // pass 2 holds 2 panels; the rest are in flight
+      t = panel_slots(inst->h) >= (use_rows ? 2 : 4) ? kPanelT : 0;   // panel kernel: pass 2 holds 2 panels; the rest are in flight
     } else if (use_stream) {
       t = kMaxTT;
       while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
@@ -396,7 +411,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
     if (!g.tiles.empty() && (long long)g.tiles.size() + nt > capacity) break;
     auto is = inst_slot.find(uniq[k]);
     if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
-    smem = std::max(smem, use_panel ? panel_smem_bytes(h.npad, nslots, cs)
+    smem = std::max(smem, use_rows ? rows_smem_bytes(h.npad, nslots, cs) : use_panel ? panel_smem_bytes(h.npad, nslots, cs)
                           : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
     if (use_panel) g.nw_max = std::max(g.nw_max, h.pn.nw);
     for (int ti = 0; ti < nt; ti++) {
@@ -411,7 +426,7 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
         scheduled->push_back(b);
       }
       t.work_off = (long long)work_d;
-      work_d += use_panel ? cs * panel_work_doubles(h.npad, h.m) : tile_work_doubles(h.n, h.m, tt);
+      work_d += use_rows ? rows_work_doubles(h.npad, h.m, cs) : use_panel ? cs * panel_work_doubles(h.npad, h.m) : tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
       g.tile_bytes_iter.push_back(use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
       g.tile_bytes_check.push_back(use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
@@ -453,9 +468,11 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   // the direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
   g.use_stream = g_tune_threads == 0;
   g.use_panel = g_tune_threads == 0;
-  if (const char *e = std::getenv("BQP_KERNEL")) {        // tests / A-B runs: "panel" (default when possible), "stream", "direct"
+  g.use_rows = true;
+  if (const char *e = std::getenv("BQP_KERNEL")) {        // tests / A-B runs: "rows" (default when possible), "panel", "stream", "direct"
     if (!std::strcmp(e, "stream")) g.use_panel = false;
     else if (!std::strcmp(e, "direct")) g.use_panel = g.use_stream = false;
+    else if (!std::strcmp(e, "panel")) g.use_rows = false;
   }
   g.stage_bytes = kStageValBytes;
   g.w_in_stage = true;
@@ -542,7 +559,11 @@ int bqp_batch_run(void) {
     if (rc) return rc;
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
-    rc = g.use_panel
+    rc = (g.use_panel && g.use_rows)
+             ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                                (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
+                                g.smem, g.stream)
+         : g.use_panel
              ? launch_admm_panel(g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
                                  g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
                                  (int *)g.d_ti.p, g.smem, g.stream)
@@ -591,11 +612,12 @@ int bqp_batch_run(void) {
   g.timing.kernel_ms = ms;
   g.timing.launches = launches;
   g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
-  if (g.use_panel) {
+  if (g.use_panel && g.use_rows) g.timing.threads = kRowsThreads;
+  else if (g.use_panel) {
     const int nwc = g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max;
-    g.timing.threads = ((nwc + kPanelP1Tiles - 1) / kPanelP1Tiles + (nwc + 1) / 2 + kPanelUpdWarps + 1) * 32;
+    g.timing.threads = panel_cta_warps(nwc) * 32;
   }
-  g.timing.kernel = g.use_panel ? 2 : (g.use_stream ? 1 : 0);
+  g.timing.kernel = g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
   g.timing.ring_slots = first_slots;
   g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
   g.round_h2d_total = h2d_extra;

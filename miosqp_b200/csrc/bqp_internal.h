@@ -84,8 +84,19 @@ constexpr int kPanelRows = 8;                       // one 8-row mma tile per pa
 constexpr int kPanelT = 8;                          // nodes per tile of the panel kernel (N of the mma)
 constexpr int kPanelMaxWarps = 16;                  // column tiles of 32 (npad <= 512), one consumer warp each
 constexpr int kPanelCtaWarps = 8;                   // consumer warps per CTA; wider problems run as a cluster pair of CTAs
-constexpr int kPanelP1Tiles = 1;                    // column tiles per pass-1 warp (pass-2 warps own two)
-constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin
+#ifndef BQP_P1_TILES
+#define BQP_P1_TILES 1
+#endif
+#ifndef BQP_P1_SETS
+#define BQP_P1_SETS 1
+#endif
+constexpr int kPanelP1Tiles = BQP_P1_TILES;         // column tiles per pass-1 warp (pass-2 warps own two)
+// pass-1 warp SETS: set s handles the panels whose global panel counter is congruent to s.  With 2 sets the per-panel
+// synchronisation tail of one set (mbarrier wait, flow control, partial store + DSMEM copy) overlaps the other set's mma work
+constexpr int kPanelP1Sets = BQP_P1_SETS;
+constexpr int kPanelUpdWarps = 3;                   // update warps (row-space z / y / x updates), panels dealt round-robin 
+// warps of a panel-kernel CTA that streams `nwc` column tiles: pass-1 sets, pass-2 warps, update warps, producer
+constexpr int panel_cta_warps(int nwc) { return (nwc + kPanelP1Tiles - 1) / kPanelP1Tiles * kPanelP1Sets + (nwc + 1) / 2 + kPanelUpdWarps + 1; }
 struct HostPanels {
   bool built = false;
   int nw = 0, npm = 0, npa = 0;                     // column tiles; panels of M (and P); panels of A
@@ -96,6 +107,15 @@ struct HostPanels {
   long long check_bytes() const { return (long long)(2 * npa + npm) * panel_bytes(); }     // A twice + P
   long long launch_bytes() const { return (long long)(npa + npm) * panel_bytes(); }        // prologue A pass + objective P pass
 };
+
+// ---- row-split cluster kernel (bqp_rows.cu): same panel stream, CTA r of a cluster of C owns the panels k = r (mod C)
+#ifndef BQP_ROWS_GROUPS
+#define BQP_ROWS_GROUPS 2
+#endif
+constexpr int kRowsT = 8;                           // nodes per tile (N of the mma)
+constexpr int kRowsGroupWarps = 4;                  // warps per group, each multiplying a quarter of the column tiles
+constexpr int kRowsGroups = BQP_ROWS_GROUPS;        // groups per CTA, each taking whole panels through all stages
+constexpr int kRowsThreads = (kRowsGroups * kRowsGroupWarps + 4) * 32;   // + the producer warpgroup (one lane issues the TMA copies)
 
 // Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
 // KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
@@ -182,6 +202,15 @@ size_t panel_smem_bytes(int npad, int nslots, int cs);                          
 int launch_admm_panel(int cs, int nw_max, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                       const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters,
                       size_t smem_bytes, void *stream);
+// rows kernel, per tile, [row][8]: z, y, l, u, dy, A x, A dx (m padded to 8); x, dx, P x, objective operand, x snapshot (npad
+// rows each); column-space partials of the three check passes per (CTA, group)
+BQP_HD inline size_t rows_work_doubles(int npad, int m, int cs) {
+  return (size_t)kRowsT * (7 * (size_t)((m + 7) / 8 * 8) + (5 + 3 * (size_t)cs * kRowsGroups) * (size_t)npad);
+}
+size_t rows_smem_bytes(int npad, int nslots, int cs);                                 // bqp_rows.cu
+int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+                     const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
+                     void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

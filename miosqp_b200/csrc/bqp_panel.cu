@@ -56,7 +56,9 @@ constexpr int kHBmul = 2;
 constexpr int kHB = kHBmul * kPanelUpdWarps;   // hand-off buffers; buffer b = panel % kHB always belongs to update warp b % kPanelUpdWarps
 constexpr int kPH = kPanelRows / 8;            // 8-row mma tiles per panel
 constexpr int kP1T = kPanelP1Tiles;
-constexpr int kPanelThreads = ((kPanelCtaWarps + kP1T - 1) / kP1T + (kPanelCtaWarps + 1) / 2 + kPanelUpdWarps + 1) * 32;
+constexpr int kSets = kPanelP1Sets;
+constexpr int kPanelThreads = panel_cta_warps(kPanelCtaWarps) * 32;
+static_assert(kPanelThreads <= 1024, "panel kernel CTA too large");
 constexpr int kTileDoubles = kPR * 32;   // one column tile of one panel
 
 // ------------------------------------------------------------------ mbarrier / TMA / cluster wrappers (PTX)
@@ -232,7 +234,8 @@ struct ConsumerBase {
 template <int CS>
 struct P1Warp : ConsumerBase<CS> {
   using B = ConsumerBase<CS>;
-  int pidx;                          // this warp's partial slot (index over the P1 warps of both CTAs)
+  int pidx;                          // this warp's partial slot (index over the P1 warps of ONE set of both CTAs)
+  int set;                           // this warp handles the panels with global counter g % kSets == set
   // pass 1 over `npanels` panels with the column vector src ([column - src_col0][8 nodes])
   __device__ __forceinline__ void pass(int npanels, const double *src, int src_col0) {
     const Lay &L = B::L;
@@ -244,6 +247,7 @@ struct P1Warp : ConsumerBase<CS> {
       for (int ks = 0; ks < 8; ks++)
         bx[tl][ks] = (tl < kP1T && tl < B::ntl) ? src[(size_t)(32 * (B::wg0 + tl) + 4 * ks + tq - src_col0) * T8 + gq] : 0.0;
     for (int k = 0; k < npanels; k++) {
+      if (kSets > 1 && (B::g % kSets) != set) { B::advance(); continue; }     // the other set's panel
       TSTAMP(*this, 5);
       mbar_wait(L.full + 8u * B::slot, B::phase);
       TSTAMP(*this, 0);
@@ -553,7 +557,8 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   const int w0 = rank == 0 ? 0 : nwh, NWc = rank == 0 ? nwh : NW - nwh;
   const int slot_bytes = NWc * (kTileDoubles * 8);
   const int nwslots = (int)(blockDim.x >> 5) - KU - 1;     // consumer warp slots of this launch
-  const int np1 = (NWc + kP1T - 1) / kP1T, np2 = (NWc + 1) / 2, ncons = np1 + np2;   // pass-1 / pass-2 warps of this CTA
+  // pass-1 warps of ONE set / of all sets / pass-2 warps of this CTA
+  const int np1 = (NWc + kP1T - 1) / kP1T, np1w = np1 * kSets, np2 = (NWc + 1) / 2, ncons = np1w + np2;
   const int np1_r0 = (nwh + kP1T - 1) / kP1T, npt = np1_r0 + (CS == 2 ? (NW - nwh + kP1T - 1) / kP1T : 0);
   const int nthr_cu = (ncons + KU) * 32, nthr_all = (ncons + KU + 1) * 32;
   const bool is_consumer = warp < ncons, is_update = warp >= nwslots && warp < nwslots + KU, is_producer = warp == nwslots + KU;
@@ -585,7 +590,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   }
   L.cnt = &S.upd_cnt[0][0];
   if (tid == 0) {
-    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, ncons); }
+    for (int s = 0; s < nslots; s++) { mbar_init(L.full + 8u * s, 1); mbar_init(L.empty + 8u * s, np1 + np2); }
     // "partials full" / check barriers: one arrival per LOCAL pass-1 / pass-2 warp; the peer's share arrives as transaction bytes
     for (int s = 0; s < kHB; s++) {
       mbar_init(L.pf + 8u * s, np1); mbar_init(L.ud + 8u * s, 1); mbar_init(L.uc + 8u * s, np2);
@@ -888,11 +893,13 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   const int gq = lane >> 2, tq = lane & 3;
   const int ncthr = ncons * 32;
   int iter;
-  if (warp < np1) {
+  if (warp < np1w) {
     // ------------------------------------------------------------- pass-1 warp
     P1Warp<CS> C;
-    C.init(L, lane, kP1T * warp, min(kP1T, NWc - kP1T * warp));
-    C.pidx = (rank == 0 ? 0 : np1_r0) + warp;
+    const int wi = warp % np1;                         // position inside its set
+    C.init(L, lane, kP1T * wi, min(kP1T, NWc - kP1T * wi));
+    C.pidx = (rank == 0 ? 0 : np1_r0) + wi;
+    C.set = warp / np1;
     C.pass(npa, W.gxs, 0);                            // z = A x0 (first round)
     named_bar(4, ncthr);                              // b' of the pass-2 warps is in vs
     for (iter = iter_begin + 1; iter <= iter_end; iter++) {
@@ -923,7 +930,7 @@ admm_panel_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   }
   // --------------------------------------------------------------- pass-2 warp
   P2Warp<CS> C;
-  const int pw = warp - np1;
+  const int pw = warp - np1w;
   C.init(L, lane, 2 * pw, min(2, NWc - 2 * pw));
   double acc[2][4][2];
   // b' = sigma x - q + A'(rho z - y) for this warp's columns, from the pass-2 accumulators (C fragments), into vs (read
@@ -1046,7 +1053,7 @@ static int launch_p(int nw_max, int nslots, double *d_state, const DevInstance *
   const int nwc = CS == 2 ? (nw_max + 1) / 2 : nw_max;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ntiles * CS), 1, 1);
-  cfg.blockDim = dim3((unsigned)(((nwc + kP1T - 1) / kP1T + (nwc + 1) / 2 + kPanelUpdWarps + 1) * 32), 1, 1);
+  cfg.blockDim = dim3((unsigned)(panel_cta_warps(nwc) * 32), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -131,6 +131,29 @@ class MIOSQP(object):
         self.work.set_x0(x0)
 
 
+def setup_many(problems, settings, qp_settings, threads=0):
+    """`MIOSQP().setup(...)` for many MIQPs sharing their settings: the factorisations run on all host threads
+    (engine.setup_many / bqp_setup_many).  problems: dicts with P, q, A, l, u, i_idx, i_l, i_u (problems.random_miqp)."""
+    start = time()
+    datas = []
+    for pr in problems:
+        i_l = pr.get('i_l'); i_u = pr.get('i_u')
+        i_l = -np.inf * np.ones(len(pr['i_idx'])) if i_l is None else i_l
+        i_u = np.inf * np.ones(len(pr['i_idx'])) if i_u is None else i_u
+        datas.append(Data(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], i_l, i_u))
+    qp = dict(qp_settings or {})
+    qps = engine.setup_many([(d.P, d.q, d.A, d.l, d.u, d.i_idx) for d in datas], threads=threads, **qp)
+    out = []
+    per = (time() - start) / max(1, len(datas))
+    for d, s in zip(datas, qps):
+        m = MIOSQP()
+        m.data = d
+        m.work = Workspace(d, dict(settings), dict(qp), solver=s)
+        m.work.setup_time = per
+        out.append(m)
+    return out
+
+
 def solve_many(solvers, on_batch=None):
     """Solve several set-up MIOSQP objects together: every step flattens the unsolved leaves of ALL frontiers into
     one node batch (one kernel launch).  Each instance's result is identical to its own `solve()`.

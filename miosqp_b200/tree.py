@@ -67,13 +67,13 @@ class Node(object):
 class Workspace(object):
     """Frontier (`leaves`), incumbent and counters of one MIQP; one device-resident factor per workspace."""
 
-    def __init__(self, data, settings, qp_settings=None):
+    def __init__(self, data, settings, qp_settings=None, solver=None):
         self.data = data
         self.settings = settings
         self.qp_settings = {} if qp_settings is None else qp_settings
-        # factor once: P and A never change afterwards (workspace.py:63-68)
-        self.solver = engine.BatchedQP().setup(data.P, data.q, data.A, data.l, data.u, i_idx=data.i_idx,
-                                               **self.qp_settings)
+        # factor once: P and A never change afterwards (workspace.py:63-68); `solver`: already set up (miqp.setup_many)
+        self.solver = solver if solver is not None else engine.BatchedQP().setup(
+            data.P, data.q, data.A, data.l, data.u, i_idx=data.i_idx, **self.qp_settings)
         self.first_run = 1
         self.setup_time = self.solve_time = self.run_time = 0.
         self.batches = 0            # kernel launches issued for this workspace

@@ -25,6 +25,26 @@ def panel_threads(n, cluster=None):
     return (nwc + (nwc + 1) // 2 + 4) * 32     # pass-1 warps (one column tile each) + pass-2 warps (two each) + 3 update + 1 producer
 
 
+ROWS_THREADS = 12 * 32     # row-split cluster kernel (bqp_rows.cu): 2 groups x 4 consumer warps + the producer warpgroup
+
+
+@pytest.fixture(params=["rows", "panel"])
+def dense_kernel(request, monkeypatch):
+    """dense-A problems with npad <= 512 run on the row-split cluster kernel (default) or, with BQP_KERNEL=panel, on round 1's
+    column-split panel kernel; both must agree with the oracle"""
+    if request.param == "panel":
+        monkeypatch.setenv("BQP_KERNEL", "panel")
+    return request.param
+
+
+def expect_dense(kind, n, cluster=None):
+    t = engine.last_timing()
+    if kind == "rows":
+        assert t["kernel"] == 3 and t["threads"] == ROWS_THREADS, t
+    else:
+        assert t["kernel"] == 2 and t["threads"] == panel_threads(n, cluster), t
+
+
 def _close(a, b, tol=TOL):
     a = np.asarray(a, float); b = np.asarray(b, float)
     assert np.array_equal(np.isnan(a), np.isnan(b))
@@ -168,18 +188,18 @@ def test_update_q(oracle_mod):
 
 # ---------------------------------------------------------------- fused single-pass panel kernel (bqp_panel.cu)
 @pytest.mark.parametrize("tt", [1, 2, 4, 8])
-def test_panel_kernel_tile_widths(oracle_mod, tt):
+def test_panel_kernel_tile_widths(oracle_mod, tt, dense_kernel):
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == panel_threads(130)
+    expect_dense(dense_kernel, 130)
     assert engine.last_timing()["tile_nodes"] == tt
 
 
-def test_panel_kernel_cold_start_and_infeasible(oracle_mod):
-    """zero warm start (prologue z = A x0 pass) and contradictory bounds (certificate path) through the panel kernel"""
+def test_panel_kernel_cold_start_and_infeasible(oracle_mod, dense_kernel):
+    """zero warm start (prologue z = A x0 pass) and contradictory bounds (certificate path) through the dense kernels"""
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 7, 12, QP, oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == panel_threads(130)
+    expect_dense(dense_kernel, 130)
     P, q, A, l, u, i_idx = problems.extend(pr)
     o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
     e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
@@ -198,6 +218,7 @@ def test_panel_kernel_cold_start_and_infeasible(oracle_mod):
 @pytest.mark.parametrize("tt", [1, 4, 8])
 def test_panel_kernel_cluster_pair_uneven_split(oracle_mod, tt, monkeypatch):
     """n = 130 has 5 column tiles: forced onto a cluster pair, CTA 0 takes 3 and CTA 1 takes 2 of them"""
+    monkeypatch.setenv("BQP_KERNEL", "panel")
     monkeypatch.setenv("BQP_PANEL_CLUSTER", "2")
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 9, 6, QP, warm="root", tuning=(tt, 0), oracle_mod=oracle_mod)
@@ -205,18 +226,37 @@ def test_panel_kernel_cluster_pair_uneven_split(oracle_mod, tt, monkeypatch):
     _compare(pr, 6, 13, dict(QP, max_iter=60, eps_abs=1e-6, eps_rel=1e-6), tuning=(tt, 0), oracle_mod=oracle_mod)
 
 
-def test_panel_kernel_cluster_pair_cfg2_cold(oracle_mod):
-    """cfg 2 shape through the cluster pair (16 column tiles, 8 per CTA), cold start"""
+def test_panel_kernel_cluster_pair_cfg2_cold(oracle_mod, dense_kernel):
+    """cfg 2 shape through the cluster pair (16 column tiles; rows kernel: 66 row panels of A per CTA), cold start"""
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=2)[0]
     _compare(pr, 5, 21, QP, oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == panel_threads(500)
+    expect_dense(dense_kernel, 500)
 
 
-def test_panel_kernel_max_iter(oracle_mod):
+@pytest.mark.parametrize("cs", [1, 2, 4])
+def test_rows_kernel_cluster_sizes(oracle_mod, cs, monkeypatch):
+    """row-split kernel on 1, 2 and 4 CTAs per tile (cfg 2 shape, warm and cold start, max_iter path): the per-iteration
+    DSMEM exchange (x~ all-gather, reduce-scatter of A'w, all-gather of b') and the global-memory check path"""
+    monkeypatch.setenv("BQP_ROWS_CLUSTER", str(cs))
+    pr = problems.random_miqp(500, 1000, 50, 0.7, seed=3)[0]
+    _compare(pr, 8, 5, QP, warm="root", oracle_mod=oracle_mod)
+    expect_dense("rows", 500)
+    _compare(pr, 3, 6, dict(QP, max_iter=60, eps_abs=1e-6, eps_rel=1e-6), oracle_mod=oracle_mod)
+
+
+def test_rows_kernel_odd_tiles(oracle_mod):
+    """column tiles not a multiple of the 4 warps of a group (n = 130: 5 tiles; n = 40: 2 tiles), single CTA"""
+    for n, m, p, seed in ((130, 200, 10, 4), (40, 50, 6, 9)):
+        pr = problems.random_miqp(n, m, p, 0.7, seed=seed)[0]
+        _compare(pr, 9, 6, QP, warm="root", oracle_mod=oracle_mod)
+        expect_dense("rows", n)
+
+
+def test_panel_kernel_max_iter(oracle_mod, dense_kernel):
     """nodes that run into max_iter (incl. the x10 'inaccurate' pass) agree with the oracle"""
     pr = problems.random_miqp(130, 200, 10, 0.7, seed=4)[0]
     _compare(pr, 6, 13, dict(QP, max_iter=60, eps_abs=1e-6, eps_rel=1e-6), oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == panel_threads(130)
+    expect_dense(dense_kernel, 130)
 
 
 # ---------------------------------------------------------------- TMA-streamed kernel (bqp_stream.cu)
@@ -242,7 +282,12 @@ def test_three_kernels_same_results(monkeypatch):
     x0 = np.zeros((7, 130)); y0 = np.zeros((7, 210))
     e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
     r0 = e.solve_batch(ls, us, x0, y0)
-    assert engine.last_timing()["threads"] == panel_threads(130)
+    expect_dense("rows", 130)
+    monkeypatch.setenv("BQP_KERNEL", "panel")
+    rp = e.solve_batch(ls, us, x0, y0)
+    expect_dense("panel", 130)
+    assert list(r0.status) == list(rp.status) and list(r0.iters) == list(rp.iters)
+    _close(r0.x, rp.x); _close(r0.y, rp.y); _close(r0.lower, rp.lower)
     monkeypatch.setenv("BQP_KERNEL", "stream")
     r1 = e.solve_batch(ls, us, x0, y0)
     assert engine.last_timing()["threads"] == STREAM_THREADS
@@ -258,11 +303,11 @@ def test_three_kernels_same_results(monkeypatch):
     _close(r1.x, r2.x); _close(r1.y, r2.y); _close(r1.lower, r2.lower)
 
 
-def test_cfg2_size_leaves(oracle_mod):
+def test_cfg2_size_leaves(oracle_mod, dense_kernel):
     """BASELINE cfg 2 shape (n=500, m=1000, |i_idx|=50): 8 leaves of one instance in one tile."""
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=1)[0]
     _compare(pr, 8, 9, QP, warm="root", oracle_mod=oracle_mod)
-    assert engine.last_timing()["threads"] == panel_threads(500)
+    expect_dense(dense_kernel, 500)
 
 
 def test_cfg2_size_leaves_stream_kernel(oracle_mod, monkeypatch):
@@ -272,7 +317,7 @@ def test_cfg2_size_leaves_stream_kernel(oracle_mod, monkeypatch):
     assert engine.last_timing()["threads"] == STREAM_THREADS
 
 
-@pytest.mark.parametrize("kernel", ["panel", "stream"])
+@pytest.mark.parametrize("kernel", ["rows", "panel", "stream"])
 def test_rounds_and_retiling_are_bit_identical(monkeypatch, kernel):
     """The streamed kernel runs in rounds of BQP_ROUND_ITERS iterations; between rounds finished nodes drop out and
     the rest are re-tiled (other tile widths, other tile mates), resuming from the saved ADMM state.  The result of

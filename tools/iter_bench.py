@@ -26,23 +26,25 @@ a = ap.parse_args()
 base = problems.extend(problems.random_miqp(a.n, a.m, a.p, a.density, seed=1, count=1)[0])
 P, q, A, l, u, i_idx = base
 rng = np.random.default_rng(0)
-qps, L, U, X0, Y0 = [], [], [], [], []
-for k in range(a.instances):      # distinct device copies of the same matrices (distinct HBM addresses)
-    e = engine.BatchedQP().setup(P, q * (1 + 0.01 * k), A, l, u, i_idx=i_idx, eps_abs=1e-12, eps_rel=1e-12,
-                                 eps_prim_inf=1e-12, eps_dual_inf=1e-12, max_iter=a.iters, check_termination=a.iters)
-    ls, us = problems.branched_nodes(l, u, len(i_idx), a.leaves, rng)
-    for b in range(a.leaves):
-        qps.append(e); L.append(ls[b]); U.append(us[b]); X0.append(np.zeros(a.n)); Y0.append(np.zeros(A.shape[0]))
+st = dict(eps_abs=1e-12, eps_rel=1e-12, eps_prim_inf=1e-12, eps_dual_inf=1e-12, max_iter=a.iters, check_termination=a.iters)
+# distinct device copies of the same matrices (distinct HBM addresses), host halves of the setup on all host threads
+es = engine.setup_many([(P, q * (1 + 0.01 * k), A, l, u, i_idx) for k in range(a.instances)], **st)
 engine.set_tuning(a.tile_nodes, a.threads)
-rb = engine.ResidentBatch(qps, L, U, X0, Y0)
-ms = []
-for _ in range(4):
-    rb.run()
-    ms.append(engine.last_timing()["kernel_ms"])
-rb.download()
-t = engine.last_timing()
-best = min(ms[1:])
-per_iter_us = 1e3 * best / a.iters
-print("tiles=%d T=%d threads=%d smem=%d  kernel %.2f ms  -> %.1f us/iteration/tile-wave, streamed %.0f GB/s, node-iters/s %.3e" % (
-    t["tiles"], t["tile_nodes"], t["threads"], t["smem_bytes"], best, per_iter_us, t["stream_bytes"] / best / 1e6,
-    t["node_iters"] / best * 1e3))
+for count in sorted(set([1, a.instances])):
+    qps, L, U, X0, Y0 = [], [], [], [], []
+    for e in es[:count]:
+        ls, us = problems.branched_nodes(l, u, len(i_idx), a.leaves, rng)
+        for b in range(a.leaves):
+            qps.append(e); L.append(ls[b]); U.append(us[b]); X0.append(np.zeros(a.n)); Y0.append(np.zeros(A.shape[0]))
+    rb = engine.ResidentBatch(qps, L, U, X0, Y0)
+    ms = []
+    for _ in range(4):
+        rb.run()
+        ms.append(engine.last_timing()["kernel_ms"])
+    rb.download()
+    t = engine.last_timing()
+    best = min(ms[1:])
+    per_iter_us = 1e3 * best / a.iters
+    print("%s instances=%d tiles=%d T=%d threads=%d smem=%d slots=%d kernel %.2f ms  -> %.1f us/iteration/tile-wave, streamed %.0f GB/s, node-iters/s %.3e" % (
+        os.environ.get("BQP_LIB_SUFFIX", ""), count, t["tiles"], t["tile_nodes"], t["threads"], t["smem_bytes"], t["ring_slots"], best, per_iter_us,
+        t["stream_bytes"] / best / 1e6, t["node_iters"] / best * 1e3), flush=True)
