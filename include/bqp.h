@@ -13,6 +13,8 @@
  *                            (frontier of many MIQP instances, BASELINE cfg 2)
  *   bqp_bnb_solve         <- MIOSQP.solve(): the B&B while-loop itself, natively  solver.py:85-172
  *   bqp_bnb_solve_many    <- the same for several MIQPs in lock-step (one launch per B&B step over all frontiers)
+ *   bqp_bnb_solve_async   <- the same, every MIQP advancing at its own pace on its own stream (no lock-step)
+ *   bqp_ctx_*             <- one solve context (stream + staging) per host thread: the reference's one osqp object per Workspace
  *   bqp_setup_many        <- setup of many problems, host halves on all host threads
  *   BQP_* status codes    <- osqp.constant('OSQP_*')                        node.py:88,128-129
  *   bqp_free              <- garbage collection of the osqp object
@@ -120,6 +122,21 @@ int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *o
 int bqp_last_timing(bqp_timing *t);
 int bqp_free(bqp_handle h);
 
+/* Explicit solve contexts.  The handle-less calls above share ONE process-wide context (one stream, one set of staging
+ * buffers, one resident batch); a bqp_ctx is the same thing as an object: its own CUDA stream, pinned staging and device
+ * buffers, so several host threads can each drive their own frontier on the same device at the same time (their kernels
+ * overlap on the GPU) -- what miOSQP's one-`osqp`-object-per-Workspace gives the reference (workspace.py:63).
+ * run_to_completion != 0: every tile runs until its last node terminates (one launch per call) instead of rounds of 100
+ * ADMM iterations re-tiled by the host -- the right shape when the call holds one small tile.  A context is not
+ * thread-safe; different contexts are independent.  bqp_free / bqp_update_q synchronise every context of the device. */
+typedef struct bqp_context *bqp_ctx;
+int bqp_ctx_create(int device, int run_to_completion, bqp_ctx *out);
+int bqp_ctx_solve_multi(bqp_ctx ctx, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                        const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                        const bqp_node_out *out);
+int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t);
+int bqp_ctx_free(bqp_ctx ctx);
+
 /* ---- native branch-and-bound replay (miosqp_b200/csrc/bqp_bnb.cpp) ------------------------------------------------
  * bqp_bnb_solve <- MIOSQP.solve(): the while-loop of solver.py:85-123 with workspace.py:128-384 and node.py:96-143,
  * every open leaf solved by the batched engine (one bqp_solve_multi per B&B step, plus `speculation` look-ahead nodes).
@@ -164,12 +181,21 @@ int bqp_bnb_solve_many(int count, const bqp_handle *h, const bqp_problem *const 
                        const double *const *x_incumbent, const double *upper_incumbent, bqp_solve_many_fn fn, void *ctx,
                        double *const *x, bqp_bnb_result *res, int *const *decisions, int decisions_cap);
 
+/* asynchronous variant: `threads` host threads (0 = min(count, 128)), each with its own solve context (CUDA stream), take the MIQPs
+ * from a shared counter and run each one's loop (replay -> one launch of its unsolved leaves + look-ahead, run to
+ * completion -> replay ...) independently: no MIQP waits for another one's slowest leaf, and the GPU's block scheduler
+ * packs the tiles of all of them.  Every tree's result equals its own bqp_bnb_solve. */
+int bqp_bnb_solve_async(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                        const double *const *x_incumbent, const double *upper_incumbent, double *const *x, bqp_bnb_result *res,
+                        int *const *decisions, int decisions_cap, int threads);
+
 /* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
 int bqp_set_tuning(int tile_nodes, int threads);
 
 /* introspection (tests, roofline arithmetic) */
 int bqp_get_dims(bqp_handle h, int *n, int *m, int *npad, long long *factor_bytes, long long *check_bytes);
 int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c);
+int bqp_handle_device(bqp_handle h);   /* CUDA device ordinal the problem lives on */
 int bqp_device_count(void);
 const char *bqp_strerror(int code);
 const char *bqp_version(void);

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <atomic>
 #include <thread>
@@ -38,7 +39,7 @@ namespace {
     }                                              \
   } while (0)
 
-cudaError_t g_last_cuda = cudaSuccess;
+thread_local cudaError_t g_last_cuda = cudaSuccess;
 int g_tune_tt = 0, g_tune_threads = 0;
 
 template <class Tp>
@@ -62,19 +63,22 @@ int upload_mat(bqp_instance *inst, const HostMat &M, DevMat *D) {
   return BQP_OK;
 }
 
-// grow-only buffers of the (single, process-wide) batch context
+// grow-only buffers of a batch context.  Device buffers come from the stream-ordered allocator (cudaMallocAsync on the
+// context's stream): cudaMalloc / cudaFree synchronise the whole device, which with many contexts in flight made every
+// growing buffer wait for every other context's running kernel (measured: 134 s instead of 5 s for 100 asynchronous trees).
+// Pinned host buffers start at 256 KiB and double, so they are reallocated a handful of times per context at most.
 struct Buf {
   void *p = nullptr; size_t cap = 0; bool pinned = false;
-  int reserve(size_t bytes) {
+  int reserve(size_t bytes, cudaStream_t st) {
     if (bytes <= cap) return BQP_OK;
-    release();
-    size_t want = std::max(bytes, cap * 2);
-    if (pinned) CK(cudaHostAlloc(&p, want, cudaHostAllocDefault)); else CK(cudaMalloc(&p, want));
+    const size_t want = std::max(std::max(bytes, cap * 2), (size_t)256 * 1024);
+    release(st);
+    if (pinned) CK(cudaHostAlloc(&p, want, cudaHostAllocDefault)); else CK(cudaMallocAsync(&p, want, st));
     cap = want;
     return BQP_OK;
   }
-  void release() {
-    if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+  void release(cudaStream_t st) {
+    if (p) { if (pinned) cudaFreeHost(p); else cudaFreeAsync(p, st); }
     p = nullptr; cap = 0;
   }
 };
@@ -99,21 +103,40 @@ struct BatchCtx {
   std::vector<int> tile_check_every;
   bqp_timing timing{};
   bool resident = false, ran = false;
+  int round_override = -1;      // >= 0: rounds of that many ADMM iterations (0 = run every tile to completion) whatever BQP_ROUND_ITERS says
+  bool blocking_sync = false;   // wait on a blocking event instead of spinning (many contexts driven by many host threads)
+  cudaEvent_t ev_block = nullptr;
 };
-BatchCtx g;
+BatchCtx g0;                    // the context behind the handle-less entry points (bqp_solve_multi, bqp_batch_*)
+std::mutex g_ctx_mu;
+std::vector<BatchCtx *> g_ctxs{&g0};   // every live context: bqp_free / bqp_update_q must not pull data from under a running one
 
-int ctx_init(int device) {
+// wait for everything queued on the context's stream
+cudaError_t ctx_sync(BatchCtx &g) {
+  if (!g.blocking_sync) return cudaStreamSynchronize(g.stream);
+  cudaError_t e = cudaEventRecord(g.ev_block, g.stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(g.ev_block);
+}
+
+void ctx_release(BatchCtx &g) {
+  if (!g.stream) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state}) b->release(g.stream);
+  cudaStreamSynchronize(g.stream);
+  for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
+  if (g.ev_block) { cudaEventDestroy(g.ev_block); g.ev_block = nullptr; }
+  cudaStreamDestroy(g.stream); g.stream = nullptr;
+  g.resident = g.ran = false;
+}
+
+int ctx_init(BatchCtx &g, int device) {
   if (g.device == device && g.stream) return BQP_OK;
-  if (g.stream) {   // switching devices: drop everything
-    cudaSetDevice(g.device);
-    cudaStreamSynchronize(g.stream);
-    for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state}) b->release();
-    for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
-    cudaStreamDestroy(g.stream); g.stream = nullptr;
-  }
+  ctx_release(g);   // switching devices: drop everything
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto &e : g.ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&g.ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
   g.device = device;
   return BQP_OK;
 }
@@ -127,8 +150,8 @@ int to_device(bqp_instance *inst) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h.s.device));
   if (prop.major < 10) return BQP_E_CUDA;   // sm_100a code only
-  CK(cudaSetDevice(h.s.device));
   inst->device = h.s.device;
+  CK(cudaSetDevice(h.s.device));
   DevInstance &d = inst->d;
   d.n = h.n; d.m = h.m; d.npad = h.npad; d.n_int = h.n_int;
   int rc;
@@ -257,11 +280,16 @@ int bqp_setup_many(int count, const bqp_problem *const *p, const bqp_settings *s
 
 int bqp_free(bqp_handle h) {
   if (!h) return BQP_OK;
-  if (h->on_device) {
+  if (!h->allocs.empty()) {      // also after a partial upload that failed half way (on_device is set last)
     cudaSetDevice(h->device);
-    if (g.stream && g.device == h->device) cudaStreamSynchronize(g.stream);
+    {
+      std::lock_guard<std::mutex> lk(g_ctx_mu);
+      for (BatchCtx *c : g_ctxs) {
+        if (c->stream && c->device == h->device) cudaStreamSynchronize(c->stream);
+        for (auto &ni : c->node_inst) if (ni == h) { c->resident = false; break; }
+      }
+    }
     for (void *p : h->allocs) cudaFree(p);
-    for (auto &ni : g.node_inst) if (ni == h) { g.resident = false; break; }
   }
   delete h;
   return BQP_OK;
@@ -273,7 +301,10 @@ int bqp_update_q(bqp_handle h, const double *q) {
   h->d.nq = h->h.nq;
   if (h->on_device) {
     CK(cudaSetDevice(h->device));
-    if (g.stream && g.device == h->device) CK(cudaStreamSynchronize(g.stream));
+    {
+      std::lock_guard<std::mutex> lk(g_ctx_mu);
+      for (BatchCtx *c : g_ctxs) if (c->stream && c->device == h->device) CK(cudaStreamSynchronize(c->stream));
+    }
     CK(cudaMemcpy(h->d_q, h->h.q.data(), sizeof(double) * h->h.n, cudaMemcpyHostToDevice));
   }
   return BQP_OK;
@@ -290,7 +321,7 @@ int bqp_set_tuning(int tile_nodes, int threads) {
 // the tile table.  Nodes are grouped by (problem, iterations done so far); groups with the least progress go first, and
 // when more tiles exist than the GPU holds at once (`capacity`) the rest wait for the next launch -- so every launch is
 // one full wave, and stragglers are re-tiled ever narrower as the frontier drains.  `scheduled` returns the chosen nodes.
-static int plan_round(const std::vector<int> &alive, const std::vector<int> &progress, const std::vector<double> &remaining,
+static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vector<int> &progress, const std::vector<double> &remaining,
                       std::vector<int> *scheduled) {
   int ndev_sms = 148;
   cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
@@ -436,20 +467,20 @@ static int plan_round(const std::vector<int> &alive, const std::vector<int> &pro
   }
   g.ntiles = (int)g.tiles.size(); g.tt = tt; g.smem = smem; g.nslots = nslots; g.slot_bytes = use_stream ? slot_size(tt) : slot_bytes;
   int rc;
-  if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
-  if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles))) return rc;
-  if ((rc = g.d_work.reserve(work_d * 8))) return rc;
-  if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size()))) return rc;
-  if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size()))) return rc;
+  if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles, g.stream))) return rc;
+  if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles, g.stream))) return rc;
+  if ((rc = g.d_work.reserve(work_d * 8, g.stream))) return rc;
+  if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size(), g.stream))) return rc;
+  if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size(), g.stream))) return rc;
   CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaStreamSynchronize(g.stream));   // tiles / dinst are stack-lifetime host memory
+  CK(ctx_sync(g));   // tiles / dinst are stack-lifetime host memory
   g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
   return BQP_OK;
 }
 
-int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
-                     const double *const *x0, const double *const *y0) {
+static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                        const double *const *x0, const double *const *y0) {
   if (B <= 0 || !handles || !l || !u || !x0 || !y0) return BQP_E_ARG;
   g.resident = false; g.ran = false;
   for (int b = 0; b < B; b++) {
@@ -460,7 +491,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     for (int i = 0; i < m; i++)
       if (l[b][i] > u[b][i]) return BQP_E_BOUNDS;   // osqp update_bounds raises
   }
-  int rc = ctx_init(handles[0]->device);
+  int rc = ctx_init(g, handles[0]->device);
   if (rc) return rc;
   CK(cudaSetDevice(g.device));
 
@@ -498,6 +529,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   if ((g.use_stream || g.use_panel) && g.round_ok) {
     int r = 100;
     if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
+    if (g.round_override >= 0) r = g.round_override;
     g.round_iters = r <= 0 ? 0 : ((r + check0 - 1) / check0) * check0;
   }
 
@@ -509,13 +541,13 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
     in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
   }
   g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
-  if ((rc = g.h_in.reserve(in_d * 8))) return rc;
-  if ((rc = g.h_out.reserve(out_d * 8))) return rc;
-  if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
-  if ((rc = g.d_in.reserve(in_d * 8))) return rc;
-  if ((rc = g.d_out.reserve(out_d * 8))) return rc;
-  if ((rc = g.d_ns.reserve(sizeof(NodeScalars) * (size_t)B))) return rc;
-  if ((rc = g.d_state.reserve(std::max<size_t>(st_d, 1) * 8))) return rc;
+  if ((rc = g.h_in.reserve(in_d * 8, g.stream))) return rc;
+  if ((rc = g.h_out.reserve(out_d * 8, g.stream))) return rc;
+  if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B, g.stream))) return rc;
+  if ((rc = g.d_in.reserve(in_d * 8, g.stream))) return rc;
+  if ((rc = g.d_out.reserve(out_d * 8, g.stream))) return rc;
+  if ((rc = g.d_ns.reserve(sizeof(NodeScalars) * (size_t)B, g.stream))) return rc;
+  if ((rc = g.d_state.reserve(std::max<size_t>(st_d, 1) * 8, g.stream))) return rc;
   // pack the per-node inputs: l[m] u[m] x0[n] y0[m]
   double *hin = (double *)g.h_in.p;
   for (int b = 0; b < B; b++) {
@@ -529,7 +561,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   CK(cudaEventRecord(g.ev[0], g.stream));
   CK(cudaMemcpyAsync(g.d_in.p, hin, in_d * 8, cudaMemcpyHostToDevice, g.stream));
   CK(cudaEventRecord(g.ev[1], g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(ctx_sync(g));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
   g.timing = bqp_timing{};
@@ -540,7 +572,7 @@ int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, c
   return BQP_OK;
 }
 
-int bqp_batch_run(void) {
+static int batch_run(BatchCtx &g) {
   if (!g.resident) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
   std::vector<int> alive(g.B), progress(g.B, 0), scheduled;
@@ -555,7 +587,7 @@ int bqp_batch_run(void) {
   long long first_smem = 0;
   CK(cudaEventRecord(g.ev[1], g.stream));
   while (!alive.empty()) {
-    int rc = plan_round(alive, progress, remaining, &scheduled);
+    int rc = plan_round(g, alive, progress, remaining, &scheduled);
     if (rc) return rc;
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
@@ -578,7 +610,7 @@ int bqp_batch_run(void) {
     launches++;
     CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(ctx_sync(g));
     const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
     const int *ti = (const int *)g.h_ti.p;
     for (int t = 0; t < g.ntiles; t++) {
@@ -606,7 +638,7 @@ int bqp_batch_run(void) {
     alive.swap(next);
   }
   CK(cudaEventRecord(g.ev[2], g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(ctx_sync(g));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
   g.timing.kernel_ms = ms;
@@ -625,14 +657,14 @@ int bqp_batch_run(void) {
   return BQP_OK;
 }
 
-int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *out) {
+static int batch_download(BatchCtx &g, double *const *x, double *const *y, const bqp_node_out *out) {
   if (!g.resident || !g.ran) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaEventRecord(g.ev[3], g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(ctx_sync(g));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
   g.timing.d2h_ms = ms;
@@ -659,13 +691,55 @@ int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *o
   return BQP_OK;
 }
 
+static int solve_multi(BatchCtx &g, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                       const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                       const bqp_node_out *out) {
+  int rc = batch_upload(g, B, handles, l, u, x0, y0);
+  if (rc) return rc;
+  if ((rc = batch_run(g))) return rc;
+  return batch_download(g, x, y, out);
+}
+
+int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                     const double *const *x0, const double *const *y0) { return batch_upload(g0, B, handles, l, u, x0, y0); }
+int bqp_batch_run(void) { return batch_run(g0); }
+int bqp_batch_download(double *const *x, double *const *y, const bqp_node_out *out) { return batch_download(g0, x, y, out); }
 int bqp_solve_multi(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
                     const double *const *x0, const double *const *y0, double *const *x, double *const *y,
-                    const bqp_node_out *out) {
-  int rc = bqp_batch_upload(B, handles, l, u, x0, y0);
-  if (rc) return rc;
-  if ((rc = bqp_batch_run())) return rc;
-  return bqp_batch_download(x, y, out);
+                    const bqp_node_out *out) { return solve_multi(g0, B, handles, l, u, x0, y0, x, y, out); }
+
+/* ---- explicit contexts: one stream + staging buffers each, usable from different host threads at the same time */
+struct bqp_context { BatchCtx c; };
+int bqp_ctx_create(int device, int run_to_completion, bqp_ctx *out) {
+  if (!out) return BQP_E_ARG;
+  *out = nullptr;
+  bqp_context *ctx = new (std::nothrow) bqp_context();
+  if (!ctx) return BQP_E_ALLOC;
+  ctx->c.blocking_sync = true;
+  ctx->c.round_override = run_to_completion ? 0 : -1;
+  int rc = ctx_init(ctx->c, device);
+  if (rc) { ctx_release(ctx->c); delete ctx; return rc; }
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctxs.push_back(&ctx->c); }
+  *out = ctx;
+  return BQP_OK;
+}
+int bqp_ctx_free(bqp_ctx ctx) {
+  if (!ctx) return BQP_OK;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), &ctx->c), g_ctxs.end()); }
+  ctx_release(ctx->c);
+  delete ctx;
+  return BQP_OK;
+}
+int bqp_ctx_solve_multi(bqp_ctx ctx, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                        const double *const *x0, const double *const *y0, double *const *x, double *const *y,
+                        const bqp_node_out *out) {
+  if (!ctx) return BQP_E_ARG;
+  return solve_multi(ctx->c, B, handles, l, u, x0, y0, x, y, out);
+}
+int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t) {
+  if (!ctx || !t) return BQP_E_ARG;
+  *t = ctx->c.timing;
+  return BQP_OK;
 }
 
 int bqp_solve_batch(bqp_handle h, int B, const double *l, const double *u, const double *x0, const double *y0,
@@ -684,7 +758,7 @@ int bqp_solve_batch(bqp_handle h, int B, const double *l, const double *u, const
 
 int bqp_last_timing(bqp_timing *t) {
   if (!t) return BQP_E_ARG;
-  *t = g.timing;
+  *t = g0.timing;
   return BQP_OK;
 }
 
@@ -705,6 +779,8 @@ int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c) {
   if (c) *c = h->h.c;
   return BQP_OK;
 }
+
+int bqp_handle_device(bqp_handle h) { return h ? h->device : -1; }
 
 int bqp_device_count(void) {
   int n = 0;

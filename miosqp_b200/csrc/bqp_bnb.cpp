@@ -10,11 +10,14 @@
 // It talks to the engine only through the public entry point bqp_solve_multi -- or through a caller-supplied solve
 // function (CPU tests drive it with the oracle; nothing here links to oracle/).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/bqp.h"
@@ -62,6 +65,7 @@ struct Tree {
   std::vector<int> decisions;
   int batches = 0; long long batched_nodes = 0, spec_nodes = 0, spec_hits = 0;
   bqp_handle h = nullptr; bqp_solve_fn fn = nullptr; void *ctx = nullptr;
+  bqp_ctx ectx = nullptr;                        // engine context (own stream) of the thread driving this tree, if any
   Vec tmp;
 
   // y = M x in CSC column order: the loop scipy's csc_matvec runs
@@ -173,7 +177,8 @@ struct Tree {
       std::vector<bqp_handle> hs(B, h);
       bqp_node_out out; std::memset(&out, 0, sizeof(out));
       out.status = status.data(); out.iters = iters.data();
-      rc = bqp_solve_multi(B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), &out);
+      rc = ectx ? bqp_ctx_solve_multi(ectx, B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), &out)
+                : bqp_solve_multi(B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), px.data(), py.data(), &out);
     }
     if (rc) return rc;
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -376,4 +381,51 @@ extern "C" int bqp_bnb_solve_many(int count, const bqp_handle *h, const bqp_prob
   }
   for (int k = 0; k < count; k++) trees[(size_t)k]->finish(p[k], x[k], &res[k], decisions ? decisions[k] : nullptr, decisions_cap);
   return rc;
+}
+
+// Asynchronous variant (include/bqp.h): the lock-step driver above makes every tree wait, at every B&B step, for the slowest
+// leaf of all trees; here each tree runs its own loop on its own engine context (CUDA stream), and the device's block
+// scheduler interleaves the tiles of all of them.  Trees do not interact, so each result equals bqp_bnb_solve's.
+extern "C" int bqp_bnb_solve_async(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                                   const double *const *x_incumbent, const double *upper_incumbent, double *const *x,
+                                   bqp_bnb_result *res, int *const *decisions, int decisions_cap, int threads) {
+  if (count <= 0 || !h || !p || !s || !x || !res) return BQP_E_ARG;
+  for (int k = 0; k < count; k++) if (!problem_ok(p[k]) || !x[k] || !h[k]) return BQP_E_ARG;
+  int nt = threads > 0 ? threads : 128;
+  nt = std::max(1, std::min(nt, count));
+  std::atomic<int> next(0), first_err(BQP_OK);
+  // engine contexts are kept for later calls (a closed-loop user calls this once per sampling instant): creating one costs
+  // stream + event + first-use allocations
+  static std::mutex pool_mu;
+  static std::vector<std::pair<int, bqp_ctx>> pool_ctx;     // (device, context)
+  auto take_ctx = [&](int device, bqp_ctx *out) {
+    {
+      std::lock_guard<std::mutex> lk(pool_mu);
+      for (size_t i = 0; i < pool_ctx.size(); i++)
+        if (pool_ctx[i].first == device) { *out = pool_ctx[i].second; pool_ctx.erase(pool_ctx.begin() + (long)i); return (int)BQP_OK; }
+    }
+    return bqp_ctx_create(device, 1, out);
+  };
+  auto worker = [&]() {
+    bqp_ctx ectx = nullptr; int edev = -1;
+    for (;;) {
+      const int k = next.fetch_add(1);
+      if (k >= count) break;
+      Tree t;
+      t.init(h[k], p[k], &s[k], x_incumbent ? x_incumbent[k] : nullptr, upper_incumbent ? upper_incumbent[k] : kInf);
+      int rc = BQP_OK;
+      const int dev = bqp_handle_device(h[k]);
+      if (ectx && edev != dev) { std::lock_guard<std::mutex> lk(pool_mu); pool_ctx.emplace_back(edev, ectx); ectx = nullptr; }
+      if (!ectx) { rc = take_ctx(dev, &ectx); edev = dev; }
+      if (!rc) { t.ectx = ectx; rc = t.run(); }
+      t.finish(p[k], x[k], &res[k], decisions ? decisions[k] : nullptr, decisions_cap);
+      if (rc) { int ok = BQP_OK; first_err.compare_exchange_strong(ok, rc); }
+    }
+    if (ectx) { std::lock_guard<std::mutex> lk(pool_mu); pool_ctx.emplace_back(edev, ectx); }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+  worker();
+  for (auto &th : pool) th.join();
+  return first_err.load();
 }

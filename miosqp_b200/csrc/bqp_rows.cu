@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "bqp_internal.h"
 
 namespace bqp {
@@ -975,8 +977,14 @@ size_t rows_smem_bytes(int npad, int nslots, int cs) {
 template <int CS>
 static int launch_r(int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
                     double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(admm_rows_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return BQP_E_CUDA;
+  // many host threads launch concurrently (one context each): raise the attribute only when it has to grow
+  static std::atomic<size_t> smem_set{0};
+  cudaError_t e = cudaSuccess;
+  if (smem_set.load() < smem) {
+    e = cudaFuncSetAttribute(admm_rows_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e != cudaSuccess) return BQP_E_CUDA;
+    smem_set.store((size_t)kMaxSmem);
+  }
   int prefetch_panels = 4;   // L2 prefetch distance of the producer, in panels of this CTA
   if (const char *pk = getenv("BQP_ROWS_PREFETCH")) prefetch_panels = atoi(pk);
   cudaLaunchConfig_t cfg = {};

@@ -10,6 +10,11 @@ built or no B200 is visible, calls raise.
 import ctypes as C
 import os
 
+# More hardware work queues than the default 8: tiles launched from different solve contexts (streams) must not queue
+# behind each other (tools/ctx_concurrency.py: 64 contexts take 101 ms per round with 8 queues, 63 ms with 32).  Read by the
+# CUDA driver when the process initialises CUDA, so it has to be in the environment before that.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import scipy.sparse as spa
 
@@ -100,7 +105,8 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
            "bqp_debug_host_panel_kkt_solve",
-           "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many"]
+           "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
+           "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device"]
 
 _lib = None
 
@@ -137,6 +143,13 @@ def lib():
         L.bqp_setup_many.argtypes = [C.c_int, C.POINTER(C.POINTER(_Problem)), C.POINTER(_Settings), pp, C.c_int, C.c_int]
         L.bqp_bnb_solve_many.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp, C.c_void_p, vp,
                                          _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int]
+        L.bqp_bnb_solve_async.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp,
+                                          _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, C.c_int]
+        L.bqp_ctx_create.argtypes = [C.c_int, C.c_int, pp]
+        L.bqp_ctx_free.argtypes = [vp]
+        L.bqp_ctx_solve_multi.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, pp, pp, C.POINTER(_NodeOut)]
+        L.bqp_ctx_last_timing.argtypes = [vp, C.POINTER(Timing)]
+        L.bqp_handle_device.argtypes = [vp]
         L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
                                     C.POINTER(_BnbResult), _ip, C.c_int]
         _lib = L
@@ -387,10 +400,11 @@ def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.
     return x, out, decisions
 
 
-def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None):
-    """Lock-step native replay over several set-up problems (bqp_bnb_solve_many): one launch per B&B step covers all
-    their frontiers.  Arguments are sequences of equal length; `many_fn` (tests) replaces the engine.
-    Returns a list of (x, result dict, decisions)."""
+def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None, async_threads=None):
+    """Native replay over several set-up problems.  Lock-step (bqp_bnb_solve_many): one launch per B&B step covers all
+    their frontiers.  async_threads is not None (bqp_bnb_solve_async, 0 = automatic): every problem advances at its own
+    pace on its own CUDA stream, driven by a pool of host threads.  Arguments are sequences of equal length; `many_fn`
+    (tests) replaces the engine.  Returns a list of (x, result dict, decisions)."""
     count = len(qps)
     built = [_bnb_problem(d) for d in datas]
     pptr = (C.POINTER(_Problem) * count)(*[C.pointer(b[0]) for b in built])
@@ -405,14 +419,52 @@ def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents
     handles = None if many_fn is not None else (C.c_void_p * count)(*[q._h.value for q in qps])
     x_ptrs = (_dp * count)(*[_d(x) for x in xs])
     dec_ptrs = (_ip * count)(*[_i(d) for d in decs])
-    rc = lib().bqp_bnb_solve_many(count, handles, pptr, sts, xin_ptrs, _d(uppers),
-                                  C.cast(many_fn, C.c_void_p) if many_fn is not None else None, None, x_ptrs, res, dec_ptrs, cap)
+    if async_threads is not None and many_fn is None:
+        rc = lib().bqp_bnb_solve_async(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, int(async_threads))
+    else:
+        rc = lib().bqp_bnb_solve_many(count, handles, pptr, sts, xin_ptrs, _d(uppers),
+                                      C.cast(many_fn, C.c_void_p) if many_fn is not None else None, None, x_ptrs, res, dec_ptrs, cap)
     _check(rc)
     out = []
     for k in range(count):
         r = {name: getattr(res[k], name) for name, _ in _BnbResult._fields_}
         out.append((xs[k], r, [(int(decs[k][2 * j]), int(decs[k][2 * j + 1])) for j in range(min(r["n_decisions"], cap))]))
     return out
+
+
+class Context(object):
+    """One solve context (include/bqp.h bqp_ctx): its own CUDA stream and staging buffers, so several host threads can
+    each run `solve_multi` on the same device at the same time (ctypes releases the GIL during the call)."""
+
+    def __init__(self, device=0, run_to_completion=True):
+        self._c = C.c_void_p()
+        _check(lib().bqp_ctx_create(int(device), 1 if run_to_completion else 0, C.byref(self._c)))
+
+    def free(self):
+        if getattr(self, "_c", None) is not None and self._c.value:
+            lib().bqp_ctx_free(self._c)
+            self._c = None
+
+    def __del__(self):
+        self.free()
+
+    def solve_multi(self, qps, l, u, x0, y0):
+        B = len(qps)
+        res = [_alloc_result(1, q.n, q.m) for q in qps]
+        sc = _Scalars()
+        sc.status = np.empty(B, dtype=np.int32); sc.iters = np.empty(B, dtype=np.int32)
+        sc.obj = np.empty(B); sc.pri_res = np.empty(B); sc.dua_res = np.empty(B); sc.lower = np.empty(B)
+        ls = [_f64(v) for v in l]; us = [_f64(v) for v in u]; xs = [_f64(v) for v in x0]; ys = [_f64(v) for v in y0]
+        out = _NodeOut(_i(sc.status), _i(sc.iters), _d(sc.obj), _d(sc.pri_res), _d(sc.dua_res), _d(sc.lower))
+        hs = (C.c_void_p * B)(*[q._h.value for q in qps])
+        _check(lib().bqp_ctx_solve_multi(self._c, B, hs, _ptr_array(ls), _ptr_array(us), _ptr_array(xs), _ptr_array(ys),
+                                         _ptr_array([r.x[0] for r in res]), _ptr_array([r.y[0] for r in res]), C.byref(out)))
+        return [r.x[0] for r in res], [r.y[0] for r in res], sc
+
+    def last_timing(self):
+        t = Timing()
+        _check(lib().bqp_ctx_last_timing(self._c, C.byref(t)))
+        return t.as_dict()
 
 
 def _alloc_result(B, n, m):

@@ -154,20 +154,22 @@ def setup_many(problems, settings, qp_settings, threads=0):
     return out
 
 
-def solve_many(solvers, on_batch=None):
-    """Solve several set-up MIOSQP objects together: every step flattens the unsolved leaves of ALL frontiers into
-    one node batch (one kernel launch).  Each instance's result is identical to its own `solve()`.
-    `on_batch(n_nodes, seconds)` is called after every launch (benchmarks)."""
+def solve_many(solvers, on_batch=None, async_threads=None):
+    """Solve several set-up MIOSQP objects together.  Lock-step (default): every step flattens the unsolved leaves of ALL
+    frontiers into one node batch (one kernel launch).  async_threads is not None (native replay only; 0 = automatic):
+    every MIQP runs its own replay/launch loop on its own CUDA stream (bqp_bnb_solve_async), so none waits for another
+    one's slowest leaf.  Either way each instance's result is identical to its own `solve()`.
+    `on_batch(n_nodes, seconds)` is called after every launch of the Python lock-step loop (benchmarks)."""
     for s in solvers:
         s._begin()
     if solvers and all(s.work.settings.get('replay') == 'native' for s in solvers):
-        # the lock-step loop itself in C++ (bqp_bnb_solve_many): same launches, no interpreter time per node
+        # the loop itself in C++ (bqp_bnb_solve_many / bqp_bnb_solve_async): no interpreter time per node
         works = [s.work for s in solvers]
         many_fn = engine.native_solve_many_fn([w.solver for w in works])
         outs = engine.bnb_solve_many([w.solver for w in works], [w.data for w in works], [w.settings for w in works],
                                      [w.qp_settings['eps_abs'] for w in works],
                                      [(w.x if np.isfinite(w.upper_glob) else None) for w in works],
-                                     [w.upper_glob for w in works], many_fn=many_fn)
+                                     [w.upper_glob for w in works], many_fn=many_fn, async_threads=async_threads)
         return [s._absorb_native(x, r, d) for s, (x, r, d) in zip(solvers, outs)]
     active = list(solvers)
     while active:

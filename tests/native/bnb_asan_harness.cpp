@@ -45,3 +45,9 @@ int main() {
 }
 extern "C" int bqp_solve_multi(int, const bqp_handle *, const double *const *, const double *const *, const double *const *,
                                const double *const *, double *const *, double *const *, const bqp_node_out *) { return BQP_E_CUDA; }
+// the engine entry points bqp_bnb.cpp links against (never reached here: the harness drives the replay through its own solve function)
+extern "C" int bqp_ctx_solve_multi(bqp_ctx, int, const bqp_handle *, const double *const *, const double *const *, const double *const *,
+                                   const double *const *, double *const *, double *const *, const bqp_node_out *) { return BQP_E_CUDA; }
+extern "C" int bqp_ctx_create(int, int, bqp_ctx *) { return BQP_E_CUDA; }
+extern "C" int bqp_ctx_free(bqp_ctx) { return BQP_OK; }
+extern "C" int bqp_handle_device(bqp_handle) { return -1; }
