@@ -10,7 +10,12 @@ Workspace.add_left/add_right create children (/root/reference/miosqp/workspace.p
 One STEP = one pass of the hot path over that frontier batch: every leaf's full OSQP ADMM solve
 (Node.solve, /root/reference/miosqp/node.py:96-143), all leaves concurrently in one kernel launch.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--instances I]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--instances I] [--mode both|frontier|bnb]
+
+The same line carries, under "bnb", the reference's OWN use of the path: branch-and-bound TO COMPLETION over the same 100
+instances with the reference's settings (/root/reference/examples/random_miqp/run_example.py:98-116; loop solver.py:85-123),
+every relaxation on the engine, all trees sharing one rolling engine session (bqp_bnb_solve_rolling): consumed QP relaxations
+per second by wall clock (host replay, H2D and D2H inside), next to the same B&B on the CPU oracle (bounded sample).
 
 value   : leaves solved per second, inputs resident in HBM, CUDA-event time of the launches.
 e2e     : the same through the public host-buffer call (pack + H2D + launch + D2H inside the timed region).
@@ -154,6 +159,15 @@ def run_oracle_sample(insts_nodes, threads, repeats=1):
     return best, len(S), iters
 
 
+def kernel_source_sha256(rel):
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()
+    except OSError:
+        return None
+
+
 def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, dev_s_max, e2e_s_max, wall_max,
                  tm, tm2, iters, status, factor_mb, inst0, clocks, t_setup, root_iters):
     """The JSON line of the bench contract (kept separate from the GPU code so that it is unit-tested on CPU)."""
@@ -170,10 +184,11 @@ def build_report(args, world, workload, B, B_all, iters_all, node_iters, dev_s, 
     kernel = {0: "admm_tile_kernel<%d>", 1: "admm_stream_kernel<%d>", 2: "admm_panel_kernel (%d nodes per tile)",
               3: "admm_rows_kernel (%d nodes per tile)"}[int(tm.get("kernel", 1))] % tm["tile_nodes"]
     traffic, traffic_src, traffic_scope = None, None, None
-    try:   # dram__bytes_read+write of the captured launch of this kernel, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+    try:   # dram__bytes_read+write of one captured launch of this kernel (ncu --set full), valid only for the kernel source it
+        # was captured from: the capture records the sha256 of the kernel's .cu file and a different source nulls it
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)
-        if tr["kernel"] == kernel:
+        if tr["kernel"] == kernel and tr.get("kernel_source_sha256") == kernel_source_sha256(tr.get("kernel_source", "")):
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             traffic_src = tr["source"]
             traffic_scope = tr.get("scope")
@@ -222,7 +237,10 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
-    ap.add_argument("--parallel-setup", action="store_true", help="bqp_setup_many: factorise the instances on all host threads")
+    ap.add_argument("--parallel-setup", action="store_true", help="(default now) bqp_setup_many: factorise the instances on all host threads")
+    ap.add_argument("--serial-setup", action="store_true", help="one bqp_setup per instance")
+    ap.add_argument("--mode", default="both", choices=["both", "frontier", "bnb"],
+                    help="frontier: the batched-frontier step (value, e2e, roofline); bnb: B&B to completion; both (default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -248,8 +266,10 @@ def main():
 
     # ---- setup (untimed): instances, device-resident factors, root relaxations, leaf batch
     t_setup = time.perf_counter()
-    insts = make_instances(args.instances, seed=1 + rank)
-    if args.parallel_setup:     # host halves of the 100 factorisations on all host threads (untimed either way)
+    from miosqp_b200 import problems as _problems
+    raw = _problems.random_miqp(N_VAR, M_CON, P_INT, DENSITY, seed=1 + rank, count=args.instances)
+    insts = [_problems.extend(pr) for pr in raw]
+    if not args.serial_setup:   # host halves of the 100 factorisations on all host threads (untimed either way)
         qps = engine.setup_many(insts, device=local_rank, **QP_SETTINGS)
     else:
         qps = [engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, device=local_rank, **QP_SETTINGS)
@@ -323,25 +343,166 @@ def main():
                            tm, tm2, np.asarray(sc.iters), np.asarray(sc.status),
                            sum(qp.dims()["factor_bytes"] for qp in qps) / 1e6, insts[0], clocks, t_setup, root_iters)
         if not args.no_cpu_baseline:
-            S = min(B, 8 * cores)
-            sample = [(insts[owner[b]], L[b], U[b], X0[b], Y0[b]) for b in range(S)]
+            # every leaf of `cores` instances spread uniformly over the (longest-first) submission order
+            pos = sorted(set(int(v) for v in np.linspace(0, len(order) - 1, min(len(order), cores)).round()))
+            chosen = set(int(order[k]) for k in pos)
+            sample = [(insts[owner[b]], L[b], U[b], X0[b], Y0[b]) for b in range(B) if owner[b] in chosen]
             secs, nodes, its = run_oracle_sample(sample, cores)
             out["cpu_baseline"] = {"value": nodes / secs, "unit": "QP/s", "cores": cores, "kind": "port",
-                                   "sample": "first %d leaves of the step's batch, CPU oracle (oracle/osqp_oracle.c), %d threads, %.1f s" % (
-                                       nodes, cores, secs),
+                                   "sample": "all %d leaves of %d instances spread uniformly over the step's (longest-first) batch, CPU "
+                                             "oracle (oracle/osqp_oracle.c; parity with PyPI osqp unpinned), %d threads, %.1f s" % (
+                                                 nodes, len(chosen), cores, secs),
                                    "admm_node_iters_per_s": its / secs}
             try:    # the reference's own execution model: one node at a time on one core (SURVEY 8d asks for both figures)
-                s1, n1, i1 = run_oracle_sample(sample[:8], 1)
+                s1, n1, i1 = run_oracle_sample(sample[::max(1, len(sample) // 8)][:8], 1)
                 out["cpu_baseline"]["single_core"] = {"value": n1 / s1, "unit": "QP/s", "cores": 1,
-                                                      "sample": "first %d leaves of the step's batch, one thread, %.1f s" % (n1, s1),
+                                                      "sample": "%d of those leaves, one thread, %.1f s" % (n1, s1),
                                                       "admm_node_iters_per_s": i1 / s1}
             except Exception as e:      # never lose the bench line over an extra figure
                 out["cpu_baseline"]["single_core"] = {"error": repr(e)}
+    bnb = None
+    if args.mode in ("both", "bnb"):
+        rb = None                      # the resident frontier batch is not needed any more
+        bnb = bnb_section(args, raw, qps, rank, world, cores, torch, dist)
+    if rank == 0:
+        if bnb is not None:
+            out["bnb"] = bnb
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+BNB_WORKLOAD = ("random_miqp n=%d m=%d |i_idx|=%d density=%.1f, %%d instances/GPU, branch-and-bound TO COMPLETION with the reference's "
+                "settings (run_example.py:98-116), every relaxation on the engine" % (N_VAR, M_CON, P_INT, DENSITY))
+
+
+def oracle_many_fn(oracles, threads):
+    """bqp_solve_many_fn (include/bqp.h) backed by the CPU oracle: the native B&B replay then runs the reference's loop on the
+    host cores -- the CPU arm of the B&B numbers.  Only this function touches oracle/ in the B&B section."""
+    from oracle import oracle
+    from miosqp_b200 import engine
+
+    def fn(ctx, B, owner, l, u, x0, y0, x, y, status, iters):
+        try:
+            os_ = [oracles[int(owner[b])] for b in range(B)]
+            arr = lambda pp, b, size: np.ctypeslib.as_array(pp[b], shape=(size,))
+            Ls = [np.array(arr(l, b, os_[b].m)) for b in range(B)]; Us = [np.array(arr(u, b, os_[b].m)) for b in range(B)]
+            X0 = [np.array(arr(x0, b, os_[b].n)) for b in range(B)]; Y0 = [np.array(arr(y0, b, os_[b].m)) for b in range(B)]
+            xs, ys, st, it, _ = oracle.solve_multi(os_, Ls, Us, X0, Y0, threads=threads)
+            for b in range(B):
+                arr(x, b, os_[b].n)[:] = xs[b]; arr(y, b, os_[b].m)[:] = ys[b]; status[b] = int(st[b]); iters[b] = int(it[b])
+            return 0
+        except Exception:       # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return -1
+    return engine.SOLVE_MANY_FN(fn)
+
+
+def bnb_cpu(raw, count, threads, max_iter_bb=None):
+    """The same B&B on the CPU oracle for the first `count` instances: one tree per host thread, each running the reference's
+    sequential loop (native replay + oracle solves, one relaxation at a time) -- trees are independent, so this is the
+    embarrassingly parallel CPU execution with no thread waiting for another.  Returns (seconds, consumed nodes, iters, outs)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    from miosqp_b200 import engine, problems
+    from miosqp_b200.problem_data import Data
+    datas, fns = [], []
+    for pr in raw[:count]:
+        d = Data(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'])
+        o = oracle.OSQP(); o.setup(d.P, d.q, d.A, d.l, d.u, **QP_SETTINGS)
+        datas.append(d); fns.append(oracle_many_fn([o], 1))
+    st = dict(problems.RANDOM_MIQP_SETTINGS)
+    if max_iter_bb:
+        st['max_iter_bb'] = max_iter_bb
+
+    def one(k):     # ctypes releases the GIL inside the native replay and inside the oracle's solve
+        return engine.bnb_solve_many([None], [datas[k]], [st], [QP_SETTINGS['eps_abs']], [None], [np.inf], many_fn=fns[k])[0]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        outs = list(ex.map(one, range(count)))
+    secs = time.perf_counter() - t0
+    return secs, sum(r["iter_num"] - 1 for _, r, _ in outs), sum(int(r["osqp_iter"]) for _, r, _ in outs), outs
+
+
+def bnb_section(args, raw, qps, rank, world, cores, torch, dist):
+    """B&B to completion over this rank's instances on the engine (rolling session), max over ranks; CPU arm on rank 0."""
+    import miosqp_b200
+    from miosqp_b200 import engine, problems, miqp
+    solvers = miqp.wrap_many(raw, qps, dict(problems.RANDOM_MIQP_SETTINGS, replay='native'), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+    runs = {}
+    for driver in ("rolling", "lockstep"):
+        for s in solvers:
+            s.work.reset(); s.work.first_run = 0
+            s.work.batches = s.work.batched_nodes = s.work.spec_nodes = s.work.spec_hits = 0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = miosqp_b200.solve_many(solvers, rolling=(driver == "rolling"))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        works = [s.work for s in solvers]
+        tm = engine.last_timing()
+        consumed = sum(w.iter_num - 1 for w in works)
+        iters = sum(int(w.osqp_iter) for w in works)
+        solved = sum(int(w.batched_nodes) for w in works)
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        c = torch.tensor([consumed, iters, solved], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        wall_max = float(t.item()); consumed_all, iters_all, solved_all = [float(v) for v in c.tolist()]
+        runs[driver] = {"wall_s": wall_max, "qp_consumed": int(consumed_all), "qp_solved": int(solved_all),
+                        "qp_per_s": consumed_all / wall_max, "admm_node_iters_per_s": iters_all / wall_max,
+                        "status": {st: [r.status for r in res].count(st) for st in sorted(set(r.status for r in res))}}
+        if driver == "rolling":
+            runs[driver].update({"launches": int(tm["launches"]), "kernel_ms": tm["kernel_ms"],
+                                 "mean_tiles_per_launch": tm["tile_iters"] / max(1.0, 100.0 * tm["launches"]),
+                                 "mean_live_nodes_per_tile_iteration": iters / max(1.0, float(tm["tile_iters"])),
+                                 "h2d_bytes": int(tm["h2d_bytes"]), "d2h_bytes": int(tm["d2h_bytes"])})
+            sig = [(r.status, float(r.upper_glob), w.iter_num, int(w.osqp_iter), list(map(tuple, w.decisions))) for r, w in zip(res, works)]
+        else:
+            # the rolling session runs sparse rounds on clusters of 4 (other summation order): decisions, node and iteration
+            # counts must be identical, incumbents agree to 1e-9
+            sig2 = [(r.status, float(r.upper_glob), w.iter_num, int(w.osqp_iter), list(map(tuple, w.decisions))) for r, w in zip(res, works)]
+            runs[driver]["same_decisions_and_counts_as_rolling"] = bool(
+                [(a[0], a[2], a[3], a[4]) for a in sig] == [(a[0], a[2], a[3], a[4]) for a in sig2])
+            runs[driver]["max_rel_incumbent_difference_to_rolling"] = float(max(abs(a[1] - b[1]) / (1 + abs(b[1])) for a, b in zip(sig, sig2)))
+    if rank != 0:
+        return None
+    gold = None
+    gp = os.path.join(ROOT, "tests", "golden", "bnb_cfg2.json")
+    if os.path.exists(gp):      # rank 0 draws seed 1: its first instances are the golden ones (unmodified reference on the oracle)
+        g = json.load(open(gp))
+        gold = True
+        for i in range(min(len(sig), len(g))):
+            r = g["cfg2_inst%d" % i]["result"]
+            gold = gold and (sig[i][4] == [tuple(d) for d in r["decisions"]] and sig[i][0] == r["status"] and sig[i][2] == r["iter_num"]
+                             and sig[i][3] == r["osqp_iter"] and abs(sig[i][1] - r["upper_glob"]) <= 1e-9 * (1 + abs(r["upper_glob"])))
+    ro = runs["rolling"]
+    out = {"workload": BNB_WORKLOAD % args.instances, "driver": "rolling engine session shared by all trees (bqp_bnb_solve_rolling), native replay",
+           "metric": "QP-relaxations/sec (consumed by the B&B, wall clock incl. host replay and all copies)",
+           "value": ro["qp_per_s"], "unit": "QP/s",
+           "e2e": {"value": ro["qp_per_s"], "unit": "QP/s", "h2d_bytes_per_run": ro.get("h2d_bytes"), "d2h_bytes_per_run": ro.get("d2h_bytes")},
+           "rolling": ro, "lockstep": runs["lockstep"],
+           "decisions_identical_to_reference_golden": gold,
+           "golden": "tests/golden/bnb_cfg2.json: first 3 instances, UNMODIFIED reference package on the CPU oracle (make_bnb_golden.py --cfg2)"}
+    if not args.no_cpu_baseline:
+        try:
+            cnt = max(1, min(args.instances, cores))
+            secs, nodes, its, _ = bnb_cpu(raw, cnt, cores, max_iter_bb=int(os.environ.get("BENCH_BNB_CPU_NODES", "12")))
+            out["cpu"] = {"value": nodes / secs, "unit": "QP/s", "cores": cores, "kind": "port",
+                          "sample": "first %d instances, B&B cut at %s nodes each (the reference's max_iter_bb), one tree per host thread running "
+                                    "the reference's sequential loop, %d threads, CPU oracle, %.1f s" % (cnt, os.environ.get("BENCH_BNB_CPU_NODES", "12"), cores, secs),
+                          "admm_node_iters_per_s": its / secs,
+                          # the cut keeps the top of every tree, whose relaxations need more iterations than the average node of a
+                          # full run: QP/s at the full run's mean iteration count per node, the figure to compare `value` with
+                          "qp_per_s_at_full_run_mean_iters": (its / secs) / (ro["admm_node_iters_per_s"] / ro["qp_per_s"])}
+        except Exception as e:      # never lose the bench line over the CPU arm
+            out["cpu"] = {"error": repr(e)}
+    return out
 
 
 def reference_arm(args, cores, workload):

@@ -137,6 +137,18 @@ int bqp_ctx_solve_multi(bqp_ctx ctx, int B, const bqp_handle *handles, const dou
 int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t);
 int bqp_ctx_free(bqp_ctx ctx);
 
+/* Rolling session on a context (ctx == NULL: the process-wide one): the resident batch is OPEN -- nodes are appended
+ * while earlier ones are still iterating, every bqp_session_round is ONE launch (a round of 100 ADMM iterations over the
+ * running nodes, critical path first, at most one tile per SM pair) and reports the nodes that terminated in it, whose
+ * results bqp_session_fetch then copies out.  This is how many B&B trees share one GPU without waiting for each other's
+ * slowest leaf: a tree whose leaves have terminated is replayed and its children join the next round.
+ * ids count from 0 in append order; finished_ids[cap]; out arrays of bqp_session_fetch have length 1. */
+int bqp_session_begin(bqp_ctx ctx);
+int bqp_session_append(bqp_ctx ctx, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                       const double *const *x0, const double *const *y0, int *first_id);
+int bqp_session_round(bqp_ctx ctx, int *finished_ids, int cap, int *n_finished, int *running);
+int bqp_session_fetch(bqp_ctx ctx, int id, double *x, double *y, const bqp_node_out *out);
+
 /* ---- native branch-and-bound replay (miosqp_b200/csrc/bqp_bnb.cpp) ------------------------------------------------
  * bqp_bnb_solve <- MIOSQP.solve(): the while-loop of solver.py:85-123 with workspace.py:128-384 and node.py:96-143,
  * every open leaf solved by the batched engine (one bqp_solve_multi per B&B step, plus `speculation` look-ahead nodes).
@@ -188,6 +200,12 @@ int bqp_bnb_solve_many(int count, const bqp_handle *h, const bqp_problem *const 
 int bqp_bnb_solve_async(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
                         const double *const *x_incumbent, const double *upper_incumbent, double *const *x, bqp_bnb_result *res,
                         int *const *decisions, int decisions_cap, int threads);
+
+/* rolling variant (one context, one stream): all trees share a bqp_session; after every round the trees whose outstanding
+ * leaves have all terminated are replayed and their new leaves appended.  Each tree's result equals its own bqp_bnb_solve. */
+int bqp_bnb_solve_rolling(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                          const double *const *x_incumbent, const double *upper_incumbent, double *const *x, bqp_bnb_result *res,
+                          int *const *decisions, int decisions_cap, int *rounds);
 
 /* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
 int bqp_set_tuning(int tile_nodes, int threads);

@@ -77,6 +77,20 @@ struct Buf {
     cap = want;
     return BQP_OK;
   }
+  // grow keeping the first `used` bytes (rolling sessions append nodes to resident buffers)
+  int reserve_keep(size_t bytes, size_t used, cudaStream_t st) {
+    if (bytes <= cap) return BQP_OK;
+    const size_t want = std::max(std::max(bytes, cap * 2), (size_t)256 * 1024);
+    void *q = nullptr;
+    if (pinned) CK(cudaHostAlloc(&q, want, cudaHostAllocDefault)); else CK(cudaMallocAsync(&q, want, st));
+    if (p && used) {
+      if (pinned) { CK(cudaStreamSynchronize(st)); std::memcpy(q, p, used); }
+      else CK(cudaMemcpyAsync(q, p, used, cudaMemcpyDeviceToDevice, st));
+    }
+    release(st);
+    p = q; cap = want;
+    return BQP_OK;
+  }
   void release(cudaStream_t st) {
     if (p) { if (pinned) cudaFreeHost(p); else cudaFreeAsync(p, st); }
     p = nullptr; cap = 0;
@@ -103,6 +117,12 @@ struct BatchCtx {
   std::vector<int> tile_check_every;
   bqp_timing timing{};
   bool resident = false, ran = false;
+  // rolling session (bqp_session_*): nodes are appended while others are still iterating
+  bool session = false;
+  std::vector<int> s_alive, s_progress; std::vector<double> s_dist, s_remaining;
+  size_t s_in_d = 0, s_out_d = 0, s_st_d = 0;
+  long long s_tile_iters = 0, s_bytes = 0; int s_launches = 0; double s_kernel_ms = 0;
+  bool auto_cluster = false;    // rows kernel: clusters of 4 when the round holds few tiles (results then depend on the schedule in the last bits)
   int round_override = -1;      // >= 0: rounds of that many ADMM iterations (0 = run every tile to completion) whatever BQP_ROUND_ITERS says
   bool blocking_sync = false;   // wait on a blocking event instead of spinning (many contexts driven by many host threads)
   cudaEvent_t ev_block = nullptr;
@@ -343,7 +363,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     if (const char *e = std::getenv("BQP_PANEL_CLUSTER")) { const int v = std::atoi(e); if (v == 2 || (v == 1 && cs == 1)) cs = v; }
   }
   g.cs = cs;
-  const int capacity = rounds ? ndev_sms / cs : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
+  int capacity = rounds ? ndev_sms / cs : (1 << 30);   // streamed / panel kernels: one CTA per SM (registers, smem)
   auto panel_slots = [&](const HostInstance &h) {   // ring slots (this CTA's share of one panel each) beside the vectors
     if (use_rows) {   // full-width panels
       const long long fixed = (long long)rows_smem_bytes(h.npad, 0, cs) + 256, sb = (long long)h.pn.nw * kPanelRows * 32 * 8;
@@ -385,6 +405,17 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       if (it == gid.end()) { gid[key] = (int)members.size(); members.emplace_back(); uniq.push_back(h); gprog.push_back(progress[b]); it = gid.find(key); }
       members[it->second].push_back(b);
     }
+  }
+  if (use_rows && g.auto_cluster && cs == 2 && rounds) {
+    // few tiles left (rolling B&B sessions: most trees are finished or between steps): a cluster of 4 per tile halves the
+    // per-iteration latency (45 us instead of 80 at n = 500) and the idle SMs cost nothing.  Opt-in: the summation order of
+    // the column sums depends on the cluster size, so a node's last bits then depend on the schedule
+    bool quad = true;
+    for (auto *inst : uniq) quad = quad && inst->h.pn.nw % 4 == 0;
+    long long nt = 0;
+    for (auto &mb : members) nt += ((long long)mb.size() + kPanelT - 1) / kPanelT;
+    const int cap4 = (ndev_sms - 16) / 4;     // clusters of 4 cannot use every SM of every GPC (measured: 33 at a time on 148 SMs)
+    if (quad && nt <= cap4) { cs = 4; g.cs = 4; capacity = cap4; }
   }
   const int slot_bytes = g.stage_bytes;
   if (use_panel && !use_rows && cs == 1)
@@ -479,6 +510,51 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   return BQP_OK;
 }
 
+// engine selection over the nodes of the batch / session (g.node_inst): the row-split kernel when every problem has a dense
+// panel layout, else the TMA-streamed kernel when every problem has a streamed layout (bqp_set_tuning(threads>0) forces the
+// direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
+static void select_kernel(BatchCtx &g) {
+  g.use_stream = g_tune_threads == 0;
+  g.use_panel = g_tune_threads == 0;
+  g.use_rows = true;
+  if (const char *e = std::getenv("BQP_KERNEL")) {        // tests / A-B runs: "rows" (default when possible), "panel", "stream", "direct"
+    if (!std::strcmp(e, "stream")) g.use_panel = false;
+    else if (!std::strcmp(e, "direct")) g.use_panel = g.use_stream = false;
+    else if (!std::strcmp(e, "panel")) g.use_rows = false;
+  }
+  g.stage_bytes = kStageValBytes;
+  g.w_in_stage = true;
+  g.max_iter_all = 0; g.round_ok = true;
+  const int check0 = g.node_inst[0]->h.s.check_termination;
+  int want = 2;
+  bqp_instance *last = nullptr;
+  for (bqp_instance *inst : g.node_inst) {
+    if (inst == last) continue;      // nodes of one problem are usually adjacent
+    last = inst;
+    const HostInstance &h = inst->h;
+    const HostStream &st = h.st;
+    if (!h.pn.built) g.use_panel = false;
+    if (!st.built || (int)st.groups.size() > 96) g.use_stream = false;   // 96 = groups cached in shared memory
+    else g.stage_bytes = std::max(g.stage_bytes, st.slot_bytes);
+    if (!inst->d.w_in_stage) g.w_in_stage = false;
+    g.max_iter_all = std::max(g.max_iter_all, h.s.max_iter);
+    if (h.s.check_termination != check0) g.round_ok = false;
+    want = std::max(want, std::max(h.Ab.nslices, h.At.nslices));
+  }
+  if (g.use_panel) g.use_stream = false;
+  if (!g.use_stream) g.w_in_stage = false;
+  g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
+  // rounds: the streamed kernels run `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
+  // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
+  g.round_iters = 0;
+  if ((g.use_stream || g.use_panel) && g.round_ok) {
+    int r = 100;
+    if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
+    if (g.round_override >= 0) r = g.round_override;
+    g.round_iters = r <= 0 ? 0 : ((r + check0 - 1) / check0) * check0;
+  }
+}
+
 static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
                         const double *const *x0, const double *const *y0) {
   if (B <= 0 || !handles || !l || !u || !x0 || !y0) return BQP_E_ARG;
@@ -495,44 +571,6 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
   if (rc) return rc;
   CK(cudaSetDevice(g.device));
 
-  // engine: the TMA-streamed kernel when every problem has a streamed layout (bqp_set_tuning(threads>0) forces
-  // the direct-load kernel); CTA shape of the direct-load kernel: one warp per 32-row slice of the widest panel
-  g.use_stream = g_tune_threads == 0;
-  g.use_panel = g_tune_threads == 0;
-  g.use_rows = true;
-  if (const char *e = std::getenv("BQP_KERNEL")) {        // tests / A-B runs: "rows" (default when possible), "panel", "stream", "direct"
-    if (!std::strcmp(e, "stream")) g.use_panel = false;
-    else if (!std::strcmp(e, "direct")) g.use_panel = g.use_stream = false;
-    else if (!std::strcmp(e, "panel")) g.use_rows = false;
-  }
-  g.stage_bytes = kStageValBytes;
-  g.w_in_stage = true;
-  g.max_iter_all = 0; g.round_ok = true;
-  int check0 = handles[0]->h.s.check_termination, want = 2;
-  for (int b = 0; b < B; b++) {
-    const HostInstance &h = handles[b]->h;
-    const HostStream &st = h.st;
-    if (!h.pn.built) g.use_panel = false;
-    if (!st.built || (int)st.groups.size() > 96) g.use_stream = false;   // 96 = groups cached in shared memory
-    else g.stage_bytes = std::max(g.stage_bytes, st.slot_bytes);
-    if (!handles[b]->d.w_in_stage) g.w_in_stage = false;
-    g.max_iter_all = std::max(g.max_iter_all, h.s.max_iter);
-    if (h.s.check_termination != check0) g.round_ok = false;
-    want = std::max(want, std::max(h.Ab.nslices, h.At.nslices));
-  }
-  if (g.use_panel) g.use_stream = false;
-  if (!g.use_stream) g.w_in_stage = false;
-  g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
-  // rounds: the streamed kernel runs `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
-  // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
-  g.round_iters = 0;
-  if ((g.use_stream || g.use_panel) && g.round_ok) {
-    int r = 100;
-    if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
-    if (g.round_override >= 0) r = g.round_override;
-    g.round_iters = r <= 0 ? 0 : ((r + check0 - 1) / check0) * check0;
-  }
-
   g.node_inst.assign(B, nullptr); g.in_off.assign(B, 0); g.out_off.assign(B, 0); g.state_off.assign(B, 0);
   size_t in_d = 0, out_d = 0, st_d = 0;
   for (int b = 0; b < B; b++) {
@@ -541,6 +579,10 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
     in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
   }
   g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
+  g.session = false;
+  g.auto_cluster = false;
+  if (const char *e = std::getenv("BQP_ROWS_AUTO_CLUSTER")) g.auto_cluster = std::atoi(e) != 0;
+  select_kernel(g);
   if ((rc = g.h_in.reserve(in_d * 8, g.stream))) return rc;
   if ((rc = g.h_out.reserve(out_d * 8, g.stream))) return rc;
   if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B, g.stream))) return rc;
@@ -572,77 +614,62 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
   return BQP_OK;
 }
 
-static int batch_run(BatchCtx &g) {
-  if (!g.resident) return BQP_E_ARG;
-  CK(cudaSetDevice(g.device));
-  std::vector<int> alive(g.B), progress(g.B, 0), scheduled;
-  // scheduling hint per running node: distance to the tolerance at its last check (reported by the panel kernel) and the
-  // number of iterations it is predicted to need still, from the geometric decay of that distance between two rounds
+// one launch over (a capacity-bounded subset of) the running nodes; finished nodes leave `alive`
+static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &progress, std::vector<double> &dist,
+                     std::vector<double> &remaining, std::vector<int> *finished, long long *tile_iters, long long *bytes) {
   const double kUnknown = 1e30;
-  std::vector<double> dist(g.B, NAN), remaining(g.B, kUnknown);
-  const bool predict = std::getenv("BQP_NO_PREDICT") == nullptr;
-  for (int b = 0; b < g.B; b++) alive[b] = b;
-  long long tile_iters = 0, bytes = 0, h2d_extra = 0;
-  int launches = 0, first_tiles = 0, first_tt = 0, first_slots = 0;
-  long long first_smem = 0;
-  CK(cudaEventRecord(g.ev[1], g.stream));
-  while (!alive.empty()) {
-    int rc = plan_round(g, alive, progress, remaining, &scheduled);
-    if (rc) return rc;
-    h2d_extra += g.round_h2d_bytes;
-    if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
-    rc = (g.use_panel && g.use_rows)
-             ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
-                                (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
-                                g.smem, g.stream)
-         : g.use_panel
-             ? launch_admm_panel(g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
-                                 g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
-                                 (int *)g.d_ti.p, g.smem, g.stream)
-         : g.use_stream
-             ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, g.w_in_stage ? 1 : 0, (double *)g.d_state.p,
-                                  (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
-                                  (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
-             : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
-                           (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
-                           (int *)g.d_ti.p, g.smem, g.stream);
-    if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
-    launches++;
-    CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
-    CK(ctx_sync(g));
-    const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
-    const int *ti = (const int *)g.h_ti.p;
-    for (int t = 0; t < g.ntiles; t++) {
-      tile_iters += ti[t];
-      const int ce = g.tile_check_every[t];
-      bytes += (long long)ti[t] * g.tile_bytes_iter[t] + (long long)(ti[t] / ce + ((ti[t] % ce) ? 1 : 0)) * g.tile_bytes_check[t] + g.tile_bytes_launch[t];
-    }
-    std::vector<char> done(g.B, 0);
-    for (int b : scheduled) {
-      if (hs[b].status == BQP_UNSOLVED) {
-        const int before = progress[b];
-        progress[b] = hs[b].iters;   // iterations completed so far (its tile's iter_end)
-        const double d = hs[b].pri_res;
-        if (predict && d == d && d > 0) {
-          if (dist[b] == dist[b] && dist[b] > d && d > 1.0 && progress[b] > before)
-            remaining[b] = std::log(d) / std::log(dist[b] / d) * (progress[b] - before);
-          else if (dist[b] == dist[b]) remaining[b] = kUnknown * 0.5;   // not converging yet: behind the unknown ones only
-          dist[b] = d;
-        }
-      } else done[b] = 1;
-    }
-    std::vector<int> next;
-    for (int b : alive) if (!done[b]) next.push_back(b);
-    if (next.size() == alive.size() && scheduled.empty()) return BQP_E_CUDA;
-    alive.swap(next);
-  }
-  CK(cudaEventRecord(g.ev[2], g.stream));
+  static const bool predict = std::getenv("BQP_NO_PREDICT") == nullptr;
+  std::vector<int> scheduled;
+  int rc = plan_round(g, alive, progress, remaining, &scheduled);
+  if (rc) return rc;
+  rc = (g.use_panel && g.use_rows)
+           ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                              (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
+                              g.smem, g.stream)
+       : g.use_panel
+           ? launch_admm_panel(g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
+                               g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                               (int *)g.d_ti.p, g.smem, g.stream)
+       : g.use_stream
+           ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, g.w_in_stage ? 1 : 0, (double *)g.d_state.p,
+                                (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
+                                (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
+           : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+                         (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
+                         (int *)g.d_ti.p, g.smem, g.stream);
+  if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
+  CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
   CK(ctx_sync(g));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
-  g.timing.kernel_ms = ms;
-  g.timing.launches = launches;
+  const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
+  const int *ti = (const int *)g.h_ti.p;
+  for (int t = 0; t < g.ntiles; t++) {
+    *tile_iters += ti[t];
+    const int ce = g.tile_check_every[t];
+    *bytes += (long long)ti[t] * g.tile_bytes_iter[t] + (long long)(ti[t] / ce + ((ti[t] % ce) ? 1 : 0)) * g.tile_bytes_check[t] + g.tile_bytes_launch[t];
+  }
+  std::vector<char> done(g.B, 0);
+  for (int b : scheduled) {
+    if (hs[b].status == BQP_UNSOLVED) {
+      const int before = progress[b];
+      progress[b] = hs[b].iters;   // iterations completed so far (its tile's iter_end)
+      const double d = hs[b].pri_res;
+      if (predict && d == d && d > 0) {
+        if (dist[b] == dist[b] && dist[b] > d && d > 1.0 && progress[b] > before)
+          remaining[b] = std::log(d) / std::log(dist[b] / d) * (progress[b] - before);
+        else if (dist[b] == dist[b]) remaining[b] = kUnknown * 0.5;   // not converging yet: behind the unknown ones only
+        dist[b] = d;
+      }
+    } else { done[b] = 1; if (finished) finished->push_back(b); }
+  }
+  std::vector<int> next;
+  for (int b : alive) if (!done[b]) next.push_back(b);
+  if (next.size() == alive.size() && scheduled.empty()) return BQP_E_CUDA;
+  alive.swap(next);
+  return BQP_OK;
+}
+
+static void fill_launch_timing(BatchCtx &g, int first_tiles, int first_tt, long long first_smem, int first_slots) {
   g.timing.tiles = first_tiles; g.timing.tile_nodes = first_tt; g.timing.smem_bytes = first_smem;
   if (g.use_panel && g.use_rows) g.timing.threads = kRowsThreads;
   else if (g.use_panel) {
@@ -651,9 +678,132 @@ static int batch_run(BatchCtx &g) {
   }
   g.timing.kernel = g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
   g.timing.ring_slots = first_slots;
+}
+
+static int batch_run(BatchCtx &g) {
+  if (!g.resident || g.session) return BQP_E_ARG;
+  CK(cudaSetDevice(g.device));
+  std::vector<int> alive(g.B), progress(g.B, 0);
+  // scheduling hint per running node: distance to the tolerance at its last check (reported by the kernel) and the
+  // number of iterations it is predicted to need still, from the geometric decay of that distance between two rounds
+  std::vector<double> dist(g.B, NAN), remaining(g.B, 1e30);
+  for (int b = 0; b < g.B; b++) alive[b] = b;
+  long long tile_iters = 0, bytes = 0, h2d_extra = 0;
+  int launches = 0, first_tiles = 0, first_tt = 0, first_slots = 0;
+  long long first_smem = 0;
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  while (!alive.empty()) {
+    int rc = run_round(g, alive, progress, dist, remaining, nullptr, &tile_iters, &bytes);
+    if (rc) return rc;
+    h2d_extra += g.round_h2d_bytes;
+    if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
+    launches++;
+  }
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(ctx_sync(g));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
+  g.timing.kernel_ms = ms;
+  g.timing.launches = launches;
+  fill_launch_timing(g, first_tiles, first_tt, first_smem, first_slots);
   g.timing.tile_iters = tile_iters; g.timing.stream_bytes = bytes;
   g.round_h2d_total = h2d_extra;
   g.ran = true;
+  return BQP_OK;
+}
+
+// ---- rolling session: nodes join a resident batch while others are still iterating; every call of session_round is one
+// launch (one round of ADMM iterations over a capacity-bounded, critical-path-first subset of the running nodes)
+static int session_begin(BatchCtx &g) {
+  g.resident = false; g.ran = false; g.session = true;
+  g.auto_cluster = true;
+  if (const char *e = std::getenv("BQP_ROWS_AUTO_CLUSTER")) g.auto_cluster = std::atoi(e) != 0;
+  g.B = 0; g.node_inst.clear(); g.in_off.clear(); g.out_off.clear(); g.state_off.clear();
+  g.s_alive.clear(); g.s_progress.clear(); g.s_dist.clear(); g.s_remaining.clear();
+  g.s_in_d = g.s_out_d = g.s_st_d = 0;
+  g.s_tile_iters = g.s_bytes = 0; g.s_launches = 0; g.s_kernel_ms = 0;
+  g.timing = bqp_timing{};
+  return BQP_OK;
+}
+
+static int session_append(BatchCtx &g, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                          const double *const *x0, const double *const *y0, int *first_id) {
+  if (!g.session || B <= 0 || !handles || !l || !u || !x0 || !y0) return BQP_E_ARG;
+  for (int b = 0; b < B; b++) {
+    if (!handles[b] || !l[b] || !u[b] || !x0[b] || !y0[b]) return BQP_E_ARG;
+    if (!handles[b]->on_device) return BQP_E_CUDA;
+    if (handles[b]->device != handles[0]->device || (g.B > 0 && handles[b]->device != g.device)) return BQP_E_ARG;
+    const int m = handles[b]->h.m;
+    for (int i = 0; i < m; i++)
+      if (l[b][i] > u[b][i]) return BQP_E_BOUNDS;
+  }
+  int rc = ctx_init(g, handles[0]->device);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  const int B0 = g.B;
+  const size_t in0 = g.s_in_d, out0 = g.s_out_d, st0 = g.s_st_d;
+  size_t in_d = in0, out_d = out0, st_d = st0;
+  for (int b = 0; b < B; b++) {
+    const HostInstance &h = handles[b]->h;
+    g.in_off.push_back((long long)in_d); g.out_off.push_back((long long)out_d); g.state_off.push_back((long long)st_d);
+    g.node_inst.push_back(handles[b]);
+    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
+    g.s_alive.push_back(B0 + b); g.s_progress.push_back(0); g.s_dist.push_back(NAN); g.s_remaining.push_back(1e30);
+  }
+  g.B = B0 + B; g.s_in_d = in_d; g.s_out_d = out_d; g.s_st_d = st_d;
+  g.in_doubles = in_d; g.out_doubles = out_d;
+  select_kernel(g);
+  if (g.round_iters <= 0) return BQP_E_UNSUPPORTED;      // a session needs a kernel that runs in rounds
+  if ((rc = g.h_in.reserve((in_d - in0) * 8, g.stream))) return rc;        // staging of the new nodes only
+  if ((rc = g.h_out.reserve_keep(out_d * 8, out0 * 8, g.stream))) return rc;
+  if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)g.B, g.stream))) return rc;
+  if ((rc = g.d_in.reserve_keep(in_d * 8, in0 * 8, g.stream))) return rc;
+  if ((rc = g.d_out.reserve_keep(out_d * 8, out0 * 8, g.stream))) return rc;
+  if ((rc = g.d_ns.reserve_keep(sizeof(NodeScalars) * (size_t)g.B, sizeof(NodeScalars) * (size_t)B0, g.stream))) return rc;
+  if ((rc = g.d_state.reserve_keep(std::max<size_t>(st_d, 1) * 8, st0 * 8, g.stream))) return rc;
+  double *hin = (double *)g.h_in.p;
+  for (int b = 0; b < B; b++) {
+    const HostInstance &h = handles[b]->h;
+    double *p = hin + (g.in_off[B0 + b] - (long long)in0);
+    std::memcpy(p, l[b], 8 * (size_t)h.m);
+    std::memcpy(p + h.m, u[b], 8 * (size_t)h.m);
+    std::memcpy(p + 2 * (size_t)h.m, x0[b], 8 * (size_t)h.n);
+    std::memcpy(p + 2 * (size_t)h.m + h.n, y0[b], 8 * (size_t)h.m);
+  }
+  CK(cudaMemcpyAsync((double *)g.d_in.p + in0, hin, (in_d - in0) * 8, cudaMemcpyHostToDevice, g.stream));
+  CK(ctx_sync(g));        // the staging buffer is reused by the next append
+  g.timing.h2d_bytes += (long long)((in_d - in0) * 8);
+  g.resident = true;
+  if (first_id) *first_id = B0;
+  return BQP_OK;
+}
+
+static int session_round(BatchCtx &g, std::vector<int> *finished) {
+  if (!g.session || !g.resident) return BQP_E_ARG;
+  if (g.s_alive.empty()) return BQP_OK;
+  CK(cudaSetDevice(g.device));
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  const size_t f0 = finished->size();
+  int rc = run_round(g, g.s_alive, g.s_progress, g.s_dist, g.s_remaining, finished, &g.s_tile_iters, &g.s_bytes);
+  if (rc) return rc;
+  // results of the nodes that terminated in this launch: x | y into the pinned mirror of the output buffer
+  for (size_t k = f0; k < finished->size(); k++) {
+    const int b = (*finished)[k];
+    const HostInstance &h = g.node_inst[b]->h;
+    CK(cudaMemcpyAsync((double *)g.h_out.p + g.out_off[b], (const double *)g.d_out.p + g.out_off[b], 8 * ((size_t)h.n + h.m),
+                       cudaMemcpyDeviceToHost, g.stream));
+    g.timing.d2h_bytes += (long long)(8 * ((size_t)h.n + h.m));
+  }
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(ctx_sync(g));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
+  g.s_kernel_ms += ms;
+  if (g.s_launches == 0) fill_launch_timing(g, g.ntiles, g.tt, (long long)g.smem, (g.use_panel || g.use_stream) ? g.nslots : 0);
+  g.s_launches++;
+  g.timing.kernel_ms = g.s_kernel_ms; g.timing.launches = g.s_launches;
+  g.timing.tile_iters = g.s_tile_iters; g.timing.stream_bytes = g.s_bytes;
+  g.timing.h2d_bytes += g.round_h2d_bytes;
   return BQP_OK;
 }
 
@@ -735,6 +885,42 @@ int bqp_ctx_solve_multi(bqp_ctx ctx, int B, const bqp_handle *handles, const dou
                         const bqp_node_out *out) {
   if (!ctx) return BQP_E_ARG;
   return solve_multi(ctx->c, B, handles, l, u, x0, y0, x, y, out);
+}
+int bqp_session_begin(bqp_ctx ctx) { return session_begin(ctx ? ctx->c : g0); }
+int bqp_session_append(bqp_ctx ctx, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
+                       const double *const *x0, const double *const *y0, int *first_id) {
+  return session_append(ctx ? ctx->c : g0, B, handles, l, u, x0, y0, first_id);
+}
+int bqp_session_round(bqp_ctx ctx, int *finished_ids, int cap, int *n_finished, int *running) {
+  BatchCtx &g = ctx ? ctx->c : g0;
+  std::vector<int> fin;
+  const int rc = session_round(g, &fin);
+  if (rc) return rc;
+  if ((int)fin.size() > cap || (!finished_ids && !fin.empty())) return BQP_E_ARG;
+  for (size_t k = 0; k < fin.size(); k++) finished_ids[k] = fin[k];
+  if (n_finished) *n_finished = (int)fin.size();
+  if (running) *running = (int)g.s_alive.size();
+  return BQP_OK;
+}
+int bqp_session_fetch(bqp_ctx ctx, int id, double *x, double *y, const bqp_node_out *out) {
+  BatchCtx &g = ctx ? ctx->c : g0;
+  if (!g.session || id < 0 || id >= g.B) return BQP_E_ARG;
+  const NodeScalars &r = ((const NodeScalars *)g.h_ns.p)[id];
+  if (r.status == BQP_UNSOLVED) return BQP_E_ARG;        // still running
+  const HostInstance &h = g.node_inst[id]->h;
+  const double *ho = (const double *)g.h_out.p + g.out_off[id];
+  if (x) std::memcpy(x, ho, 8 * (size_t)h.n);
+  if (y) std::memcpy(y, ho + h.n, 8 * (size_t)h.m);
+  if (out) {
+    if (out->status) out->status[0] = r.status;
+    if (out->iters) out->iters[0] = r.iters;
+    if (out->obj) out->obj[0] = r.obj;
+    if (out->pri_res) out->pri_res[0] = r.pri_res;
+    if (out->dua_res) out->dua_res[0] = r.dua_res;
+    if (out->lower) out->lower[0] = r.lower;
+  }
+  g.timing.node_iters += r.iters;
+  return BQP_OK;
 }
 int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t) {
   if (!ctx || !t) return BQP_E_ARG;

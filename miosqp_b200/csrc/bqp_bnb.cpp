@@ -429,3 +429,99 @@ extern "C" int bqp_bnb_solve_async(int count, const bqp_handle *h, const bqp_pro
   for (auto &th : pool) th.join();
   return first_err.load();
 }
+
+// Rolling variant (include/bqp.h): one engine session shared by all trees.  A round is one launch; after it, every tree whose
+// outstanding leaves have all terminated absorbs their results, replays (advance) and appends its next unsolved leaves
+// (+ look-ahead), which join the next round next to the leaves of the other trees that are still iterating.
+extern "C" int bqp_bnb_solve_rolling(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
+                                     const double *const *x_incumbent, const double *upper_incumbent, double *const *x,
+                                     bqp_bnb_result *res, int *const *decisions, int decisions_cap, int *rounds) {
+  if (count <= 0 || !h || !p || !s || !x || !res) return BQP_E_ARG;
+  for (int k = 0; k < count; k++) if (!problem_ok(p[k]) || !x[k] || !h[k]) return BQP_E_ARG;
+  std::vector<std::unique_ptr<Tree>> trees;
+  for (int k = 0; k < count; k++) {
+    trees.emplace_back(new Tree());
+    trees.back()->init(h[k], p[k], &s[k], x_incumbent ? x_incumbent[k] : nullptr, upper_incumbent ? upper_incumbent[k] : kInf);
+  }
+  struct Pending { int tree; Node *node; std::chrono::steady_clock::time_point t0; };
+  std::vector<Pending> pend;                      // by session node id
+  std::vector<int> outstanding((size_t)count, 0);
+  std::vector<char> active((size_t)count, 1);
+  int rc = bqp_session_begin(nullptr), nrounds = 0;
+  std::vector<int> fin;
+  while (!rc) {
+    // replay every tree that waits for nothing and collect its next leaves.  The replay of one node costs two sparse
+    // mat-vecs on the host (objective at the clipped point, feasibility of the rounded point: ~1 ms at n = 500), the trees
+    // are independent: spread them over host threads
+    std::vector<int> ready;
+    for (int k = 0; k < count; k++) if (active[(size_t)k] && outstanding[(size_t)k] == 0) ready.push_back(k);
+    std::vector<std::vector<Node *>> got(ready.size());
+    std::vector<int> adv(ready.size(), 0);
+    {
+      std::atomic<size_t> nexti(0);
+      auto work = [&]() {
+        for (;;) {
+          const size_t i = nexti.fetch_add(1);
+          if (i >= ready.size()) break;
+          Tree &t = *trees[(size_t)ready[i]];
+          adv[i] = t.advance();
+          if (adv[i] == 1) t.collect(got[i]);
+        }
+      };
+      const size_t nth = std::min<size_t>(ready.size(), std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+      std::vector<std::thread> pool;
+      for (size_t t = 1; t < nth; t++) pool.emplace_back(work);
+      work();
+      for (auto &th : pool) th.join();
+    }
+    std::vector<Node *> batch; std::vector<int> owner;
+    for (size_t i = 0; i < ready.size() && !rc; i++) {
+      const int k = ready[i];
+      if (adv[i] < 0) { rc = adv[i]; break; }
+      if (adv[i] == 0) { active[(size_t)k] = 0; continue; }
+      batch.insert(batch.end(), got[i].begin(), got[i].end());
+      owner.insert(owner.end(), got[i].size(), k);
+      outstanding[(size_t)k] = (int)got[i].size();
+      trees[(size_t)k]->batches++;
+    }
+    if (rc) break;
+    if (!batch.empty()) {
+      const int B = (int)batch.size();
+      std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
+      std::vector<bqp_handle> hs(B);
+      for (int j = 0; j < B; j++) {
+        Node &nd = *batch[(size_t)j];
+        hs[j] = h[owner[(size_t)j]];
+        pl[j] = nd.l.data(); pu[j] = nd.u.data(); px0[j] = nd.x->data(); py0[j] = nd.y->data();
+      }
+      int first_id = 0;
+      rc = bqp_session_append(nullptr, B, hs.data(), pl.data(), pu.data(), px0.data(), py0.data(), &first_id);
+      if (rc) break;
+      if ((size_t)first_id != pend.size()) { rc = BQP_E_ARG; break; }
+      const auto now = std::chrono::steady_clock::now();
+      for (int j = 0; j < B; j++) { pend.push_back({owner[(size_t)j], batch[(size_t)j], now}); trees[(size_t)owner[(size_t)j]]->batched_nodes++; }
+    }
+    bool any = false;
+    for (int k = 0; k < count; k++) any = any || outstanding[(size_t)k] > 0;
+    if (!any) break;                              // every tree is finished
+    fin.assign(pend.size(), 0);
+    int nfin = 0, running = 0;
+    rc = bqp_session_round(nullptr, fin.data(), (int)fin.size(), &nfin, &running);
+    if (rc) break;
+    nrounds++;
+    const auto now = std::chrono::steady_clock::now();
+    for (int j = 0; j < nfin && !rc; j++) {
+      Pending &pd = pend[(size_t)fin[(size_t)j]];
+      int status = BQP_UNSOLVED, iters = 0;
+      bqp_node_out out; std::memset(&out, 0, sizeof(out));
+      out.status = &status; out.iters = &iters;
+      rc = bqp_session_fetch(nullptr, fin[(size_t)j], pd.node->cx->data(), pd.node->cy->data(), &out);
+      // a node's time = from the append to the end of the round it terminated in, shared by the tree's leaves in flight
+      Tree::absorb(*pd.node, status, iters, std::chrono::duration<double>(now - pd.t0).count() / 2.0);
+      outstanding[(size_t)pd.tree]--;
+    }
+  }
+  for (int k = 0; k < count; k++) trees[(size_t)k]->finish(p[k], x[k], &res[k], decisions ? decisions[k] : nullptr, decisions_cap);
+  if (rounds) *rounds = nrounds;
+  return rc;
+}

@@ -106,7 +106,8 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
            "bqp_debug_host_panel_kkt_solve",
            "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
-           "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device"]
+           "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device",
+           "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
 
 _lib = None
 
@@ -145,6 +146,12 @@ def lib():
                                          _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int]
         L.bqp_bnb_solve_async.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp,
                                           _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, C.c_int]
+        L.bqp_bnb_solve_rolling.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp,
+                                            _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, _ip]
+        L.bqp_session_begin.argtypes = [vp]
+        L.bqp_session_append.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, _ip]
+        L.bqp_session_round.argtypes = [vp, _ip, C.c_int, _ip, _ip]
+        L.bqp_session_fetch.argtypes = [vp, C.c_int, _dp, _dp, C.POINTER(_NodeOut)]
         L.bqp_ctx_create.argtypes = [C.c_int, C.c_int, pp]
         L.bqp_ctx_free.argtypes = [vp]
         L.bqp_ctx_solve_multi.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, pp, pp, C.POINTER(_NodeOut)]
@@ -400,7 +407,7 @@ def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.
     return x, out, decisions
 
 
-def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None, async_threads=None):
+def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None, async_threads=None, rolling=False):
     """Native replay over several set-up problems.  Lock-step (bqp_bnb_solve_many): one launch per B&B step covers all
     their frontiers.  async_threads is not None (bqp_bnb_solve_async, 0 = automatic): every problem advances at its own
     pace on its own CUDA stream, driven by a pool of host threads.  Arguments are sequences of equal length; `many_fn`
@@ -419,7 +426,11 @@ def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents
     handles = None if many_fn is not None else (C.c_void_p * count)(*[q._h.value for q in qps])
     x_ptrs = (_dp * count)(*[_d(x) for x in xs])
     dec_ptrs = (_ip * count)(*[_i(d) for d in decs])
-    if async_threads is not None and many_fn is None:
+    if rolling and many_fn is None:
+        # one engine session shared by all trees: a tree whose leaves have terminated rejoins the next round (bqp_bnb_solve_rolling)
+        nr = C.c_int(0)
+        rc = lib().bqp_bnb_solve_rolling(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, C.byref(nr))
+    elif async_threads is not None and many_fn is None:
         rc = lib().bqp_bnb_solve_async(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, int(async_threads))
     else:
         rc = lib().bqp_bnb_solve_many(count, handles, pptr, sts, xin_ptrs, _d(uppers),

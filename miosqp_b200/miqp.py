@@ -154,11 +154,28 @@ def setup_many(problems, settings, qp_settings, threads=0):
     return out
 
 
-def solve_many(solvers, on_batch=None, async_threads=None):
+def wrap_many(problems, qps, settings, qp_settings):
+    """MIOSQP objects around problems whose factors are already resident (`qps`: engine.BatchedQP, same order): what
+    setup_many does after the factorisation."""
+    out = []
+    for pr, s in zip(problems, qps):
+        i_l = pr.get('i_l'); i_u = pr.get('i_u')
+        i_l = -np.inf * np.ones(len(pr['i_idx'])) if i_l is None else i_l
+        i_u = np.inf * np.ones(len(pr['i_idx'])) if i_u is None else i_u
+        m = MIOSQP()
+        m.data = Data(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], i_l, i_u)
+        m.work = Workspace(m.data, dict(settings), dict(qp_settings or {}), solver=s)
+        out.append(m)
+    return out
+
+
+def solve_many(solvers, on_batch=None, async_threads=None, rolling=False):
     """Solve several set-up MIOSQP objects together.  Lock-step (default): every step flattens the unsolved leaves of ALL
     frontiers into one node batch (one kernel launch).  async_threads is not None (native replay only; 0 = automatic):
     every MIQP runs its own replay/launch loop on its own CUDA stream (bqp_bnb_solve_async), so none waits for another
-    one's slowest leaf.  Either way each instance's result is identical to its own `solve()`.
+    one's slowest leaf.  rolling=True (native replay only): all trees share one engine session; after every round of 100 ADMM
+    iterations the trees whose leaves have terminated are replayed and their children join the next launch
+    (bqp_bnb_solve_rolling).  Either way each instance's result is identical to its own `solve()`.
     `on_batch(n_nodes, seconds)` is called after every launch of the Python lock-step loop (benchmarks)."""
     for s in solvers:
         s._begin()
@@ -169,7 +186,7 @@ def solve_many(solvers, on_batch=None, async_threads=None):
         outs = engine.bnb_solve_many([w.solver for w in works], [w.data for w in works], [w.settings for w in works],
                                      [w.qp_settings['eps_abs'] for w in works],
                                      [(w.x if np.isfinite(w.upper_glob) else None) for w in works],
-                                     [w.upper_glob for w in works], many_fn=many_fn, async_threads=async_threads)
+                                     [w.upper_glob for w in works], many_fn=many_fn, async_threads=async_threads, rolling=rolling)
         return [s._absorb_native(x, r, d) for s, (x, r, d) in zip(solvers, outs)]
     active = list(solvers)
     while active:

@@ -51,3 +51,8 @@ extern "C" int bqp_ctx_solve_multi(bqp_ctx, int, const bqp_handle *, const doubl
 extern "C" int bqp_ctx_create(int, int, bqp_ctx *) { return BQP_E_CUDA; }
 extern "C" int bqp_ctx_free(bqp_ctx) { return BQP_OK; }
 extern "C" int bqp_handle_device(bqp_handle) { return -1; }
+extern "C" int bqp_session_begin(bqp_ctx) { return BQP_E_CUDA; }
+extern "C" int bqp_session_append(bqp_ctx, int, const bqp_handle *, const double *const *, const double *const *, const double *const *,
+                                  const double *const *, int *) { return BQP_E_CUDA; }
+extern "C" int bqp_session_round(bqp_ctx, int *, int, int *, int *) { return BQP_E_CUDA; }
+extern "C" int bqp_session_fetch(bqp_ctx, int, double *, double *, const bqp_node_out *) { return BQP_E_CUDA; }

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     a = ap.parse_args()
     import miosqp_b200
-    from miosqp_b200 import problems, miqp
+    from miosqp_b200 import problems, miqp, engine
     prs = problems.random_miqp(500, 1000, 50, 0.7, seed=a.seed, count=a.instances)
     golden = {}
     gp = os.path.join(ROOT, "tests", "golden", "bnb_cfg2.json")
@@ -47,7 +47,7 @@ def main():
             s.work.reset(); s.work.first_run = 0
             s.work.batches = s.work.batched_nodes = s.work.spec_nodes = s.work.spec_hits = 0
         t0 = time.perf_counter()
-        res = miosqp_b200.solve_many(solvers, async_threads=(a.threads if mode == "async" else None))
+        res = miosqp_b200.solve_many(solvers, async_threads=(a.threads if mode == "async" else None), rolling=(mode == "rolling"))
         wall = time.perf_counter() - t0
         works = [s.work for s in solvers]
         consumed = sum(w.iter_num - 1 for w in works)
@@ -72,6 +72,7 @@ def main():
                           "launches": int(sum(w.batches for w in works)) if mode == "async" else int(max(w.batches for w in works)),
                           "spec_hit_rate": sum(w.spec_hits for w in works) / float(max(1, sum(w.spec_nodes for w in works))),
                           "status": {st: [r.status for r in res].count(st) for st in set(r.status for r in res)},
+                          "engine_timing_default_ctx": {k: engine.last_timing()[k] for k in ("launches", "kernel_ms", "tile_iters", "tiles", "tile_nodes")},
                           "same_as_first_run": same, "golden_instances_ok": gold_ok,
                           "nodes_per_instance_max": max(w.iter_num - 1 for w in works)}), flush=True)
 
