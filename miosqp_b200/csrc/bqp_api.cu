@@ -753,7 +753,7 @@ static int session_append(BatchCtx &g, int B, const bqp_handle *handles, const d
   g.B = B0 + B; g.s_in_d = in_d; g.s_out_d = out_d; g.s_st_d = st_d;
   g.in_doubles = in_d; g.out_doubles = out_d;
   select_kernel(g);
-  if (g.round_iters <= 0) return BQP_E_UNSUPPORTED;      // a session needs a kernel that runs in rounds
+  // (a kernel without rounds -- the direct-load kernel of small problems -- finishes every running node in one "round")
   if ((rc = g.h_in.reserve((in_d - in0) * 8, g.stream))) return rc;        // staging of the new nodes only
   if ((rc = g.h_out.reserve_keep(out_d * 8, out0 * 8, g.stream))) return rc;
   if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)g.B, g.stream))) return rc;
