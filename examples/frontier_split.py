@@ -42,7 +42,10 @@ def main(argv=None):
             ctx = (rank, world, None, torch.device("cuda", local))
         else:
             dist.init_process_group("gloo")
-            ctx = (rank, world, None)
+            ctx = (rank, world, None, torch.device("cpu"))
+    if ctx is not None:
+        from miosqp_b200 import sharding
+        ctx = sharding.DistCtx.of(ctx)
     import miosqp_b200
     from miosqp_b200 import problems
 
@@ -62,7 +65,11 @@ def main(argv=None):
                           "status": r.status, "upper_glob": float(r.upper_glob), "nodes": w.iter_num - 1, "admm_iters": int(w.osqp_iter),
                           "launches": w.batches, "solved_nodes": w.batched_nodes, "speculation": args.speculation,
                           "spec_hit_rate": w.spec_hits / float(max(1, w.spec_nodes)), "solve_s": wall, "setup_s": t_setup,
-                          "qp_per_s_consumed": (w.iter_num - 1) / wall, "qp_per_s_solved": w.batched_nodes / wall}))
+                          "qp_per_s_consumed": (w.iter_num - 1) / wall, "qp_per_s_solved": w.batched_nodes / wall,
+                          "exchange": None if ctx is None else {
+                              "collective": "one all_gather_into_tensor of packed [status, iters, seconds, x, y] rows + one all-reduce(MIN) of the incumbent per B&B step",
+                              "backend": args.dist_backend, "steps": ctx.exchanges, "seconds_total": ctx.exchange_s,
+                              "ms_per_step": 1e3 * ctx.exchange_s / max(1, ctx.exchanges), "bytes_gathered_total": ctx.exchange_bytes}}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -75,6 +75,10 @@ class MIOSQP(object):
         """settings['replay'] = 'native': the same loop in C++ (csrc/bqp_bnb.cpp, bqp_bnb_solve) -- no interpreter time
         per node; one call in, the reference's Results out.  Leaves `work` as the Python replay would."""
         work = self.work
+        if not work.leaves and work.iter_num > 1:
+            # the tree is finished (a second solve() without update_vectors): the reference's loop -- and the Python replay --
+            # find no leaf and return what they have; do not rebuild the tree from its root
+            return self._finish()
         x, r, decisions = engine.bnb_solve(work.solver, work.data, work.settings, work.qp_settings['eps_abs'],
                                            work.x if np.isfinite(work.upper_glob) else None, work.upper_glob)
         return self._absorb_native(x, r, decisions)
@@ -103,17 +107,18 @@ class MIOSQP(object):
         return Results(work.x, work.upper_glob, work.run_time, work.status, work.osqp_solve_time, work.osqp_iter_avg)
 
     def solve(self, dist_ctx=None):
-        """dist_ctx = (rank, world, group): split every frontier batch across the ranks' GPUs (config 4); all ranks
-        replay the same tree and agree on the incumbent with one all-reduce(MIN) per B&B step."""
+        """dist_ctx = sharding.DistCtx or a (rank, world, group[, device]) tuple: split every frontier batch across the ranks'
+        GPUs (config 4); all ranks replay the same tree and agree on the incumbent with one all-reduce(MIN) per B&B step."""
         self._begin()
         if self.work.settings.get('replay') == 'native' and dist_ctx is None:
             return self._solve_native()
+        if dist_ctx is not None:
+            from . import sharding
+            dist_ctx = sharding.DistCtx.of(dist_ctx)
         while self._replay():
             self.work.solve_pending(dist_ctx)
             if dist_ctx is not None:
-                from . import sharding
-                best, same = sharding.agree_incumbent(self.work.upper_glob, group=dist_ctx[2],
-                                                      device=dist_ctx[3] if len(dist_ctx) > 3 else None)
+                best, same = sharding.agree_incumbent(self.work.upper_glob, ctx=dist_ctx)
                 if not same:
                     raise RuntimeError("replicated B&B replays diverged: incumbent %r vs global %r" % (self.work.upper_glob, best))
         return self._finish()

@@ -109,8 +109,9 @@ class Workspace(object):
             node.cached = (int(scalars.status[k]), int(scalars.iters[k]), share, xs[k], ys[k])
 
     def solve_pending(self, dist_ctx=None):
-        """One launch over every unsolved open leaf.  With dist_ctx = (rank, world, group) the batch is dealt
-        round-robin to the ranks, each solves its share on its own GPU, and one all-gather returns all results."""
+        """One launch over every unsolved open leaf.  With dist_ctx (sharding.DistCtx, or a (rank, world, group[, device])
+        tuple) the batch is dealt round-robin to the ranks, each solves its share on its own GPU, and one
+        all_gather_into_tensor returns all results."""
         nodes = self.pending()
         if not nodes:
             return 0
@@ -124,8 +125,8 @@ class Workspace(object):
             mine = list(range(len(nodes)))
         else:
             from . import sharding
-            rank, world, group = dist_ctx
-            mine = sharding.split_nodes(len(nodes), rank, world)
+            dist_ctx = sharding.DistCtx.of(dist_ctx)
+            mine = sharding.split_nodes(len(nodes), dist_ctx.rank, dist_ctx.world)
         local = {}
         if mine:
             sub = [nodes[k] for k in mine]
@@ -136,7 +137,7 @@ class Workspace(object):
             for j, k in enumerate(mine):
                 local[k] = (int(sc.status[j]), int(sc.iters[j]), dt * float(sc.iters[j]) / total, xs[j], ys[j])
         if dist_ctx is not None:
-            merged = sharding.exchange_node_results(local, len(nodes), rank, world, group)
+            merged = sharding.exchange_node_results(local, len(nodes), self.data.n, self.data.m + self.data.n_int, dist_ctx)
         else:
             merged = [local[k] for k in range(len(nodes))]
         for node, res in zip(nodes, merged):

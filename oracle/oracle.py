@@ -63,6 +63,9 @@ def normalize_settings(kw):
     s = dict(DEFAULTS)
     for k, v in kw.items():
         k = _ALIASES.get(k, k)
+        if k == "adaptive_rho" and v:
+            # the parity contract is a fixed rho: refuse, as the engine does, instead of silently ignoring
+            raise ValueError("adaptive_rho is outside the parity contract of this oracle (fixed rho, typed per row at setup)")
         if k in s:
             s[k] = v
         elif k in _IGNORED:

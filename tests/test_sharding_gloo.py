@@ -47,7 +47,10 @@ def _worker(rank, world, port, mode, out_dir):
         # "frontier+lookahead": the batch every rank splits also carries look-ahead nodes (settings['speculation']):
         # this is what gives a single-instance frontier (2 real nodes per B&B step) enough nodes to spread over GPUs
         m = build("small_seed5", speculation=0 if mode == "frontier" else 16)
-        r = m.solve(dist_ctx=(rank, world, None))
+        import torch
+        # 3-tuple (host tensors) on even, 4-tuple with an explicit device on odd runs of the parametrisation: both forms callers use
+        ctx = (rank, world, None) if mode == "frontier" else (rank, world, None, torch.device("cpu"))
+        r = m.solve(dist_ctx=ctx)
         allres = [("small_seed5", r.status, float(r.upper_glob), [list(d) for d in m.work.decisions], m.work.batched_nodes,
                    m.work.batches, m.work.spec_hits)]
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:

@@ -57,6 +57,26 @@ def test_native_replay_matches_reference_cpu(cpu_engine, name, speculation):
     assert w.leaves == [] and w.batches >= 1
 
 
+def test_second_solve_without_update_returns_the_stored_result_cpu(cpu_engine):
+    """solve() twice without update_vectors: the reference's loop finds no leaf left and returns what it has; so must the
+    native replay (it used to rebuild the tree from its root with the old incumbent: other counters, other averages)"""
+    import miosqp_b200
+    pr = problems.random_miqp(40, 40, 20, 0.7, seed=3)[0]
+    outs = {}
+    for replay in (None, 'native'):
+        m = miosqp_b200.MIOSQP()
+        m.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                dict(problems.RANDOM_MIQP_SETTINGS, replay=replay), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+        r1 = m.solve(); w = m.work
+        first = (r1.status, float(r1.upper_glob), w.iter_num, int(w.osqp_iter), w.batches, float(r1.osqp_iter_avg))
+        r2 = m.solve()
+        assert (r2.status, float(r2.upper_glob), w.iter_num, int(w.osqp_iter), w.batches, float(r2.osqp_iter_avg)) == first
+        assert np.array_equal(r1.x, r2.x)
+        outs[replay] = first
+    a, b = outs[None], outs['native']
+    assert a[0] == b[0] and a[2:] == b[2:] and abs(a[1] - b[1]) <= 1e-12 * (1 + abs(a[1]))   # (objective summed in another order)
+
+
 @pytest.mark.parametrize("rule", [0, 1])
 def test_native_equals_python_replay_with_lookahead_cpu(cpu_engine, rule):
     """Same launches, same look-ahead choices, same adoptions as tree.py -- not just the same answer."""
