@@ -213,6 +213,11 @@ int bqp_set_tuning(int tile_nodes, int threads);
 /* introspection (tests, roofline arithmetic) */
 int bqp_get_dims(bqp_handle h, int *n, int *m, int *npad, long long *factor_bytes, long long *check_bytes);
 int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c);
+/* guard of the explicit reduced inverse used by the dense-A kernels: *error = largest relative difference between KKT solves
+ * through the inverse and through the LDL' factor over 4 probe right-hand sides (NaN: no dense layout was tried);
+ * *in_use = 1 when the dense layout passed (error <= 1e-10, BQP_INVERSE_TOL) and the problem runs on the dense kernels,
+ * 0 when it was dropped or never built and the problem runs on the LDL' kernels. */
+int bqp_get_inverse_guard(bqp_handle h, double *error, int *in_use);
 int bqp_handle_device(bqp_handle h);   /* CUDA device ordinal the problem lives on */
 int bqp_device_count(void);
 const char *bqp_strerror(int code);

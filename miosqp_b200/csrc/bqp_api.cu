@@ -42,26 +42,33 @@ namespace {
 thread_local cudaError_t g_last_cuda = cudaSuccess;
 int g_tune_tt = 0, g_tune_threads = 0;
 
-template <class Tp>
-int upload(bqp_instance *inst, const std::vector<Tp> &v, const Tp **out) {
-  void *p = nullptr;
-  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(Tp);
-  CK(cudaMalloc(&p, bytes));
-  inst->allocs.push_back(p);
-  if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
-  *out = (const Tp *)p;
-  return BQP_OK;
-}
-
-int upload_mat(bqp_instance *inst, const HostMat &M, DevMat *D) {
-  D->rows = M.rows; D->cols = M.cols; D->nslices = M.nslices;
-  int rc;
-  if ((rc = upload(inst, M.sptr, &D->sptr))) return rc;
-  if ((rc = upload(inst, M.iptr, &D->iptr))) return rc;
-  if ((rc = upload(inst, M.vals, &D->vals))) return rc;
-  if ((rc = upload(inst, M.idx, &D->idx))) return rc;
-  return BQP_OK;
-}
+// Device image of one set-up problem: every array goes into ONE allocation through ONE host-to-device copy (round 1 made
+// a cudaMalloc + cudaMemcpy per array, ~25 per instance: 2 500 synchronous driver calls for the 100 instances of config 2).
+struct Arena {
+  struct Item { const void *src; size_t bytes, off; const void **out; };
+  std::vector<Item> items;
+  size_t total = 0;
+  template <class Tp>
+  void add(const std::vector<Tp> &v, const Tp **out) {
+    const size_t bytes = v.size() * sizeof(Tp);
+    items.push_back({v.empty() ? nullptr : (const void *)v.data(), bytes, total, (const void **)out});
+    total += (std::max<size_t>(bytes, 1) + 255) & ~size_t(255);      // 256-byte aligned: TMA sources need 16
+  }
+  void add_mat(const HostMat &M, DevMat *D) {
+    D->rows = M.rows; D->cols = M.cols; D->nslices = M.nslices;
+    add(M.sptr, &D->sptr); add(M.iptr, &D->iptr); add(M.vals, &D->vals); add(M.idx, &D->idx);
+  }
+  int commit(bqp_instance *inst) {
+    void *base = nullptr;
+    CK(cudaMalloc(&base, std::max<size_t>(total, 256)));
+    inst->allocs.push_back(base);
+    std::vector<unsigned char> stage(total);
+    for (auto &it : items) if (it.bytes) std::memcpy(stage.data() + it.off, it.src, it.bytes);
+    if (total) CK(cudaMemcpy(base, stage.data(), total, cudaMemcpyHostToDevice));
+    for (auto &it : items) *it.out = (const unsigned char *)base + it.off;
+    return BQP_OK;
+  }
+};
 
 // grow-only buffers of a batch context.  Device buffers come from the stream-ordered allocator (cudaMallocAsync on the
 // context's stream): cudaMalloc / cudaFree synchronise the whole device, which with many contexts in flight made every
@@ -174,29 +181,14 @@ int to_device(bqp_instance *inst) {
   CK(cudaSetDevice(h.s.device));
   DevInstance &d = inst->d;
   d.n = h.n; d.m = h.m; d.npad = h.npad; d.n_int = h.n_int;
-  int rc;
-  if ((rc = upload_mat(inst, h.At, &d.At))) return rc;
-  if ((rc = upload_mat(inst, h.Ab, &d.Ab))) return rc;
-  if ((rc = upload_mat(inst, h.Pm, &d.Pm))) return rc;
-  if ((rc = upload(inst, h.Lcol, &d.Lcol))) return rc;
-  if ((rc = upload(inst, h.Lrow, &d.Lrow))) return rc;
-  if ((rc = upload(inst, h.D2inv, &d.D2inv))) return rc;
-  if ((rc = upload(inst, h.rho, &d.rho))) return rc;
-  if ((rc = upload(inst, h.rho_inv, &d.rho_inv))) return rc;
-  if ((rc = upload(inst, h.q, &d.q))) return rc;
-  inst->d_q = const_cast<double *>(d.q);
-  if ((rc = upload(inst, h.D, &d.D))) return rc;
-  if ((rc = upload(inst, h.Dinv, &d.Dinv))) return rc;
-  if ((rc = upload(inst, h.E, &d.E))) return rc;
-  if ((rc = upload(inst, h.Einv, &d.Einv))) return rc;
-  if ((rc = upload(inst, h.i_idx, &d.i_idx))) return rc;
+  Arena ar;
+  ar.add_mat(h.At, &d.At); ar.add_mat(h.Ab, &d.Ab); ar.add_mat(h.Pm, &d.Pm);
+  ar.add(h.Lcol, &d.Lcol); ar.add(h.Lrow, &d.Lrow); ar.add(h.D2inv, &d.D2inv);
+  ar.add(h.rho, &d.rho); ar.add(h.rho_inv, &d.rho_inv); ar.add(h.q, &d.q);
+  ar.add(h.D, &d.D); ar.add(h.Dinv, &d.Dinv); ar.add(h.E, &d.E); ar.add(h.Einv, &d.Einv); ar.add(h.i_idx, &d.i_idx);
   d.stream = nullptr; d.groups = nullptr; d.w_in_stage = 0;
   if (h.st.built) {
-    const unsigned char *dstream = nullptr;
-    const StreamGroup *dgroups = nullptr;
-    if ((rc = upload(inst, h.st.data, &dstream))) return rc;
-    if ((rc = upload(inst, h.st.groups, &dgroups))) return rc;
-    d.stream = dstream; d.groups = dgroups;
+    ar.add(h.st.data, &d.stream); ar.add(h.st.groups, &d.groups);
     const HostStream &st = h.st;
     d.g_at[0] = st.range[GK_AT][0]; d.g_at[1] = st.range[GK_AT][1];
     d.g_fw[0] = st.fw[0]; d.g_fw[1] = st.fw[1];
@@ -209,11 +201,13 @@ int to_device(bqp_instance *inst) {
   }
   d.pstream = nullptr; d.p_nw = d.p_npm = d.p_npa = 0; d.p_panel_doubles = d.p_offA = d.p_offP = 0;
   if (h.pn.built) {
-    const double *dp = nullptr;
-    if ((rc = upload(inst, h.pn.data, &dp))) return rc;
-    d.pstream = dp; d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
+    ar.add(h.pn.data, &d.pstream);
+    d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
     d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
   }
+  int rc = ar.commit(inst);
+  if (rc) return rc;
+  inst->d_q = const_cast<double *>(d.q);
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
   d.eps_pinf = h.s.eps_prim_inf; d.eps_dinf = h.s.eps_dual_inf;
@@ -963,6 +957,13 @@ int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c) {
   if (D) std::memcpy(D, h->h.D.data(), 8 * (size_t)h->h.n);
   if (E) std::memcpy(E, h->h.E.data(), 8 * (size_t)h->h.m);
   if (c) *c = h->h.c;
+  return BQP_OK;
+}
+
+int bqp_get_inverse_guard(bqp_handle h, double *error, int *in_use) {
+  if (!h) return BQP_E_ARG;
+  if (error) *error = h->h.pn_inverse_error;
+  if (in_use) *in_use = h->h.pn.built ? 1 : 0;
   return BQP_OK;
 }
 

@@ -1,5 +1,6 @@
 // bqp_internal.h -- shared declarations of the B200 batched QP engine (host setup <-> kernels <-> C ABI).
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <vector>
@@ -137,6 +138,11 @@ struct HostInstance {
   std::vector<double> Lcol, Lrow, D2inv;
   HostStream st;                         // streamed layout (built for problems large enough for the TMA kernel)
   HostPanels pn;                         // row-panel layout of the fused single-pass kernel (dense A, npad <= 512)
+  // guard of the explicit reduced inverse: largest relative difference, over a few probe right-hand sides, between a KKT
+  // solve through the panels (x~ = M b) and through the LDL' substitution; NaN when no panel layout was tried.  Above the
+  // threshold (1e-10, BQP_INVERSE_TOL) the panel layout is dropped and the problem runs on the LDL' kernels
+  double pn_inverse_error = NAN;
+  bool pn_rejected = false;
   long long factor_bytes() const {   // bytes one ADMM iteration streams: A', L fwd, L bwd, A, D2inv
     return (long long)(Lcol.size() + Lrow.size() + D2inv.size()) * 8 + At.stream_bytes() + Ab.stream_bytes();
   }

@@ -545,6 +545,34 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     const double density = (m > 0) ? (double)A.x.size() / ((double)m * n) : 1.0;
     if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density) build_panels(h, arows, prows, S);
   }
+  // The panel kernels apply M = (P + sigma I + A' rho A)^-1 explicitly; forming an inverse is not backward stable, and
+  // with a tiny sigma, a rank-deficient P or rows typed rho x 1e3 the reduced matrix can be badly conditioned.  Probe it:
+  // the same KKT right-hand sides through the panels and through the LDL' substitution (the oracle's path) must agree
+  h->pn_inverse_error = NAN; h->pn_rejected = false;
+  if (h->pn.built) {
+    double tol = 1e-10;
+    if (const char *e = std::getenv("BQP_INVERSE_TOL")) tol = std::atof(e);
+    double worst = 0.0;
+    std::vector<double> r1((size_t)n + m), r2((size_t)n + m);
+    for (int probe = 0; probe < 4; probe++) {
+      uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)(probe + 1);
+      for (int k = 0; k < n + m; k++) {
+        double v;
+        if (probe == 0) v = 1.0;
+        else if (probe == 1) v = (k & 1) ? -1.0 : 1.0;
+        else { st ^= st << 13; st ^= st >> 7; st ^= st << 17; v = (double)(st >> 11) / 9007199254740992.0 - 0.5; }
+        r1[(size_t)k] = r2[(size_t)k] = v;
+      }
+      host_kkt_solve(h, r1.data());
+      host_panel_kkt_solve(h, r2.data());
+      double nrm = 0.0, dif = 0.0;
+      for (int j = 0; j < n; j++) { nrm = std::max(nrm, std::fabs(r1[(size_t)j])); dif = std::max(dif, std::fabs(r1[(size_t)j] - r2[(size_t)j])); }
+      const double rel = dif / std::max(nrm, 1e-300);
+      worst = (rel == rel) ? std::max(worst, rel) : INFINITY;
+    }
+    h->pn_inverse_error = worst;
+    if (!(worst <= tol)) { h->pn = HostPanels(); h->pn_rejected = true; }
+  }
   return BQP_OK;
 }
 

@@ -107,7 +107,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_debug_host_panel_kkt_solve",
            "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
            "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device",
-           "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
+           "bqp_get_inverse_guard", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
 
 _lib = None
 
@@ -157,6 +157,7 @@ def lib():
         L.bqp_ctx_solve_multi.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, pp, pp, C.POINTER(_NodeOut)]
         L.bqp_ctx_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.bqp_handle_device.argtypes = [vp]
+        L.bqp_get_inverse_guard.argtypes = [vp, _dp, _ip]
         L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
                                     C.POINTER(_BnbResult), _ip, C.c_int]
         _lib = L
@@ -283,6 +284,13 @@ class BatchedQP(object):
         fb, cb = C.c_longlong(), C.c_longlong()
         _check(lib().bqp_get_dims(self._h, C.byref(n), C.byref(m), C.byref(npad), C.byref(fb), C.byref(cb)))
         return dict(n=n.value, m=m.value, npad=npad.value, factor_bytes=fb.value, check_bytes=cb.value)
+
+    def inverse_guard(self):
+        """(error, in_use): how well KKT solves through the explicit reduced inverse of the dense-A kernels agree with the LDL'
+        factor (largest relative difference over 4 probes), and whether the dense layout is in use (include/bqp.h)."""
+        err = C.c_double(); use = C.c_int()
+        _check(lib().bqp_get_inverse_guard(self._h, C.byref(err), C.byref(use)))
+        return err.value, bool(use.value)
 
     def scaling(self):
         D = np.empty(self.n); E = np.empty(self.m); c = C.c_double()

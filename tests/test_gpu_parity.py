@@ -339,3 +339,43 @@ def test_rounds_and_retiling_are_bit_identical(monkeypatch, kernel):
         assert np.array_equal(r0.status, r1.status) and np.array_equal(r0.iters, r1.iters)
         for a, b in ((r0.x, r1.x), (r0.y, r1.y), (r0.lower, r1.lower), (r0.obj, r1.obj), (r0.pri_res, r1.pri_res)):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+# ---------------------------------------------------------------- guard of the explicit reduced inverse
+def _ill_conditioned():
+    """sigma = 1e-6, P of rank n/4, 40 equality rows (rho x 1e3): the reduced matrix P + sigma I + A' rho A is badly scaled"""
+    import scipy.sparse as spa
+    n, m = 130, 200
+    rng = np.random.default_rng(0)
+    Pt = spa.random(n, n // 4, density=0.7, random_state=1)
+    P = spa.csc_matrix(Pt @ Pt.T)
+    A = spa.random(m, n, density=0.7, random_state=2, format='csc')
+    l = -1 + rng.random(m); u = 1 + rng.random(m)
+    l[:40] = u[:40] = 0.1 * rng.standard_normal(40)
+    return P, rng.standard_normal(n), A, l, u
+
+
+@pytest.mark.parametrize("branch", ["inverse", "ldl"])
+def test_inverse_guard_both_branches(oracle_mod, branch, monkeypatch):
+    """bqp_setup probes KKT solves through the explicit inverse against the LDL' factor; above the threshold the dense layout
+    is dropped and the problem runs on the LDL' (stream) kernel.  Both branches agree with the oracle on a badly scaled problem."""
+    if branch == "ldl":
+        monkeypatch.setenv("BQP_INVERSE_TOL", "1e-12")       # this problem probes at ~1e-11: rejected
+    P, q, A, l, u = _ill_conditioned()
+    n, m = 130, 200
+    e = engine.BatchedQP().setup(P, q, A, l, u, **QP)
+    err, in_use = e.inverse_guard()
+    assert 1e-13 < err < 1e-10 and in_use == (branch == "inverse")
+    rng = np.random.default_rng(5)
+    ls = np.tile(l, (6, 1)); us = np.tile(u, (6, 1))
+    for b in range(1, 6):                                      # a few rows tightened per node
+        rows = 40 + rng.choice(m - 40, size=5, replace=False)
+        us[b, rows] = ls[b, rows] + 0.5 * (us[b, rows] - ls[b, rows])
+    x0 = np.zeros((6, n)); y0 = np.zeros((6, m))
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+    xo, yo, so, io, extra = o.solve_batch(ls, us, x0, y0, threads=6)
+    r = e.solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["kernel"] == (3 if branch == "inverse" else 1)
+    assert list(r.status) == list(so) and list(r.iters) == list(io)
+    tol = 1e-9 if branch == "ldl" else 1e-7                    # the inverse carries its probed 1e-11 through ~1000 iterations
+    _close(r.x, xo, tol); _close(r.y, yo, tol)
