@@ -239,6 +239,11 @@ def main():
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--parallel-setup", action="store_true", help="(default now) bqp_setup_many: factorise the instances on all host threads")
     ap.add_argument("--serial-setup", action="store_true", help="one bqp_setup per instance")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "mpc"],
+                    help="cfg2 (default): BASELINE config 2, the headline; mpc: BASELINE config 3, the power-converter MPC closed loop "
+                         "(horizon 10, --mpc-steps sampling instants, warm-started), ms per MPC step and consumed QP/s, CPU oracle beside it")
+    ap.add_argument("--mpc-steps", type=int, default=1000)
+    ap.add_argument("--mpc-cpu-steps", type=int, default=40)
     ap.add_argument("--mode", default="both", choices=["both", "frontier", "bnb"],
                     help="frontier: the batched-frontier step (value, e2e, roofline); bnb: B&B to completion; both (default)")
     args = ap.parse_args()
@@ -254,6 +259,8 @@ def main():
         if rank != 0:
             return 0
         return reference_arm(args, cores, workload)
+    if args.workload == "mpc":
+        return mpc_workload(args, cores) if rank == 0 else 0
 
     import torch
     import torch.distributed as dist
@@ -503,6 +510,60 @@ def bnb_section(args, raw, qps, rank, world, cores, torch, dist):
         except Exception as e:      # never lose the bench line over the CPU arm
             out["cpu"] = {"error": repr(e)}
     return out
+
+
+def mpc_workload(args, cores):
+    """BASELINE config 3: examples/power_converter closed loop (power_converter.py:589-649), horizon N = 10, first
+    --mpc-steps sampling instants, every MIQP warm-started from the shifted previous plan (set_x0) and solved by the native
+    B&B replay with look-ahead on the engine.  CPU arm: the same loop, same replay, relaxations on the CPU oracle one at a
+    time (the reference's execution model), first --mpc-cpu-steps instants (the start-up transient: the heaviest steps)."""
+    import torch
+    from miosqp_b200 import power_converter as pc, engine
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU path")
+    pc.closed_loop(2, N=10, speculation=0, replay='native').solver.work.solver.free()        # CUDA context, first-launch costs
+    out = {"metric": "ms per MPC step (closed loop, horizon 10)", "unit": "ms", "higher_is_better": False, "n_gpus": 1, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": "power_converter MPC N=10, %d sampling instants, warm-started (BASELINE config 3)" % args.mpc_steps}}
+    runs = {}
+    for K in (128, 32):
+        t0 = time.perf_counter()
+        r = pc.closed_loop(args.mpc_steps if K == 128 else min(args.mpc_steps, args.mpc_cpu_steps), N=10, speculation=K, replay='native')
+        wall = time.perf_counter() - t0
+        w = r.solver.work
+        steps = len(r.status)
+        runs[K] = {"steps": steps, "ms_per_mpc_step": 1e3 * wall / steps, "qp_consumed": int(r.nodes.sum()), "qp_solved": int(w.batched_nodes),
+                   "qp_per_s_consumed": float(r.nodes.sum()) / wall, "launches_per_step": w.batches / float(steps),
+                   "admm_iters": int(r.admm_iters.sum()), "node_limit_steps": sum(s != 'Solved' for s in r.status),
+                   "mean_torque": float(r.torque.mean()), "switching_frequency_hz": r.switching_frequency}
+        if K == 128:
+            Ugpu = r.U.copy(); nodes_gpu = r.nodes.copy()
+        w.solver.free()
+    out["value"] = runs[128]["ms_per_mpc_step"]
+    out["lookahead_128"] = runs[128]; out["lookahead_32_first_steps"] = runs[32]
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ["FAKE_ENGINE_THREADS"] = "1"
+        import fake_engine                      # oracle-backed stand-in for the engine (test infrastructure): the CPU arm
+        real = (engine.BatchedQP, engine.solve_multi)
+        engine.BatchedQP, engine.solve_multi = fake_engine.FakeBatchedQP, fake_engine.solve_multi
+        try:
+            S = min(args.mpc_steps, args.mpc_cpu_steps)
+            t0 = time.perf_counter()
+            rc = pc.closed_loop(S, N=10, speculation=0, replay='native')
+            wall = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rg = None
+        finally:
+            engine.BatchedQP, engine.solve_multi = real
+        same = bool(np.array_equal(rc.U, Ugpu[:, :S]) and np.array_equal(rc.nodes, nodes_gpu[:S]))
+        out["cpu_baseline"] = {"value": 1e3 * wall / S, "unit": "ms per MPC step", "cores": 1, "kind": "port",
+                               "sample": "first %d sampling instants, native replay + CPU oracle, one relaxation at a time (the reference's "
+                                         "execution model), %.1f s" % (S, wall),
+                               "qp_per_s_consumed": float(rc.nodes.sum()) / wall, "qp_consumed": int(rc.nodes.sum()),
+                               "same_inputs_and_node_counts_as_gpu": same}
+        out["gpu_over_cpu_on_the_same_steps"] = out["cpu_baseline"]["value"] / runs[32]["ms_per_mpc_step"]
+    print(json.dumps(out))
+    return 0
 
 
 def reference_arm(args, cores, workload):

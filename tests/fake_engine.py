@@ -3,9 +3,13 @@ TEST-ONLY stand-in for the CUDA engine, backed by the CPU oracle, so the host-si
 (miosqp_b200/tree.py, miqp.py) can be exercised where there is no GPU.  It is installed by the
 `cpu_engine` fixture (monkeypatching miosqp_b200.engine); nothing in the product imports it.
 """
+import os
+
 import numpy as np
 
 from oracle import oracle
+
+THREADS = int(os.environ.get("FAKE_ENGINE_THREADS", "4"))      # bench.py's CPU arm sets 1: one relaxation at a time
 
 
 class Scalars(object):
@@ -40,7 +44,7 @@ class FakeBatchedQP(object):
                 arr = lambda pp, k, size: np.ctypeslib.as_array(pp[k], shape=(size,))
                 L = np.array([arr(l, b, m) for b in range(B)]); U = np.array([arr(u, b, m) for b in range(B)])
                 X0 = np.array([arr(x0, b, n) for b in range(B)]); Y0 = np.array([arr(y0, b, m) for b in range(B)])
-                xs, ys, st, it, _ = o.solve_batch(L, U, X0, Y0, threads=4)
+                xs, ys, st, it, _ = o.solve_batch(L, U, X0, Y0, threads=THREADS)
                 for b in range(B):
                     arr(x, b, n)[:] = xs[b]; arr(y, b, m)[:] = ys[b]; status[b] = int(st[b]); iters[b] = int(it[b])
                 return 0
@@ -60,7 +64,7 @@ class FakeBatchedQP(object):
 
 
 def solve_multi(qps, l, u, x0, y0):
-    xs, ys, st, it, _ = oracle.solve_multi([q.o for q in qps], l, u, x0, y0, threads=4)
+    xs, ys, st, it, _ = oracle.solve_multi([q.o for q in qps], l, u, x0, y0, threads=THREADS)
     sc = Scalars()
     sc.status = np.array(st); sc.iters = np.array(it)
     return xs, ys, sc
@@ -78,7 +82,7 @@ def native_solve_many_fn(qps):
             os_ = [oracles[k] for k in own]
             L = [np.array(arr(l, b, os_[b].m)) for b in range(B)]; U = [np.array(arr(u, b, os_[b].m)) for b in range(B)]
             X0 = [np.array(arr(x0, b, os_[b].n)) for b in range(B)]; Y0 = [np.array(arr(y0, b, os_[b].m)) for b in range(B)]
-            xs, ys, st, it, _ = oracle.solve_multi(os_, L, U, X0, Y0, threads=4)
+            xs, ys, st, it, _ = oracle.solve_multi(os_, L, U, X0, Y0, threads=THREADS)
             for b in range(B):
                 arr(x, b, os_[b].n)[:] = xs[b]; arr(y, b, os_[b].m)[:] = ys[b]; status[b] = int(st[b]); iters[b] = int(it[b])
             return 0

@@ -10,6 +10,7 @@ status, node count, total ADMM iterations, branching decisions).
 
     python tests/golden/make_mpc_golden.py
 """
+import hashlib
 import os
 import sys
 import types
@@ -18,7 +19,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-STEPS = 8
+STEPS = 120          # the first 8 with their full branching sequences (round 1), the rest with a sha256 of it
+FULL_DECISIONS = 8
 N_HORIZON = 10
 
 class _Stub(types.ModuleType):
@@ -82,7 +84,11 @@ def main():
         out["sol_%d" % k] = np.array(u_full, dtype=float)
         out["obj_%d" % k] = np.array(float(obj))
         out["stats_%d" % k] = np.array([w.iter_num, w.osqp_iter])
-        out["dec_%d" % k] = np.array(decisions, dtype=np.int64).reshape(-1, 2)
+        dec = np.array(decisions, dtype=np.int64).reshape(-1, 2)
+        if k < FULL_DECISIONS:
+            out["dec_%d" % k] = dec
+        out["dech_%d" % k] = np.frombuffer(hashlib.sha256(dec.tobytes()).digest(), dtype=np.uint8)
+        out["status_%d" % k] = np.array(str(w.status))
         print("step", k, "status", w.status, "obj %.6f" % obj, "nodes", w.iter_num - 1, "admm", w.osqp_iter, "branchings", len(decisions))
         x = np.asarray(model.simulate_one_step(x, u0)[0], dtype=float).flatten()
         u_prev = np.append(u_full[nu:], u_full[-nu:])
