@@ -136,6 +136,13 @@ int bqp_ctx_solve_multi(bqp_ctx ctx, int B, const bqp_handle *handles, const dou
                         const bqp_node_out *out);
 int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t);
 int bqp_ctx_free(bqp_ctx ctx);
+/* Dense-A problems normally run on a fixed cluster size chosen from the problem alone (2 CTAs per tile at n = 500), so that
+ * a node's result does not depend on what else is in the launch -- bit for bit.  on != 0 lets the context (NULL: the
+ * process-wide one) spread a tile over 4 or 8 CTAs whenever a launch holds few tiles (<= 33 / <= 16): the per-iteration
+ * latency drops from 80 us to 45 / ~25 us at n = 500, which is what a single B&B tree (two leaves per step) is bound by.
+ * The summation order of the column sums then depends on the schedule: results agree to rounding, not to the last bit.
+ * Rolling sessions (bqp_session_*) have it on by default; BQP_ROWS_AUTO_CLUSTER=0/1 overrides everything. */
+int bqp_ctx_set_auto_cluster(bqp_ctx ctx, int on);
 
 /* Rolling session on a context (ctx == NULL: the process-wide one): the resident batch is OPEN -- nodes are appended
  * while earlier ones are still iterating, every bqp_session_round is ONE launch (a round of 100 ADMM iterations over the

@@ -129,6 +129,7 @@ struct BatchCtx {
   std::vector<int> s_alive, s_progress; std::vector<double> s_dist, s_remaining;
   size_t s_in_d = 0, s_out_d = 0, s_st_d = 0;
   long long s_tile_iters = 0, s_bytes = 0; int s_launches = 0; double s_kernel_ms = 0;
+  bool auto_cluster_default = false;   // what closed batches (bqp_solve_multi on this context) use; bqp_ctx_set_auto_cluster
   bool auto_cluster = false;    // rows kernel: clusters of 4 when the round holds few tiles (results then depend on the schedule in the last bits)
   int round_override = -1;      // >= 0: rounds of that many ADMM iterations (0 = run every tile to completion) whatever BQP_ROUND_ITERS says
   bool blocking_sync = false;   // wait on a blocking event instead of spinning (many contexts driven by many host threads)
@@ -351,7 +352,9 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     bool wide = false, even = true, quad = true;
     for (int b : alive) { const int nw = g.node_inst[b]->h.pn.nw; wide = wide || nw > kPanelCtaWarps; even = even && nw % 2 == 0; quad = quad && nw % 4 == 0; }
     cs = (wide && even) ? 2 : 1;
-    if (const char *e = std::getenv("BQP_ROWS_CLUSTER")) { const int v = std::atoi(e); if (v == 1 || (v == 2 && even) || (v == 4 && quad)) cs = v; }
+    bool oct8 = quad;
+    for (int b : alive) oct8 = oct8 && g.node_inst[b]->h.pn.nw % 8 == 0;
+    if (const char *e = std::getenv("BQP_ROWS_CLUSTER")) { const int v = std::atoi(e); if (v == 1 || (v == 2 && even) || (v == 4 && quad) || (v == 8 && oct8)) cs = v; }
   } else if (use_panel) {
     for (int b : alive) if (g.node_inst[b]->h.pn.nw > kPanelCtaWarps) cs = 2;
     if (const char *e = std::getenv("BQP_PANEL_CLUSTER")) { const int v = std::atoi(e); if (v == 2 || (v == 1 && cs == 1)) cs = v; }
@@ -363,7 +366,10 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       const long long fixed = (long long)rows_smem_bytes(h.npad, 0, cs) + 256, sb = (long long)h.pn.nw * kPanelRows * 32 * 8;
       long long cap = 8;
       if (const char *e = std::getenv("BQP_ROWS_SLOTS")) cap = std::max(2, std::atoi(e));
-      return (int)std::min<long long>(cap, ((long long)kMaxSmem - fixed) / sb);
+      // a multiple of the groups per CTA: every ring slot then belongs to ONE group for the whole launch.  (With 3 slots and
+      // 2 groups a group waits on the parity of a slot whose previous phase belongs to the other group: the wait can alias.)
+      const long long ns = std::min<long long>(cap, ((long long)kMaxSmem - fixed) / sb);
+      return (int)(ns - ns % kRowsGroups);
     }
     const long long fixed = (long long)panel_smem_bytes(h.npad, 0, cs) + 256;
     const long long sb = (long long)(cs == 2 ? (h.pn.nw + 1) / 2 : h.pn.nw) * kPanelRows * 32 * 8;
@@ -409,7 +415,11 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     long long nt = 0;
     for (auto &mb : members) nt += ((long long)mb.size() + kPanelT - 1) / kPanelT;
     const int cap4 = (ndev_sms - 16) / 4;     // clusters of 4 cannot use every SM of every GPC (measured: 33 at a time on 148 SMs)
-    if (quad && nt <= cap4) { cs = 4; g.cs = 4; capacity = cap4; }
+    bool oct = quad;
+    for (auto *inst : uniq) oct = oct && inst->h.pn.nw % 8 == 0;
+    const int cap8 = 8;                       // clusters of 8: 16 of them took two waves (measured), 8 run at once
+    if (oct && nt <= cap8) { cs = 8; g.cs = 8; capacity = cap8; }
+    else if (quad && nt <= cap4) { cs = 4; g.cs = 4; capacity = cap4; }
   }
   const int slot_bytes = g.stage_bytes;
   if (use_panel && !use_rows && cs == 1)
@@ -574,7 +584,7 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
   }
   g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
   g.session = false;
-  g.auto_cluster = false;
+  g.auto_cluster = g.auto_cluster_default;
   if (const char *e = std::getenv("BQP_ROWS_AUTO_CLUSTER")) g.auto_cluster = std::atoi(e) != 0;
   select_kernel(g);
   if ((rc = g.h_in.reserve(in_d * 8, g.stream))) return rc;
@@ -914,6 +924,11 @@ int bqp_session_fetch(bqp_ctx ctx, int id, double *x, double *y, const bqp_node_
     if (out->lower) out->lower[0] = r.lower;
   }
   g.timing.node_iters += r.iters;
+  return BQP_OK;
+}
+int bqp_ctx_set_auto_cluster(bqp_ctx ctx, int on) {
+  BatchCtx &g = ctx ? ctx->c : g0;
+  g.auto_cluster_default = on != 0;
   return BQP_OK;
 }
 int bqp_ctx_last_timing(bqp_ctx ctx, bqp_timing *t) {

@@ -1009,6 +1009,7 @@ int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_i
   if (cs == 1) return launch_r<1>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
   if (cs == 2) return launch_r<2>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
   if (cs == 4) return launch_r<4>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  if (cs == 8) return launch_r<8>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
   return BQP_E_ARG;
 }
 

@@ -107,7 +107,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_debug_host_panel_kkt_solve",
            "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
            "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device",
-           "bqp_get_inverse_guard", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
+           "bqp_get_inverse_guard", "bqp_ctx_set_auto_cluster", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
 
 _lib = None
 
@@ -157,6 +157,7 @@ def lib():
         L.bqp_ctx_solve_multi.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, pp, pp, C.POINTER(_NodeOut)]
         L.bqp_ctx_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.bqp_handle_device.argtypes = [vp]
+        L.bqp_ctx_set_auto_cluster.argtypes = [vp, C.c_int]
         L.bqp_get_inverse_guard.argtypes = [vp, _dp, _ip]
         L.bqp_bnb_solve.argtypes = [vp, C.POINTER(_Problem), C.POINTER(_BnbSettings), _dp, C.c_double, C.c_void_p, vp, _dp,
                                     C.POINTER(_BnbResult), _ip, C.c_int]
@@ -212,6 +213,12 @@ def normalize_settings(kw):
 
 def set_tuning(tile_nodes=0, threads=0):
     _check(lib().bqp_set_tuning(int(tile_nodes), int(threads)))
+
+
+def set_auto_cluster(on, ctx=None):
+    """Let launches with few tiles spread each tile over 4 or 8 CTAs (include/bqp.h bqp_ctx_set_auto_cluster): lower
+    per-iteration latency for single trees, results equal to rounding instead of bit for bit.  ctx None: the default context."""
+    _check(lib().bqp_ctx_set_auto_cluster(ctx._c if ctx is not None else None, 1 if on else 0))
 
 
 def device_count():
@@ -407,12 +414,23 @@ def bnb_solve(qp, data, settings, eps_abs, x_incumbent=None, upper_incumbent=np.
     cap = max(1, int(settings['max_iter_bb']))
     dec = np.zeros(2 * cap, dtype=np.int32)
     xin = _f64(x_incumbent) if x_incumbent is not None and np.isfinite(upper_incumbent) else None
-    rc = lib().bqp_bnb_solve(handle, C.byref(prob), C.byref(st), _d(xin) if xin is not None else None, float(upper_incumbent),
-                             C.cast(fn, C.c_void_p) if fn is not None else None, None, _d(x), C.byref(res), _i(dec), cap)
+    auto = fn is None and bool(settings.get('cluster_auto', True))
+    if auto:        # a single tree offers two leaves per step: spread its one tile over more SMs (see set_auto_cluster)
+        set_auto_cluster(True)
+    try:
+        rc = _bnb_solve_call(handle, prob, st, xin, upper_incumbent, fn, x, res, dec, cap)
+    finally:
+        if auto:
+            set_auto_cluster(False)
     _check(rc)
     out = {k: getattr(res, k) for k, _ in _BnbResult._fields_}
     decisions = [(int(dec[2 * k]), int(dec[2 * k + 1])) for k in range(min(res.n_decisions, cap))]
     return x, out, decisions
+
+
+def _bnb_solve_call(handle, prob, st, xin, upper_incumbent, fn, x, res, dec, cap):
+    return lib().bqp_bnb_solve(handle, C.byref(prob), C.byref(st), _d(xin) if xin is not None else None, float(upper_incumbent),
+                             C.cast(fn, C.c_void_p) if fn is not None else None, None, _d(x), C.byref(res), _i(dec), cap)
 
 
 def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents, many_fn=None, async_threads=None, rolling=False):

@@ -233,9 +233,9 @@ def test_panel_kernel_cluster_pair_cfg2_cold(oracle_mod, dense_kernel):
     expect_dense(dense_kernel, 500)
 
 
-@pytest.mark.parametrize("cs", [1, 2, 4])
+@pytest.mark.parametrize("cs", [1, 2, 4, 8])
 def test_rows_kernel_cluster_sizes(oracle_mod, cs, monkeypatch):
-    """row-split kernel on 1, 2 and 4 CTAs per tile (cfg 2 shape, warm and cold start, max_iter path): the per-iteration
+    """row-split kernel on 1, 2, 4 and 8 CTAs per tile (cfg 2 shape, warm and cold start, max_iter path): the per-iteration
     DSMEM exchange (x~ all-gather, reduce-scatter of A'w, all-gather of b') and the global-memory check path"""
     monkeypatch.setenv("BQP_ROWS_CLUSTER", str(cs))
     pr = problems.random_miqp(500, 1000, 50, 0.7, seed=3)[0]
