@@ -143,6 +143,9 @@ int bqp_ctx_free(bqp_ctx ctx);
  * The summation order of the column sums then depends on the schedule: results agree to rounding, not to the last bit.
  * Rolling sessions (bqp_session_*) have it on by default; BQP_ROWS_AUTO_CLUSTER=0/1 overrides everything. */
 int bqp_ctx_set_auto_cluster(bqp_ctx ctx, int on);
+/* the context shares the device with `parts` - 1 other contexts that are busy at the same time: it plans at most 1 / parts
+ * of the SMs per launch (rounds, automatic cluster sizes) */
+int bqp_ctx_set_sm_share(bqp_ctx ctx, int parts);
 
 /* Rolling session on a context (ctx == NULL: the process-wide one): the resident batch is OPEN -- nodes are appended
  * while earlier ones are still iterating, every bqp_session_round is ONE launch (a round of 100 ADMM iterations over the
@@ -208,11 +211,13 @@ int bqp_bnb_solve_async(int count, const bqp_handle *h, const bqp_problem *const
                         const double *const *x_incumbent, const double *upper_incumbent, double *const *x, bqp_bnb_result *res,
                         int *const *decisions, int decisions_cap, int threads);
 
-/* rolling variant (one context, one stream): all trees share a bqp_session; after every round the trees whose outstanding
- * leaves have all terminated are replayed and their new leaves appended.  Each tree's result equals its own bqp_bnb_solve. */
+/* rolling variant: the trees share a bqp_session; after every round the trees whose outstanding leaves have all terminated
+ * are replayed and their new leaves appended.  sessions > 1 deals the trees to that many sessions (own context, stream and
+ * host thread each), so that one session's host replay overlaps the others' rounds (<= 0: one session, the measured best).  Each tree's result
+ * equals its own bqp_bnb_solve up to the rounding of the cluster size (bqp_ctx_set_auto_cluster). */
 int bqp_bnb_solve_rolling(int count, const bqp_handle *h, const bqp_problem *const *p, const bqp_bnb_settings *s,
                           const double *const *x_incumbent, const double *upper_incumbent, double *const *x, bqp_bnb_result *res,
-                          int *const *decisions, int decisions_cap, int *rounds);
+                          int *const *decisions, int decisions_cap, int *rounds, int sessions);
 
 /* tuning knobs (0 = automatic): nodes per tile (1,2,4,8) and threads per CTA (multiple of 32, <= 512) */
 int bqp_set_tuning(int tile_nodes, int threads);

@@ -129,6 +129,7 @@ struct BatchCtx {
   std::vector<int> s_alive, s_progress; std::vector<double> s_dist, s_remaining;
   size_t s_in_d = 0, s_out_d = 0, s_st_d = 0;
   long long s_tile_iters = 0, s_bytes = 0; int s_launches = 0; double s_kernel_ms = 0;
+  int sm_parts = 1;                    // this context plans for 1 / sm_parts of the SMs (other contexts are busy beside it)
   bool auto_cluster_default = false;   // what closed batches (bqp_solve_multi on this context) use; bqp_ctx_set_auto_cluster
   bool auto_cluster = false;    // rows kernel: clusters of 4 when the round holds few tiles (results then depend on the schedule in the last bits)
   int round_override = -1;      // >= 0: rounds of that many ADMM iterations (0 = run every tile to completion) whatever BQP_ROUND_ITERS says
@@ -340,6 +341,9 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
                       std::vector<int> *scheduled) {
   int ndev_sms = 148;
   cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, g.device);
+  const int all_sms = ndev_sms;
+  ndev_sms = std::max(8, ndev_sms / g.sm_parts);
+  (void)all_sms;
   const bool use_stream = g.use_stream, use_panel = g.use_panel, w_in_stage = g.w_in_stage;
   const bool rounds = (use_stream || use_panel) && g.round_iters > 0;
   // panel kernel: problems wider than one CTA's consumer warps run as cluster pairs (2 SMs per tile)
@@ -414,10 +418,10 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     for (auto *inst : uniq) quad = quad && inst->h.pn.nw % 4 == 0;
     long long nt = 0;
     for (auto &mb : members) nt += ((long long)mb.size() + kPanelT - 1) / kPanelT;
-    const int cap4 = (ndev_sms - 16) / 4;     // clusters of 4 cannot use every SM of every GPC (measured: 33 at a time on 148 SMs)
+    const int cap4 = (all_sms - 16) / 4 / g.sm_parts;     // clusters of 4 cannot use every SM of every GPC (measured: 33 at a time on 148 SMs)
     bool oct = quad;
     for (auto *inst : uniq) oct = oct && inst->h.pn.nw % 8 == 0;
-    const int cap8 = 8;                       // clusters of 8: 16 of them took two waves (measured), 8 run at once
+    const int cap8 = 8 / g.sm_parts;          // clusters of 8: 16 of them took two waves (measured), 8 run at once
     if (oct && nt <= cap8) { cs = 8; g.cs = 8; capacity = cap8; }
     else if (quad && nt <= cap4) { cs = 4; g.cs = 4; capacity = cap4; }
   }
@@ -924,6 +928,11 @@ int bqp_session_fetch(bqp_ctx ctx, int id, double *x, double *y, const bqp_node_
     if (out->lower) out->lower[0] = r.lower;
   }
   g.timing.node_iters += r.iters;
+  return BQP_OK;
+}
+int bqp_ctx_set_sm_share(bqp_ctx ctx, int parts) {
+  BatchCtx &g = ctx ? ctx->c : g0;
+  g.sm_parts = parts < 1 ? 1 : parts;
   return BQP_OK;
 }
 int bqp_ctx_set_auto_cluster(bqp_ctx ctx, int on) {

@@ -107,7 +107,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_debug_host_panel_kkt_solve",
            "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
            "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device",
-           "bqp_get_inverse_guard", "bqp_ctx_set_auto_cluster", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
+           "bqp_get_inverse_guard", "bqp_ctx_set_auto_cluster", "bqp_ctx_set_sm_share", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
 
 _lib = None
 
@@ -147,7 +147,8 @@ def lib():
         L.bqp_bnb_solve_async.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp,
                                           _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, C.c_int]
         L.bqp_bnb_solve_rolling.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp,
-                                            _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, _ip]
+                                            _pp_d, C.POINTER(_BnbResult), C.POINTER(_ip), C.c_int, _ip, C.c_int]
+        L.bqp_ctx_set_sm_share.argtypes = [vp, C.c_int]
         L.bqp_session_begin.argtypes = [vp]
         L.bqp_session_append.argtypes = [vp, C.c_int, pp, pp, pp, pp, pp, _ip]
         L.bqp_session_round.argtypes = [vp, _ip, C.c_int, _ip, _ip]
@@ -455,7 +456,8 @@ def bnb_solve_many(qps, datas, settings, eps_abs, x_incumbents, upper_incumbents
     if rolling and many_fn is None:
         # one engine session shared by all trees: a tree whose leaves have terminated rejoins the next round (bqp_bnb_solve_rolling)
         nr = C.c_int(0)
-        rc = lib().bqp_bnb_solve_rolling(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, C.byref(nr))
+        rc = lib().bqp_bnb_solve_rolling(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, C.byref(nr),
+                                         int(rolling) if rolling is not True else 0)
     elif async_threads is not None and many_fn is None:
         rc = lib().bqp_bnb_solve_async(count, handles, pptr, sts, xin_ptrs, _d(uppers), x_ptrs, res, dec_ptrs, cap, int(async_threads))
     else:

@@ -56,3 +56,4 @@ extern "C" int bqp_session_append(bqp_ctx, int, const bqp_handle *, const double
                                   const double *const *, int *) { return BQP_E_CUDA; }
 extern "C" int bqp_session_round(bqp_ctx, int *, int, int *, int *) { return BQP_E_CUDA; }
 extern "C" int bqp_session_fetch(bqp_ctx, int, double *, double *, const bqp_node_out *) { return BQP_E_CUDA; }
+extern "C" int bqp_ctx_set_sm_share(bqp_ctx, int) { return BQP_OK; }

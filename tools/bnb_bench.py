@@ -47,7 +47,10 @@ def main():
             s.work.reset(); s.work.first_run = 0
             s.work.batches = s.work.batched_nodes = s.work.spec_nodes = s.work.spec_hits = 0
         t0 = time.perf_counter()
-        res = miosqp_b200.solve_many(solvers, async_threads=(a.threads if mode == "async" else None), rolling=(mode == "rolling"))
+        roll = False
+        if mode.startswith("rolling"):              # rolling = automatic number of sessions, rolling1 / rolling2 / ... = that many
+            roll = int(mode[7:]) if mode[7:] else True
+        res = miosqp_b200.solve_many(solvers, async_threads=(a.threads if mode == "async" else None), rolling=roll)
         wall = time.perf_counter() - t0
         works = [s.work for s in solvers]
         consumed = sum(w.iter_num - 1 for w in works)
