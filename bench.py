@@ -239,9 +239,11 @@ def main():
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--parallel-setup", action="store_true", help="(default now) bqp_setup_many: factorise the instances on all host threads")
     ap.add_argument("--serial-setup", action="store_true", help="one bqp_setup per instance")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "mpc"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "mpc", "cfg4"],
                     help="cfg2 (default): BASELINE config 2, the headline; mpc: BASELINE config 3, the power-converter MPC closed loop "
-                         "(horizon 10, --mpc-steps sampling instants, warm-started), ms per MPC step and consumed QP/s, CPU oracle beside it")
+                         "(horizon 10, --mpc-steps sampling instants, warm-started), ms per MPC step and consumed QP/s, CPU oracle beside it; "
+                         "cfg4: BASELINE config 4, one n=2000 m=4000 |i_idx|=200 MIQP (5 %% dense), B&B cut at --cfg4-nodes nodes")
+    ap.add_argument("--cfg4-nodes", type=int, default=40)
     ap.add_argument("--mpc-steps", type=int, default=1000)
     ap.add_argument("--mpc-cpu-steps", type=int, default=40)
     ap.add_argument("--mode", default="both", choices=["both", "frontier", "bnb"],
@@ -261,6 +263,8 @@ def main():
         return reference_arm(args, cores, workload)
     if args.workload == "mpc":
         return mpc_workload(args, cores) if rank == 0 else 0
+    if args.workload == "cfg4":
+        return cfg4_workload(args, cores) if rank == 0 else 0
 
     import torch
     import torch.distributed as dist
@@ -562,6 +566,76 @@ def mpc_workload(args, cores):
                                "qp_per_s_consumed": float(rc.nodes.sum()) / wall, "qp_consumed": int(rc.nodes.sum()),
                                "same_inputs_and_node_counts_as_gpu": same}
         out["gpu_over_cpu_on_the_same_steps"] = out["cpu_baseline"]["value"] / runs[32]["ms_per_mpc_step"]
+    print(json.dumps(out))
+    return 0
+
+
+def cfg4_workload(args, cores):
+    """BASELINE config 4 on ONE GPU: random_miqp n=2000 m=4000 |i_idx|=200 density 0.05, the reference's B&B cut at
+    --cfg4-nodes nodes (its own max_iter_bb), native replay.  The tree offers two leaves per step (one tile of the TMA-streamed
+    two-sweep kernel, one CTA): the figure that matters is the time per ADMM iteration of that tile, reported with the factor
+    bytes one iteration streams (L2-resident) and the SURVEY 8d algorithmic bytes.  CPU arm: the same B&B on the oracle."""
+    import torch
+    import scipy.sparse as spa
+    from miosqp_b200 import engine, problems, miqp
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU path")
+    n, m, p, dens = 2000, 4000, 200, 0.05
+    raw = problems.random_miqp(n, m, p, dens, seed=1)
+    st = dict(problems.RANDOM_MIQP_SETTINGS, replay='native', max_iter_bb=args.cfg4_nodes)
+    t0 = time.perf_counter()
+    solver = miqp.setup_many(raw, st, dict(problems.RANDOM_MIQP_QP_SETTINGS))[0]
+    t_setup = time.perf_counter() - t0
+    runs = []
+    for rep in range(2):        # first run warms the context up
+        solver.work.reset(); solver.work.first_run = 0
+        solver.work.batches = solver.work.batched_nodes = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = solver.solve()
+        torch.cuda.synchronize()
+        runs.append(time.perf_counter() - t0)
+    w = solver.work
+    wall = runs[-1]
+    nodes, iters = w.iter_num - 1, int(w.osqp_iter)
+    dims = w.solver.dims()
+    P, q, A, l, u, i_idx = problems.extend(raw[0])
+    nnzA, nnz_triuP = A.nnz, spa.triu(P).nnz
+    nnzL = nnzA + n * (n - 1) // 2                      # constraints-first elimination: A' A fills the trailing block
+    N = n + A.shape[0]
+    T = 2
+    alg = 8.0 * (2 * n + 6 * A.shape[0]) + (24.0 * nnzL + 16.0 * N) / T + 12.0 * (2 * nnzA + nnz_triuP) / 25 / T
+    # every step holds the two children: the step's tile runs max(iters of the two) iterations; approximate the tile-iterations by
+    # half the node-iterations (siblings need similar counts) -- reported as such
+    tile_iters = iters / 2.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"metric": "QP-relaxations/sec", "value": nodes / wall, "unit": "QP/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f64",
+           "data": "synthetic", "vs_baseline": None,
+           "config": {"workload": "random_miqp n=2000 m=4000 |i_idx|=200 density=0.05 (BASELINE config 4), one tree, B&B cut at %d nodes, "
+                                  "native replay, 1 GPU" % args.cfg4_nodes, "qp_settings": QP_SETTINGS},
+           "status": r.status, "qp_consumed": nodes, "admm_iters": iters, "launches": int(w.batches), "wall_s": wall, "setup_s": t_setup,
+           "us_per_admm_iteration_of_the_tile": 1e6 * wall / max(1.0, tile_iters),
+           "e2e": {"value": nodes / wall, "unit": "QP/s", "note": "host buffers, replay and copies inside (the B&B loop has no device-resident variant)"},
+           "roofline": {"bound": "hbm", "kernel": "admm_stream_kernel (one CTA per tile, two leaves)", "unit": "GB/s", "peak": peak,
+                        "algorithmic_bytes_per_node_iter": alg, "achieved": alg * iters / wall / 1e9, "frac": alg * iters / wall / 1e9 / peak,
+                        "streamed_factor_bytes_per_tile_iteration": int(dims["factor_bytes"]),
+                        "streamed_gbs_into_one_sm": dims["factor_bytes"] * tile_iters / wall / 1e9, "traffic": None,
+                        "note": "one tile = one CTA = one SM streams the 28.8 MB factor + A twice per iteration out of L2 (126 MB): the "
+                                "kernel is bound by what one SM can pull, not by HBM; 147 SMs idle.  A multi-CTA kernel for one large tile "
+                                "is the next step (DESIGN section 9)"}}
+    if not args.no_cpu_baseline:
+        try:
+            secs, cn, cits, outs = bnb_cpu(raw, 1, 1, max_iter_bb=args.cfg4_nodes)
+            out["cpu_baseline"] = {"value": cn / secs, "unit": "QP/s", "cores": 1, "kind": "port",
+                                   "sample": "the same B&B (cut at %d nodes) on the CPU oracle, one relaxation at a time, %.1f s" % (args.cfg4_nodes, secs),
+                                   "admm_node_iters_per_s": cits / secs, "same_node_and_iteration_counts_as_gpu": bool(cn == nodes and cits == iters)}
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(out))
     return 0
 
