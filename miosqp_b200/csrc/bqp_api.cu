@@ -114,8 +114,9 @@ struct BatchCtx {
   int B = 0, ntiles = 0, tt = 0, threads = 0;
   bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
   int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
-  std::vector<long long> in_off, state_off;
-  Buf d_state;
+  std::vector<long long> in_off, state_off, corr_off;
+  Buf d_state, d_corr;
+  size_t corr_d = 0;             // doubles used in d_corr
   size_t smem = 0, in_doubles = 0, out_doubles = 0;
   std::vector<bqp_instance *> node_inst;
   std::vector<long long> out_off;
@@ -125,6 +126,7 @@ struct BatchCtx {
   bqp_timing timing{};
   bool resident = false, ran = false;
   // rolling session (bqp_session_*): nodes are appended while others are still iterating
+  bool eq2_unsupported = false;   // a problem set up with eq_rho == 2 would run on a kernel without the Woodbury correction
   bool session = false;
   std::vector<int> s_alive, s_progress; std::vector<double> s_dist, s_remaining;
   size_t s_in_d = 0, s_out_d = 0, s_st_d = 0;
@@ -151,7 +153,7 @@ void ctx_release(BatchCtx &g) {
   if (!g.stream) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state}) b->release(g.stream);
+  for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state, &g.d_corr}) b->release(g.stream);
   cudaStreamSynchronize(g.stream);
   for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
   if (g.ev_block) { cudaEventDestroy(g.ev_block); g.ev_block = nullptr; }
@@ -207,6 +209,8 @@ int to_device(bqp_instance *inst) {
     d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
     d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
   }
+  d.p_mint = nullptr; d.eq2 = h.s.eq_rho == 2 ? 1 : 0; d.rho_base = h.s.rho;
+  if (d.eq2) ar.add(h.mint, &d.p_mint);
   int rc = ar.commit(inst);
   if (rc) return rc;
   inst->d_q = const_cast<double *>(d.q);
@@ -493,6 +497,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       for (int q = lo; q < hi; q++) {
         const int b = members[k][q];
         t.node[q - lo] = b; t.in_off[q - lo] = g.in_off[b]; t.out_off[q - lo] = g.out_off[b]; t.state_off[q - lo] = g.state_off[b];
+        t.corr_off[q - lo] = (size_t)b < g.corr_off.size() ? g.corr_off[b] : -1;
         scheduled->push_back(b);
       }
       t.work_off = (long long)work_d;
@@ -515,6 +520,77 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
   CK(ctx_sync(g));   // tiles / dinst are stack-lifetime host memory
   g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
+  return BQP_OK;
+}
+
+// eq_rho == 2 (per-node rho typing, osqp >= 0.4 update_bounds): a node whose integer-bound rows fall into another rho class
+// than at setup (a branched binary variable: l = u, rho x 1e3) changes the reduced KKT matrix by a DIAGONAL term -- the
+// integer rows of A_ext are rows of the identity (data.py:5-33) -- K_node = K + sum_{j in S} delta_j e_j e_j'.  The explicit
+// inverse is corrected by Woodbury:  K_node^-1 = M - M[:,S] G M[S,:],  G = (diag(1/delta) + M_SS)^-1  (|S| <= depth).
+// Per node the kernel gets S and G; M[:,S] = rows of M (symmetric) kept per problem (DevInstance::p_mint).
+// Appends the blocks of nodes [first, first + count) to the context's correction buffer.
+static int build_corrections(BatchCtx &g, int first, int count, const bqp_handle *handles, const double *const *l, const double *const *u) {
+  std::vector<double> stage;
+  const size_t base = g.corr_d;
+  g.corr_off.resize((size_t)first + count, -1);
+  for (int b = 0; b < count; b++) {
+    const HostInstance &h = handles[b]->h;
+    g.corr_off[(size_t)first + b] = -1;
+    if (h.s.eq_rho != 2) continue;
+    const int m = h.m, ni = h.n_int;
+    auto cls = [&](int i, double lo, double up) {
+      lo = std::max(lo, -kInfty) * h.E[i]; up = std::min(up, kInfty) * h.E[i];
+      if (lo < -kInfty * kMinScaling && up > kInfty * kMinScaling) return kRhoMin;
+      if (up - lo < kRhoTol) return kRhoEqFactor * h.s.rho;
+      return h.s.rho;
+    };
+    for (int i = 0; i < m - ni; i++)
+      if (cls(i, l[b][i], u[b][i]) != h.rho[i]) return BQP_E_UNSUPPORTED;     // only the integer-bound rows may change class
+    std::vector<int> ks; std::vector<double> delta;
+    for (int k = 0; k < ni; k++) {
+      const int i = m - ni + k, j = h.i_idx[k];
+      const double r = cls(i, l[b][i], u[b][i]);
+      if (r == h.rho[i]) continue;
+      const double a = h.E[i] * h.D[j];                // the scaled entry of the identity row
+      ks.push_back(k); delta.push_back((r - h.rho[i]) * a * a);
+    }
+    const int nS = (int)ks.size();
+    if (nS == 0) continue;
+    if (nS > 64) return BQP_E_UNSUPPORTED;             // the kernel's per-node scratch (bqp_rows.cu kMaxS)
+    // G = (diag(1/delta) + M_SS)^-1 by Gauss-Jordan with partial pivoting (nS <= n_int)
+    std::vector<double> Wm((size_t)nS * 2 * nS, 0.0);
+    for (int a = 0; a < nS; a++) {
+      for (int c = 0; c < nS; c++) Wm[(size_t)a * 2 * nS + c] = host_panel_M(&h, h.i_idx[ks[a]], h.i_idx[ks[c]]);
+      Wm[(size_t)a * 2 * nS + a] += 1.0 / delta[a];
+      Wm[(size_t)a * 2 * nS + nS + a] = 1.0;
+    }
+    for (int c = 0; c < nS; c++) {
+      int piv = c;
+      for (int a = c + 1; a < nS; a++) if (std::fabs(Wm[(size_t)a * 2 * nS + c]) > std::fabs(Wm[(size_t)piv * 2 * nS + c])) piv = a;
+      if (Wm[(size_t)piv * 2 * nS + c] == 0.0) return BQP_E_NONCONVEX;
+      if (piv != c) for (int e = 0; e < 2 * nS; e++) std::swap(Wm[(size_t)piv * 2 * nS + e], Wm[(size_t)c * 2 * nS + e]);
+      const double inv = 1.0 / Wm[(size_t)c * 2 * nS + c];
+      for (int e = 0; e < 2 * nS; e++) Wm[(size_t)c * 2 * nS + e] *= inv;
+      for (int a = 0; a < nS; a++) {
+        if (a == c) continue;
+        const double f = Wm[(size_t)a * 2 * nS + c];
+        if (f == 0.0) continue;
+        for (int e = 0; e < 2 * nS; e++) Wm[(size_t)a * 2 * nS + e] -= f * Wm[(size_t)c * 2 * nS + e];
+      }
+    }
+    g.corr_off[(size_t)first + b] = (long long)(base + stage.size());
+    stage.push_back((double)nS);
+    for (int a = 0; a < nS; a++) stage.push_back((double)ks[a]);
+    for (int a = 0; a < nS; a++) stage.push_back((double)h.i_idx[ks[a]]);
+    for (int a = 0; a < nS; a++)
+      for (int c = 0; c < nS; c++) stage.push_back(0.5 * (Wm[(size_t)a * 2 * nS + nS + c] + Wm[(size_t)c * 2 * nS + nS + a]));   // symmetrised
+  }
+  if (stage.empty()) return BQP_OK;
+  int rc;
+  if ((rc = g.d_corr.reserve_keep((base + stage.size()) * 8, base * 8, g.stream))) return rc;
+  CK(cudaMemcpyAsync((double *)g.d_corr.p + base, stage.data(), stage.size() * 8, cudaMemcpyHostToDevice, g.stream));
+  CK(ctx_sync(g));        // `stage` is pageable stack-lifetime memory
+  g.corr_d = base + stage.size();
   return BQP_OK;
 }
 
@@ -549,6 +625,8 @@ static void select_kernel(BatchCtx &g) {
     if (h.s.check_termination != check0) g.round_ok = false;
     want = std::max(want, std::max(h.Ab.nslices, h.At.nslices));
   }
+  g.eq2_unsupported = false;
+  for (bqp_instance *inst : g.node_inst) if (inst->h.s.eq_rho == 2 && !(g.use_panel && g.use_rows)) g.eq2_unsupported = true;
   if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
   g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
@@ -588,9 +666,12 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
   }
   g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
   g.session = false;
+  g.corr_d = 0; g.corr_off.clear();
+  if ((rc = build_corrections(g, 0, B, handles, l, u))) return rc;
   g.auto_cluster = g.auto_cluster_default;
   if (const char *e = std::getenv("BQP_ROWS_AUTO_CLUSTER")) g.auto_cluster = std::atoi(e) != 0;
   select_kernel(g);
+  if (g.eq2_unsupported) return BQP_E_UNSUPPORTED;
   if ((rc = g.h_in.reserve(in_d * 8, g.stream))) return rc;
   if ((rc = g.h_out.reserve(out_d * 8, g.stream))) return rc;
   if ((rc = g.h_ns.reserve(sizeof(NodeScalars) * (size_t)B, g.stream))) return rc;
@@ -633,7 +714,7 @@ static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &pro
   rc = (g.use_panel && g.use_rows)
            ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
                               (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
-                              g.smem, g.stream)
+                              g.smem, (const double *)g.d_corr.p, g.stream)
        : g.use_panel
            ? launch_admm_panel(g.cs, g.nw_max, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p,
                                g.ntiles, (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
@@ -729,6 +810,7 @@ static int session_begin(BatchCtx &g) {
   g.B = 0; g.node_inst.clear(); g.in_off.clear(); g.out_off.clear(); g.state_off.clear();
   g.s_alive.clear(); g.s_progress.clear(); g.s_dist.clear(); g.s_remaining.clear();
   g.s_in_d = g.s_out_d = g.s_st_d = 0;
+  g.corr_d = 0; g.corr_off.clear();
   g.s_tile_iters = g.s_bytes = 0; g.s_launches = 0; g.s_kernel_ms = 0;
   g.timing = bqp_timing{};
   return BQP_OK;
@@ -761,6 +843,8 @@ static int session_append(BatchCtx &g, int B, const bqp_handle *handles, const d
   g.B = B0 + B; g.s_in_d = in_d; g.s_out_d = out_d; g.s_st_d = st_d;
   g.in_doubles = in_d; g.out_doubles = out_d;
   select_kernel(g);
+  if (g.eq2_unsupported) return BQP_E_UNSUPPORTED;
+  if ((rc = build_corrections(g, B0, B, handles, l, u))) return rc;
   // (a kernel without rounds -- the direct-load kernel of small problems -- finishes every running node in one "round")
   if ((rc = g.h_in.reserve((in_d - in0) * 8, g.stream))) return rc;        // staging of the new nodes only
   if ((rc = g.h_out.reserve_keep(out_d * 8, out0 * 8, g.stream))) return rc;

@@ -143,6 +143,9 @@ struct HostInstance {
   // threshold (1e-10, BQP_INVERSE_TOL) the panel layout is dropped and the problem runs on the LDL' kernels
   double pn_inverse_error = NAN;
   bool pn_rejected = false;
+  // eq_rho == 2 (per-node rho typing of the integer-bound rows, what osqp >= 0.4 does in update_bounds): rows i_idx[k] of M
+  // in natural order, [n_int][npad] -- the columns of the Woodbury correction of the explicit inverse (bqp_api.cu)
+  std::vector<double> mint;
   long long factor_bytes() const {   // bytes one ADMM iteration streams: A', L fwd, L bwd, A, D2inv
     return (long long)(Lcol.size() + Lrow.size() + D2inv.size()) * 8 + At.stream_bytes() + Ab.stream_bytes();
   }
@@ -159,6 +162,7 @@ int host_stream_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_stream_matvec_P(const HostInstance *h, const double *in, double *out);
 int host_panel_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_panel_matvec_P(const HostInstance *h, const double *in, double *out);
+double host_panel_M(const HostInstance *h, int r, int c);      // entry (r, c) of the explicit reduced inverse
 
 struct DevInstance {
   int n, m, npad, n_int;
@@ -168,6 +172,7 @@ struct DevInstance {
   int w_in_stage;   // 1: every A' group is dense -> its input vector chunks ride in the TMA stages (no m x T vector in smem)
   // row-panel layout (fused single-pass kernel)
   const double *pstream; int p_nw, p_npm, p_npa; long long p_panel_doubles, p_offA, p_offP;
+  const double *p_mint; int eq2; double rho_base;      // eq_rho == 2: rows of M of the integer variables; untyped rho
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -185,6 +190,7 @@ struct DevTile {
   long long in_off[kMaxTT];      // doubles into the packed input buffer: l[m] u[m] x0[n] y0[m]
   long long out_off[kMaxTT];     // doubles into the packed output buffer: x[n] y[m]
   long long state_off[kMaxTT];   // doubles into the ADMM state buffer (scaled x[n] z[m] y[m]) used to resume a node
+  long long corr_off[kMaxTT];    // eq_rho == 2: doubles into the correction buffer ([nS][k_s ...][j_s ...][G nS x nS]), -1: none
   long long work_off;            // doubles into the state workspace
 };
 
@@ -216,7 +222,7 @@ BQP_HD inline size_t rows_work_doubles(int npad, int m, int cs) {
 size_t rows_smem_bytes(int npad, int nslots, int cs);                                 // bqp_rows.cu
 int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
-                     void *stream);
+                     const double *d_corr, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

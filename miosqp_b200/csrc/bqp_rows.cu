@@ -45,6 +45,7 @@ constexpr int kCons = kG * kW;             // consumer warps
 constexpr int kConsThreads = kCons * 32;
 constexpr int kTileD = 256;                // doubles of one column tile of one panel (8 rows x 32 columns)
 constexpr int kFinN = 16;
+constexpr int kMaxS = 64;                  // eq_rho == 2: re-typed integer rows per node the scratch holds (n_int <= 64 with the dense kernels' part buffer)
 constexpr int kXR = 16;                    // x-iterate elements a consumer thread keeps in registers (npad * 8 / 256 at most)
 // Registers: each SM sub-partition holds 16 K registers and hosts every fourth warp, so 12 warps get 168 registers each at
 // launch.  The consumer warps need ~200 (B fragments of 128 columns, 32 accumulators, 8 mma chains), the producer warpgroup
@@ -236,6 +237,23 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       if constexpr (MODE == RM_CHK_P) { s0 = ld2(W.gdx); }
     }
     RSTAMP(X, 5);
+    double rho2[2] = {rho, rho}, rinv2[2] = {rinv, rinv};
+    if constexpr (MODE == RM_A_ITER || MODE == RM_A_INIT || MODE == RM_A_RESUME) {
+      // eq_rho == 2: the integer-bound rows are typed per node from the node's own (scaled) bounds, as osqp >= 0.4 does
+      if (I.eq2 && live && row >= m - I.n_int) {
+        double2 lo2, up2;
+        if constexpr (MODE == RM_A_ITER) { lo2 = s2; up2 = s3; }
+        else { lo2 = __ldcg(reinterpret_cast<const double2 *>(W.gl) + e2); up2 = __ldcg(reinterpret_cast<const double2 *>(W.gu) + e2); }
+        const double lo_[2] = {lo2.x, lo2.y}, up_[2] = {up2.x, up2.y};
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double rr = I.rho_base;
+          if (lo_[i] < -kInfty * kMinScaling && up_[i] > kInfty * kMinScaling) rr = kRhoMin;
+          else if (up_[i] - lo_[i] < kRhoTol) rr = kRhoEqFactor * I.rho_base;
+          rho2[i] = rr; rinv2[i] = 1.0 / rr;
+        }
+      }
+    }
     mbar_wait(X.full + 8u * slot, phase);
     RSTAMP(X, 0);
     const double *slotp = reinterpret_cast<const double *>(X.ring + (size_t)slot * X.slot_bytes) + X.tile0 * kTileD;
@@ -306,18 +324,18 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           const double zr = alpha * sum[i] + oma * a0[i];
-          double z = zr + rinv * a1[i];
+          double z = zr + rinv2[i] * a1[i];
           z = fmin(fmax(z, lo[i]), up[i]);
-          dy[i] = rho * (zr - z); yn[i] = a1[i] + dy[i]; zn[i] = z;
-          u[i] = fma(rho, z, -yn[i]);
+          dy[i] = rho2[i] * (zr - z); yn[i] = a1[i] + dy[i]; zn[i] = z;
+          u[i] = fma(rho2[i], z, -yn[i]);
         }
         st2(W.gz, zn[0], zn[1]); st2(W.gy, yn[0], yn[1]);
         if (do_check) st2(W.gdy, dy[0], dy[1]);
       } else if constexpr (MODE == RM_A_INIT) {
         st2(W.gz, sum[0], sum[1]);
-        u[0] = fma(rho, sum[0], -a1[0]); u[1] = fma(rho, sum[1], -a1[1]);
+        u[0] = fma(rho2[0], sum[0], -a1[0]); u[1] = fma(rho2[1], sum[1], -a1[1]);
       } else if constexpr (MODE == RM_A_RESUME) {
-        u[0] = fma(rho, a0[0], -a1[0]); u[1] = fma(rho, a0[1], -a1[1]);
+        u[0] = fma(rho2[0], a0[0], -a1[0]); u[1] = fma(rho2[1], a0[1], -a1[1]);
       } else if constexpr (MODE == RM_CHK_A1) {
         st2(W.gax, sum[0], sum[1]);
         u[0] = a1[0]; u[1] = a1[1];
@@ -526,7 +544,8 @@ template <int CS>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                  double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
-                 int *__restrict__ tile_iters, int nslots, double *__restrict__ state, int prefetch_panels) {
+                 int *__restrict__ tile_iters, int nslots, double *__restrict__ state, int prefetch_panels,
+                 const double *__restrict__ corr) {
   constexpr int T = T8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -803,6 +822,30 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     cons_bar();                                           // local x~ rows visible
     if constexpr (CS > 1) { mbar_wait(X.xbar, X.xph); X.xph ^= 1u; }
     PSTAMP(2);
+    if (I.eq2) {
+      // eq_rho == 2: Woodbury correction of the explicit inverse over the re-typed integer rows of every node,
+      //   x~ <- x~ - M[:,S] G (x~[S])     (warp w <-> node w; every CTA of the cluster corrects its full copy identically)
+      if (warp < nn && S.tile.corr_off[warp] >= 0) {
+        const double *cb = corr + S.tile.corr_off[warp];
+        const int nS = (int)cb[0];
+        const double *ksd = cb + 1, *jsd = cb + 1 + nS, *G = cb + 1 + 2 * nS;
+        double *sc = reinterpret_cast<double *>(X.part) + warp * 2 * kMaxS;       // c = x~[S], then t = G c (group partial buffers are idle)
+        for (int a = lane; a < nS; a += 32) sc[a] = X.colx[(size_t)((int)jsd[a]) * T + warp];
+        __syncwarp();
+        for (int a = lane; a < nS; a += 32) {
+          double t_a = 0.0;
+          for (int c = 0; c < nS; c++) t_a = fma(__ldg(G + (size_t)c * nS + a), sc[c], t_a);      // G symmetric: column-wise, coalesced
+          sc[kMaxS + a] = t_a;
+        }
+        __syncwarp();
+        for (int j = lane; j < np; j += 32) {
+          double acc_j = 0.0;
+          for (int a = 0; a < nS; a++) acc_j = fma(__ldg(I.p_mint + (size_t)((int)ksd[a]) * np + j), sc[kMaxS + a], acc_j);
+          X.colx[(size_t)j * T + warp] -= acc_j;
+        }
+      }
+      cons_bar();
+    }
     // x = alpha x~ + (1 - alpha) x_prev for the columns this CTA finalises; then z~ = A x~, update, b'
     load_bx<false>(bx, X.colx, X.tile0, X.ntl, lane);
     {
@@ -976,7 +1019,7 @@ size_t rows_smem_bytes(int npad, int nslots, int cs) {
 
 template <int CS>
 static int launch_r(int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
-                    double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, cudaStream_t st) {
+                    double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, const double *d_corr, cudaStream_t st) {
   // many host threads launch concurrently (one context each): raise the attribute only when it has to grow
   static std::atomic<size_t> smem_set{0};
   cudaError_t e = cudaSuccess;
@@ -997,19 +1040,19 @@ static int launch_r(int nslots, double *d_state, const DevInstance *d_insts, con
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, admm_rows_kernel<CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
-                         prefetch_panels);
+                         prefetch_panels, d_corr);
   return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? BQP_OK : BQP_E_CUDA;
 }
 
 int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
-                     void *stream) {
+                     const double *d_corr, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (nslots < 2) return BQP_E_ARG;
-  if (cs == 1) return launch_r<1>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  if (cs == 2) return launch_r<2>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  if (cs == 4) return launch_r<4>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
-  if (cs == 8) return launch_r<8>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, st);
+  if (cs == 1) return launch_r<1>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
+  if (cs == 2) return launch_r<2>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
+  if (cs == 4) return launch_r<4>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
+  if (cs == 8) return launch_r<8>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
   return BQP_E_ARG;
 }
 

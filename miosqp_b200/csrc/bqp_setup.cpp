@@ -573,8 +573,18 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     h->pn_inverse_error = worst;
     if (!(worst <= tol)) { h->pn = HostPanels(); h->pn_rejected = true; }
   }
+  h->mint.clear();
+  if (s->eq_rho == 2) {
+    // per-node re-typing corrects the explicit inverse by a Woodbury term over the re-typed integer rows: dense kernels only
+    if (!h->pn.built) return BQP_E_UNSUPPORTED;
+    h->mint.assign((size_t)std::max(h->n_int, 1) * np_, 0.0);
+    for (int k = 0; k < h->n_int; k++)
+      for (int c = 0; c < np_; c++) h->mint[(size_t)k * np_ + c] = h->pn.data[panel_pos(h->i_idx[k], c, np_)];
+  }
   return BQP_OK;
 }
+
+double host_panel_M(const HostInstance *h, int r, int c) { return h->pn.data[panel_pos(r, c, h->npad)]; }
 
 // ---- host-only debug restatements of what the kernel does with the streamed layouts (tests only)
 void host_matvec(const HostMat &M, const double *in, double *out) {

@@ -204,9 +204,9 @@ def normalize_settings(kw):
             continue
         else:
             raise TypeError("unknown OSQP setting %r" % k)
-    if s["eq_rho"] not in (0, 1, False, True):
-        raise ValueError("eq_rho must be 0 or 1: rho is typed per row once at setup (per-node re-typing, eq_rho=2, "
-                         "exists only in the CPU oracle, to measure what this contract costs)")
+    if s["eq_rho"] not in (0, 1, 2, False, True):
+        raise ValueError("eq_rho must be 0, 1 (rho typed per row once at setup: the default contract) or 2 (the integer-bound rows "
+                         "re-typed per node, what osqp >= 0.4 does in update_bounds; dense-A problems only)")
     if isinstance(s["scaling"], bool):
         s["scaling"] = 10 if s["scaling"] else 0
     return s

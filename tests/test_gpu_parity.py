@@ -379,3 +379,26 @@ def test_inverse_guard_both_branches(oracle_mod, branch, monkeypatch):
     assert list(r.status) == list(so) and list(r.iters) == list(io)
     tol = 1e-9 if branch == "ldl" else 1e-7                    # the inverse carries its probed 1e-11 through ~1000 iterations
     _close(r.x, xo, tol); _close(r.y, yo, tol)
+
+
+# ---------------------------------------------------------------- eq_rho = 2: per-node rho typing
+@pytest.mark.parametrize("shape", [(130, 200, 10, 4, 9), (500, 1000, 50, 3, 8)])
+def test_per_node_rho_typing_woodbury(oracle_mod, shape):
+    """eq_rho = 2: a branched binary variable turns its bound row into an equality (l = u), which osqp >= 0.4 re-types to
+    rho x 1e3 and refactors for (App. A.3).  The engine corrects the explicit inverse by a Woodbury term over those rows;
+    the oracle refactors per node.  Same statuses, iteration counts and iterates."""
+    n, m, p, seed, count = shape
+    pr = problems.random_miqp(n, m, p, 0.7, seed=seed)[0]
+    s2 = dict(QP, eq_rho=2)
+    _compare(pr, count, 6, s2, warm="root", oracle_mod=oracle_mod)
+    expect_dense("rows", n)
+    # and it is a different contract: other iterates (and, at config-2 size, other iteration counts) than with setup-only typing
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    ls, us = problems.branched_nodes(l, u, len(i_idx), count, np.random.default_rng(6))
+    x0 = np.zeros((count, n)); y0 = np.zeros((count, A.shape[0]))
+    r1 = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP).solve_batch(ls, us, x0, y0)
+    r2 = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **s2).solve_batch(ls, us, x0, y0)
+    assert np.nanmax(np.abs(r1.y[1:] - r2.y[1:])) > 1e-6
+    if n == 500:
+        assert list(r1.iters) != list(r2.iters)
+    _close(r1.lower[1:], r2.lower[1:], 5e-2)          # same optima to the solver tolerance
