@@ -109,11 +109,13 @@ struct BatchCtx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   Buf h_in{nullptr, 0, true}, h_out{nullptr, 0, true}, h_ns{nullptr, 0, true}, h_ti{nullptr, 0, true};
-  Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts;
+  Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts, d_gbar;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
+  bool use_grid = false; int grid_ctas = 0;
   bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
-  int round_iters = 0, max_iter_all = 0; long long round_h2d_bytes = 0, round_h2d_total = 0;
+  int round_iters = 0, max_iter_all = 0;
+  long long round_h2d_bytes = 0, round_h2d_total = 0;
   std::vector<long long> in_off, state_off, corr_off;
   Buf d_state, d_corr;
   size_t corr_d = 0;             // doubles used in d_corr
@@ -153,7 +155,7 @@ void ctx_release(BatchCtx &g) {
   if (!g.stream) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_state, &g.d_corr}) b->release(g.stream);
+  for (Buf *b : {&g.h_in, &g.h_out, &g.h_ns, &g.h_ti, &g.d_in, &g.d_out, &g.d_ns, &g.d_ti, &g.d_work, &g.d_tiles, &g.d_insts, &g.d_gbar, &g.d_state, &g.d_corr}) b->release(g.stream);
   cudaStreamSynchronize(g.stream);
   for (auto &e : g.ev) { cudaEventDestroy(e); e = nullptr; }
   if (g.ev_block) { cudaEventDestroy(g.ev_block); g.ev_block = nullptr; }
@@ -209,11 +211,20 @@ int to_device(bqp_instance *inst) {
     d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
     d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
   }
+  d.g_M = d.g_P = nullptr; d.g_arp = d.g_aci = d.g_trp = d.g_tci = nullptr; d.g_avl = d.g_tvl = nullptr; d.g_npm = 0;
+  const double *g_mp = nullptr;
+  if (h.gd.built) {
+    ar.add(h.gd.MP, &g_mp);
+    ar.add(h.gd.arp, &d.g_arp); ar.add(h.gd.aci, &d.g_aci); ar.add(h.gd.avl, &d.g_avl);
+    ar.add(h.gd.trp, &d.g_trp); ar.add(h.gd.tci, &d.g_tci); ar.add(h.gd.tvl, &d.g_tvl);
+    d.g_npm = h.gd.npm;
+  }
   d.p_mint = nullptr; d.eq2 = h.s.eq_rho == 2 ? 1 : 0; d.rho_base = h.s.rho;
   if (d.eq2) ar.add(h.mint, &d.p_mint);
   int rc = ar.commit(inst);
   if (rc) return rc;
   inst->d_q = const_cast<double *>(d.q);
+  if (h.gd.built) { d.g_M = g_mp; d.g_P = g_mp + h.gd.offP; }
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
   d.eps_pinf = h.s.eps_prim_inf; d.eps_dinf = h.s.eps_dual_inf;
@@ -413,6 +424,53 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       if (it == gid.end()) { gid[key] = (int)members.size(); members.emplace_back(); uniq.push_back(h); gprog.push_back(progress[b]); it = gid.find(key); }
       members[it->second].push_back(b);
     }
+  }
+  if (g.use_grid) {
+    // one tile = up to 8 leaves of one problem on EVERY SM; the tiles of a launch run one after the other inside the kernel
+    g.tiles.clear();
+    g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_bytes_launch.clear();
+    scheduled->clear();
+    std::vector<DevInstance> dinst;
+    std::map<bqp_instance *, int> inst_slot;
+    size_t work_d = 0, smem = 0;
+    for (size_t k = 0; k < members.size(); k++) {
+      const HostInstance &h = uniq[k]->h;
+      const int cnt = (int)members[k].size(), nt = (cnt + kMaxTT - 1) / kMaxTT;
+      auto is = inst_slot.find(uniq[k]);
+      if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
+      smem = std::max(smem, grid_smem_bytes(h.npad, h.m, h.n, g.grid_ctas));
+      for (int ti = 0; ti < nt; ti++) {
+        const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
+        DevTile t{};
+        t.inst = is->second; t.nn = hi - lo; t.iter_begin = 0; t.iter_end = h.s.max_iter;
+        for (int q = lo; q < hi; q++) {
+          const int b = members[k][q];
+          t.node[q - lo] = b; t.in_off[q - lo] = g.in_off[b]; t.out_off[q - lo] = g.out_off[b]; t.state_off[q - lo] = g.state_off[b];
+          t.corr_off[q - lo] = -1;
+          scheduled->push_back(b);
+        }
+        t.work_off = (long long)work_d;
+        work_d += grid_work_doubles(h.npad, h.m, g.grid_ctas);
+        g.tiles.push_back(t);
+        g.tile_bytes_iter.push_back(h.gd.iter_bytes(h.npad));
+        g.tile_bytes_check.push_back(2LL * h.npad * h.npad * 8 + 2 * 12LL * (long long)(h.gd.avl.size() + h.gd.tvl.size()));
+        g.tile_bytes_launch.push_back((long long)h.npad * h.npad * 8);
+        g.tile_check_every.push_back(h.s.check_termination);
+      }
+    }
+    g.ntiles = (int)g.tiles.size(); g.tt = kMaxTT; g.smem = smem; g.nslots = 0; g.slot_bytes = 0; g.cs = 1;
+    int rc;
+    if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles, g.stream))) return rc;
+    if ((rc = g.d_ti.reserve(sizeof(int) * (size_t)g.ntiles, g.stream))) return rc;
+    if ((rc = g.d_work.reserve(work_d * 8, g.stream))) return rc;
+    if ((rc = g.d_tiles.reserve(sizeof(DevTile) * g.tiles.size(), g.stream))) return rc;
+    if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size(), g.stream))) return rc;
+    if ((rc = g.d_gbar.reserve(sizeof(unsigned), g.stream))) return rc;
+    CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(ctx_sync(g));
+    g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
+    return BQP_OK;
   }
   if (use_rows && g.auto_cluster && cs == 2 && rounds) {
     // few tiles left (rolling B&B sessions: most trees are finished or between steps): a cluster of 4 per tile halves the
@@ -627,13 +685,38 @@ static void select_kernel(BatchCtx &g) {
   }
   g.eq2_unsupported = false;
   for (bqp_instance *inst : g.node_inst) if (inst->h.s.eq_rho == 2 && !(g.use_panel && g.use_rows)) g.eq2_unsupported = true;
+  // whole-GPU kernel: every problem of the batch has the layout (config 4) and nothing asked for another kernel
+  g.use_grid = false;
+  if (!g.use_panel && g_tune_threads == 0 && !std::getenv("BQP_KERNEL")) {
+    bool all = true;
+    size_t smem = 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device);
+    last = nullptr;
+    for (bqp_instance *inst : g.node_inst) {
+      if (inst == last) continue;
+      last = inst;
+      if (!inst->h.gd.built) { all = false; break; }
+      smem = std::max(smem, grid_smem_bytes(inst->h.npad, inst->h.m, inst->h.n, sms));
+    }
+    if (all && smem <= (size_t)kMaxSmem) {
+      const int ctas = grid_max_ctas(g.device, smem);
+      if (ctas > 0) { g.use_grid = true; g.grid_ctas = ctas; g.use_stream = false; }
+    }
+  }
+  if (const char *e = std::getenv("BQP_KERNEL")) if (!std::strcmp(e, "grid")) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device);
+    g.use_grid = true; g.use_panel = g.use_stream = false; g.grid_ctas = sms;
+    for (bqp_instance *inst : g.node_inst) if (!inst->h.gd.built) g.use_grid = false;
+  }
   if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
   g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
   // rounds: the streamed kernels run `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
   // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
   g.round_iters = 0;
-  if ((g.use_stream || g.use_panel) && g.round_ok) {
+  if ((g.use_stream || g.use_panel) && g.round_ok && !g.use_grid) {
     int r = 100;
     if (const char *e = std::getenv("BQP_ROUND_ITERS")) r = std::atoi(e);
     if (g.round_override >= 0) r = g.round_override;
@@ -711,7 +794,11 @@ static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &pro
   std::vector<int> scheduled;
   int rc = plan_round(g, alive, progress, remaining, &scheduled);
   if (rc) return rc;
-  rc = (g.use_panel && g.use_rows)
+  rc = g.use_grid
+           ? launch_admm_grid(g.grid_ctas, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
+                              (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, (unsigned *)g.d_gbar.p,
+                              g.smem, g.stream)
+       : (g.use_panel && g.use_rows)
            ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
                               (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
                               g.smem, (const double *)g.d_corr.p, g.stream)
@@ -765,7 +852,8 @@ static void fill_launch_timing(BatchCtx &g, int first_tiles, int first_tt, long 
     const int nwc = g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max;
     g.timing.threads = panel_cta_warps(nwc) * 32;
   }
-  g.timing.kernel = g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
+  g.timing.kernel = g.use_grid ? 4 : g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
+  if (g.use_grid) { g.timing.threads = 512; g.timing.tiles = g.grid_ctas; }
   g.timing.ring_slots = first_slots;
 }
 
@@ -1071,7 +1159,7 @@ int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c) {
 int bqp_get_inverse_guard(bqp_handle h, double *error, int *in_use) {
   if (!h) return BQP_E_ARG;
   if (error) *error = h->h.pn_inverse_error;
-  if (in_use) *in_use = h->h.pn.built ? 1 : 0;
+  if (in_use) *in_use = (h->h.pn.built || h->h.gd.built) ? 1 : 0;
   return BQP_OK;
 }
 

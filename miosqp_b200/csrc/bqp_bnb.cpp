@@ -15,6 +15,7 @@
 #include <thread>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -68,21 +69,55 @@ struct Tree {
   bqp_ctx ectx = nullptr;                        // engine context (own stream) of the thread driving this tree, if any
   Vec tmp;
 
-  // y = M x in CSC column order: the loop scipy's csc_matvec runs
-  static void matvec(const Csc &M, const double *x, double *y) {
+  // y = M x in CSC column order: the loop scipy's csc_matvec runs.  Large matrices (config 4: P is a dense 2000 x 2000, 8 ms
+  // per product on one core, more than the GPU needs for the whole relaxation) are split by ROW RANGE over host threads:
+  // every y[r] still receives its terms in ascending column order, so the result is bit-identical to the serial loop.
+  // Needs ascending row indices inside every column (checked once per matrix).
+  static bool sorted_rows(const Csc &M) {
+    for (int j = 0; j < M.cols; j++)
+      for (int k = M.p[j] + 1; k < M.p[j + 1]; k++) if (M.i[k] <= M.i[k - 1]) return false;
+    return true;
+  }
+  static void matvec_rows(const Csc &M, const double *x, double *y, int r0, int r1) {
+    for (int r = r0; r < r1; r++) y[r] = 0.0;
+    for (int j = 0; j < M.cols; j++) {
+      const int *b = M.i + M.p[j], *e = M.i + M.p[j + 1];
+      const int *lo = (r0 == 0) ? b : std::lower_bound(b, e, r0);
+      const double xj = x[j];
+      for (const int *k = lo; k < e && *k < r1; k++) y[*k] += M.x[k - M.i] * xj;
+    }
+  }
+  int par_P = -1, par_A = -1;                    // -1 not examined, 0 serial, > 0 host threads
+  static int par_threads(const Csc &M) {
+    const long long nnz = M.p[M.cols];
+    if (nnz < 400000 || !sorted_rows(M)) return 0;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(2u, std::min(16u, hw ? hw : 2u));
+  }
+  static void matvec(const Csc &M, const double *x, double *y, int threads = 0) {
+    if (threads > 1) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < threads; t++)
+        th.emplace_back(matvec_rows, std::cref(M), x, y, (int)((long long)M.rows * t / threads), (int)((long long)M.rows * (t + 1) / threads));
+      matvec_rows(M, x, y, 0, (int)((long long)M.rows / threads));
+      for (auto &t : th) t.join();
+      return;
+    }
     for (int r = 0; r < M.rows; r++) y[r] = 0.0;
     for (int j = 0; j < M.cols; j++) { const double xj = x[j]; for (int k = M.p[j]; k < M.p[j + 1]; k++) y[M.i[k]] += M.x[k] * xj; }
   }
   double obj(const Vec &x) {                     // data.py:99-103
     tmp.resize(std::max(n, m_ext));
-    matvec(P, x.data(), tmp.data());
+    if (par_P < 0) par_P = par_threads(P);
+    matvec(P, x.data(), tmp.data(), par_P);
     double a = 0.0, b = 0.0;
     for (int j = 0; j < n; j++) { a += x[j] * tmp[j]; b += q[j] * x[j]; }
     return .5 * a + b;
   }
   bool satisfies_lin(const Vec &x, const Vec &l, const Vec &u) {      // workspace.py:232-243
     tmp.resize(std::max(n, m_ext));
-    matvec(A, x.data(), tmp.data());
+    if (par_A < 0) par_A = par_threads(A);
+    matvec(A, x.data(), tmp.data(), par_A);
     for (int r = 0; r < m_ext; r++) if (tmp[r] < l[r] - s.eps_abs || tmp[r] > u[r] + s.eps_abs) return false;
     return true;
   }

@@ -118,6 +118,20 @@ constexpr int kRowsGroupWarps = 4;                  // warps per group, each mul
 constexpr int kRowsGroups = BQP_ROWS_GROUPS;        // groups per CTA, each taking whole panels through all stages
 constexpr int kRowsThreads = (kRowsGroups * kRowsGroupWarps + 4) * 32;   // + the producer warpgroup (one lane issues the TMA copies)
 
+// ---- whole-GPU kernel for ONE large tile (bqp_grid.cu): dense-reduced problems wider than the rows kernel's 512 columns
+// (BASELINE config 4: n = 2000, m = 4200, A 5 % dense).  Same restated iteration  x~ = M b,  z~ = A x~,  b' = sigma x - q +
+// A'(rho z - y)  with the explicit reduced inverse M, but every SM of the GPU works on the same tile: M and P as 8-row
+// fragment-ordered panels (the rows kernel's panel format, npad columns), A and A' as CSR (f64 value + i32 column).
+struct HostGridL {
+  bool built = false;
+  int npm = 0;                                      // 8-row panels of M (and of P)
+  std::vector<double> MP;                           // [M panels | P panels]
+  long long offP = 0;                               // doubles
+  std::vector<int> arp, aci, trp, tci;              // CSR of A (m rows) and of A' (n rows)
+  std::vector<double> avl, tvl;
+  long long iter_bytes(int npad) const { return (long long)npad * npad * 8 + 12LL * (long long)(avl.size() + tvl.size()); }
+};
+
 // Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
 // KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
 // streamed as the A panels and the dense trailing supernode L22 D2 L22' = P + sigma I + A' diag(rho) A).
@@ -138,6 +152,7 @@ struct HostInstance {
   std::vector<double> Lcol, Lrow, D2inv;
   HostStream st;                         // streamed layout (built for problems large enough for the TMA kernel)
   HostPanels pn;                         // row-panel layout of the fused single-pass kernel (dense A, npad <= 512)
+  HostGridL gd;                          // whole-GPU layout (npad > 512, memory permitting)
   // guard of the explicit reduced inverse: largest relative difference, over a few probe right-hand sides, between a KKT
   // solve through the panels (x~ = M b) and through the LDL' substitution; NaN when no panel layout was tried.  Above the
   // threshold (1e-10, BQP_INVERSE_TOL) the panel layout is dropped and the problem runs on the LDL' kernels
@@ -161,6 +176,7 @@ void host_matvec(const HostMat &M, const double *in, double *out);
 int host_stream_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_stream_matvec_P(const HostInstance *h, const double *in, double *out);
 int host_panel_kkt_solve(const HostInstance *h, double *rhs_xz);
+int host_grid_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_panel_matvec_P(const HostInstance *h, const double *in, double *out);
 double host_panel_M(const HostInstance *h, int r, int c);      // entry (r, c) of the explicit reduced inverse
 
@@ -173,6 +189,8 @@ struct DevInstance {
   // row-panel layout (fused single-pass kernel)
   const double *pstream; int p_nw, p_npm, p_npa; long long p_panel_doubles, p_offA, p_offP;
   const double *p_mint; int eq2; double rho_base;      // eq_rho == 2: rows of M of the integer variables; untyped rho
+  // whole-GPU layout (bqp_grid.cu)
+  const double *g_M, *g_P; const int *g_arp, *g_aci, *g_trp, *g_tci; const double *g_avl, *g_tvl; int g_npm;
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -223,6 +241,15 @@ size_t rows_smem_bytes(int npad, int nslots, int cs);                           
 int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
                      const double *d_corr, void *stream);
+// whole-GPU kernel: per tile, [row][8]: b, x~, x, dx, P x, P dx, objective operand (npad rows each); w, y, projected dy (m rows
+// each); per-CTA partial norms [G][16][8]
+BQP_HD inline size_t grid_work_doubles(int npad, int m, int nctas) {
+  return (size_t)8 * (7 * (size_t)npad + 3 * (size_t)((m + 7) / 8 * 8) + 16 * (size_t)nctas);
+}
+size_t grid_smem_bytes(int npad, int m, int n, int nctas);                            // bqp_grid.cu
+int grid_max_ctas(int device, size_t smem_bytes);                                     // co-resident CTAs of the cooperative launch
+int launch_admm_grid(int nctas, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
+                     double *d_work, NodeScalars *d_ns, int *d_tile_iters, unsigned *d_barrier, size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

@@ -327,11 +327,10 @@ void append_panels(HostPanels &pn, const std::vector<double> &X, int rows, int n
     for (int c = 0; c < npad; c++) pn.data[base + panel_pos(r, c, npad)] = X[(size_t)r * npad + c];
 }
 
-// S: column-major npad x npad, unit-lower L22 strictly below the diagonal (after the LDL' above); D2inv its inverse pivots
-void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &prows, const std::vector<double> &S) {
-  const int n = h->n, m = h->m, np_ = h->npad;
-  HostPanels &pn = h->pn;
-  pn = HostPanels();
+// S: column-major npad x npad, unit-lower L22 strictly below the diagonal (after the LDL' above); D2inv its inverse pivots.
+// Returns M = (P + sigma I + A' rho A)^-1 = L22^-T D2^-1 L22^-1, row-major npad x npad (zero beyond n).
+std::vector<double> reduced_inverse(const HostInstance *h, const std::vector<double> &S) {
+  const int n = h->n, np_ = h->npad;
   // X = inv(L22) (unit lower, row-major, leading n x n block), row by row: X[r][:] = e_r - sum_{k<r} L[r][k] X[k][:]
   std::vector<double> X((size_t)n * n, 0.0);
   for (int r = 0; r < n; r++) {
@@ -358,6 +357,14 @@ void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vec
   }
   for (int i = 0; i < n; i++)
     for (int j = 0; j < i; j++) M[(size_t)j * np_ + i] = M[(size_t)i * np_ + j];
+  return M;
+}
+
+void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &prows, const std::vector<double> &S) {
+  const int n = h->n, m = h->m, np_ = h->npad;
+  HostPanels &pn = h->pn;
+  pn = HostPanels();
+  const std::vector<double> M = reduced_inverse(h, S);
   std::vector<double> Ad((size_t)std::max(m, 1) * np_, 0.0), Pd((size_t)np_ * np_, 0.0);
   for (int r = 0; r < m; r++)
     for (auto &e : arows[r]) Ad[(size_t)r * np_ + e.first] = e.second;
@@ -373,6 +380,38 @@ void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vec
   pn.offP = (long long)pn.data.size();
   append_panels(pn, Pd, np_, np_);
   pn.built = true;
+}
+
+// whole-GPU layout: M and P as panels (no dense A), A and A' as CSR
+void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &atrows, const std::vector<Row> &prows,
+                const std::vector<double> &S) {
+  const int n = h->n, np_ = h->npad;
+  HostGridL &gd = h->gd;
+  gd = HostGridL();
+  HostPanels tmp;
+  {
+    const std::vector<double> M = reduced_inverse(h, S);
+    append_panels(tmp, M, np_, np_);
+  }
+  gd.offP = (long long)tmp.data.size();
+  {
+    std::vector<double> Pd((size_t)np_ * np_, 0.0);
+    for (int r = 0; r < n; r++)
+      for (auto &e : prows[r]) Pd[(size_t)r * np_ + e.first] = e.second;
+    append_panels(tmp, Pd, np_, np_);
+  }
+  gd.MP.swap(tmp.data);
+  gd.npm = np_ / kPanelRows;
+  auto csr = [](const std::vector<Row> &rows, std::vector<int> &rp, std::vector<int> &ci, std::vector<double> &vl) {
+    rp.assign(rows.size() + 1, 0);
+    for (size_t r = 0; r < rows.size(); r++) {
+      for (auto &e : rows[r]) { ci.push_back(e.first); vl.push_back(e.second); }
+      rp[r + 1] = (int)ci.size();
+    }
+  };
+  csr(arows, gd.arp, gd.aci, gd.avl);
+  csr(atrows, gd.trp, gd.tci, gd.tvl);
+  gd.built = true;
 }
 
 }  // namespace
@@ -573,6 +612,37 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     h->pn_inverse_error = worst;
     if (!(worst <= tol)) { h->pn = HostPanels(); h->pn_rejected = true; }
   }
+  // whole-GPU layout: dense-reduced problems too wide for the rows kernel (config 4).  Same guard of the explicit inverse
+  h->gd = HostGridL();
+  {
+    int want = 1, max_np = 2880;                       // x~ of 8 leaves staged in shared memory: 64 npad bytes of the 227 KB
+    if (const char *e = std::getenv("BQP_GRID")) want = std::atoi(e);
+    if (want && !h->pn.built && !h->pn_rejected && np_ > 32 * kPanelMaxWarps && np_ <= max_np && s->eq_rho != 2) {
+      build_grid(h, arows, atrows, prows, S);
+      double tol = 1e-10;
+      if (const char *e = std::getenv("BQP_INVERSE_TOL")) tol = std::atof(e);
+      double worst = 0.0;
+      std::vector<double> r1((size_t)n + m), r2((size_t)n + m);
+      for (int probe = 0; probe < 3; probe++) {
+        uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)(probe + 1);
+        for (int k = 0; k < n + m; k++) {
+          double v;
+          if (probe == 0) v = 1.0;
+          else if (probe == 1) v = (k & 1) ? -1.0 : 1.0;
+          else { st ^= st << 13; st ^= st >> 7; st ^= st << 17; v = (double)(st >> 11) / 9007199254740992.0 - 0.5; }
+          r1[(size_t)k] = r2[(size_t)k] = v;
+        }
+        host_kkt_solve(h, r1.data());
+        host_grid_kkt_solve(h, r2.data());
+        double nrm = 0.0, dif = 0.0;
+        for (int j = 0; j < n; j++) { nrm = std::max(nrm, std::fabs(r1[(size_t)j])); dif = std::max(dif, std::fabs(r1[(size_t)j] - r2[(size_t)j])); }
+        const double rel = dif / std::max(nrm, 1e-300);
+        worst = (rel == rel) ? std::max(worst, rel) : INFINITY;
+      }
+      h->pn_inverse_error = worst;
+      if (!(worst <= tol)) { h->gd = HostGridL(); h->pn_rejected = true; }
+    }
+  }
   h->mint.clear();
   if (s->eq_rho == 2) {
     // per-node re-typing corrects the explicit inverse by a Woodbury term over the re-typed integer rows: dense kernels only
@@ -747,6 +817,31 @@ int host_panel_kkt_solve(const HostInstance *h, double *rhs) {
   for (int i = 0; i < m; i++) {
     double acc = 0;
     for (int j = 0; j < np_; j++) acc = std::fma(at(pn.offA, i, j), xt[j], acc);
+    rhs[n + i] = h->rho[i] * (acc - rhs[n + i]);
+  }
+  for (int j = 0; j < n; j++) rhs[j] = xt[j];
+  return BQP_OK;
+}
+
+// the same through the whole-GPU layout (M panels, CSR A and A')
+int host_grid_kkt_solve(const HostInstance *h, double *rhs) {
+  const HostGridL &gd = h->gd;
+  if (!gd.built) return BQP_E_UNSUPPORTED;
+  const int n = h->n, m = h->m, np_ = h->npad;
+  std::vector<double> b(np_, 0.0), xt(np_, 0.0);
+  for (int j = 0; j < n; j++) {
+    double acc = 0;
+    for (int k = gd.trp[j]; k < gd.trp[j + 1]; k++) acc = std::fma(gd.tvl[k], h->rho[gd.tci[k]] * rhs[n + gd.tci[k]], acc);
+    b[j] = rhs[j] + acc;
+  }
+  for (int r = 0; r < n; r++) {
+    double acc = 0;
+    for (int j = 0; j < n; j++) acc = std::fma(gd.MP[panel_pos(r, j, np_)], b[j], acc);
+    xt[r] = acc;
+  }
+  for (int i = 0; i < m; i++) {
+    double acc = 0;
+    for (int k = gd.arp[i]; k < gd.arp[i + 1]; k++) acc = std::fma(gd.avl[k], xt[gd.aci[k]], acc);
     rhs[n + i] = h->rho[i] * (acc - rhs[n + i]);
   }
   for (int j = 0; j < n; j++) rhs[j] = xt[j];

@@ -402,3 +402,61 @@ def test_per_node_rho_typing_woodbury(oracle_mod, shape):
     if n == 500:
         assert list(r1.iters) != list(r2.iters)
     _close(r1.lower[1:], r2.lower[1:], 5e-2)          # same optima to the solver tolerance
+
+
+# ---------------------------------------------------------------- whole-GPU kernel for one large tile (bqp_grid.cu, config 4's shape)
+GRID_THREADS = 512
+
+
+@pytest.mark.parametrize("case", [(600, 900, 20, 0.05, 11, "zero"), (600, 900, 20, 0.05, 5, "root"), (1100, 1500, 30, 0.03, 3, "root")])
+def test_grid_kernel_against_oracle(oracle_mod, case):
+    """Problems wider than the rows kernel's 512 columns run on every SM at once (explicit reduced inverse as panels, A and A'
+    as CSR, three grid-wide barriers per iteration): same statuses, iteration counts and iterates as the oracle's LDL' path."""
+    n, m, p, dens, count, warm = case
+    pr = problems.random_miqp(n, m, p, dens, seed=12)[0]
+    r, e = _compare(pr, count, 13, QP, warm=warm, oracle_mod=oracle_mod)
+    t = engine.last_timing()
+    assert t["kernel"] == 4 and t["threads"] == GRID_THREADS and t["launches"] == 1, t
+    err, in_use = e.inverse_guard()
+    assert err < 1e-10
+
+
+def test_grid_kernel_infeasible_and_max_iter(oracle_mod):
+    pr = problems.random_miqp(600, 900, 20, 0.05, seed=12)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    n, m = A.shape[1], A.shape[0]
+    ls = np.tile(l, (4, 1)); us = np.tile(u, (4, 1))
+    ls[1, 0] = 50.0; us[1, 0] = 60.0          # row 0 cannot reach 50
+    ls[3, 1] = -60.0; us[3, 1] = -50.0
+    x0 = np.zeros((4, n)); y0 = np.zeros((4, m))
+    seen = set()
+    for st in (QP, dict(QP, max_iter=75), dict(QP, max_iter=40, eps_abs=1e-7, eps_rel=1e-7)):
+        o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **st)
+        e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **st)
+        xo, yo, so, io, extra = o.solve_batch(ls, us, x0, y0)
+        r = e.solve_batch(ls, us, x0, y0)
+        assert engine.last_timing()["kernel"] == 4
+        assert list(r.status) == list(so) and list(r.iters) == list(io), (list(r.status), list(so), list(r.iters), list(io))
+        for b in range(4):
+            if so[b] in (1, -2):
+                xo[b, i_idx] = np.minimum(np.maximum(xo[b, i_idx], ls[b, -len(i_idx):]), us[b, -len(i_idx):])
+        _close(r.x, xo); _close(r.y, yo)
+        seen |= set(int(v) for v in so)
+    assert seen & {-3, 3} and seen & {-2, 2} and 1 in seen, seen      # certificates, the x10 pass at max_iter, plain optima
+
+
+def test_grid_and_stream_kernels_agree(monkeypatch):
+    """BQP_GRID=0 at setup keeps the problem on the LDL' stream kernel (one CTA per tile): same statuses and iteration counts,
+    iterates to 1e-9 -- the explicit inverse against the triangular sweeps on the GPU itself."""
+    pr = problems.random_miqp(600, 900, 20, 0.05, seed=14)[0]
+    P, q, A, l, u, i_idx = problems.extend(pr)
+    n, m = A.shape[1], A.shape[0]
+    ls, us = problems.branched_nodes(l, u, len(i_idx), 7, np.random.default_rng(3))
+    x0 = np.zeros((7, n)); y0 = np.zeros((7, m))
+    rg = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP).solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["kernel"] == 4
+    monkeypatch.setenv("BQP_GRID", "0")
+    rs = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP).solve_batch(ls, us, x0, y0)
+    assert engine.last_timing()["kernel"] == 1
+    assert list(rg.status) == list(rs.status) and list(rg.iters) == list(rs.iters)
+    _close(rg.x, rs.x); _close(rg.y, rs.y); _close(rg.lower, rs.lower)

@@ -176,7 +176,8 @@ def test_qp_settings_contract():
         engine.normalize_settings({"adaptive_rho": True})        # outside the parity contract, never silently ignored
     with pytest.raises(TypeError):
         engine.normalize_settings({"no_such_setting": 1})
+    assert engine.normalize_settings({"eq_rho": 2})["eq_rho"] == 2     # per-node re-typing: Woodbury path of the rows kernel
     with pytest.raises(ValueError):
-        engine.normalize_settings({"eq_rho": 2})                 # per-node re-typing exists in the oracle only
+        engine.normalize_settings({"eq_rho": 3})
     s = engine.normalize_settings({"eps_inf": 1e-5, "eps_unb": 1e-6, "polishing": False, "verbose": True})
     assert s["eps_prim_inf"] == 1e-5 and s["eps_dual_inf"] == 1e-6

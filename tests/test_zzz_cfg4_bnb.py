@@ -43,8 +43,16 @@ def test_cfg4_node_limited_bnb_cpu(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_cfg4_node_limited_bnb_stream_kernel(monkeypatch):
+    from miosqp_b200 import engine
+    monkeypatch.setenv("BQP_GRID", "0")
+    _run(speculation=4)
+    assert engine.last_timing()["kernel"] == 1          # the TMA-streamed two-sweep kernel (one CTA per tile)
+
+
+@pytest.mark.gpu
 def test_cfg4_node_limited_bnb_engine():
     from miosqp_b200 import engine
     w = _run(speculation=4)
-    assert engine.last_timing()["kernel"] == 1          # the TMA-streamed two-sweep kernel (sparse A, n > 512)
+    assert engine.last_timing()["kernel"] == 4          # the whole-GPU kernel (n > 512: one tile on every SM)
     assert w.spec_nodes > 0          # look-ahead nodes rode along (a 9-node dive never returns to them: no adoption expected)
