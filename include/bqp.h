@@ -62,6 +62,12 @@ typedef struct {
   int check_termination;  /* residual test period (osqp default 25), >= 1 */
   int eq_rho;             /* 1: type rho per row ONCE at setup (equality x1e3, free rows RHO_MIN) */
   int device;             /* CUDA device ordinal */
+  /* osqp adaptive_rho with a FIXED interval (a multiple of check_termination; osqp's automatic interval is derived from
+   * wall-clock setup time and is not reproducible: refused).  Every node starts from `rho` and adapts on its own
+   * (adapt_rho / compute_rho_estimate of osqp 0.6); runs on the whole-GPU kernel through the spectral form of the reduced
+   * KKT inverse, K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V': any rho per node without refactorisation. */
+  int adaptive_rho, adaptive_rho_interval;
+  double adaptive_rho_tolerance;   /* osqp default 5 */
 } bqp_settings;
 
 /* QP  min 1/2 x'Px + q'x  s.t. l <= Ax <= u ;  P upper-triangular CSC, A CSC (m x n).

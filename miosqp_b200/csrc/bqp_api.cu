@@ -212,19 +212,24 @@ int to_device(bqp_instance *inst) {
     d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
   }
   d.g_M = d.g_P = nullptr; d.g_arp = d.g_aci = d.g_trp = d.g_tci = nullptr; d.g_avl = d.g_tvl = nullptr; d.g_npm = 0;
+  d.g_V = d.g_mu = nullptr; d.g_rtype = nullptr; d.adaptive = 0; d.adapt_interval = 0; d.adapt_tol = 5.0;
   const double *g_mp = nullptr;
   if (h.gd.built) {
     ar.add(h.gd.MP, &g_mp);
     ar.add(h.gd.arp, &d.g_arp); ar.add(h.gd.aci, &d.g_aci); ar.add(h.gd.avl, &d.g_avl);
     ar.add(h.gd.trp, &d.g_trp); ar.add(h.gd.tci, &d.g_tci); ar.add(h.gd.tvl, &d.g_tvl);
     d.g_npm = h.gd.npm;
+    if (h.gd.spectral) {
+      ar.add(h.gd.mu, &d.g_mu); ar.add(h.rtype, &d.g_rtype);
+      d.adaptive = 1; d.adapt_interval = h.s.adaptive_rho_interval; d.adapt_tol = h.s.adaptive_rho_tolerance;
+    }
   }
   d.p_mint = nullptr; d.eq2 = h.s.eq_rho == 2 ? 1 : 0; d.rho_base = h.s.rho;
   if (d.eq2) ar.add(h.mint, &d.p_mint);
   int rc = ar.commit(inst);
   if (rc) return rc;
   inst->d_q = const_cast<double *>(d.q);
-  if (h.gd.built) { d.g_M = g_mp; d.g_P = g_mp + h.gd.offP; }
+  if (h.gd.built) { d.g_M = g_mp; d.g_P = g_mp + h.gd.offP; d.g_V = h.gd.spectral ? g_mp + h.gd.offV : nullptr; }
   d.c = h.c; d.cinv = h.cinv; d.nq = h.nq;
   d.sigma = h.s.sigma; d.alpha = h.s.alpha; d.eps_abs = h.s.eps_abs; d.eps_rel = h.s.eps_rel;
   d.eps_pinf = h.s.eps_prim_inf; d.eps_dinf = h.s.eps_dual_inf;
@@ -248,6 +253,7 @@ void bqp_default_settings(bqp_settings *s) {
   s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6; s->eps_abs = 1e-3; s->eps_rel = 1e-3;
   s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4; s->max_iter = 4000; s->scaling = 10;
   s->check_termination = 25; s->eq_rho = 1; s->device = 0;
+  s->adaptive_rho = 0; s->adaptive_rho_interval = 0; s->adaptive_rho_tolerance = 5.0;
 }
 
 int bqp_debug_host_setup(const bqp_problem *p, const bqp_settings *s, bqp_handle *out) {
@@ -710,6 +716,7 @@ static void select_kernel(BatchCtx &g) {
     g.use_grid = true; g.use_panel = g.use_stream = false; g.grid_ctas = sms;
     for (bqp_instance *inst : g.node_inst) if (!inst->h.gd.built) g.use_grid = false;
   }
+  for (bqp_instance *inst : g.node_inst) if (inst->h.s.adaptive_rho && !(g.use_grid && inst->h.gd.spectral)) g.eq2_unsupported = true;
   if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
   g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));

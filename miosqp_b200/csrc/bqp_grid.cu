@@ -19,6 +19,10 @@
 // column owners A'y, A' dy; per-CTA partial norms go to global memory and EVERY CTA reduces them in the same canonical
 // order -- identical decisions everywhere, nothing to broadcast.  All norms are maxima (order-free); the four sums
 // (x'Px, q'x, the two certificate products) are added CTA by CTA in index order.
+// ADAPTIVE RHO (osqp adapt_rho, settings adaptive_rho with a fixed interval): the M phase becomes x~ = V (d . (V' b)) with
+// d = 1 / (1 + (rho_leaf - rho0) mu) -- the spectral form of K(rho)^-1 built at setup (bqp_setup.cpp build_grid) -- so every
+// leaf of the tile carries its OWN rho and a rho update costs nothing but one extra A' pass; the estimate uses the same scaled
+// norms as osqp's compute_rho_estimate, evaluated with the termination check the interval coincides with.
 // Every cross-CTA vector is read with ld.global.cg (L2); every wait is bounded and traps instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -37,7 +41,7 @@ namespace {
 constexpr int T8 = 8;
 constexpr int kGW = 16;                    // warps per CTA
 constexpr int kGT = kGW * 32;              // threads per CTA
-constexpr int kFinN = 16;
+constexpr int kFinN = 24;                 // 16 quantities of the termination tests + 7 scaled norms of osqp's compute_rho_estimate
 constexpr int kTileD = 256;                // doubles of one column tile of one panel (8 rows x 32 columns)
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -55,6 +59,8 @@ struct GridShared {
   double fin[kFinN][T8];
   int status[T8], iters[T8], newly[T8];
   int remaining;
+  double rho_t[T8];                          // adaptive rho: the leaf's current rho (osqp settings->rho after osqp_update_rho)
+  int rho_changed;
 };
 
 // grid-wide barrier: a monotone arrival counter in global memory (reset by the host before the launch); CTA-level
@@ -63,13 +69,12 @@ __device__ __forceinline__ void grid_sync(unsigned *ctr, unsigned &target, unsig
   __syncthreads();
   if (threadIdx.x == 0) {
     target += G;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // fire-and-forget arrival (no round trip before the polling starts); release orders this CTA's writes (cumulative over bar.sync)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     const long long t0 = clock64();
     while (ld_acquire_u32(ctr) < target) {
       if (clock64() - t0 > 8000000000LL) __trap();     // ~4 s
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -138,6 +143,9 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     }
     if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
     __syncthreads();
+    if (tid < T) S.rho_t[tid] = S.I.rho_base;
+    if (tid == 0) S.rho_changed = 0;
+    __syncthreads();
     const DevInstance &I = S.I;
     const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, NW = np / 32, npm = I.g_npm;
     const int m8 = (m + 7) / 8 * 8;
@@ -155,7 +163,15 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     // per-tile workspace in global memory (L2 resident), [row][8 leaves]
     double *gb = work + S.tile.work_off, *gxt = gb + (size_t)np * T, *gx = gxt + (size_t)np * T, *gdx = gx + (size_t)np * T;
     double *gpx = gdx + (size_t)np * T, *gpdx = gpx + (size_t)np * T, *gxo = gpdx + (size_t)np * T;
-    double *gw = gxo + (size_t)np * T, *gy = gw + (size_t)m8 * T, *gdyp = gy + (size_t)m8 * T, *gpart = gdyp + (size_t)m8 * T;
+    double *gc = gxo + (size_t)np * T;       // adaptive rho: d . (V' b)
+    double *gw = gc + (size_t)np * T, *gy = gw + (size_t)m8 * T, *gdyp = gy + (size_t)m8 * T, *gpart = gdyp + (size_t)m8 * T;
+    const bool adaptive = I.adaptive != 0;
+    // rho of row i for leaf t: typed once at setup; with adaptive rho the inequality / equality rows follow the leaf's rho
+    auto row_rho = [&](int i, int t) -> double {
+      if (!adaptive) return __ldg(I.rho + i);
+      const int ty = __ldg(I.g_rtype + i);
+      return ty == 0 ? S.rho_t[t] : (ty == 1 ? kRhoEqFactor * S.rho_t[t] : kRhoMin);
+    };
     const int max_iter = I.max_iter, check_every = I.check_every;
     const double alpha = I.alpha, oma = 1.0 - I.alpha, sigma = I.sigma;
 
@@ -242,7 +258,7 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       const double s = sparse_row<true>(I.g_avl, I.g_aci, __ldg(I.g_arp + i), __ldg(I.g_arp + i + 1), vec, lane);
       if (lane < T) {
         sz[il * T + lane] = s;
-        gw[(size_t)i * T + lane] = fma(__ldg(I.rho + i), s, -sy[il * T + lane]);
+        gw[(size_t)i * T + lane] = fma(row_rho(i, lane), s, -sy[il * T + lane]);
       }
     }
     grid_sync(barrier, bar_target, (unsigned)G);
@@ -262,7 +278,18 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       GSTAMP(7);
       stage(gb);
       GSTAMP(0);
-      dense_pass(I.g_M, [&](int row, int pair, double a, double b) { st2(gxt, row, pair, a, b); });
+      if (!adaptive) {
+        dense_pass(I.g_M, [&](int row, int pair, double a, double b) { st2(gxt, row, pair, a, b); });
+      } else {
+        // x~ = V (d . (V' b)),  d = 1 / (1 + (rho_leaf - rho0) mu_row)
+        dense_pass(I.g_M, [&](int row, int pair, double a, double b) {
+          const double mu = __ldg(I.g_mu + row);
+          st2(gc, row, pair, a / (1.0 + (S.rho_t[2 * pair] - I.rho_base) * mu), b / (1.0 + (S.rho_t[2 * pair + 1] - I.rho_base) * mu));
+        });
+        grid_sync(barrier, bar_target, (unsigned)G);
+        stage(gc);
+        dense_pass(I.g_V, [&](int row, int pair, double a, double b) { st2(gxt, row, pair, a, b); });
+      }
       GSTAMP(1);
       grid_sync(barrier, bar_target, (unsigned)G);
       GSTAMP(2);
@@ -274,7 +301,7 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
         const double zt = sparse_row<true>(I.g_avl, I.g_aci, __ldg(I.g_arp + i), __ldg(I.g_arp + i + 1), vec, lane);
         if (lane < T) {
           const int e = il * T + lane;
-          const double rho = __ldg(I.rho + i), rinv = __ldg(I.rho_inv + i);
+          const double rho = row_rho(i, lane), rinv = adaptive ? 1.0 / rho : __ldg(I.rho_inv + i);
           const double zr = alpha * zt + oma * sz[e], yo = sy[e];
           double z = zr + rinv * yo;
           z = fmin(fmax(z, sl[e]), su[e]);
@@ -320,6 +347,8 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       double v[kFinN];
       v[0] = v[1] = v[2] = v[5] = v[6] = v[7] = v[8] = v[10] = v[12] = v[13] = 0.0;
       v[3] = v[4] = v[9] = v[11] = 0.0; v[14] = -INFINITY; v[15] = INFINITY;
+#pragma unroll
+      for (int q = 16; q < kFinN; q++) v[q] = 0.0;          // scaled norms of compute_rho_estimate: |Ax - z|, |z|, |Ax|, |Px + q + A'y|, |q|, |A'y|, |Px|
       {
         for (int il = warp; il < nr; il += kGW) {
           const int i = r0 + il;
@@ -330,6 +359,7 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
             v[5] = fmax(v[5], fabs(ei * (ax - z)));
             v[6] = fmax(v[6], fabs(ei * ax));
             v[7] = fmax(v[7], fabs(ei * z));
+            v[16] = fmax(v[16], fabs(ax - z)); v[17] = fmax(v[17], fabs(z)); v[18] = fmax(v[18], fabs(ax));
             const double w = ei * adx;
             if (up < kInfty * kMinScaling) v[14] = fmax(v[14], w);
             if (lo > -kInfty * kMinScaling) v[15] = fmin(v[15], w);
@@ -357,6 +387,7 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
           v[0] = fmax(v[0], fabs(di * (px + qj + aty)));
           v[1] = fmax(v[1], fabs(di * px));
           v[2] = fmax(v[2], fabs(di * aty));
+          v[19] = fmax(v[19], fabs(px + qj + aty)); v[20] = fmax(v[20], fabs(qj)); v[21] = fmax(v[21], fabs(aty)); v[22] = fmax(v[22], fabs(px));
           v[3] += xj * px;
           v[4] += qj * xj;
           v[12] = fmax(v[12], fabs(di * atd));
@@ -366,7 +397,7 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
         }
       }
       // CTA partials: lanes < 8 of every warp hold leaf `lane`; warps in order; then to global, [cta][16][8]
-      const int op[kFinN] = {0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 2};
+      const int op[kFinN] = {0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0};
       if (lane < T)
 #pragma unroll
         for (int q = 0; q < kFinN; q++) red[(q * kGW + warp) * T + lane] = v[q];
@@ -458,6 +489,31 @@ admm_grid_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       }
       __syncthreads();
       if (S.remaining == 0) break;
+      if (adaptive && iter % I.adapt_interval == 0) {
+        // osqp adapt_rho: rho_new = rho sqrt(pri / dua) on the normalised SCALED residuals; adopted outside [rho / tol, rho tol]
+        if (tid < T && tid < nn && S.status[tid] == BQP_UNSOLVED) {
+          const int t = tid;
+          const double pri = S.fin[16][t] / (fmax(S.fin[17][t], S.fin[18][t]) + 1e-10);
+          const double dua = S.fin[19][t] / (fmax(fmax(S.fin[20][t], S.fin[21][t]), S.fin[22][t]) + 1e-10);
+          const double rho = S.rho_t[t];
+          double rn = rho * sqrt(pri / (dua + 1e-10));
+          rn = fmin(fmax(rn, kRhoMin), 1e6);
+          if (rn > rho * I.adapt_tol || rn < rho / I.adapt_tol) { S.rho_t[t] = rn; S.rho_changed = 1; }
+        }
+        __syncthreads();
+        if (S.rho_changed) {
+          // the right-hand side of the next iteration carries rho: w = rho z - y and b' = sigma x - q + A' w again
+          for (int e = tid; e < nr * T; e += kGT) {
+            const int il = e / T, t = e % T;
+            gw[(size_t)(r0 + il) * T + t] = fma(row_rho(r0 + il, t), sz[e], -sy[e]);
+          }
+          grid_sync(barrier, bar_target, (unsigned)G);
+          col_phase(false);
+          grid_sync(barrier, bar_target, (unsigned)G);
+          if (tid == 0) S.rho_changed = 0;
+          __syncthreads();
+        }
+      }
     }
 
 #ifdef BQP_GRID_DEBUG

@@ -125,8 +125,10 @@ constexpr int kRowsThreads = (kRowsGroups * kRowsGroupWarps + 4) * 32;   // + th
 struct HostGridL {
   bool built = false;
   int npm = 0;                                      // 8-row panels of M (and of P)
-  std::vector<double> MP;                           // [M panels | P panels]
-  long long offP = 0;                               // doubles
+  std::vector<double> MP;                           // [M panels | P panels], spectral (adaptive rho): [V' panels | V panels | P panels]
+  long long offP = 0, offV = 0;                     // doubles
+  bool spectral = false;                            // K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V' (bqp_setup.cpp build_grid)
+  std::vector<double> mu;                           // generalised eigenvalues, npad entries
   std::vector<int> arp, aci, trp, tci;              // CSR of A (m rows) and of A' (n rows)
   std::vector<double> avl, tvl;
   long long iter_bytes(int npad) const { return (long long)npad * npad * 8 + 12LL * (long long)(avl.size() + tvl.size()); }
@@ -143,6 +145,7 @@ struct HostInstance {
   std::vector<double> q;                 // scaled linear cost
   double nq = 0;                         // || Dinv q ||_inf (scaled q), constant between update_q calls
   std::vector<double> rho, rho_inv;
+  std::vector<int> rtype;                // osqp constr_type per row at setup: -1 loose (RHO_MIN), 0 inequality (rho), 1 equality (1e3 rho)
   std::vector<int> i_idx;
   HostMat At, Ab, Pm;                    // A' (n x m), A (m x n), P full symmetric (n x n); all scaled
   // Blocked dense tail.  Lcol: block column J = rows J*32..npad of 32 columns, column-major (ld = npad-J*32);
@@ -191,6 +194,8 @@ struct DevInstance {
   const double *p_mint; int eq2; double rho_base;      // eq_rho == 2: rows of M of the integer variables; untyped rho
   // whole-GPU layout (bqp_grid.cu)
   const double *g_M, *g_P; const int *g_arp, *g_aci, *g_trp, *g_tci; const double *g_avl, *g_tvl; int g_npm;
+  // adaptive rho (spectral form): g_M = V' panels, g_V = V panels, g_mu = eigenvalues, g_rtype = row types
+  const double *g_V, *g_mu; const int *g_rtype; int adaptive, adapt_interval; double adapt_tol;
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -241,10 +246,10 @@ size_t rows_smem_bytes(int npad, int nslots, int cs);                           
 int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
                      const double *d_corr, void *stream);
-// whole-GPU kernel: per tile, [row][8]: b, x~, x, dx, P x, P dx, objective operand (npad rows each); w, y, projected dy (m rows
-// each); per-CTA partial norms [G][16][8]
+// whole-GPU kernel: per tile, [row][8]: b, x~, x, dx, P x, P dx, objective operand, d . (V' b) (npad rows each); w, y, projected
+// dy (m rows each); per-CTA partial norms [G][24][8]
 BQP_HD inline size_t grid_work_doubles(int npad, int m, int nctas) {
-  return (size_t)8 * (7 * (size_t)npad + 3 * (size_t)((m + 7) / 8 * 8) + 16 * (size_t)nctas);
+  return (size_t)8 * (8 * (size_t)npad + 3 * (size_t)((m + 7) / 8 * 8) + 24 * (size_t)nctas);
 }
 size_t grid_smem_bytes(int npad, int m, int n, int nctas);                            // bqp_grid.cu
 int grid_max_ctas(int device, size_t smem_bytes);                                     // co-resident CTAs of the cooperative launch

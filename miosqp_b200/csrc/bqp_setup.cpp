@@ -329,6 +329,137 @@ void append_panels(HostPanels &pn, const std::vector<double> &X, int rows, int n
 
 // S: column-major npad x npad, unit-lower L22 strictly below the diagonal (after the LDL' above); D2inv its inverse pivots.
 // Returns M = (P + sigma I + A' rho A)^-1 = L22^-T D2^-1 L22^-1, row-major npad x npad (zero beyond n).
+// X = inv(L22) (unit lower, row-major n x n)
+std::vector<double> unit_lower_inverse(const HostInstance *h, const std::vector<double> &S) {
+  const int n = h->n, np_ = h->npad;
+  std::vector<double> X((size_t)n * n, 0.0);
+  for (int r = 0; r < n; r++) {
+    double *xr = &X[(size_t)r * n];
+    for (int k = 0; k < r; k++) {
+      const double l = S[(size_t)k * np_ + r];
+      if (l == 0.0) continue;
+      const double *xk = &X[(size_t)k * n];
+      for (int c = 0; c <= k; c++) xr[c] -= l * xk[c];
+    }
+    xr[r] = 1.0;
+  }
+  return X;
+}
+
+// ---- symmetric eigenproblem: Householder tridiagonalisation + implicit QL (the EISPACK tred2 / tql2 pair).
+// Z is row-major n x n, symmetric on input; on output ROW j of Z is the eigenvector of eigenvalue d[j] (kept transposed so
+// that the plane rotations of the QL sweep run over contiguous memory).
+void sym_eig(int n, std::vector<double> &Z, std::vector<double> &d) {
+  std::vector<double> e(n, 0.0), V(Z);
+  d.assign(n, 0.0);
+  auto A = [&](int r, int c) -> double & { return V[(size_t)r * n + c]; };
+  for (int j = 0; j < n; j++) d[j] = A(n - 1, j);
+  for (int i = n - 1; i > 0; i--) {
+    double scale = 0.0, hsum = 0.0;
+    for (int k = 0; k < i; k++) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; j++) { d[j] = A(i - 1, j); A(i, j) = 0.0; A(j, i) = 0.0; }
+    } else {
+      for (int k = 0; k < i; k++) { d[k] /= scale; hsum += d[k] * d[k]; }
+      double f = d[i - 1], g = std::sqrt(hsum);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      hsum -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; j++) e[j] = 0.0;
+      for (int j = 0; j < i; j++) {
+        f = d[j];
+        A(j, i) = f;
+        g = e[j] + A(j, j) * f;
+        for (int k = j + 1; k <= i - 1; k++) { g += A(k, j) * d[k]; e[k] += A(k, j) * f; }
+        e[j] = g;
+      }
+      f = 0.0;
+      for (int j = 0; j < i; j++) { e[j] /= hsum; f += e[j] * d[j]; }
+      const double hh = f / (hsum + hsum);
+      for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+      for (int j = 0; j < i; j++) {
+        f = d[j]; g = e[j];
+        for (int k = j; k <= i - 1; k++) A(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = A(i - 1, j);
+        A(i, j) = 0.0;
+      }
+    }
+    d[i] = hsum;
+  }
+  for (int i = 0; i < n - 1; i++) {                    // accumulate the transformations
+    A(n - 1, i) = A(i, i);
+    A(i, i) = 1.0;
+    const double hsum = d[i + 1];
+    if (hsum != 0.0) {
+      for (int k = 0; k <= i; k++) d[k] = A(k, i + 1) / hsum;
+      for (int j = 0; j <= i; j++) {
+        double g = 0.0;
+        for (int k = 0; k <= i; k++) g += A(k, i + 1) * A(k, j);
+        for (int k = 0; k <= i; k++) A(k, j) -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; k++) A(k, i + 1) = 0.0;
+  }
+  for (int j = 0; j < n; j++) { d[j] = A(n - 1, j); A(n - 1, j) = 0.0; }
+  A(n - 1, n - 1) = 1.0;
+  e[0] = 0.0;
+  for (int r = 0; r < n; r++)                          // Z = V' : eigenvector columns become rows
+    for (int c = 0; c < n; c++) Z[(size_t)c * n + r] = V[(size_t)r * n + c];
+  V.clear(); V.shrink_to_fit();
+  for (int i = 1; i < n; i++) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = std::ldexp(1.0, -52);
+  for (int l = 0; l < n; l++) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) { if (std::fabs(e[m]) <= eps * tst1) break; m++; }
+    if (m > l) {
+      int sweeps = 0;
+      do {
+        if (++sweeps > 200) break;                     // never seen; the guard of the inverse catches a bad decomposition
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2.0 * e[l]);
+        double r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double hh = g - d[l];
+        for (int i = l + 2; i < n; i++) d[i] -= hh;
+        f += hh;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+        const double el1 = e[l + 1];
+        for (int i = m - 1; i >= l; i--) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          hh = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = hh + s * (c * g + s * d[i]);
+          double *zi = &Z[(size_t)i * n], *zi1 = &Z[(size_t)(i + 1) * n];
+          for (int k = 0; k < n; k++) {
+            const double t = zi1[k];
+            zi1[k] = s * zi[k] + c * t;
+            zi[k] = c * zi[k] - s * t;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1);
+    }
+    d[l] += f;
+    e[l] = 0.0;
+  }
+}
+
 std::vector<double> reduced_inverse(const HostInstance *h, const std::vector<double> &S) {
   const int n = h->n, np_ = h->npad;
   // X = inv(L22) (unit lower, row-major, leading n x n block), row by row: X[r][:] = e_r - sum_{k<r} L[r][k] X[k][:]
@@ -389,7 +520,70 @@ void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vecto
   HostGridL &gd = h->gd;
   gd = HostGridL();
   HostPanels tmp;
-  {
+  if (h->s.adaptive_rho) {
+    // Adaptive rho (osqp adapt_rho): rho_vec = rho x {1, 1e3} on the inequality / equality rows, RHO_MIN on the
+    // loose ones, so K(rho) = K0 + (rho - rho0) S1 with K0 = K(rho0) the matrix factorised above and S1 = A' diag(type weight) A.
+    // With K0 = L L' and L^-1 S1 L^-T = Q diag(mu) Q':  K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V',  V = L^-T Q  (mu < 1/rho0).
+    // The kernel applies x~ = V (d . (V' b)) with the leaf's own rho in d: ANY rho per leaf, no refactorisation, same stream for
+    // the 8 leaves of a tile.  At rho = rho0 this is V V' = K0^-1, as well conditioned as the factor itself.
+    const int m = h->m;
+    std::vector<double> X = unit_lower_inverse(h, S);            // L = L22 D2^(1/2):  L^-1 = D2^(-1/2) X
+    std::vector<double> S1((size_t)n * n, 0.0);
+    for (int r = 0; r < m; r++) {
+      const double wgt = h->rtype[r] == 0 ? 1.0 : (h->rtype[r] == 1 ? kRhoEqFactor : 0.0);
+      if (wgt == 0.0) continue;
+      const auto &row = arows[r];
+      for (size_t a = 0; a < row.size(); a++) {
+        const double va = wgt * row[a].second;
+        double *dst = &S1[(size_t)row[a].first * n];
+        for (size_t b = 0; b < row.size(); b++) dst[row[b].first] += va * row[b].second;
+      }
+    }
+    // T = X S1 (X lower triangular), C = T X' scaled by D2^(-1/2) on both sides
+    std::vector<double> Tm((size_t)n * n, 0.0), C((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) {
+      double *ti = &Tm[(size_t)i * n];
+      for (int k = 0; k <= i; k++) {
+        const double x = X[(size_t)i * n + k];
+        if (x == 0.0) continue;
+        const double *sk = &S1[(size_t)k * n];
+        for (int j = 0; j < n; j++) ti[j] += x * sk[j];
+      }
+    }
+    S1.clear(); S1.shrink_to_fit();
+    std::vector<double> dh(n);
+    for (int i = 0; i < n; i++) dh[i] = std::sqrt(h->D2inv[i]);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j <= i; j++) {
+        const double *ti = &Tm[(size_t)i * n], *xj = &X[(size_t)j * n];
+        double acc = 0.0;
+        for (int k = 0; k <= j; k++) acc += ti[k] * xj[k];
+        C[(size_t)i * n + j] = C[(size_t)j * n + i] = acc * dh[i] * dh[j];
+      }
+    Tm.clear(); Tm.shrink_to_fit();
+    std::vector<double> mu;
+    sym_eig(n, C, mu);                                             // row j of C: eigenvector q_j
+    // W = V' = Q' D2^(-1/2) X  (row j of W = (L^-T q_j)')
+    std::vector<double> W((size_t)np_ * np_, 0.0), Vm((size_t)np_ * np_, 0.0);
+    for (int j = 0; j < n; j++) {
+      double *wj = &W[(size_t)j * np_];
+      const double *qj = &C[(size_t)j * n];
+      for (int k = 0; k < n; k++) {
+        const double f = qj[k] * dh[k];
+        if (f == 0.0) continue;
+        const double *xk = &X[(size_t)k * n];
+        for (int i = 0; i <= k; i++) wj[i] += f * xk[i];
+      }
+    }
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) Vm[(size_t)i * np_ + j] = W[(size_t)j * np_ + i];
+    gd.mu.assign(np_, 0.0);
+    for (int j = 0; j < n; j++) gd.mu[j] = mu[j];
+    append_panels(tmp, W, np_, np_);
+    gd.offV = (long long)tmp.data.size();
+    append_panels(tmp, Vm, np_, np_);
+    gd.spectral = true;
+  } else {
     const std::vector<double> M = reduced_inverse(h, S);
     append_panels(tmp, M, np_, np_);
   }
@@ -434,6 +628,11 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     return BQP_E_ARG;
   for (int r = 0; r < m; r++)
     if (p->l[r] > p->u[r]) return BQP_E_BOUNDS;
+  if (s->adaptive_rho) {
+    // a fixed interval that coincides with termination checks (osqp rounds its automatic interval to one, too)
+    if (s->adaptive_rho_interval <= 0 || s->adaptive_rho_interval % s->check_termination != 0 || !(s->adaptive_rho_tolerance > 1.0)) return BQP_E_ARG;
+    if (s->eq_rho == 2) return BQP_E_UNSUPPORTED;
+  }
   h->n = n; h->m = m; h->npad = ((n + kNB - 1) / kNB) * kNB; h->n_int = p->n_int; h->s = *s;
   h->i_idx.assign(p->i_idx, p->i_idx + p->n_int);
   for (int k = 0; k < p->n_int; k++)
@@ -465,13 +664,13 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
   ruiz(P, A, h->q, s->scaling, h);
 
   // rho typing on the SCALED, clamped root bounds
-  h->rho.resize(m); h->rho_inv.resize(m);
+  h->rho.resize(m); h->rho_inv.resize(m); h->rtype.assign(m, 0);
   for (int r = 0; r < m; r++) {
     double lo = std::max(p->l[r], -kInfty) * h->E[r], up = std::min(p->u[r], kInfty) * h->E[r];
     double rho = s->rho;
     if (s->eq_rho) {
-      if (lo < -kInfty * kMinScaling && up > kInfty * kMinScaling) rho = kRhoMin;
-      else if (up - lo < kRhoTol) rho = kRhoEqFactor * s->rho;
+      if (lo < -kInfty * kMinScaling && up > kInfty * kMinScaling) { rho = kRhoMin; h->rtype[r] = -1; }
+      else if (up - lo < kRhoTol) { rho = kRhoEqFactor * s->rho; h->rtype[r] = 1; }
     }
     h->rho[r] = rho; h->rho_inv[r] = 1.0 / rho;
   }
@@ -582,7 +781,7 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     double min_density = 0.34;
     if (const char *e = std::getenv("BQP_PANEL_MIN_DENSITY")) min_density = std::atof(e);
     const double density = (m > 0) ? (double)A.x.size() / ((double)m * n) : 1.0;
-    if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density) build_panels(h, arows, prows, S);
+    if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density && !s->adaptive_rho) build_panels(h, arows, prows, S);
   }
   // The panel kernels apply M = (P + sigma I + A' rho A)^-1 explicitly; forming an inverse is not backward stable, and
   // with a tiny sigma, a rank-deficient P or rows typed rho x 1e3 the reduced matrix can be badly conditioned.  Probe it:
@@ -617,7 +816,10 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
   {
     int want = 1, max_np = 2880;                       // x~ of 8 leaves staged in shared memory: 64 npad bytes of the 227 KB
     if (const char *e = std::getenv("BQP_GRID")) want = std::atoi(e);
-    if (want && !h->pn.built && !h->pn_rejected && np_ > 32 * kPanelMaxWarps && np_ <= max_np && s->eq_rho != 2) {
+    // BQP_GRID_ALL=1 (experiments: one config-2 tile on the whole GPU): also for problems the rows kernel serves; run with BQP_KERNEL=grid
+    const bool all_sizes = std::getenv("BQP_GRID_ALL") && std::atoi(std::getenv("BQP_GRID_ALL")) != 0;
+    const bool wide = (all_sizes || s->adaptive_rho) ? true : (!h->pn.built && np_ > 32 * kPanelMaxWarps);
+    if (want && wide && !h->pn_rejected && np_ <= max_np && s->eq_rho != 2) {
       build_grid(h, arows, atrows, prows, S);
       double tol = 1e-10;
       if (const char *e = std::getenv("BQP_INVERSE_TOL")) tol = std::atof(e);
@@ -639,10 +841,11 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
         const double rel = dif / std::max(nrm, 1e-300);
         worst = (rel == rel) ? std::max(worst, rel) : INFINITY;
       }
-      h->pn_inverse_error = worst;
-      if (!(worst <= tol)) { h->gd = HostGridL(); h->pn_rejected = true; }
+      if (!h->pn.built) h->pn_inverse_error = worst;
+      if (!(worst <= tol)) { h->gd = HostGridL(); if (!h->pn.built) h->pn_rejected = true; }
     }
   }
+  if (s->adaptive_rho && !(h->gd.built && h->gd.spectral)) return BQP_E_UNSUPPORTED;
   h->mint.clear();
   if (s->eq_rho == 2) {
     // per-node re-typing corrects the explicit inverse by a Woodbury term over the re-typed integer rows: dense kernels only
@@ -834,6 +1037,19 @@ int host_grid_kkt_solve(const HostInstance *h, double *rhs) {
     for (int k = gd.trp[j]; k < gd.trp[j + 1]; k++) acc = std::fma(gd.tvl[k], h->rho[gd.tci[k]] * rhs[n + gd.tci[k]], acc);
     b[j] = rhs[j] + acc;
   }
+  if (gd.spectral) {       // x~ = V (V' b) at the setup rho (d = 1)
+    std::vector<double> c(np_, 0.0);
+    for (int r = 0; r < n; r++) {
+      double acc = 0;
+      for (int j = 0; j < n; j++) acc = std::fma(gd.MP[panel_pos(r, j, np_)], b[j], acc);
+      c[r] = acc;
+    }
+    for (int r = 0; r < n; r++) {
+      double acc = 0;
+      for (int j = 0; j < n; j++) acc = std::fma(gd.MP[(size_t)gd.offV + panel_pos(r, j, np_)], c[j], acc);
+      xt[r] = acc;
+    }
+  } else
   for (int r = 0; r < n; r++) {
     double acc = 0;
     for (int j = 0; j < n; j++) acc = std::fma(gd.MP[panel_pos(r, j, np_)], b[j], acc);

@@ -31,14 +31,14 @@ CONSTANTS = {
 
 # OSQP setting names understood by the engine, with OSQP's defaults
 DEFAULTS = dict(rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4,
-                eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25, eq_rho=1, device=0)
+                eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25, eq_rho=1, device=0,
+                adaptive_rho=0, adaptive_rho_interval=0, adaptive_rho_tolerance=5.0)
 # pre-0.1.3 names found in /root/reference/max_iter_examples/*.pickle
 ALIASES = {"eps_inf": "eps_prim_inf", "eps_unb": "eps_dual_inf"}
 # accepted and ignored (no effect on the iterates of the parity contract)
 IGNORED = {"verbose", "polish", "polishing", "warm_start", "time_limit", "linsys_solver", "delta",
            "polish_refine_iter", "pol_refine_iter", "scaling_iter", "scaling_norm", "early_terminate",
-           "early_terminate_interval", "auto_rho", "adaptive_rho_interval", "adaptive_rho_fraction",
-           "adaptive_rho_tolerance"}
+           "early_terminate_interval", "auto_rho", "adaptive_rho_fraction"}
 
 
 class BqpError(RuntimeError):
@@ -50,7 +50,8 @@ class _Settings(C.Structure):
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double),
                 ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
                 ("max_iter", C.c_int), ("scaling", C.c_int), ("check_termination", C.c_int),
-                ("eq_rho", C.c_int), ("device", C.c_int)]
+                ("eq_rho", C.c_int), ("device", C.c_int),
+                ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int), ("adaptive_rho_tolerance", C.c_double)]
 
 
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -193,10 +194,6 @@ def normalize_settings(kw):
         k = ALIASES.get(k, k)
         if k in s:
             s[k] = v
-        elif k == "adaptive_rho":
-            if v:
-                raise ValueError("adaptive_rho is outside the engine's parity contract (rho is fixed; "
-                                 "every node is a pure function of (l,u,x0,y0))")
         elif k == "scaled_termination":
             if v:
                 raise ValueError("scaled_termination is not supported")
@@ -209,6 +206,16 @@ def normalize_settings(kw):
                          "re-typed per node, what osqp >= 0.4 does in update_bounds; dense-A problems only)")
     if isinstance(s["scaling"], bool):
         s["scaling"] = 10 if s["scaling"] else 0
+    s["adaptive_rho"] = 1 if s["adaptive_rho"] else 0
+    s["adaptive_rho_interval"] = int(s["adaptive_rho_interval"])
+    if s["adaptive_rho"]:
+        # osqp's default (interval 0) derives the interval from wall-clock setup time: not reproducible, so a node would not
+        # be a pure function of (l, u, x0, y0) -- refused; a fixed interval on the termination-check grid is the contract
+        if s["adaptive_rho_interval"] <= 0 or s["adaptive_rho_interval"] % int(s["check_termination"]) != 0:
+            raise ValueError("adaptive_rho needs a fixed adaptive_rho_interval > 0 that is a multiple of check_termination "
+                             "(osqp's automatic, timing-based interval is not reproducible)")
+        if s["eq_rho"] == 2:
+            raise ValueError("adaptive_rho and eq_rho = 2 (per-node re-typing) cannot be combined")
     return s
 
 

@@ -41,20 +41,22 @@ class _Settings(C.Structure):
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double),
                 ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
                 ("max_iter", C.c_int), ("scaling", C.c_int), ("check_termination", C.c_int),
-                ("scaled_termination", C.c_int), ("eq_rho", C.c_int)]
+                ("scaled_termination", C.c_int), ("eq_rho", C.c_int),
+                ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int), ("adaptive_rho_tolerance", C.c_double)]
 
 
 class _Info(C.Structure):
     _fields_ = [("status", C.c_int), ("iter", C.c_int), ("obj_val", C.c_double),
-                ("pri_res", C.c_double), ("dua_res", C.c_double), ("solve_time", C.c_double)]
+                ("pri_res", C.c_double), ("dua_res", C.c_double), ("solve_time", C.c_double),
+                ("rho_updates", C.c_int), ("rho_final", C.c_double)]
 
 
 DEFAULTS = dict(rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4,
                 eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25,
-                scaled_termination=0, eq_rho=1)
+                scaled_termination=0, eq_rho=1, adaptive_rho=0, adaptive_rho_interval=0, adaptive_rho_tolerance=5.0)
 _ALIASES = {"eps_inf": "eps_prim_inf", "eps_unb": "eps_dual_inf"}
-_IGNORED = {"verbose", "polish", "polishing", "warm_start", "adaptive_rho", "adaptive_rho_interval",
-            "adaptive_rho_fraction", "adaptive_rho_tolerance", "time_limit", "linsys_solver",
+_IGNORED = {"verbose", "polish", "polishing", "warm_start",
+            "adaptive_rho_fraction", "time_limit", "linsys_solver",
             "delta", "polish_refine_iter", "pol_refine_iter", "scaling_iter", "scaling_norm",
             "early_terminate", "early_terminate_interval", "auto_rho", "scaled_termination_"}
 
@@ -63,9 +65,6 @@ def normalize_settings(kw):
     s = dict(DEFAULTS)
     for k, v in kw.items():
         k = _ALIASES.get(k, k)
-        if k == "adaptive_rho" and v:
-            # the parity contract is a fixed rho: refuse, as the engine does, instead of silently ignoring
-            raise ValueError("adaptive_rho is outside the parity contract of this oracle (fixed rho, typed per row at setup)")
         if k in s:
             s[k] = v
         elif k in _IGNORED:
@@ -74,6 +73,12 @@ def normalize_settings(kw):
             raise TypeError("unknown OSQP setting %r" % k)
     if isinstance(s["scaling"], bool):
         s["scaling"] = 10 if s["scaling"] else 0
+    s["adaptive_rho"] = 1 if s["adaptive_rho"] else 0
+    if s["adaptive_rho"] and not int(s["adaptive_rho_interval"]) > 0:
+        # osqp's automatic interval (0) is derived from wall-clock setup time: not reproducible, refused as the engine does
+        raise ValueError("adaptive_rho needs a fixed adaptive_rho_interval > 0 (the automatic, timing-based interval of osqp "
+                         "is not reproducible and is outside the parity contract)")
+    s["adaptive_rho_interval"] = int(s["adaptive_rho_interval"])
     return s
 
 
@@ -206,7 +211,8 @@ class OSQP(object):
             raise ValueError("Lower bound must be lower than or equal to upper bound")
         status = np.array([i.status for i in infos]); iters = np.array([i.iter for i in infos])
         extra = dict(obj=np.array([i.obj_val for i in infos]), pri_res=np.array([i.pri_res for i in infos]),
-                     dua_res=np.array([i.dua_res for i in infos]), solve_time=np.array([i.solve_time for i in infos]))
+                     dua_res=np.array([i.dua_res for i in infos]), solve_time=np.array([i.solve_time for i in infos]),
+                     rho_updates=np.array([i.rho_updates for i in infos]), rho_final=np.array([i.rho_final for i in infos]))
         return x, y, status, iters, extra
 
     def dims(self):

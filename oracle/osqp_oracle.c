@@ -37,6 +37,7 @@
 #define MIN_SCALING 1e-4
 #define MAX_SCALING 1e4
 #define RHO_MIN 1e-6
+#define RHO_MAX 1e6
 #define RHO_TOL 1e-4
 #define RHO_EQ_OVER_RHO_INEQ 1e3
 #define DIVISION_TOL (1.0 / OSQP_INFTY)
@@ -49,11 +50,17 @@ enum {
 typedef struct {
   double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
   int max_iter, scaling, check_termination, scaled_termination, eq_rho;
+  /* adaptive rho with a FIXED interval: osqp's automatic interval (adaptive_rho_interval = 0) is derived
+   * from wall-clock setup time and is not reproducible, so it is not offered.  Every node starts from settings.rho (a node
+   * is a pure function of its inputs; the reference's one osqp object carries the adapted rho from node to node). */
+  int adaptive_rho, adaptive_rho_interval;
+  double adaptive_rho_tolerance;
 } OracleSettings;
 
 typedef struct {
   int status, iter;
   double obj_val, pri_res, dua_res, solve_time;
+  int rho_updates; double rho_final;
 } OracleInfo;
 
 typedef struct {
@@ -517,6 +524,7 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
                       const double *x0, const double *y0, double *x_out, double *y_out, OracleInfo *info) {
   int n = w->n, m = w->m; const OracleSettings *S = &w->s;
   struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+  info->rho_updates = 0; info->rho_final = S->rho;
   double *l = malloc(8 * (m + 1)), *u = malloc(8 * (m + 1));
   for (int i = 0; i < m; i++) {
     if (l_in[i] > u_in[i]) { free(l); free(u); return 1; }
@@ -547,6 +555,19 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
       w = &tw; S = &w->s; refactored = 1;
     }
   }
+  /* adaptive rho: constraint type per row (osqp constr_type: -1 loose, 1 equality, 0 inequality) from the bounds the typing
+   * in effect looked at -- the root's at setup (eq_rho 1), this node's (eq_rho 2), none (eq_rho 0) */
+  const int adapt = S->adaptive_rho && S->adaptive_rho_interval > 0 && m > 0;
+  int *ctype = NULL; double rho_cur = S->rho;
+  if (adapt) {
+    ctype = calloc((size_t)m, sizeof(int));
+    const double *tl = S->eq_rho == 2 ? l : w->l, *tu = S->eq_rho == 2 ? u : w->u;
+    for (int i = 0; i < m && S->eq_rho; i++) {
+      if (tl[i] < -OSQP_INFTY * MIN_SCALING && tu[i] > OSQP_INFTY * MIN_SCALING) ctype[i] = -1;
+      else if (tu[i] - tl[i] < RHO_TOL) ctype[i] = 1;
+    }
+    if (!rv) { rv = malloc(8 * (size_t)m); ri = malloc(8 * (size_t)m); memcpy(rv, w->rho_vec, 8 * (size_t)m); memcpy(ri, w->rho_inv_vec, 8 * (size_t)m); }
+  }
   for (int j = 0; j < n; j++) s->x[j] = w->Dinv[j] * x0[j];
   for (int i = 0; i < m; i++) s->y[i] = w->c * w->Einv[i] * y0[i];
   mat_vec_A(w, s->x, s->z);
@@ -575,6 +596,43 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
       update_info(w, s, q, &r, &nAx, &nz, &nPx, &nAty, &nq);
       if (check_termination(w, s, q, l, u, &r, nAx, nz, nPx, nAty, nq, 0, &status)) break;
     }
+    if (adapt && iter % S->adaptive_rho_interval == 0) {
+      /* osqp_solve: update_info if this iteration had no check, then adapt_rho -> compute_rho_estimate on the SCALED
+       * residuals and norms (plain inf-norms of the solver's own vectors), update when outside [rho / tol, rho * tol] */
+      if (!checked) update_info(w, s, q, &r, &nAx, &nz, &nPx, &nAty, &nq);
+      double pr = 0, n1 = 0, n2 = 0, dr = 0, d1 = 0, d2 = 0, d3 = 0;
+      for (int i = 0; i < m; i++) {
+        double a = fabs(s->Ax[i] - s->z[i]); if (a > pr) pr = a;
+        a = fabs(s->z[i]); if (a > n1) n1 = a;
+        a = fabs(s->Ax[i]); if (a > n2) n2 = a;
+      }
+      for (int j = 0; j < n; j++) {
+        double a = fabs(s->Px[j] + q[j] + s->Aty[j]); if (a > dr) dr = a;
+        a = fabs(q[j]); if (a > d1) d1 = a;
+        a = fabs(s->Aty[j]); if (a > d2) d2 = a;
+        a = fabs(s->Px[j]); if (a > d3) d3 = a;
+      }
+      pr /= (fmax(n1, n2) + 1e-10);
+      dr /= (fmax(fmax(d1, d2), d3) + 1e-10);
+      double rho_new = rho_cur * sqrt(pr / (dr + 1e-10));
+      rho_new = fmin(fmax(rho_new, RHO_MIN), RHO_MAX);
+      if (rho_new > rho_cur * S->adaptive_rho_tolerance || rho_new < rho_cur / S->adaptive_rho_tolerance) {
+        for (int i = 0; i < m; i++) {
+          if (ctype[i] == 0) rv[i] = rho_new; else if (ctype[i] == 1) rv[i] = RHO_EQ_OVER_RHO_INEQ * rho_new;
+          ri[i] = 1.0 / rv[i];
+        }
+        OracleWork nw = *w; nw.rho_vec = rv; nw.rho_inv_vec = ri;
+        nw.perm = NULL; nw.Lp = NULL; nw.Li = NULL; nw.Lx = NULL; nw.Dd = NULL; nw.Ddinv = NULL; nw.etree = NULL;
+        int frc = factor_kkt(&nw);
+        if (refactored) { free(tw.perm); free(tw.Lp); free(tw.Li); free(tw.Lx); free(tw.Dd); free(tw.Ddinv); free(tw.etree); refactored = 0; }
+        if (frc != 0) {
+          free(nw.perm); free(nw.Lp); free(nw.Li); free(nw.Lx); free(nw.Dd); free(nw.Ddinv); free(nw.etree);
+          free(rv); free(ri); free(l); free(u); free(ctype); return 2;
+        }
+        tw = nw; w = &tw; S = &w->s; refactored = 1; rho_cur = rho_new;
+        info->rho_updates++;
+      }
+    }
   }
   if (iter > S->max_iter) iter = S->max_iter;
   if (status == ST_UNSOLVED) {
@@ -593,7 +651,8 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
   else info->obj_val = r.obj;
   for (int j = 0; j < n; j++) x_out[j] = infeas ? NAN : w->D[j] * s->x[j];
   for (int i = 0; i < m; i++) y_out[i] = infeas ? NAN : w->cinv * w->E[i] * s->y[i];
-  free(l); free(u);
+  info->rho_final = rho_cur;
+  free(l); free(u); free(ctype);
   if (refactored) { free(tw.perm); free(tw.Lp); free(tw.Li); free(tw.Lx); free(tw.Dd); free(tw.Ddinv); free(tw.etree); }
   free(rv); free(ri);
   clock_gettime(CLOCK_MONOTONIC, &t1);

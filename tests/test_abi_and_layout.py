@@ -93,3 +93,21 @@ def test_bad_arguments():
         engine.BatchedQP().setup(-P, q, A, l, u, i_idx=i_idx, host_only=True)       # not positive semidefinite
     with pytest.raises(ValueError):
         engine.BatchedQP().setup(P, q[:-1], A, l, u, i_idx=i_idx, host_only=True)
+
+
+def test_adaptive_rho_settings_and_spectral_layout():
+    """adaptive_rho needs a fixed interval on the termination-check grid; the host then builds the spectral form of the
+    reduced inverse (V, mu) and probes it against the LDL' factor like the explicit inverse."""
+    from miosqp_b200 import problems
+    with pytest.raises(ValueError):
+        engine.normalize_settings({"adaptive_rho": True, "adaptive_rho_interval": 30})          # not a multiple of 25
+    with pytest.raises(ValueError):
+        engine.normalize_settings({"adaptive_rho": True, "adaptive_rho_interval": 50, "eq_rho": 2})
+    s = engine.normalize_settings({"adaptive_rho": True, "adaptive_rho_interval": 50})
+    assert s["adaptive_rho"] == 1 and s["adaptive_rho_tolerance"] == 5.0
+    for shape in [(60, 90, 6, 0.5, 2), (130, 200, 10, 0.7, 4), (300, 450, 12, 0.05, 5)]:
+        n, m, p, d, seed = shape
+        P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(n, m, p, d, seed=seed)[0])
+        e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, host_only=True, adaptive_rho=True, adaptive_rho_interval=25)
+        err, in_use = e.inverse_guard()
+        assert in_use and err < 1e-10, (shape, err)

@@ -426,8 +426,8 @@ def test_grid_kernel_infeasible_and_max_iter(oracle_mod):
     P, q, A, l, u, i_idx = problems.extend(pr)
     n, m = A.shape[1], A.shape[0]
     ls = np.tile(l, (4, 1)); us = np.tile(u, (4, 1))
-    ls[1, 0] = 50.0; us[1, 0] = 60.0          # row 0 cannot reach 50
-    ls[3, 1] = -60.0; us[3, 1] = -50.0
+    ls[1, 0] = 1e4; us[1, 0] = 2e4            # row 0 cannot reach 1e4 (certificate at iteration 125 on the oracle)
+    ls[3, 1] = -2e4; us[3, 1] = -1e4
     x0 = np.zeros((4, n)); y0 = np.zeros((4, m))
     seen = set()
     for st in (QP, dict(QP, max_iter=75), dict(QP, max_iter=40, eps_abs=1e-7, eps_rel=1e-7)):
@@ -460,3 +460,26 @@ def test_grid_and_stream_kernels_agree(monkeypatch):
     assert engine.last_timing()["kernel"] == 1
     assert list(rg.status) == list(rs.status) and list(rg.iters) == list(rs.iters)
     _close(rg.x, rs.x); _close(rg.y, rs.y); _close(rg.lower, rs.lower)
+
+
+# ---------------------------------------------------------------- adaptive rho on the GPU (second half)
+@pytest.mark.parametrize("case", [(130, 200, 10, 0.7, 4, 9, 25), (500, 1000, 50, 0.7, 1, 8, 50), (600, 900, 20, 0.05, 12, 5, 100),
+                                  (50, 100, 5, 0.7, 1, 6, 25)])
+def test_adaptive_rho_against_oracle(oracle_mod, case):
+    """osqp adaptive_rho with a fixed interval: every leaf adapts its own rho (the whole-GPU kernel applies the reduced KKT
+    inverse in spectral form, x~ = V (d(rho) . (V' b)), so a rho update needs no refactorisation); the oracle refactors
+    numerically like osqp_update_rho.  Same statuses, iteration counts and iterates."""
+    n, m, p, dens, seed, count, interval = case
+    pr = problems.random_miqp(n, m, p, dens, seed=seed)[0]
+    st = dict(QP, adaptive_rho=True, adaptive_rho_interval=interval)
+    r, e = _compare(pr, count, 21, st, warm="root", oracle_mod=oracle_mod)
+    assert engine.last_timing()["kernel"] == 4
+    if n == 500:
+        # and it is what it is for: the fixed rho = 0.1 needs several times the iterations on this problem class
+        P, q, A, l, u, i_idx = problems.extend(pr)
+        ls, us = problems.branched_nodes(l, u, len(i_idx), count, np.random.default_rng(21))
+        o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, **QP)
+        root = o.solve_node(l, u, np.zeros(n), np.zeros(A.shape[0]))
+        x0 = np.tile(np.nan_to_num(root.x), (count, 1)); y0 = np.tile(np.nan_to_num(root.y), (count, 1))
+        rf = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP).solve_batch(ls, us, x0, y0)
+        assert r.iters.sum() * 2 < rf.iters.sum(), (list(r.iters), list(rf.iters))

@@ -65,10 +65,14 @@ def test_replay_49_in_one_launch(oracle_mod):
 
 
 @pytest.mark.gpu
-def test_cfg4_shape_fixed_iterations(oracle_mod):
-    """BASELINE config 4 shape (n=2000, m=4000, |i_idx|=200, 5 % dense): the streamed kernel with sparse A groups
-    and a 64-block dense tail; 2 leaves, iterates compared after a fixed 100 iterations (status max_iter)."""
+@pytest.mark.parametrize("kernel", ["grid", "stream"])
+def test_cfg4_shape_fixed_iterations(oracle_mod, kernel, monkeypatch):
+    """BASELINE config 4 shape (n=2000, m=4000, |i_idx|=200, 5 % dense) on the whole-GPU kernel (default) and, with BQP_GRID=0
+    at setup, on the streamed kernel with sparse A groups and a 64-block dense tail; 2 leaves, iterates compared after a
+    fixed 100 iterations (status max_iter)."""
     from miosqp_b200 import problems
+    if kernel == "stream":
+        monkeypatch.setenv("BQP_GRID", "0")
     pr = problems.random_miqp(2000, 4000, 200, 0.05, seed=1)[0]
     P, q, A, l, u, i_idx = problems.extend(pr)
     s = dict(eps_abs=1e-9, eps_rel=1e-9, eps_prim_inf=1e-9, eps_dual_inf=1e-9, max_iter=100)
@@ -78,7 +82,8 @@ def test_cfg4_shape_fixed_iterations(oracle_mod):
     x0 = np.zeros((2, 2000)); y0 = np.zeros((2, 4200))
     xo, yo, so, io, extra = o.solve_batch(ls, us, x0, y0, threads=2)
     r = e.solve_batch(ls, us, x0, y0)
-    assert engine.last_timing()["threads"] == 13 * 32
+    t = engine.last_timing()
+    assert (t["kernel"], t["threads"]) == ((4, 512) if kernel == "grid" else (1, 13 * 32)), t
     assert list(r.status) == list(so) and list(r.iters) == list(io) == [100, 100]
     for b in range(2):
         xo[b, i_idx] = np.minimum(np.maximum(xo[b, i_idx], ls[b, -200:]), us[b, -200:])
