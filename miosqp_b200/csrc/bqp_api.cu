@@ -209,7 +209,7 @@ int to_device(bqp_instance *inst) {
   if (h.pn.built) {
     ar.add(h.pn.data, &d.pstream);
     d.p_nw = h.pn.nw; d.p_npm = h.pn.npm; d.p_npa = h.pn.npa;
-    d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP;
+    d.p_panel_doubles = h.pn.panel_doubles; d.p_offA = h.pn.offA; d.p_offP = h.pn.offP; d.p_offV = h.pn.offV;
   }
   d.g_M = d.g_P = nullptr; d.g_arp = d.g_aci = d.g_trp = d.g_tci = nullptr; d.g_avl = d.g_tvl = nullptr; d.g_npm = 0;
   d.g_V = d.g_mu = nullptr; d.g_rtype = nullptr; d.adaptive = 0; d.adapt_interval = 0; d.adapt_tol = 5.0;
@@ -223,6 +223,10 @@ int to_device(bqp_instance *inst) {
       ar.add(h.gd.mu, &d.g_mu); ar.add(h.rtype, &d.g_rtype);
       d.adaptive = 1; d.adapt_interval = h.s.adaptive_rho_interval; d.adapt_tol = h.s.adaptive_rho_tolerance;
     }
+  }
+  if (h.pn.built && h.pn.spectral) {      // rows kernel, adaptive rho
+    ar.add(h.pn.mu, &d.g_mu); ar.add(h.rtype, &d.g_rtype);
+    d.adaptive = 1; d.adapt_interval = h.s.adaptive_rho_interval; d.adapt_tol = h.s.adaptive_rho_tolerance;
   }
   d.p_mint = nullptr; d.eq2 = h.s.eq_rho == 2 ? 1 : 0; d.rho_base = h.s.rho;
   if (d.eq2) ar.add(h.mint, &d.p_mint);
@@ -716,7 +720,8 @@ static void select_kernel(BatchCtx &g) {
     g.use_grid = true; g.use_panel = g.use_stream = false; g.grid_ctas = sms;
     for (bqp_instance *inst : g.node_inst) if (!inst->h.gd.built) g.use_grid = false;
   }
-  for (bqp_instance *inst : g.node_inst) if (inst->h.s.adaptive_rho && !(g.use_grid && inst->h.gd.spectral)) g.eq2_unsupported = true;
+  for (bqp_instance *inst : g.node_inst)
+    if (inst->h.s.adaptive_rho && !((g.use_grid && inst->h.gd.spectral) || (g.use_panel && g.use_rows && inst->h.pn.spectral))) g.eq2_unsupported = true;
   if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
   g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
@@ -752,7 +757,7 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
   for (int b = 0; b < B; b++) {
     const HostInstance &h = handles[b]->h;
     g.in_off[b] = (long long)in_d; g.out_off[b] = (long long)out_d; g.state_off[b] = (long long)st_d; g.node_inst[b] = handles[b];
-    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
+    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n + 1;      // scaled x, z, y (+ the leaf's rho: adaptive rho)
   }
   g.B = B; g.in_doubles = in_d; g.out_doubles = out_d;
   g.session = false;
@@ -932,7 +937,7 @@ static int session_append(BatchCtx &g, int B, const bqp_handle *handles, const d
     const HostInstance &h = handles[b]->h;
     g.in_off.push_back((long long)in_d); g.out_off.push_back((long long)out_d); g.state_off.push_back((long long)st_d);
     g.node_inst.push_back(handles[b]);
-    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n;
+    in_d += 3 * (size_t)h.m + h.n; out_d += (size_t)h.m + h.n; st_d += 2 * (size_t)h.m + h.n + 1;      // scaled x, z, y (+ the leaf's rho: adaptive rho)
     g.s_alive.push_back(B0 + b); g.s_progress.push_back(0); g.s_dist.push_back(NAN); g.s_remaining.push_back(1e30);
   }
   g.B = B0 + B; g.s_in_d = in_d; g.s_out_d = out_d; g.s_st_d = st_d;

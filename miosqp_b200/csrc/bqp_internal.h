@@ -101,10 +101,13 @@ constexpr int panel_cta_warps(int nwc) { return (nwc + kPanelP1Tiles - 1) / kPan
 struct HostPanels {
   bool built = false;
   int nw = 0, npm = 0, npa = 0;                     // column tiles; panels of M (and P); panels of A
-  long long panel_doubles = 0, offA = 0, offP = 0;  // doubles
+  long long panel_doubles = 0, offA = 0, offP = 0, offV = 0;  // doubles
   std::vector<double> data;
+  // adaptive rho: the M slot holds V' and V follows P: K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V' (bqp_setup.cpp spectral_factors)
+  bool spectral = false;
+  std::vector<double> mu;
   long long panel_bytes() const { return panel_doubles * 8; }
-  long long iter_bytes() const { return (long long)(npm + npa) * panel_bytes(); }          // M + A
+  long long iter_bytes() const { return (long long)((spectral ? 2 : 1) * npm + npa) * panel_bytes(); }          // M (or V', V) + A
   long long check_bytes() const { return (long long)(2 * npa + npm) * panel_bytes(); }     // A twice + P
   long long launch_bytes() const { return (long long)(npa + npm) * panel_bytes(); }        // prologue A pass + objective P pass
 };
@@ -190,7 +193,7 @@ struct DevInstance {
   int g_at[2], g_fw[2], g_bw[2], g_ab[2], g_pm[2];
   int w_in_stage;   // 1: every A' group is dense -> its input vector chunks ride in the TMA stages (no m x T vector in smem)
   // row-panel layout (fused single-pass kernel)
-  const double *pstream; int p_nw, p_npm, p_npa; long long p_panel_doubles, p_offA, p_offP;
+  const double *pstream; int p_nw, p_npm, p_npa; long long p_panel_doubles, p_offA, p_offP, p_offV;
   const double *p_mint; int eq2; double rho_base;      // eq_rho == 2: rows of M of the integer variables; untyped rho
   // whole-GPU layout (bqp_grid.cu)
   const double *g_M, *g_P; const int *g_arp, *g_aci, *g_trp, *g_tci; const double *g_avl, *g_tvl; int g_npm;

@@ -44,7 +44,8 @@ constexpr int kTPW = 4;                    // column tiles per warp (npad <= 512
 constexpr int kCons = kG * kW;             // consumer warps
 constexpr int kConsThreads = kCons * 32;
 constexpr int kTileD = 256;                // doubles of one column tile of one panel (8 rows x 32 columns)
-constexpr int kFinN = 16;
+constexpr int kFinN = 16;                 // quantities of one canonical reduction
+constexpr int kFinAll = 24;               // + the 7 scaled norms of osqp's compute_rho_estimate (adaptive rho)
 constexpr int kMaxS = 64;                  // eq_rho == 2: re-typed integer rows per node the scratch holds (n_int <= 64 with the dense kernels' part buffer)
 constexpr int kXR = 16;                    // x-iterate elements a consumer thread keeps in registers (npad * 8 / 256 at most)
 // Registers: each SM sub-partition holds 16 K registers and hosts every fourth warp, so 12 warps get 168 registers each at
@@ -118,10 +119,14 @@ __device__ __forceinline__ double2 ldcg2(const double *p) { return __ldcg(reinte
 struct RowsShared {
   DevInstance I;
   DevTile tile;
-  double fin[kFinN][T8];
+  double fin[kFinAll][T8];
   int status[T8], iters[T8], newly[T8];
   double dist[T8];
   int remaining;
+  // adaptive rho: the leaf's current rho (osqp settings->rho after osqp_update_rho), 1 / rho and 1 / (1e3 rho); a change is
+  // announced to the producer warpgroup through rho_changed (one more A pass rebuilds the right-hand side)
+  double rho_t[T8], rinv_t[T8], rinveq_t[T8];
+  int rho_changed;
 };
 
 enum { RM_A_INIT = 0, RM_A_RESUME, RM_M, RM_A_ITER, RM_CHK_A1, RM_CHK_A2, RM_CHK_P, RM_OBJ_P };
@@ -146,7 +151,7 @@ struct Ctx {
 #endif
   RowsShared *S;
   Work Wk;
-  uint32_t full, empty, xbar, rbar, cbar;             // mbarrier addresses (shared window)
+  uint32_t full, empty, xbar, rbar, cbar, vbar;       // mbarrier addresses (shared window)
   double *colb, *colx, *recv, *part;                  // b (M-pass operand) | x~ (A-pass operand) | reduce-scatter inbox | group partials
   unsigned char *ring;
   uint32_t ring_u32;
@@ -159,7 +164,7 @@ struct Ctx {
   int cnt;                                            // CTA-local panel counter across passes (ring position of the next pass)
   int cmine, slot; uint32_t phase;                    // next counter value handled by this warp's group, its ring slot and phase
   int gord;                                           // panels this group has processed (owner-warp rotation, partial double buffer)
-  uint32_t xph, rph, cph;                             // phases of the cross-CTA barriers
+  uint32_t xph, rph, cph, vph;                        // phases of the cross-CTA barriers
 };
 
 template <int OP>   // 0 max, 1 sum, 2 min
@@ -195,7 +200,11 @@ __device__ __forceinline__ void load_bx(double (&bx)[kTPW][8], const double *v, 
 // One pass over the panels this CTA owns of one matrix.  MODE selects the row functor; passes with a second half
 // accumulate A_panel' w into acc (C fragments: column 32 (tile0 + tl) + 8 mt + (lane >> 2), nodes 2 (lane & 3) + {0, 1}).
 template <int CS, int MODE>
-__device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double (&bx)[kTPW][8], double (&acc)[kTPW][4][2], bool do_check) {
+__device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double (&bx)[kTPW][8], double (&acc)[kTPW][4][2], bool do_check,
+                                          double *mdst = nullptr, bool dscale = false, uint32_t mbar = 0) {
+  // RM_M only: mdst = the vector the product rows go to (this CTA's copy and every peer's); dscale = multiply row j of
+  // leaf t by 1 / (1 + (rho_t - rho0) mu_j) (adaptive rho: the first of the two passes of x~ = V (d . (V' b))); mbar = the
+  // peers' mbarrier the remote rows complete their bytes on
   const DevInstance &I = X.S->I;
   const Work &W = X.Wk;
   constexpr bool kIsA = (MODE == RM_A_INIT || MODE == RM_A_RESUME || MODE == RM_A_ITER || MODE == RM_CHK_A1 || MODE == RM_CHK_A2);
@@ -235,6 +244,12 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       if constexpr (MODE == RM_CHK_A1) { s1 = ld2(W.gy); }
       if constexpr (MODE == RM_CHK_A2) { s0 = ld2(W.gdy); s2 = ld2(W.gl); s3 = ld2(W.gu); }
       if constexpr (MODE == RM_CHK_P) { s0 = ld2(W.gdx); }
+      if constexpr (MODE == RM_M) {
+        if (dscale && owner) {
+          const double mu = __ldg(I.g_mu + row);
+          s0.x = 1.0 / (1.0 + (X.S->rho_t[2 * tq] - I.rho_base) * mu); s0.y = 1.0 / (1.0 + (X.S->rho_t[2 * tq + 1] - I.rho_base) * mu);
+        }
+      }
     }
     RSTAMP(X, 5);
     double rho2[2] = {rho, rho}, rinv2[2] = {rinv, rinv};
@@ -251,6 +266,16 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
           if (lo_[i] < -kInfty * kMinScaling && up_[i] > kInfty * kMinScaling) rr = kRhoMin;
           else if (up_[i] - lo_[i] < kRhoTol) rr = kRhoEqFactor * I.rho_base;
           rho2[i] = rr; rinv2[i] = 1.0 / rr;
+        }
+      }
+      // adaptive rho: inequality / equality rows follow the leaf's own rho (osqp_update_rho), loose rows stay at RHO_MIN
+      if (I.adaptive && live) {
+        const int ty = __ldg(I.g_rtype + row);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int t = 2 * tq + i;
+          if (ty == 0) { rho2[i] = X.S->rho_t[t]; rinv2[i] = X.S->rinv_t[t]; }
+          else if (ty == 1) { rho2[i] = kRhoEqFactor * X.S->rho_t[t]; rinv2[i] = X.S->rinveq_t[t]; }
         }
       }
     }
@@ -311,12 +336,13 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       if constexpr (MODE == RM_M) {
         // x~ rows: into this CTA's operand vector and every peer's (all-gather riding along the pass)
         if (owner) {
-          reinterpret_cast<double2 *>(X.colx)[e2] = make_double2(sum[0], sum[1]);
+          if (dscale) { sum[0] *= s0.x; sum[1] *= s0.y; }
+          reinterpret_cast<double2 *>(mdst)[e2] = make_double2(sum[0], sum[1]);
           if constexpr (CS > 1) {
-            const uint32_t off = smem_u32(X.colx) + 16u * (uint32_t)e2;
+            const uint32_t off = smem_u32(mdst) + 16u * (uint32_t)e2;
 #pragma unroll
             for (int p = 0; p < CS; p++)
-              if (p != X.rank) st_async_remote_v2(mapa(off, (uint32_t)p), sum[0], sum[1], mapa(X.xbar, (uint32_t)p));
+              if (p != X.rank) st_async_remote_v2(mapa(off, (uint32_t)p), sum[0], sum[1], mapa(mbar, (uint32_t)p));
           }
         }
       } else if constexpr (MODE == RM_A_ITER) {
@@ -559,6 +585,14 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   }
   if (tid < T) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; S.dist[tid] = NAN; }
   __syncthreads();
+  if (tid < T) {
+    // every leaf starts from the setup rho; a resumed round continues with the rho it had adapted to
+    double r0 = S.I.rho_base;
+    if (S.I.adaptive && tid < S.tile.nn && S.tile.iter_begin > 0) r0 = state[S.tile.state_off[tid] + S.I.n + 2 * (size_t)S.I.m];
+    S.rho_t[tid] = r0; S.rinv_t[tid] = 1.0 / r0; S.rinveq_t[tid] = 1.0 / (kRhoEqFactor * r0);
+  }
+  if (tid == 0) S.rho_changed = 0;
+  __syncthreads();
   const DevInstance &I = S.I;
   const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, NW = I.p_nw;
   const int npm = I.p_npm, npa = I.p_npa;
@@ -571,8 +605,8 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   X.S = &S;
   size_t off = (sizeof(RowsShared) + 15) & ~size_t(15);
   X.full = smem_u32(smem_raw + off);
-  X.empty = X.full + 8u * nslots; X.xbar = X.empty + 8u * nslots; X.rbar = X.xbar + 8u; X.cbar = X.rbar + 8u;
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3);
+  X.empty = X.full + 8u * nslots; X.xbar = X.empty + 8u * nslots; X.rbar = X.xbar + 8u; X.cbar = X.rbar + 8u; X.vbar = X.cbar + 8u;
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4);
   off = (off + 127) & ~size_t(127);
   X.colb = reinterpret_cast<double *>(smem_raw + off); off += (size_t)np * T * 8;
   X.colx = reinterpret_cast<double *>(smem_raw + off); off += (size_t)np * T * 8;
@@ -589,7 +623,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   const int tpw = (NW + kW - 1) / kW;
   X.tile0 = X.wi * tpw; X.ntl = max(0, min(tpw, NW - X.tile0));
   X.chunk_t0 = rank * chunk_nt; X.chunk_nt = chunk_nt;
-  X.cnt = 0; X.gord = 0; X.xph = X.rph = X.cph = 0;
+  X.cnt = 0; X.gord = 0; X.xph = X.rph = X.cph = X.vph = 0;
   X.cmine = X.grp; X.slot = X.grp % nslots; X.phase = 0;
   {
     double *p = work + S.tile.work_off;
@@ -602,7 +636,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   const Work &W = X.Wk;
   if (tid == 0) {
     for (int s = 0; s < nslots; s++) { mbar_init(X.full + 8u * s, 1); mbar_init(X.empty + 8u * s, kW); }
-    mbar_init(X.xbar, 1); mbar_init(X.rbar, 1); mbar_init(X.cbar, 1);
+    mbar_init(X.xbar, 1); mbar_init(X.rbar, 1); mbar_init(X.cbar, 1); mbar_init(X.vbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -662,13 +696,16 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     produce(pA, npa);
     for (int iter = iter_begin + 1; iter <= iter_end; iter++) {
       const bool do_check = (iter % check_every == 0) || iter == max_iter;
-      produce(pM, npm); produce(pA, npa);
+      produce(pM, npm);
+      if (I.adaptive) produce(I.pstream + I.p_offV, npm);   // x~ = V (d . (V' b)): the M slot holds V'
+      produce(pA, npa);
       if (!do_check) continue;
       cluster_sync_all<CS>();                            // iterates of the check in global memory
       produce(pA, npa); produce(pA, npa); produce(pP, npm);
       cluster_sync_all<CS>();                            // raw products in global memory
       named_bar(kG + 2, kRowsThreads);                   // decision published
       if (S.remaining == 0 || iter == iter_end) break;
+      if (S.rho_changed) produce(pA, npa);               // a leaf adapted its rho: the right-hand side is rebuilt
     }
     cluster_sync_all<CS>();                              // final iterates of every CTA's rows in global memory
     cluster_sync_all<CS>();                              // epilogue operand ready
@@ -686,7 +723,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   // canonical reduction of per-thread values over the 256 consumer threads: lane tree, then the warps in order.
   // v: this thread's value for node (tid & 7); returns the total in every thread with the same node
   double *red = X.part;     // the group partial buffers are idle whenever this runs (kCons * 8 doubles per quantity)
-  auto block_reduce = [&](double (&v)[kFinN], const int (&op)[kFinN], int nq) {
+  auto block_reduce = [&](double (&v)[kFinN], const int (&op)[kFinN], int nq, int q0 = 0) {
 #pragma unroll
     for (int q = 0; q < kFinN; q++) {
       if (q < nq) {
@@ -709,7 +746,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
         const double y = red[(q * kCons + w) * 8 + t];
         x = op[q] == 0 ? fmax(x, y) : (op[q] == 1 ? x + y : fmin(x, y));
       }
-      S.fin[q][t] = x;
+      S.fin[q0 + q][t] = x;
     }
     named_bar(kG + 1, kConsThreads);
   };
@@ -784,11 +821,11 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
 
   auto cons_bar = [&]() { named_bar(kG + 1, kConsThreads); };
   // start of a reduction / M pass: post the expected remote bytes of the phase
-  auto post_x = [&]() {
+  auto post_x = [&](uint32_t bar) {
     if constexpr (CS > 1) {
       if (warp == 0 && lane == 0) {
         const int own = (npm - rank + CS - 1) / CS;
-        mbar_expect_tx(X.xbar, (uint32_t)((npm - own) * 8 * T * 8));
+        mbar_expect_tx(bar, (uint32_t)((npm - own) * 8 * T * 8));
       }
     }
   };
@@ -810,17 +847,30 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
 #else
 #define PSTAMP(i) do { } while (0)
 #endif
+  const bool adaptive = I.adaptive != 0;
+  double *const xt = adaptive ? X.colb : X.colx;            // where x~ of the iteration lands
   int iter;
   for (iter = iter_begin + 1; iter <= iter_end; iter++) {
     const bool do_check = (iter % check_every == 0) || iter == max_iter;
     // x~ = M b
-    post_x();
+    post_x(X.xbar);
     load_bx<false>(bx, X.colb, X.tile0, X.ntl, lane);
     PSTAMP(0);
-    rows_pass<CS, RM_M>(X, npm, bx, acc, do_check);
+    rows_pass<CS, RM_M>(X, npm, bx, acc, do_check, X.colx, adaptive, X.xbar);
     PSTAMP(1);
     cons_bar();                                           // local x~ rows visible
     if constexpr (CS > 1) { mbar_wait(X.xbar, X.xph); X.xph ^= 1u; }
+    if (adaptive) {
+      // second pass of x~ = V (d . (V' b)): the scaled coefficients are complete in colx (every CTA's copy); the product rows go
+      // to colb, whose b every warp of the cluster has long loaded into registers (a peer reaches this pass only after it has
+      // received this CTA's last coefficient row).  Its rows complete on a barrier of their own: with more than two CTAs a fast
+      // peer's product rows can arrive while this CTA still waits for a third CTA's coefficients
+      post_x(X.vbar);
+      load_bx<false>(bx, X.colx, X.tile0, X.ntl, lane);
+      rows_pass<CS, RM_M>(X, npm, bx, acc, do_check, X.colb, false, X.vbar);
+      cons_bar();
+      if constexpr (CS > 1) { mbar_wait(X.vbar, X.vph); X.vph ^= 1u; }
+    }
     PSTAMP(2);
     if (I.eq2) {
       // eq_rho == 2: Woodbury correction of the explicit inverse over the re-typed integer rows of every node,
@@ -847,7 +897,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       cons_bar();
     }
     // x = alpha x~ + (1 - alpha) x_prev for the columns this CTA finalises; then z~ = A x~, update, b'
-    load_bx<false>(bx, X.colx, X.tile0, X.ntl, lane);
+    load_bx<false>(bx, xt, X.tile0, X.ntl, lane);
     {
       const double alpha = I.alpha, oma = 1.0 - I.alpha;
       const bool publish = do_check || iter == iter_end;     // the check passes and the epilogue read x from global memory
@@ -855,7 +905,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       for (int i = 0; i < kXR; i++) {
         if (i < X.chunk_nt) {
           const int e = xe0 + i * kConsThreads;
-          const double xp = xr[i], xn = alpha * X.colx[e] + oma * xp;
+          const double xp = xr[i], xn = alpha * xt[e] + oma * xp;
           xr[i] = xn;
           if (publish) { W.gx[e] = xn; W.gdx[e] = xn - xp; }
         }
@@ -925,12 +975,54 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
         v[9] += up * fmax(d, 0.0) + lo * fmin(d, 0.0);
       }
       block_reduce(v, op, kFinN);
+      if (adaptive && iter % I.adapt_interval == 0) {
+        // the scaled norms of osqp's compute_rho_estimate: |Ax - z|, |z|, |Ax|, |Px + q + A'y|, |q|, |A'y|, |Px| (same canonical order)
+        const int op2[kFinN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < kFinN; q++) v[q] = 0.0;
+        for (int j = s; j < n; j += kConsThreads / 8) {
+          const size_t e = (size_t)j * T + t;
+          double aty = 0.0;
+          for (int p = 0; p < CS * kG; p++) aty += __ldcg(W.parts + (size_t)p * pstride + e);
+          const double px = __ldcg(W.gpx + e), qj = __ldg(I.q + j);
+          v[3] = fmax(v[3], fabs(px + qj + aty)); v[4] = fmax(v[4], fabs(qj)); v[5] = fmax(v[5], fabs(aty)); v[6] = fmax(v[6], fabs(px));
+        }
+        for (int i = s; i < m; i += kConsThreads / 8) {
+          const size_t e = (size_t)i * T + t;
+          const double ax = __ldcg(W.gax + e), z = __ldcg(W.gz + e);
+          v[0] = fmax(v[0], fabs(ax - z)); v[1] = fmax(v[1], fabs(z)); v[2] = fmax(v[2], fabs(ax));
+        }
+        block_reduce(v, op2, 8, kFinN);
+      }
     }
     if (tid < T) decide(tid, iter);
     cons_bar();
     snapshot();
+    if (adaptive && iter % I.adapt_interval == 0) {
+      // osqp adapt_rho: rho_new = rho sqrt(pri / dua) on the normalised scaled residuals, adopted outside [rho / tol, rho tol]
+      if (tid < nn && S.status[tid] == BQP_UNSOLVED) {
+        const int t = tid;
+        const double pri = S.fin[kFinN + 0][t] / (fmax(S.fin[kFinN + 1][t], S.fin[kFinN + 2][t]) + 1e-10);
+        const double dua = S.fin[kFinN + 3][t] / (fmax(fmax(S.fin[kFinN + 4][t], S.fin[kFinN + 5][t]), S.fin[kFinN + 6][t]) + 1e-10);
+        const double rho = S.rho_t[t];
+        double rn = rho * sqrt(pri / (dua + 1e-10));
+        rn = fmin(fmax(rn, kRhoMin), 1e6);
+        if (rn > rho * I.adapt_tol || rn < rho / I.adapt_tol) {
+          S.rho_t[t] = rn; S.rinv_t[t] = 1.0 / rn; S.rinveq_t[t] = 1.0 / (kRhoEqFactor * rn);
+          S.rho_changed = 1;
+        }
+      }
+      cons_bar();
+    }
     named_bar(kG + 2, kRowsThreads);                      // ... and the producer sees the decision
     if (S.remaining == 0 || iter == iter_end) break;
+    if (S.rho_changed) {
+      // the right-hand side of the next iteration carries rho: u = rho z - y and b' = sigma x - q + A' u again
+      rows_pass<CS, RM_A_RESUME>(X, npa, bx, acc, false);
+      reduce_b<CS>(X, acc, xr);
+      if (tid == 0) S.rho_changed = 0;
+      cons_bar();
+    }
   }
 
   // ---- end of the launch: save the state of unfinished nodes, clip (node.py:128-143), objective at the clipped point
@@ -942,6 +1034,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       double *sp = state + S.tile.state_off[t];
       for (int j = tid; j < n; j += kConsThreads) sp[j] = __ldcg(W.gx + (size_t)j * T + t);
       for (int i = tid; i < m; i += kConsThreads) { sp[n + i] = __ldcg(W.gz + (size_t)i * T + t); sp[n + m + i] = __ldcg(W.gy + (size_t)i * T + t); }
+      if (tid == 0) sp[n + 2 * (size_t)m] = S.rho_t[t];
       if (tid == 0) {   // pri_res of a node that is still running carries its distance to the tolerance (scheduling hint)
         NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.dua_res = r.lower = NAN; r.pri_res = S.dist[t];
         ns[S.tile.node[t]] = r;
@@ -1009,7 +1102,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
 size_t rows_smem_bytes(int npad, int nslots, int cs) {
   const int nw = npad / 32;
   size_t off = (sizeof(RowsShared) + 15) & ~size_t(15);
-  off += sizeof(uint64_t) * (2 * (size_t)nslots + 3);
+  off += sizeof(uint64_t) * (2 * (size_t)nslots + 4);
   off = (off + 127) & ~size_t(127);
   off += (size_t)2 * npad * T8 * 8 + (size_t)kG * 2 * kW * 32 * 16;
   off += cs > 1 ? (size_t)(cs - 1) * (nw / cs) * kTileD * 8 : 0;

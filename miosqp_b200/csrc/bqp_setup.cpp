@@ -491,41 +491,16 @@ std::vector<double> reduced_inverse(const HostInstance *h, const std::vector<dou
   return M;
 }
 
-void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &prows, const std::vector<double> &S) {
-  const int n = h->n, m = h->m, np_ = h->npad;
-  HostPanels &pn = h->pn;
-  pn = HostPanels();
-  const std::vector<double> M = reduced_inverse(h, S);
-  std::vector<double> Ad((size_t)std::max(m, 1) * np_, 0.0), Pd((size_t)np_ * np_, 0.0);
-  for (int r = 0; r < m; r++)
-    for (auto &e : arows[r]) Ad[(size_t)r * np_ + e.first] = e.second;
-  for (int r = 0; r < n; r++)
-    for (auto &e : prows[r]) Pd[(size_t)r * np_ + e.first] = e.second;
-  pn.nw = np_ / 32;
-  pn.panel_doubles = (long long)kPanelRows * np_;
-  pn.npm = np_ / kPanelRows;
-  pn.npa = (m + kPanelRows - 1) / kPanelRows;
-  append_panels(pn, M, np_, np_);
-  pn.offA = (long long)pn.data.size();
-  append_panels(pn, Ad, m, np_);
-  pn.offP = (long long)pn.data.size();
-  append_panels(pn, Pd, np_, np_);
-  pn.built = true;
-}
-
-// whole-GPU layout: M and P as panels (no dense A), A and A' as CSR
-void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &atrows, const std::vector<Row> &prows,
-                const std::vector<double> &S) {
+// Adaptive rho (osqp adapt_rho): rho_vec = rho x {1, 1e3} on the inequality / equality rows, RHO_MIN on the
+// loose ones, so K(rho) = K0 + (rho - rho0) S1 with K0 = K(rho0) the matrix factorised at setup and S1 = A' diag(type weight) A.
+// With K0 = L L' and L^-1 S1 L^-T = Q diag(mu) Q':  K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V',  V = L^-T Q  (mu < 1/rho0).
+// The kernels apply x~ = V (d . (V' b)) with the leaf's own rho in d: ANY rho per leaf, no refactorisation, same stream for
+// the 8 leaves of a tile.  At rho = rho0 this is V V' = K0^-1, as well conditioned as the factor itself.
+// W = V' and Vm = V come back row-major npad x npad (zero beyond n), mu with npad entries.
+void spectral_factors(const HostInstance *h, const std::vector<Row> &arows, const std::vector<double> &S, std::vector<double> &W,
+                      std::vector<double> &Vm, std::vector<double> &mu_out) {
   const int n = h->n, np_ = h->npad;
-  HostGridL &gd = h->gd;
-  gd = HostGridL();
-  HostPanels tmp;
-  if (h->s.adaptive_rho) {
-    // Adaptive rho (osqp adapt_rho): rho_vec = rho x {1, 1e3} on the inequality / equality rows, RHO_MIN on the
-    // loose ones, so K(rho) = K0 + (rho - rho0) S1 with K0 = K(rho0) the matrix factorised above and S1 = A' diag(type weight) A.
-    // With K0 = L L' and L^-1 S1 L^-T = Q diag(mu) Q':  K(rho)^-1 = V diag(1 / (1 + (rho - rho0) mu)) V',  V = L^-T Q  (mu < 1/rho0).
-    // The kernel applies x~ = V (d . (V' b)) with the leaf's own rho in d: ANY rho per leaf, no refactorisation, same stream for
-    // the 8 leaves of a tile.  At rho = rho0 this is V V' = K0^-1, as well conditioned as the factor itself.
+  {
     const int m = h->m;
     std::vector<double> X = unit_lower_inverse(h, S);            // L = L22 D2^(1/2):  L^-1 = D2^(-1/2) X
     std::vector<double> S1((size_t)n * n, 0.0);
@@ -564,7 +539,7 @@ void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vecto
     std::vector<double> mu;
     sym_eig(n, C, mu);                                             // row j of C: eigenvector q_j
     // W = V' = Q' D2^(-1/2) X  (row j of W = (L^-T q_j)')
-    std::vector<double> W((size_t)np_ * np_, 0.0), Vm((size_t)np_ * np_, 0.0);
+    W.assign((size_t)np_ * np_, 0.0); Vm.assign((size_t)np_ * np_, 0.0);
     for (int j = 0; j < n; j++) {
       double *wj = &W[(size_t)j * np_];
       const double *qj = &C[(size_t)j * n];
@@ -577,8 +552,47 @@ void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vecto
     }
     for (int i = 0; i < n; i++)
       for (int j = 0; j < n; j++) Vm[(size_t)i * np_ + j] = W[(size_t)j * np_ + i];
-    gd.mu.assign(np_, 0.0);
-    for (int j = 0; j < n; j++) gd.mu[j] = mu[j];
+    mu_out.assign(np_, 0.0);
+    for (int j = 0; j < n; j++) mu_out[j] = mu[j];
+  }
+}
+
+void build_panels(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &prows, const std::vector<double> &S) {
+  const int n = h->n, m = h->m, np_ = h->npad;
+  HostPanels &pn = h->pn;
+  pn = HostPanels();
+  std::vector<double> M, Vm;
+  if (h->s.adaptive_rho) { spectral_factors(h, arows, S, M, Vm, pn.mu); pn.spectral = true; }      // the M slot holds V'
+  else M = reduced_inverse(h, S);
+  std::vector<double> Ad((size_t)std::max(m, 1) * np_, 0.0), Pd((size_t)np_ * np_, 0.0);
+  for (int r = 0; r < m; r++)
+    for (auto &e : arows[r]) Ad[(size_t)r * np_ + e.first] = e.second;
+  for (int r = 0; r < n; r++)
+    for (auto &e : prows[r]) Pd[(size_t)r * np_ + e.first] = e.second;
+  pn.nw = np_ / 32;
+  pn.panel_doubles = (long long)kPanelRows * np_;
+  pn.npm = np_ / kPanelRows;
+  pn.npa = (m + kPanelRows - 1) / kPanelRows;
+  append_panels(pn, M, np_, np_);
+  pn.offA = (long long)pn.data.size();
+  append_panels(pn, Ad, m, np_);
+  pn.offP = (long long)pn.data.size();
+  append_panels(pn, Pd, np_, np_);
+  pn.offV = (long long)pn.data.size();
+  if (pn.spectral) append_panels(pn, Vm, np_, np_);
+  pn.built = true;
+}
+
+// whole-GPU layout: M and P as panels (no dense A), A and A' as CSR
+void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &atrows, const std::vector<Row> &prows,
+                const std::vector<double> &S) {
+  const int n = h->n, np_ = h->npad;
+  HostGridL &gd = h->gd;
+  gd = HostGridL();
+  HostPanels tmp;
+  if (h->s.adaptive_rho) {
+    std::vector<double> W, Vm;
+    spectral_factors(h, arows, S, W, Vm, gd.mu);
     append_panels(tmp, W, np_, np_);
     gd.offV = (long long)tmp.data.size();
     append_panels(tmp, Vm, np_, np_);
@@ -781,7 +795,7 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     double min_density = 0.34;
     if (const char *e = std::getenv("BQP_PANEL_MIN_DENSITY")) min_density = std::atof(e);
     const double density = (m > 0) ? (double)A.x.size() / ((double)m * n) : 1.0;
-    if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density && !s->adaptive_rho) build_panels(h, arows, prows, S);
+    if (np_ >= 64 && np_ <= 32 * kPanelMaxWarps && density >= min_density) build_panels(h, arows, prows, S);
   }
   // The panel kernels apply M = (P + sigma I + A' rho A)^-1 explicitly; forming an inverse is not backward stable, and
   // with a tiny sigma, a rank-deficient P or rows typed rho x 1e3 the reduced matrix can be badly conditioned.  Probe it:
@@ -818,7 +832,9 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
     if (const char *e = std::getenv("BQP_GRID")) want = std::atoi(e);
     // BQP_GRID_ALL=1 (experiments: one config-2 tile on the whole GPU): also for problems the rows kernel serves; run with BQP_KERNEL=grid
     const bool all_sizes = std::getenv("BQP_GRID_ALL") && std::atoi(std::getenv("BQP_GRID_ALL")) != 0;
-    const bool wide = (all_sizes || s->adaptive_rho) ? true : (!h->pn.built && np_ > 32 * kPanelMaxWarps);
+    // adaptive rho: dense problems the rows kernel serves carry the spectral factors in their panel stream; everything else
+    // (wide, sparse or small) runs adaptively on the whole-GPU kernel
+    const bool wide = all_sizes ? true : (s->adaptive_rho ? !h->pn.built : (!h->pn.built && np_ > 32 * kPanelMaxWarps));
     if (want && wide && !h->pn_rejected && np_ <= max_np && s->eq_rho != 2) {
       build_grid(h, arows, atrows, prows, S);
       double tol = 1e-10;
@@ -845,7 +861,7 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
       if (!(worst <= tol)) { h->gd = HostGridL(); if (!h->pn.built) h->pn_rejected = true; }
     }
   }
-  if (s->adaptive_rho && !(h->gd.built && h->gd.spectral)) return BQP_E_UNSUPPORTED;
+  if (s->adaptive_rho && !((h->gd.built && h->gd.spectral) || (h->pn.built && h->pn.spectral))) return BQP_E_UNSUPPORTED;
   h->mint.clear();
   if (s->eq_rho == 2) {
     // per-node re-typing corrects the explicit inverse by a Woodbury term over the re-typed integer rows: dense kernels only
@@ -1016,6 +1032,14 @@ int host_panel_kkt_solve(const HostInstance *h, double *rhs) {
     double acc = 0;
     for (int j = 0; j < np_; j++) acc = std::fma(at(0, r, j), b[j], acc);
     xt[r] = acc;
+  }
+  if (pn.spectral) {       // the M slot held V': x~ = V (V' b) at the setup rho
+    std::vector<double> c(xt);
+    for (int r = 0; r < np_; r++) {
+      double acc = 0;
+      for (int j = 0; j < np_; j++) acc = std::fma(at(pn.offV, r, j), c[j], acc);
+      xt[r] = acc;
+    }
   }
   for (int i = 0; i < m; i++) {
     double acc = 0;

@@ -463,18 +463,22 @@ def test_grid_and_stream_kernels_agree(monkeypatch):
 
 
 # ---------------------------------------------------------------- adaptive rho on the GPU (second half)
-@pytest.mark.parametrize("case", [(130, 200, 10, 0.7, 4, 9, 25), (500, 1000, 50, 0.7, 1, 8, 50), (600, 900, 20, 0.05, 12, 5, 100),
-                                  (50, 100, 5, 0.7, 1, 6, 25)])
-def test_adaptive_rho_against_oracle(oracle_mod, case):
-    """osqp adaptive_rho with a fixed interval: every leaf adapts its own rho (the whole-GPU kernel applies the reduced KKT
-    inverse in spectral form, x~ = V (d(rho) . (V' b)), so a rho update needs no refactorisation); the oracle refactors
-    numerically like osqp_update_rho.  Same statuses, iteration counts and iterates."""
-    n, m, p, dens, seed, count, interval = case
+@pytest.mark.parametrize("case", [(130, 200, 10, 0.7, 4, 9, 25, "rows"), (500, 1000, 50, 0.7, 1, 8, 50, "rows"), (600, 900, 20, 0.05, 12, 5, 100, "grid"),
+                                  (50, 100, 5, 0.7, 1, 6, 25, "rows"), (130, 200, 10, 0.7, 4, 9, 25, "grid"), (500, 1000, 50, 0.7, 1, 8, 50, "grid"),
+                                  (200, 300, 10, 0.05, 3, 6, 25, "grid")])
+def test_adaptive_rho_against_oracle(oracle_mod, case, monkeypatch):
+    """osqp adaptive_rho with a fixed interval: every leaf adapts its own rho.  The kernels apply the reduced KKT inverse in
+    spectral form, x~ = V (d(rho) . (V' b)), so a rho update needs no refactorisation -- dense problems on the rows kernel (two
+    passes instead of the M pass), everything else on the whole-GPU kernel; the oracle refactors numerically like
+    osqp_update_rho.  Same statuses, iteration counts and iterates."""
+    n, m, p, dens, seed, count, interval, kernel = case
+    if kernel == "grid" and dens > 0.3:
+        monkeypatch.setenv("BQP_GRID_ALL", "1"); monkeypatch.setenv("BQP_KERNEL", "grid")     # dense problems default to the rows kernel
     pr = problems.random_miqp(n, m, p, dens, seed=seed)[0]
     st = dict(QP, adaptive_rho=True, adaptive_rho_interval=interval)
     r, e = _compare(pr, count, 21, st, warm="root", oracle_mod=oracle_mod)
-    assert engine.last_timing()["kernel"] == 4
-    if n == 500:
+    assert engine.last_timing()["kernel"] == (3 if kernel == "rows" else 4)
+    if n == 500 and kernel == "rows":
         # and it is what it is for: the fixed rho = 0.1 needs several times the iterations on this problem class
         P, q, A, l, u, i_idx = problems.extend(pr)
         ls, us = problems.branched_nodes(l, u, len(i_idx), count, np.random.default_rng(21))
@@ -483,3 +487,19 @@ def test_adaptive_rho_against_oracle(oracle_mod, case):
         x0 = np.tile(np.nan_to_num(root.x), (count, 1)); y0 = np.tile(np.nan_to_num(root.y), (count, 1))
         rf = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP).solve_batch(ls, us, x0, y0)
         assert r.iters.sum() * 2 < rf.iters.sum(), (list(r.iters), list(rf.iters))
+
+
+@pytest.mark.parametrize("cs", [1, 2, 4, 8])
+def test_adaptive_rho_rounds_and_clusters(oracle_mod, cs, monkeypatch):
+    """The adapted rho travels with a leaf from round to round (saved with its scaled state): rounds of 25 iterations give the
+    bits of one launch; clusters of 1 / 2 / 4 / 8 CTAs agree with the oracle."""
+    monkeypatch.setenv("BQP_ROWS_CLUSTER", str(cs))
+    pr = problems.random_miqp(250, 400, 12, 0.7, seed=9)[0]       # npad = 256: 8 column tiles, every cluster size divides them
+    st = dict(QP, adaptive_rho=True, adaptive_rho_interval=25)
+    monkeypatch.setenv("BQP_ROUND_ITERS", "0")
+    r0, e0 = _compare(pr, 7, 5, st, warm="root", oracle_mod=oracle_mod)
+    assert engine.last_timing()["kernel"] == 3 and engine.last_timing()["launches"] == 1
+    monkeypatch.setenv("BQP_ROUND_ITERS", "25")
+    r1, e1 = _compare(pr, 7, 5, st, warm="root", oracle_mod=oracle_mod)
+    assert engine.last_timing()["launches"] > 1
+    assert list(r0.iters) == list(r1.iters) and np.array_equal(r0.x, r1.x) and np.array_equal(r0.y, r1.y)
