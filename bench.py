@@ -520,7 +520,8 @@ def bnb_section(args, raw, qps, rank, world, cores, torch, dist):
     if rank != 0:
         return None
     gold = None
-    gp = os.path.join(ROOT, "tests", "golden", "bnb_cfg2.json")
+    gname = "bnb_cfg2_adaptive%d.json" % QP_SETTINGS["adaptive_rho_interval"] if QP_SETTINGS.get("adaptive_rho") else "bnb_cfg2.json"
+    gp = os.path.join(ROOT, "tests", "golden", gname)
     if os.path.exists(gp):      # rank 0 draws seed 1: its first instances are the golden ones (unmodified reference on the oracle)
         g = json.load(open(gp))
         gold = True
@@ -535,7 +536,7 @@ def bnb_section(args, raw, qps, rank, world, cores, torch, dist):
            "e2e": {"value": ro["qp_per_s"], "unit": "QP/s", "h2d_bytes_per_run": ro.get("h2d_bytes"), "d2h_bytes_per_run": ro.get("d2h_bytes")},
            "rolling": ro, "lockstep": runs["lockstep"],
            "decisions_identical_to_reference_golden": gold,
-           "golden": "tests/golden/bnb_cfg2.json: first 3 instances, UNMODIFIED reference package on the CPU oracle (make_bnb_golden.py --cfg2)"}
+           "golden": "tests/golden/%s: first 3 instances, UNMODIFIED reference package on the CPU oracle (make_bnb_golden.py --cfg2)" % gname}
     if not args.no_cpu_baseline:
         try:
             cnt = max(1, min(args.instances, cores))

@@ -164,6 +164,7 @@ struct Ctx {
   int cnt;                                            // CTA-local panel counter across passes (ring position of the next pass)
   int cmine, slot; uint32_t phase;                    // next counter value handled by this warp's group, its ring slot and phase
   int gord;                                           // panels this group has processed (owner-warp rotation, partial double buffer)
+  int pset;                                           // which half of this CTA's panels (even / odd local index) the group took in the last pass
   uint32_t xph, rph, cph, vph;                        // phases of the cross-CTA barriers
 };
 
@@ -221,6 +222,10 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       for (int mt = 0; mt < 4; mt++) acc[tl][mt][0] = acc[tl][mt][1] = 0.0;
   }
   const int npc = (npanels - X.rank + CS - 1) / CS;     // panels of this CTA: k = rank + jl * CS
+  // the two groups alternate over the CTA's panels by a counter that runs across passes: which group takes the even local
+  // panels depends on how many panels came before.  Results that are summed per group are filed under the HALF, not the group,
+  // so that their order of addition does not depend on the history of the launch (rounds, extra passes)
+  X.pset = (X.cmine - X.cnt) & 1;
   const int src_b = (lane & 3) * 4 + (lane >> 3);        // shuffle source of the B fragment of w (rows 0..3); rows 4..7: + 16
   for (; X.cmine < X.cnt + npc; X.cmine += kG) {
     const int jl = X.cmine - X.cnt;
@@ -558,7 +563,7 @@ __device__ __forceinline__ void reduce_b(Ctx<CS> &X, double (&acc)[kTPW][4][2], 
 template <int CS>
 __device__ __forceinline__ void store_parts(Ctx<CS> &X, int which, const double (&acc)[kTPW][4][2]) {
   const int lane = X.lane, gq = lane >> 2, tq = lane & 3;
-  double2 *dst = reinterpret_cast<double2 *>(X.Wk.parts + ((size_t)which * CS * kG + (size_t)X.rank * kG + X.grp) * X.np * T8);
+  double2 *dst = reinterpret_cast<double2 *>(X.Wk.parts + ((size_t)which * CS * kG + (size_t)X.rank * kG + (kG == 2 ? X.pset : X.grp)) * X.np * T8);
 #pragma unroll
   for (int tl = 0; tl < kTPW; tl++)
     if (tl < X.ntl)

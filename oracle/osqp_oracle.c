@@ -72,6 +72,7 @@ typedef struct {
   double *q, *l, *u;              /* scaled */
   double *D, *Dinv, *E, *Einv; double c, cinv;
   double *rho_vec, *rho_inv_vec;
+  int *ctype0;                    /* osqp constr_type per row as typed at setup: -1 loose, 0 inequality, 1 equality */
   /* factor of permuted KKT */
   int N; int *perm;               /* perm[new] = old */
   int *Lp, *Li; double *Lx, *Dd, *Ddinv; int *etree;
@@ -336,7 +337,7 @@ void oracle_free(OracleWork *w) {
   if (!w) return;
   free(w->Pp); free(w->Pi); free(w->Px); free(w->Ap); free(w->Ai); free(w->Ax);
   free(w->q); free(w->l); free(w->u); free(w->D); free(w->Dinv); free(w->E); free(w->Einv);
-  free(w->rho_vec); free(w->rho_inv_vec); free(w->perm); free(w->Lp); free(w->Li); free(w->Lx);
+  free(w->rho_vec); free(w->rho_inv_vec); free(w->ctype0); free(w->perm); free(w->Lp); free(w->Li); free(w->Lx);
   free(w->Dd); free(w->Ddinv); free(w->etree); free(w->x); free(w->y); free(w->z);
   free(w);
 }
@@ -364,11 +365,12 @@ OracleWork *oracle_setup(int n, int m, const int *Pp, const int *Pi, const doubl
   w->E = malloc(sizeof(double) * (m ? m : 1)); w->Einv = malloc(sizeof(double) * (m ? m : 1));
   scale_data(w);
   w->rho_vec = malloc(sizeof(double) * (m ? m : 1)); w->rho_inv_vec = malloc(sizeof(double) * (m ? m : 1));
+  w->ctype0 = calloc(m ? m : 1, sizeof(int));
   for (int i = 0; i < m; i++) {
     double r = s->rho;
     if (s->eq_rho) {
-      if (w->l[i] < -OSQP_INFTY * MIN_SCALING && w->u[i] > OSQP_INFTY * MIN_SCALING) r = RHO_MIN;
-      else if (w->u[i] - w->l[i] < RHO_TOL) r = RHO_EQ_OVER_RHO_INEQ * s->rho;
+      if (w->l[i] < -OSQP_INFTY * MIN_SCALING && w->u[i] > OSQP_INFTY * MIN_SCALING) { r = RHO_MIN; w->ctype0[i] = -1; }
+      else if (w->u[i] - w->l[i] < RHO_TOL) { r = RHO_EQ_OVER_RHO_INEQ * s->rho; w->ctype0[i] = 1; }
     }
     w->rho_vec[i] = r; w->rho_inv_vec[i] = 1.0 / r;
   }
@@ -561,10 +563,10 @@ static int solve_node(const OracleWork *w, Scratch *s, const double *l_in, const
   int *ctype = NULL; double rho_cur = S->rho;
   if (adapt) {
     ctype = calloc((size_t)m, sizeof(int));
-    const double *tl = S->eq_rho == 2 ? l : w->l, *tu = S->eq_rho == 2 ? u : w->u;
     for (int i = 0; i < m && S->eq_rho; i++) {
-      if (tl[i] < -OSQP_INFTY * MIN_SCALING && tu[i] > OSQP_INFTY * MIN_SCALING) ctype[i] = -1;
-      else if (tu[i] - tl[i] < RHO_TOL) ctype[i] = 1;
+      if (S->eq_rho != 2) { ctype[i] = w->ctype0[i]; continue; }     /* the stored bounds follow update(l, u): use the setup's typing */
+      if (l[i] < -OSQP_INFTY * MIN_SCALING && u[i] > OSQP_INFTY * MIN_SCALING) ctype[i] = -1;
+      else if (u[i] - l[i] < RHO_TOL) ctype[i] = 1;
     }
     if (!rv) { rv = malloc(8 * (size_t)m); ri = malloc(8 * (size_t)m); memcpy(rv, w->rho_vec, 8 * (size_t)m); memcpy(ri, w->rho_inv_vec, 8 * (size_t)m); }
   }

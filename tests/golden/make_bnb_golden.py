@@ -31,6 +31,10 @@ CASES = {
     "cfg1_seed3": dict(n=50, m=100, p=5, density=0.7, seed=3),
     "small_seed5": dict(n=30, m=60, p=8, density=0.5, seed=5),
     "mid_seed7": dict(n=120, m=200, p=10, density=0.7, seed=7),
+    # osqp adaptive_rho with a fixed interval (the reproducible variant of osqp's default): "qp" is merged into the QP settings
+    "cfg1_seed1_adaptive": dict(n=50, m=100, p=5, density=0.7, seed=1, qp=dict(adaptive_rho=True, adaptive_rho_interval=25)),
+    "mid_seed7_adaptive": dict(n=120, m=200, p=10, density=0.7, seed=7, qp=dict(adaptive_rho=True, adaptive_rho_interval=25)),
+    "mid_seed9_adaptive50": dict(n=300, m=500, p=20, density=0.7, seed=9, qp=dict(adaptive_rho=True, adaptive_rho_interval=50)),
 }
 
 
@@ -79,10 +83,14 @@ def main_cfg4():
 CFG2 = dict(n=500, m=1000, p=50, density=0.7, seed=1)
 
 
-def main_cfg2(count):
-    c = CFG2
+def main_cfg2(count, adaptive_interval=0):
+    c = dict(CFG2)
+    qp_extra = {}
+    if adaptive_interval:       # osqp adaptive_rho with a fixed interval (python make_bnb_golden.py --cfg2 3 --adaptive 50)
+        qp_extra = dict(adaptive_rho=True, adaptive_rho_interval=adaptive_interval)
+        c["qp"] = qp_extra
     prs = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"], count=count)
-    path = os.path.join(HERE, "bnb_cfg2.json")
+    path = os.path.join(HERE, "bnb_cfg2_adaptive%d.json" % adaptive_interval if adaptive_interval else "bnb_cfg2.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     from miosqp import node as ref_node
     for k, pr in enumerate(prs):
@@ -97,7 +105,7 @@ def main_cfg2(count):
             trace.append((int(self.status), int(self.num_iter), int(self.depth)))
         ref_node.Node.solve = solve
         try:
-            r = run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+            r = run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS), dict(problems.RANDOM_MIQP_QP_SETTINGS, **qp_extra))
         finally:
             ref_node.Node.solve = orig_solve
         r["node_trace"] = trace
@@ -111,16 +119,20 @@ def main():
     if "--cfg4" in sys.argv:
         return main_cfg4()
     if "--cfg2" in sys.argv:
-        return main_cfg2(int(sys.argv[sys.argv.index("--cfg2") + 1]))
-    out = {}
+        return main_cfg2(int(sys.argv[sys.argv.index("--cfg2") + 1]),
+                         int(sys.argv[sys.argv.index("--adaptive") + 1]) if "--adaptive" in sys.argv else 0)
+    out, out_adaptive = {}, {}
     for name, c in CASES.items():
         pr = problems.random_miqp(c["n"], c["m"], c["p"], c["density"], seed=c["seed"])[0]
-        out[name] = dict(case=c, result=run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS),
-                                                       dict(problems.RANDOM_MIQP_QP_SETTINGS)))
-        r = out[name]["result"]
+        dst = out_adaptive if "qp" in c else out       # the adaptive-rho cases live in a file of their own
+        dst[name] = dict(case=c, result=run_reference(pr, dict(problems.RANDOM_MIQP_SETTINGS),
+                                                       dict(problems.RANDOM_MIQP_QP_SETTINGS, **c.get("qp", {}))))
+        r = dst[name]["result"]
         print(name, r["status"], r["upper_glob"], "nodes", r["iter_num"] - 1, "admm", r["osqp_iter"], "branchings", len(r["decisions"]))
     with open(os.path.join(HERE, "bnb_random_miqp.json"), "w") as f:
         json.dump(out, f, indent=1)
+    with open(os.path.join(HERE, "bnb_random_miqp_adaptive.json"), "w") as f:
+        json.dump(out_adaptive, f, indent=1)
 
 
 if __name__ == "__main__":

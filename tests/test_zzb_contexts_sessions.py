@@ -161,3 +161,26 @@ def test_cfg2_size_bnb_matches_reference_golden():
     g = gold["cfg2_inst0"]["result"]
     assert [tuple(d) for d in s.work.decisions] == [tuple(d) for d in g["decisions"]] and s.work.osqp_iter == g["osqp_iter"]
     assert r.status == g["status"]
+
+
+def test_cfg2_size_bnb_adaptive_rho_matches_reference_golden():
+    """The same under osqp's adaptive_rho (fixed interval 50): the three first config-2 instances, B&B to completion on the
+    rolling session (rows kernel, spectral inverse, automatic cluster sizes), against the UNMODIFIED reference package on the
+    adaptive CPU oracle (make_bnb_golden.py --cfg2 3 --adaptive 50): identical decisions, node and iteration counts -- with
+    a fifth of the fixed-rho run's ADMM iterations."""
+    with open(os.path.join(HERE, "golden", "bnb_cfg2_adaptive50.json")) as f:
+        gold = json.load(f)
+    with open(os.path.join(HERE, "golden", "bnb_cfg2.json")) as f:
+        fixed = json.load(f)
+    prs = problems.random_miqp(500, 1000, 50, 0.7, seed=1, count=3)
+    qp = dict(problems.RANDOM_MIQP_QP_SETTINGS, adaptive_rho=True, adaptive_rho_interval=50)
+    solvers = miqp.setup_many(prs, dict(problems.RANDOM_MIQP_SETTINGS, replay='native'), qp)
+    res = miosqp_b200.solve_many(solvers, rolling=True)
+    for k in range(3):
+        g = gold["cfg2_inst%d" % k]["result"]
+        w = solvers[k].work
+        assert [tuple(d) for d in w.decisions] == [tuple(d) for d in g["decisions"]]
+        assert res[k].status == g["status"] and w.iter_num == g["iter_num"] and int(w.osqp_iter) == g["osqp_iter"]
+        assert abs(res[k].upper_glob - g["upper_glob"]) <= 1e-9 * (1 + abs(g["upper_glob"]))
+        assert np.abs(res[k].x - np.array(g["x"])).max() <= 1e-9 * (1 + np.abs(np.array(g["x"])).max())
+        assert g["osqp_iter"] * 4 < fixed["cfg2_inst%d" % k]["result"]["osqp_iter"]
