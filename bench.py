@@ -609,9 +609,10 @@ def mpc_workload(args, cores):
 
 def cfg4_workload(args, cores):
     """BASELINE config 4 on ONE GPU: random_miqp n=2000 m=4000 |i_idx|=200 density 0.05, the reference's B&B cut at
-    --cfg4-nodes nodes (its own max_iter_bb), native replay.  The tree offers two leaves per step (one tile of the TMA-streamed
-    two-sweep kernel, one CTA): the figure that matters is the time per ADMM iteration of that tile, reported with the factor
-    bytes one iteration streams (L2-resident) and the SURVEY 8d algorithmic bytes.  CPU arm: the same B&B on the oracle."""
+    --cfg4-nodes nodes (its own max_iter_bb), native replay.  The tree offers one or two leaves per step = ONE tile, solved by
+    the whole-GPU kernel (bqp_grid.cu: every SM on that tile; BQP_GRID=0 falls back to the one-CTA streamed kernel): the figure
+    that matters is the time per ADMM iteration of that tile, reported with the bytes one iteration moves (L2-resident) and the
+    SURVEY 8d algorithmic bytes.  CPU arm: the same B&B on the oracle."""
     import torch
     import scipy.sparse as spa
     from miosqp_b200 import engine, problems, miqp
@@ -645,6 +646,11 @@ def cfg4_workload(args, cores):
     # every step holds the two children: the step's tile runs max(iters of the two) iterations; approximate the tile-iterations by
     # half the node-iterations (siblings need similar counts) -- reported as such
     tile_iters = iters / 2.0
+    tm = engine.last_timing()
+    grid = int(tm.get("kernel", 1)) == 4
+    if grid:
+        tile_iters = float(iters)          # the native replay consumes one leaf per launch on this dive: a tile-iteration per node-iteration
+    kernel_ms_last = float(tm.get("kernel_ms", 0.0))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -657,14 +663,19 @@ def cfg4_workload(args, cores):
                                   "native replay, 1 GPU" % args.cfg4_nodes, "qp_settings": QP_SETTINGS},
            "status": r.status, "qp_consumed": nodes, "admm_iters": iters, "launches": int(w.batches), "wall_s": wall, "setup_s": t_setup,
            "us_per_admm_iteration_of_the_tile": 1e6 * wall / max(1.0, tile_iters),
+           "last_launch_kernel_ms": kernel_ms_last, "threads_per_cta": int(tm.get("threads", 0)), "ctas": int(tm.get("tiles", 0)),
            "e2e": {"value": nodes / wall, "unit": "QP/s", "note": "host buffers, replay and copies inside (the B&B loop has no device-resident variant)"},
-           "roofline": {"bound": "hbm", "kernel": "admm_stream_kernel (one CTA per tile, two leaves)", "unit": "GB/s", "peak": peak,
+           "roofline": {"bound": "hbm", "kernel": "admm_grid_kernel (one tile on every SM, 512 threads per CTA)" if grid else "admm_stream_kernel (one CTA per tile, two leaves)",
+                        "unit": "GB/s", "peak": peak,
                         "algorithmic_bytes_per_node_iter": alg, "achieved": alg * iters / wall / 1e9, "frac": alg * iters / wall / 1e9 / peak,
                         "streamed_factor_bytes_per_tile_iteration": int(dims["factor_bytes"]),
                         "streamed_gbs_into_one_sm": dims["factor_bytes"] * tile_iters / wall / 1e9, "traffic": None,
-                        "note": "one tile = one CTA = one SM streams the 28.8 MB factor + A twice per iteration out of L2 (126 MB): the "
-                                "kernel is bound by what one SM can pull, not by HBM; 147 SMs idle.  A multi-CTA kernel for one large tile "
-                                "is the next step (DESIGN section 9)"}}
+                        "note": ("the tile's matrices (explicit reduced inverse 32.5 MB, CSR A and A' 9.6 MB) stay in L2 (126 MB): no HBM "
+                                 "traffic to speak of, the kernel is bound by three grid-wide barriers and L2 round trips per iteration "
+                                 "(23.7 us measured with convergence off, profiles/r02_summary.md F); the wall time also holds 39 launches "
+                                 "with host replay, H2D and D2H") if grid else
+                                ("one tile = one CTA = one SM streams the 28.8 MB factor + A twice per iteration out of L2 (126 MB): the "
+                                 "kernel is bound by what one SM can pull, not by HBM; 147 SMs idle")}}
     if not args.no_cpu_baseline:
         try:
             secs, cn, cits, outs = bnb_cpu(raw, 1, 1, max_iter_bb=args.cfg4_nodes)

@@ -113,6 +113,7 @@ struct BatchCtx {
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
   bool use_grid = false; int grid_ctas = 0;
+  bool rows_ext = false;          // some problem of the batch uses eq_rho == 2 or adaptive rho: the rows kernel's extended instantiation
   bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
   int round_iters = 0, max_iter_all = 0;
   long long round_h2d_bytes = 0, round_h2d_total = 0;
@@ -695,6 +696,8 @@ static void select_kernel(BatchCtx &g) {
   }
   g.eq2_unsupported = false;
   for (bqp_instance *inst : g.node_inst) if (inst->h.s.eq_rho == 2 && !(g.use_panel && g.use_rows)) g.eq2_unsupported = true;
+  g.rows_ext = false;
+  for (bqp_instance *inst : g.node_inst) if (inst->h.s.eq_rho == 2 || inst->h.s.adaptive_rho) g.rows_ext = true;
   // whole-GPU kernel: every problem of the batch has the layout (config 4) and nothing asked for another kernel
   g.use_grid = false;
   if (!g.use_panel && g_tune_threads == 0 && !std::getenv("BQP_KERNEL")) {
@@ -811,7 +814,7 @@ static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &pro
                               (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, (unsigned *)g.d_gbar.p,
                               g.smem, g.stream)
        : (g.use_panel && g.use_rows)
-           ? launch_admm_rows(g.cs, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
+           ? launch_admm_rows(g.cs, g.rows_ext ? 1 : 0, g.nslots, (double *)g.d_state.p, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
                               (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p,
                               g.smem, (const double *)g.d_corr.p, g.stream)
        : g.use_panel

@@ -14,6 +14,8 @@
 #include <chrono>
 #include <thread>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -482,7 +484,13 @@ static int rolling_on_ctx(bqp_ctx sctx, int count, const bqp_handle *h, const bq
   std::vector<char> active((size_t)count, 1);
   int rc = bqp_session_begin(sctx), nrounds = 0;
   std::vector<int> fin;
+  // BQP_ROLLING_TIMERS=1: where the wall time of the run goes (host replay / append / round = launch + wait / fetch), to stderr
+  const bool timers = std::getenv("BQP_ROLLING_TIMERS") != nullptr;
+  double t_replay = 0, t_append = 0, t_round = 0, t_fetch = 0; long long n_fetch = 0, n_append = 0;
+  auto tick = []() { return std::chrono::steady_clock::now(); };
+  auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
   while (!rc) {
+    auto tp = tick();
     // replay every tree that waits for nothing and collect its next leaves.  The replay of one node costs two sparse
     // mat-vecs on the host (objective at the clipped point, feasibility of the rounded point: ~1 ms at n = 500), the trees
     // are independent: spread them over host threads
@@ -507,6 +515,7 @@ static int rolling_on_ctx(bqp_ctx sctx, int count, const bqp_handle *h, const bq
       work();
       for (auto &th : pool) th.join();
     }
+    t_replay += since(tp); tp = tick();
     std::vector<Node *> batch; std::vector<int> owner;
     for (size_t i = 0; i < ready.size() && !rc; i++) {
       const int k = ready[i];
@@ -534,6 +543,8 @@ static int rolling_on_ctx(bqp_ctx sctx, int count, const bqp_handle *h, const bq
       const auto now = std::chrono::steady_clock::now();
       for (int j = 0; j < B; j++) { pend.push_back({owner[(size_t)j], batch[(size_t)j], now}); trees[(size_t)owner[(size_t)j]]->batched_nodes++; }
     }
+    n_append += (long long)batch.size();
+    t_append += since(tp); tp = tick();
     bool any = false;
     for (int k = 0; k < count; k++) any = any || outstanding[(size_t)k] > 0;
     if (!any) break;                              // every tree is finished
@@ -542,6 +553,7 @@ static int rolling_on_ctx(bqp_ctx sctx, int count, const bqp_handle *h, const bq
     rc = bqp_session_round(sctx, fin.data(), (int)fin.size(), &nfin, &running);
     if (rc) break;
     nrounds++;
+    t_round += since(tp); tp = tick();
     const auto now = std::chrono::steady_clock::now();
     for (int j = 0; j < nfin && !rc; j++) {
       Pending &pd = pend[(size_t)fin[(size_t)j]];
@@ -553,7 +565,12 @@ static int rolling_on_ctx(bqp_ctx sctx, int count, const bqp_handle *h, const bq
       Tree::absorb(*pd.node, status, iters, std::chrono::duration<double>(now - pd.t0).count() / 2.0);
       outstanding[(size_t)pd.tree]--;
     }
+    n_fetch += nfin;
+    t_fetch += since(tp);
   }
+  if (timers)
+    std::fprintf(stderr, "ROLLING %d rounds: replay %.3f s, append %.3f s (%lld nodes), round %.3f s, fetch %.3f s (%lld nodes)\n", nrounds,
+                 t_replay, t_append, n_append, t_round, t_fetch, n_fetch);
   for (int k = 0; k < count; k++) trees[(size_t)k]->finish(p[k], x[k], &res[k], decisions ? decisions[k] : nullptr, decisions_cap);
   if (rounds) *rounds = nrounds;
   return rc;

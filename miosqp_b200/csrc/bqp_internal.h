@@ -246,7 +246,8 @@ BQP_HD inline size_t rows_work_doubles(int npad, int m, int cs) {
   return (size_t)kRowsT * (7 * (size_t)((m + 7) / 8 * 8) + (5 + 3 * (size_t)cs * kRowsGroups) * (size_t)npad);
 }
 size_t rows_smem_bytes(int npad, int nslots, int cs);                                 // bqp_rows.cu
-int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+// ext != 0: some problem of the launch uses per-node rho typing (eq_rho == 2) or adaptive rho (the instantiation that carries that code)
+int launch_admm_rows(int cs, int ext, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
                      const double *d_corr, void *stream);
 // whole-GPU kernel: per tile, [row][8]: b, x~, x, dx, P x, P dx, objective operand, d . (V' b) (npad rows each); w, y, projected

@@ -200,7 +200,9 @@ __device__ __forceinline__ void load_bx(double (&bx)[kTPW][8], const double *v, 
 
 // One pass over the panels this CTA owns of one matrix.  MODE selects the row functor; passes with a second half
 // accumulate A_panel' w into acc (C fragments: column 32 (tile0 + tl) + 8 mt + (lane >> 2), nodes 2 (lane & 3) + {0, 1}).
-template <int CS, int MODE>
+// EXT: the launch holds problems with per-node rho typing (eq_rho == 2) or adaptive rho; the plain instantiation carries none of
+// that code (registers, branches in the row functor)
+template <int CS, int MODE, bool EXT>
 __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double (&bx)[kTPW][8], double (&acc)[kTPW][4][2], bool do_check,
                                           double *mdst = nullptr, bool dscale = false, uint32_t mbar = 0) {
   // RM_M only: mdst = the vector the product rows go to (this CTA's copy and every peer's); dscale = multiply row j of
@@ -250,7 +252,7 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       if constexpr (MODE == RM_CHK_A2) { s0 = ld2(W.gdy); s2 = ld2(W.gl); s3 = ld2(W.gu); }
       if constexpr (MODE == RM_CHK_P) { s0 = ld2(W.gdx); }
       if constexpr (MODE == RM_M) {
-        if (dscale && owner) {
+        if (EXT && dscale && owner) {
           const double mu = __ldg(I.g_mu + row);
           s0.x = 1.0 / (1.0 + (X.S->rho_t[2 * tq] - I.rho_base) * mu); s0.y = 1.0 / (1.0 + (X.S->rho_t[2 * tq + 1] - I.rho_base) * mu);
         }
@@ -260,7 +262,7 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
     double rho2[2] = {rho, rho}, rinv2[2] = {rinv, rinv};
     if constexpr (MODE == RM_A_ITER || MODE == RM_A_INIT || MODE == RM_A_RESUME) {
       // eq_rho == 2: the integer-bound rows are typed per node from the node's own (scaled) bounds, as osqp >= 0.4 does
-      if (I.eq2 && live && row >= m - I.n_int) {
+      if (EXT && I.eq2 && live && row >= m - I.n_int) {
         double2 lo2, up2;
         if constexpr (MODE == RM_A_ITER) { lo2 = s2; up2 = s3; }
         else { lo2 = __ldcg(reinterpret_cast<const double2 *>(W.gl) + e2); up2 = __ldcg(reinterpret_cast<const double2 *>(W.gu) + e2); }
@@ -274,7 +276,7 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
         }
       }
       // adaptive rho: inequality / equality rows follow the leaf's own rho (osqp_update_rho), loose rows stay at RHO_MIN
-      if (I.adaptive && live) {
+      if (EXT && I.adaptive && live) {
         const int ty = __ldg(I.g_rtype + row);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
@@ -341,7 +343,7 @@ __device__ __forceinline__ void rows_pass(Ctx<CS> &X, int npanels, const double 
       if constexpr (MODE == RM_M) {
         // x~ rows: into this CTA's operand vector and every peer's (all-gather riding along the pass)
         if (owner) {
-          if (dscale) { sum[0] *= s0.x; sum[1] *= s0.y; }
+          if (EXT && dscale) { sum[0] *= s0.x; sum[1] *= s0.y; }
           reinterpret_cast<double2 *>(mdst)[e2] = make_double2(sum[0], sum[1]);
           if constexpr (CS > 1) {
             const uint32_t off = smem_u32(mdst) + 16u * (uint32_t)e2;
@@ -571,7 +573,7 @@ __device__ __forceinline__ void store_parts(Ctx<CS> &X, int which, const double 
       for (int mt = 0; mt < 4; mt++) dst[(32 * (X.tile0 + tl) + 8 * mt + gq) * (T8 / 2) + tq] = make_double2(acc[tl][mt][0], acc[tl][mt][1]);
 }
 
-template <int CS>
+template <int CS, bool EXT>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                  double *__restrict__ out, double *__restrict__ work, NodeScalars *__restrict__ ns,
@@ -593,7 +595,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   if (tid < T) {
     // every leaf starts from the setup rho; a resumed round continues with the rho it had adapted to
     double r0 = S.I.rho_base;
-    if (S.I.adaptive && tid < S.tile.nn && S.tile.iter_begin > 0) r0 = state[S.tile.state_off[tid] + S.I.n + 2 * (size_t)S.I.m];
+    if (EXT && S.I.adaptive && tid < S.tile.nn && S.tile.iter_begin > 0) r0 = state[S.tile.state_off[tid] + S.I.n + 2 * (size_t)S.I.m];
     S.rho_t[tid] = r0; S.rinv_t[tid] = 1.0 / r0; S.rinveq_t[tid] = 1.0 / (kRhoEqFactor * r0);
   }
   if (tid == 0) S.rho_changed = 0;
@@ -702,7 +704,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     for (int iter = iter_begin + 1; iter <= iter_end; iter++) {
       const bool do_check = (iter % check_every == 0) || iter == max_iter;
       produce(pM, npm);
-      if (I.adaptive) produce(I.pstream + I.p_offV, npm);   // x~ = V (d . (V' b)): the M slot holds V'
+      if (EXT && I.adaptive) produce(I.pstream + I.p_offV, npm);   // x~ = V (d . (V' b)): the M slot holds V'
       produce(pA, npa);
       if (!do_check) continue;
       cluster_sync_all<CS>();                            // iterates of the check in global memory
@@ -710,7 +712,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       cluster_sync_all<CS>();                            // raw products in global memory
       named_bar(kG + 2, kRowsThreads);                   // decision published
       if (S.remaining == 0 || iter == iter_end) break;
-      if (S.rho_changed) produce(pA, npa);               // a leaf adapted its rho: the right-hand side is rebuilt
+      if (EXT && S.rho_changed) produce(pA, npa);               // a leaf adapted its rho: the right-hand side is rebuilt
     }
     cluster_sync_all<CS>();                              // final iterates of every CTA's rows in global memory
     cluster_sync_all<CS>();                              // epilogue operand ready
@@ -843,7 +845,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
 
   // ---- first pass of the launch: z = A x0 (fresh nodes) and b' of the starting point
   load_bx<true>(bx, W.gx, X.tile0, X.ntl, lane);
-  if (iter_begin == 0) rows_pass<CS, RM_A_INIT>(X, npa, bx, acc, false); else rows_pass<CS, RM_A_RESUME>(X, npa, bx, acc, false);
+  if (iter_begin == 0) rows_pass<CS, RM_A_INIT, EXT>(X, npa, bx, acc, false); else rows_pass<CS, RM_A_RESUME, EXT>(X, npa, bx, acc, false);
   reduce_b<CS>(X, acc, xr);
 
 #ifdef BQP_ROWS_DEBUG
@@ -852,7 +854,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
 #else
 #define PSTAMP(i) do { } while (0)
 #endif
-  const bool adaptive = I.adaptive != 0;
+  const bool adaptive = EXT && I.adaptive != 0;
   double *const xt = adaptive ? X.colb : X.colx;            // where x~ of the iteration lands
   int iter;
   for (iter = iter_begin + 1; iter <= iter_end; iter++) {
@@ -861,7 +863,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     post_x(X.xbar);
     load_bx<false>(bx, X.colb, X.tile0, X.ntl, lane);
     PSTAMP(0);
-    rows_pass<CS, RM_M>(X, npm, bx, acc, do_check, X.colx, adaptive, X.xbar);
+    rows_pass<CS, RM_M, EXT>(X, npm, bx, acc, do_check, X.colx, adaptive, X.xbar);
     PSTAMP(1);
     cons_bar();                                           // local x~ rows visible
     if constexpr (CS > 1) { mbar_wait(X.xbar, X.xph); X.xph ^= 1u; }
@@ -872,12 +874,12 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       // peer's product rows can arrive while this CTA still waits for a third CTA's coefficients
       post_x(X.vbar);
       load_bx<false>(bx, X.colx, X.tile0, X.ntl, lane);
-      rows_pass<CS, RM_M>(X, npm, bx, acc, do_check, X.colb, false, X.vbar);
+      rows_pass<CS, RM_M, EXT>(X, npm, bx, acc, do_check, X.colb, false, X.vbar);
       cons_bar();
       if constexpr (CS > 1) { mbar_wait(X.vbar, X.vph); X.vph ^= 1u; }
     }
     PSTAMP(2);
-    if (I.eq2) {
+    if (EXT && I.eq2) {
       // eq_rho == 2: Woodbury correction of the explicit inverse over the re-typed integer rows of every node,
       //   x~ <- x~ - M[:,S] G (x~[S])     (warp w <-> node w; every CTA of the cluster corrects its full copy identically)
       if (warp < nn && S.tile.corr_off[warp] >= 0) {
@@ -918,7 +920,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     }
     cons_bar();
     PSTAMP(3);
-    rows_pass<CS, RM_A_ITER>(X, npa, bx, acc, do_check);
+    rows_pass<CS, RM_A_ITER, EXT>(X, npa, bx, acc, do_check);
     PSTAMP(4);
     reduce_b<CS>(X, acc, xr);
     PSTAMP(5);
@@ -927,11 +929,11 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     // ---- termination check (update_info + check_termination): A x | A' y,  A dx | A' dy_proj,  P x | P dx
     cluster_sync_all<CS>();
     load_bx<true>(bx, W.gx, X.tile0, X.ntl, lane);
-    rows_pass<CS, RM_CHK_A1>(X, npa, bx, acc, true); store_parts<CS>(X, 0, acc);
+    rows_pass<CS, RM_CHK_A1, EXT>(X, npa, bx, acc, true); store_parts<CS>(X, 0, acc);
     load_bx<true>(bx, W.gdx, X.tile0, X.ntl, lane);
-    rows_pass<CS, RM_CHK_A2>(X, npa, bx, acc, true); store_parts<CS>(X, 1, acc);
+    rows_pass<CS, RM_CHK_A2, EXT>(X, npa, bx, acc, true); store_parts<CS>(X, 1, acc);
     load_bx<true>(bx, W.gx, X.tile0, X.ntl, lane);
-    rows_pass<CS, RM_CHK_P>(X, npm, bx, acc, true); store_parts<CS>(X, 2, acc);
+    rows_pass<CS, RM_CHK_P, EXT>(X, npm, bx, acc, true); store_parts<CS>(X, 2, acc);
     cluster_sync_all<CS>();
     {
       // norms, every CTA redundantly, one canonical order: thread <-> (node tid & 7, rows/columns (tid >> 3) + 32 i)
@@ -1021,9 +1023,9 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
     }
     named_bar(kG + 2, kRowsThreads);                      // ... and the producer sees the decision
     if (S.remaining == 0 || iter == iter_end) break;
-    if (S.rho_changed) {
+    if (EXT && S.rho_changed) {
       // the right-hand side of the next iteration carries rho: u = rho z - y and b' = sigma x - q + A' u again
-      rows_pass<CS, RM_A_RESUME>(X, npa, bx, acc, false);
+      rows_pass<CS, RM_A_RESUME, EXT>(X, npa, bx, acc, false);
       reduce_b<CS>(X, acc, xr);
       if (tid == 0) S.rho_changed = 0;
       cons_bar();
@@ -1039,7 +1041,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
       double *sp = state + S.tile.state_off[t];
       for (int j = tid; j < n; j += kConsThreads) sp[j] = __ldcg(W.gx + (size_t)j * T + t);
       for (int i = tid; i < m; i += kConsThreads) { sp[n + i] = __ldcg(W.gz + (size_t)i * T + t); sp[n + m + i] = __ldcg(W.gy + (size_t)i * T + t); }
-      if (tid == 0) sp[n + 2 * (size_t)m] = S.rho_t[t];
+      if (EXT && tid == 0) sp[n + 2 * (size_t)m] = S.rho_t[t];
       if (tid == 0) {   // pri_res of a node that is still running carries its distance to the tolerance (scheduling hint)
         NodeScalars r; r.status = BQP_UNSOLVED; r.iters = iter_end; r.obj = r.dua_res = r.lower = NAN; r.pri_res = S.dist[t];
         ns[S.tile.node[t]] = r;
@@ -1069,7 +1071,7 @@ admm_rows_kernel(const DevInstance *__restrict__ insts, const DevTile *__restric
   }
   cluster_sync_all<CS>();
   load_bx<true>(bx, W.gxo, X.tile0, X.ntl, lane);
-  rows_pass<CS, RM_OBJ_P>(X, npm, bx, acc, false);
+  rows_pass<CS, RM_OBJ_P, EXT>(X, npm, bx, acc, false);
   cluster_sync_all<CS>();
   {
     const int t = tid & 7, s = tid >> 3;
@@ -1115,14 +1117,14 @@ size_t rows_smem_bytes(int npad, int nslots, int cs) {
   return off + (size_t)nslots * nw * kTileD * 8;
 }
 
-template <int CS>
+template <int CS, bool EXT>
 static int launch_r(int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in,
                     double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem, const double *d_corr, cudaStream_t st) {
   // many host threads launch concurrently (one context each): raise the attribute only when it has to grow
   static std::atomic<size_t> smem_set{0};
   cudaError_t e = cudaSuccess;
   if (smem_set.load() < smem) {
-    e = cudaFuncSetAttribute(admm_rows_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    e = cudaFuncSetAttribute(admm_rows_kernel<CS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return BQP_E_CUDA;
     smem_set.store((size_t)kMaxSmem);
   }
@@ -1137,20 +1139,22 @@ static int launch_r(int nslots, double *d_state, const DevInstance *d_insts, con
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, admm_rows_kernel<CS>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
+  e = cudaLaunchKernelEx(&cfg, admm_rows_kernel<CS, EXT>, d_insts, d_tiles, d_in, d_out, d_work, d_ns, d_tile_iters, nslots, d_state,
                          prefetch_panels, d_corr);
   return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? BQP_OK : BQP_E_CUDA;
 }
 
-int launch_admm_rows(int cs, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
+int launch_admm_rows(int cs, int ext, int nslots, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,
                      const double *d_in, double *d_out, double *d_work, NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes,
                      const double *d_corr, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (nslots < 2) return BQP_E_ARG;
-  if (cs == 1) return launch_r<1>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
-  if (cs == 2) return launch_r<2>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
-  if (cs == 4) return launch_r<4>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
-  if (cs == 8) return launch_r<8>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st);
+#define BQP_ROWS_LAUNCH(C)                                                                                                              \
+  if (cs == C)                                                                                                                          \
+    return ext ? launch_r<C, true>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st) \
+               : launch_r<C, false>(nslots, d_state, d_insts, d_tiles, ntiles, d_in, d_out, d_work, d_ns, d_tile_iters, smem_bytes, d_corr, st)
+  BQP_ROWS_LAUNCH(1); BQP_ROWS_LAUNCH(2); BQP_ROWS_LAUNCH(4); BQP_ROWS_LAUNCH(8);
+#undef BQP_ROWS_LAUNCH
   return BQP_E_ARG;
 }
 
