@@ -101,7 +101,7 @@ typedef struct {
   long long node_iters;     /* sum over nodes of ADMM iterations executed until that node terminated */
   long long tile_iters;     /* sum over tiles of iterations the tile ran (= max over its nodes) */
   long long stream_bytes;   /* matrix/factor bytes the kernel streamed: sum over tiles of iterations x per-iteration panel bytes (+ checks) */
-  int kernel;               /* which kernel ran: 0 direct-load tile kernel, 1 TMA-streamed two-pass kernel, 2 fused single-pass panel kernel (column-split pair), 3 row-split cluster kernel */
+  int kernel;               /* which kernel ran: 0 direct-load tile kernel, 1 TMA-streamed two-pass kernel, 2 fused single-pass panel kernel (column-split pair), 3 row-split cluster kernel, 4 whole-GPU kernel (one tile on every SM), 5 shared-memory-resident kernel (npad <= 64) */
   int ring_slots;           /* shared-memory ring depth (TMA stages / panels in flight) of the first launch */
 } bqp_timing;
 
@@ -249,7 +249,8 @@ int bqp_debug_dump_groups(bqp_handle h);   /* prints the streamed group table to
 int bqp_debug_host_kkt_solve(bqp_handle h, double *rhs_xz /* [n+m], scaled space, in place */);
 int bqp_debug_host_stream_kkt_solve(bqp_handle h, double *rhs_xz /* same, through the TMA kernel's streamed layout */);
 int bqp_debug_host_panel_kkt_solve(bqp_handle h, double *rhs_xz /* same, through the fused kernel's row panels (explicit reduced inverse) */);
-int bqp_debug_host_matvec(bqp_handle h, int which /*0: A x, 1: A' y, 2: P x, 3: P x via the streamed layout, 4: P x via the row panels*/, const double *in, double *out);
+int bqp_debug_host_small_kkt_solve(bqp_handle h, double *rhs_xz /* same, through the shared-memory-resident layout of small problems (mma fragments of the explicit reduced inverse, ELL A and A') */);
+int bqp_debug_host_matvec(bqp_handle h, int which /*0: A x, 1: A' y, 2: P x, 3: P x via the streamed layout, 4: P x via the row panels, 5: P x via the fragments of the small layout*/, const double *in, double *out);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 # A/B builds of kernel variants: BQP_BUILD_DEFS="-DBQP_P1_SETS=2 ..." BQP_LIB_SUFFIX=_v2 -> libbqp_v2.so (same digest guard)
 EXTRA_DEFS = os.environ.get("BQP_BUILD_DEFS", "").split()
 OUT = os.path.join(HERE, "libbqp%s.so" % os.environ.get("BQP_LIB_SUFFIX", ""))
-SOURCES = ["bqp_setup.cpp", "bqp_bnb.cpp", "bqp_kernels.cu", "bqp_stream.cu", "bqp_panel.cu", "bqp_rows.cu", "bqp_grid.cu", "bqp_api.cu"]
+SOURCES = ["bqp_setup.cpp", "bqp_bnb.cpp", "bqp_kernels.cu", "bqp_stream.cu", "bqp_panel.cu", "bqp_rows.cu", "bqp_grid.cu", "bqp_small.cu", "bqp_api.cu"]
 HEADERS = ["bqp_internal.h", os.path.join("..", "..", "include", "bqp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-Xptxas", "-v"]

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -107,12 +108,18 @@ struct Buf {
 struct BatchCtx {
   int device = -1;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // bqp_solve_multi on a kernel that finishes in ONE launch (no rounds: direct-load, shared-memory-resident and whole-GPU
+  // kernels -- the latency-bound B&B drivers of configs 3 and 4): upload, tile table, launch and every read-back are queued
+  // back to back and the host waits once, instead of after each of the five steps (BQP_FAST_PATH=0: the stepwise path)
+  bool want_fast = false, fast = false, out_fetched = false;
+  std::vector<DevInstance> dinst_host;
   Buf h_in{nullptr, 0, true}, h_out{nullptr, 0, true}, h_ns{nullptr, 0, true}, h_ti{nullptr, 0, true};
   Buf d_in, d_out, d_ns, d_ti, d_work, d_tiles, d_insts, d_gbar;
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
   bool use_grid = false; int grid_ctas = 0;
+  bool use_small = false;         // every problem of the batch has the shared-memory-resident layout (npad <= 64) and no dense kernel serves it
   bool rows_ext = false;          // some problem of the batch uses eq_rho == 2 or adaptive rho: the rows kernel's extended instantiation
   bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
   int round_iters = 0, max_iter_all = 0;
@@ -228,6 +235,13 @@ int to_device(bqp_instance *inst) {
   if (h.pn.built && h.pn.spectral) {      // rows kernel, adaptive rho
     ar.add(h.pn.mu, &d.g_mu); ar.add(h.rtype, &d.g_rtype);
     d.adaptive = 1; d.adapt_interval = h.s.adaptive_rho_interval; d.adapt_tol = h.s.adaptive_rho_tolerance;
+  }
+  d.s_blob = nullptr; d.s_bytes = d.s_wa = d.s_wt = d.s_mp = d.s_offP = d.s_offAv = d.s_offTv = d.s_offRho = d.s_offRinv = d.s_offE = d.s_offEinv = d.s_offAc = d.s_offTc = 0;
+  if (h.sm.built) {
+    ar.add(h.sm.blob, &d.s_blob);
+    d.s_bytes = h.sm.bytes; d.s_wa = h.sm.wa; d.s_wt = h.sm.wt; d.s_mp = h.sm.mp;
+    d.s_offP = h.sm.offP; d.s_offAv = h.sm.offAv; d.s_offTv = h.sm.offTv; d.s_offRho = h.sm.offRho; d.s_offRinv = h.sm.offRinv; d.s_offE = h.sm.offE; d.s_offEinv = h.sm.offEinv;
+    d.s_offAc = h.sm.offAc; d.s_offTc = h.sm.offTc;
   }
   d.p_mint = nullptr; d.eq2 = h.s.eq_rho == 2 ? 1 : 0; d.rho_base = h.s.rho;
   if (d.eq2) ar.add(h.mint, &d.p_mint);
@@ -441,7 +455,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     g.tiles.clear();
     g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_bytes_launch.clear();
     scheduled->clear();
-    std::vector<DevInstance> dinst;
+    std::vector<DevInstance> &dinst = g.dinst_host; dinst.clear();
     std::map<bqp_instance *, int> inst_slot;
     size_t work_d = 0, smem = 0;
     for (size_t k = 0; k < members.size(); k++) {
@@ -479,7 +493,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     if ((rc = g.d_gbar.reserve(sizeof(unsigned), g.stream))) return rc;
     CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(ctx_sync(g));
+    if (!g.fast) CK(ctx_sync(g));       // fast path: g.tiles / g.dinst_host live until the next plan, which comes after the launch's wait
     g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
     return BQP_OK;
   }
@@ -517,6 +531,8 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       while (t > 1 && stream_slots(inst->h, t) < 3) t >>= 1;   // >= 3 stages in flight per quad: measured knee
       if (t == kMaxTT) t = kMaxTT / 2;                         // T=8 is FP64/smem-issue bound per SM
       if (stream_slots(inst->h, t) < 2) t = 0;
+    } else if (g.use_small) {
+      t = kMaxTT;                                                // the 8 leaves of a tile are the N dimension of the mma
     } else {
       t = max_tile_nodes(inst->h, g.threads);
     }
@@ -531,7 +547,8 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   // ... but narrow enough to keep every SM busy when the frontier (or what is left of it) is small.  Not for the panel
   // kernel: a tile-iteration costs the same for 1..8 nodes there (the nodes are the N dimension of the mma), so splitting
   // an instance's nodes over two tiles only doubles its HBM stream
-  if (!g_tune_tt && !use_panel) {
+  // Nor for the shared-memory-resident kernel: it is bound by instruction issue, and the threads of a missing leaf still issue
+  if (!g_tune_tt && !use_panel && !g.use_small) {
     auto count_tiles = [&](int t) { long long c = 0; for (auto &mb : members) c += ((long long)mb.size() + t - 1) / t; return c; };
     while (tt > 1 && count_tiles(tt / 2) <= std::min(capacity, ndev_sms)) tt >>= 1;
   }
@@ -545,7 +562,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   g.tile_bytes_iter.clear(); g.tile_bytes_check.clear(); g.tile_check_every.clear(); g.tile_bytes_launch.clear();
   g.nw_max = 0;
   scheduled->clear();
-  std::vector<DevInstance> dinst;
+  std::vector<DevInstance> &dinst = g.dinst_host; dinst.clear();
   std::map<bqp_instance *, int> inst_slot;
   size_t work_d = 0, smem = 0;
   for (size_t k = 0; k < members.size(); k++) {
@@ -555,7 +572,8 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     auto is = inst_slot.find(uniq[k]);
     if (is == inst_slot.end()) { inst_slot[uniq[k]] = (int)dinst.size(); dinst.push_back(uniq[k]->d); is = inst_slot.find(uniq[k]); }
     smem = std::max(smem, use_rows ? rows_smem_bytes(h.npad, nslots, cs) : use_panel ? panel_smem_bytes(h.npad, nslots, cs)
-                          : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
+                          : (use_stream ? stream_smem_bytes(h.n, h.m, tt, slot_size(tt), nslots, w_in_stage)
+                             : g.use_small ? small_smem_bytes(h.npad, h.m, h.sm.bytes) : tile_smem_bytes(h.n, h.m, tt, g.threads)));
     if (use_panel) g.nw_max = std::max(g.nw_max, h.pn.nw);
     for (int ti = 0; ti < nt; ti++) {
       const int lo = (int)((long long)cnt * ti / nt), hi = (int)((long long)cnt * (ti + 1) / nt);
@@ -572,9 +590,10 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       t.work_off = (long long)work_d;
       work_d += use_rows ? rows_work_doubles(h.npad, h.m, cs) : use_panel ? cs * panel_work_doubles(h.npad, h.m) : tile_work_doubles(h.n, h.m, tt);
       g.tiles.push_back(t);
-      g.tile_bytes_iter.push_back(use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
-      g.tile_bytes_check.push_back(use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
-      g.tile_bytes_launch.push_back(use_panel ? h.pn.launch_bytes() : 0);
+      // shared-memory-resident kernel: the blob is read from global memory once per launch, nothing per iteration
+      g.tile_bytes_iter.push_back(g.use_small ? 0 : use_panel ? h.pn.iter_bytes() : (use_stream ? h.st.iter_bytes : h.factor_bytes()));
+      g.tile_bytes_check.push_back(g.use_small ? 0 : use_panel ? h.pn.check_bytes() : (use_stream ? h.st.check_bytes : h.check_bytes()));
+      g.tile_bytes_launch.push_back(g.use_small ? h.sm.bytes : use_panel ? h.pn.launch_bytes() : 0);
       g.tile_check_every.push_back(h.s.check_termination);
     }
   }
@@ -587,7 +606,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size(), g.stream))) return rc;
   CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
-  CK(ctx_sync(g));   // tiles / dinst are stack-lifetime host memory
+  if (!g.fast) CK(ctx_sync(g));   // fast path: g.tiles / g.dinst_host live until the next plan, which comes after the launch's wait
   g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
   return BQP_OK;
 }
@@ -723,11 +742,23 @@ static void select_kernel(BatchCtx &g) {
     g.use_grid = true; g.use_panel = g.use_stream = false; g.grid_ctas = sms;
     for (bqp_instance *inst : g.node_inst) if (!inst->h.gd.built) g.use_grid = false;
   }
+  // shared-memory-resident kernel: small problems (npad <= 64) that no dense kernel serves -- configs 3 and 5 -- or, with
+  // BQP_KERNEL=small, every batch whose problems all carry the layout (BQP_SMALL_ALL=1 at setup: config 1 too)
+  g.use_small = false;
+  {
+    const char *e = std::getenv("BQP_KERNEL");
+    const bool forced = e && !std::strcmp(e, "small");
+    if (g_tune_threads == 0 && !g.use_grid && (forced || (!e && !g.use_panel && !g.use_stream))) {
+      bool all = true;
+      for (bqp_instance *inst : g.node_inst) all = all && inst->h.sm.built && !inst->h.s.adaptive_rho && inst->h.s.eq_rho != 2;
+      if (all) { g.use_small = true; g.use_panel = g.use_stream = false; }
+    }
+  }
   for (bqp_instance *inst : g.node_inst)
     if (inst->h.s.adaptive_rho && !((g.use_grid && inst->h.gd.spectral) || (g.use_panel && g.use_rows && inst->h.pn.spectral))) g.eq2_unsupported = true;
   if (g.use_panel) g.use_stream = false;
   if (!g.use_stream) g.w_in_stage = false;
-  g.threads = g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
+  g.threads = g.use_small ? 256 : g.use_panel ? 0 : g.use_stream ? (kStreamWarps + 1) * 32 : (g_tune_threads ? g_tune_threads : 32 * std::min(pow2ceil(want), kMaxThreads / 32));
   // rounds: the streamed kernels run `round_iters` ADMM iterations per launch; finished nodes drop out and the rest are
   // re-tiled (narrower tiles as the frontier drains, so idle SMs pick up the stragglers).  0 = one launch.
   g.round_iters = 0;
@@ -787,12 +818,17 @@ static int batch_upload(BatchCtx &g, int B, const bqp_handle *handles, const dou
     std::memcpy(p + 2 * (size_t)h.m, x0[b], 8 * (size_t)h.n);
     std::memcpy(p + 2 * (size_t)h.m + h.n, y0[b], 8 * (size_t)h.m);
   }
+  static const bool fast_ok = !(std::getenv("BQP_FAST_PATH") && std::atoi(std::getenv("BQP_FAST_PATH")) == 0);
+  g.fast = fast_ok && g.want_fast && g.round_iters == 0;
+  g.out_fetched = false;
   CK(cudaEventRecord(g.ev[0], g.stream));
   CK(cudaMemcpyAsync(g.d_in.p, hin, in_d * 8, cudaMemcpyHostToDevice, g.stream));
   CK(cudaEventRecord(g.ev[1], g.stream));
-  CK(ctx_sync(g));
   float ms = 0;
-  cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
+  if (!g.fast) {           // h_in is this context's own pinned buffer: nothing touches it before the next upload
+    CK(ctx_sync(g));
+    cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
+  }
   g.timing = bqp_timing{};
   g.timing.h2d_ms = ms;
   g.timing.h2d_bytes = (long long)(in_d * 8);
@@ -825,12 +861,21 @@ static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &pro
            ? launch_admm_stream(g.tt, g.slot_bytes, g.nslots, g.w_in_stage ? 1 : 0, (double *)g.d_state.p,
                                 (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
                                 (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
+       : g.use_small
+           ? launch_admm_small(64, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
+                               (double *)g.d_out.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
            : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
                          (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,
                          (int *)g.d_ti.p, g.smem, g.stream);
   if (rc) { g_last_cuda = cudaGetLastError(); return rc; }
+  if (g.fast) CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(g.h_ti.p, g.d_ti.p, sizeof(int) * (size_t)g.ntiles, cudaMemcpyDeviceToHost, g.stream));
+  if (g.fast) {            // the one launch of this batch: the iterates come back behind it, one wait for everything
+    CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    g.out_fetched = true;
+  }
   CK(ctx_sync(g));
   const NodeScalars *hs = (const NodeScalars *)g.h_ns.p;
   const int *ti = (const int *)g.h_ti.p;
@@ -867,7 +912,7 @@ static void fill_launch_timing(BatchCtx &g, int first_tiles, int first_tt, long 
     const int nwc = g.cs == 2 ? (g.nw_max + 1) / 2 : g.nw_max;
     g.timing.threads = panel_cta_warps(nwc) * 32;
   }
-  g.timing.kernel = g.use_grid ? 4 : g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
+  g.timing.kernel = g.use_grid ? 4 : g.use_small ? 5 : g.use_panel ? (g.use_rows ? 3 : 2) : (g.use_stream ? 1 : 0);
   if (g.use_grid) { g.timing.threads = 512; g.timing.tiles = g.grid_ctas; }
   g.timing.ring_slots = first_slots;
 }
@@ -883,18 +928,25 @@ static int batch_run(BatchCtx &g) {
   long long tile_iters = 0, bytes = 0, h2d_extra = 0;
   int launches = 0, first_tiles = 0, first_tt = 0, first_slots = 0;
   long long first_smem = 0;
-  CK(cudaEventRecord(g.ev[1], g.stream));
+  CK(cudaEventRecord(g.fast ? g.ev[4] : g.ev[1], g.stream));
   while (!alive.empty()) {
     int rc = run_round(g, alive, progress, dist, remaining, nullptr, &tile_iters, &bytes);
     if (rc) return rc;
     h2d_extra += g.round_h2d_bytes;
     if (launches == 0) { first_tiles = g.ntiles; first_tt = g.tt; first_smem = (long long)g.smem; first_slots = (g.use_panel || g.use_stream) ? g.nslots : 0; }
     launches++;
+    if (g.fast && !alive.empty()) return BQP_E_CUDA;      // a kernel without rounds finishes every node it is given
   }
-  CK(cudaEventRecord(g.ev[2], g.stream));
-  CK(ctx_sync(g));
   float ms = 0;
-  cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
+  if (g.fast) {            // everything was waited for inside the round
+    cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]); g.timing.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]); g.timing.d2h_ms = ms;
+    cudaEventElapsedTime(&ms, g.ev[4], g.ev[2]);
+  } else {
+    CK(cudaEventRecord(g.ev[2], g.stream));
+    CK(ctx_sync(g));
+    cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]);
+  }
   g.timing.kernel_ms = ms;
   g.timing.launches = launches;
   fill_launch_timing(g, first_tiles, first_tt, first_smem, first_slots);
@@ -908,6 +960,7 @@ static int batch_run(BatchCtx &g) {
 // launch (one round of ADMM iterations over a capacity-bounded, critical-path-first subset of the running nodes)
 static int session_begin(BatchCtx &g) {
   g.resident = false; g.ran = false; g.session = true;
+  g.fast = false; g.out_fetched = false;
   g.auto_cluster = true;
   if (const char *e = std::getenv("BQP_ROWS_AUTO_CLUSTER")) g.auto_cluster = std::atoi(e) != 0;
   g.B = 0; g.node_inst.clear(); g.in_off.clear(); g.out_off.clear(); g.state_off.clear();
@@ -1005,14 +1058,16 @@ static int session_round(BatchCtx &g, std::vector<int> *finished) {
 static int batch_download(BatchCtx &g, double *const *x, double *const *y, const bqp_node_out *out) {
   if (!g.resident || !g.ran) return BQP_E_ARG;
   CK(cudaSetDevice(g.device));
-  CK(cudaEventRecord(g.ev[2], g.stream));
-  CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaEventRecord(g.ev[3], g.stream));
-  CK(ctx_sync(g));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
-  g.timing.d2h_ms = ms;
+  if (!g.out_fetched) {
+    CK(cudaEventRecord(g.ev[2], g.stream));
+    CK(cudaMemcpyAsync(g.h_out.p, g.d_out.p, g.out_doubles * 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(g.h_ns.p, g.d_ns.p, sizeof(NodeScalars) * (size_t)g.B, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    CK(ctx_sync(g));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
+    g.timing.d2h_ms = ms;
+  }
   g.timing.d2h_bytes = (long long)(g.out_doubles * 8 + sizeof(NodeScalars) * (size_t)g.B);
   g.timing.h2d_bytes = (long long)(g.in_doubles * 8) + g.round_h2d_total;
   const double *ho = (const double *)g.h_out.p;
@@ -1036,13 +1091,32 @@ static int batch_download(BatchCtx &g, double *const *x, double *const *y, const
   return BQP_OK;
 }
 
+// BQP_API_TIMERS=1: wall time of the three phases of bqp_solve_multi and the device time of its kernels, summed over the process
+struct ApiTimers {
+  bool on = std::getenv("BQP_API_TIMERS") != nullptr;
+  double up = 0, run = 0, down = 0, kernel_ms = 0; long long calls = 0;
+  ~ApiTimers() {
+    if (on && calls)
+      std::fprintf(stderr, "API %lld solve_multi calls: upload %.3f s, run %.3f s (kernels %.3f s), download %.3f s\n", calls, up, run, kernel_ms * 1e-3, down);
+  }
+};
+static ApiTimers g_at;
+static inline double at_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int solve_multi(BatchCtx &g, int B, const bqp_handle *handles, const double *const *l, const double *const *u,
                        const double *const *x0, const double *const *y0, double *const *x, double *const *y,
                        const bqp_node_out *out) {
+  const double t0 = g_at.on ? at_now() : 0.0;
+  g.want_fast = true;
   int rc = batch_upload(g, B, handles, l, u, x0, y0);
+  g.want_fast = false;
   if (rc) return rc;
+  const double t1 = g_at.on ? at_now() : 0.0;
   if ((rc = batch_run(g))) return rc;
-  return batch_download(g, x, y, out);
+  const double t2 = g_at.on ? at_now() : 0.0;
+  rc = batch_download(g, x, y, out);
+  if (g_at.on) { const double t3 = at_now(); g_at.up += t1 - t0; g_at.run += t2 - t1; g_at.down += t3 - t2; g_at.kernel_ms += g.timing.kernel_ms; g_at.calls++; }
+  return rc;
 }
 
 int bqp_batch_upload(int B, const bqp_handle *handles, const double *const *l, const double *const *u,
@@ -1174,7 +1248,7 @@ int bqp_get_scaling(bqp_handle h, double *D, double *E, double *c) {
 int bqp_get_inverse_guard(bqp_handle h, double *error, int *in_use) {
   if (!h) return BQP_E_ARG;
   if (error) *error = h->h.pn_inverse_error;
-  if (in_use) *in_use = (h->h.pn.built || h->h.gd.built) ? 1 : 0;
+  if (in_use) *in_use = (h->h.pn.built || h->h.gd.built || h->h.sm.built) ? 1 : 0;
   return BQP_OK;
 }
 
@@ -1223,10 +1297,16 @@ int bqp_debug_host_panel_kkt_solve(bqp_handle h, double *rhs_xz) {
   return host_panel_kkt_solve(&h->h, rhs_xz);
 }
 
+int bqp_debug_host_small_kkt_solve(bqp_handle h, double *rhs_xz) {
+  if (!h || !rhs_xz) return BQP_E_ARG;
+  return host_small_kkt_solve(&h->h, rhs_xz);
+}
+
 int bqp_debug_host_matvec(bqp_handle h, int which, const double *in, double *out) {
-  if (!h || !in || !out || which < 0 || which > 4) return BQP_E_ARG;
+  if (!h || !in || !out || which < 0 || which > 5) return BQP_E_ARG;
   if (which == 3) return host_stream_matvec_P(&h->h, in, out);
   if (which == 4) return host_panel_matvec_P(&h->h, in, out);
+  if (which == 5) return host_small_matvec_P(&h->h, in, out);
   host_matvec(which == 0 ? h->h.Ab : (which == 1 ? h->h.At : h->h.Pm), in, out);
   return BQP_OK;
 }

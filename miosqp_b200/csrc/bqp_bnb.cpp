@@ -31,6 +31,21 @@ using Vec = std::vector<double>;
 using VecP = std::shared_ptr<Vec>;
 constexpr double kInf = std::numeric_limits<double>::infinity();
 
+// BQP_BNB_TIMERS=1: where the wall time of the single-tree driver goes, summed over the process and printed at exit (stderr)
+struct BnbTimers {
+  bool on = std::getenv("BQP_BNB_TIMERS") != nullptr;
+  double t_collect = 0, t_engine = 0, t_absorb = 0, t_advance = 0; long long launches = 0, nodes = 0;
+  long long real_nodes = 0, max_real = 0, max_all = 0;      // per launch: iterations of its slowest open leaf / slowest node incl. look-ahead, summed
+  ~BnbTimers() {
+    if (on && launches)
+      std::fprintf(stderr, "BNB %lld launches, %lld nodes (%lld open leaves): collect %.3f s, engine %.3f s, absorb %.3f s, replay %.3f s; "
+                   "iterations of the slowest node per launch, summed: %lld over the open leaves, %lld incl. look-ahead\n", launches, nodes, real_nodes,
+                   t_collect, t_engine, t_absorb, t_advance, max_real, max_all);
+  }
+};
+static BnbTimers g_bt;
+static inline double bt_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct Node;
 using NodeP = std::shared_ptr<Node>;
 
@@ -196,7 +211,9 @@ struct Tree {
   }
   int launch() {
     std::vector<Node *> batch;
+    const double tc0 = g_bt.on ? bt_now() : 0.0;
     collect(batch);
+    if (g_bt.on) g_bt.t_collect += bt_now() - tc0;
     if (batch.empty()) return BQP_OK;
     const int B = (int)batch.size();
     std::vector<const double *> pl(B), pu(B), px0(B), py0(B);
@@ -221,7 +238,15 @@ struct Tree {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     long long total = 0; for (int b = 0; b < B; b++) total += iters[b];
     if (total < 1) total = 1;
+    const double ta0 = g_bt.on ? bt_now() : 0.0;
     for (int b = 0; b < B; b++) absorb(*batch[b], status[b], iters[b], dt * (double)iters[b] / (double)total);
+    if (g_bt.on) {
+      g_bt.t_engine += dt; g_bt.t_absorb += bt_now() - ta0; g_bt.launches++; g_bt.nodes += B;
+      int nreal = 0, mr = 0, ma = 0;
+      for (auto &lf : leaves) for (int b = 0; b < B; b++) if (batch[b] == lf.get()) { nreal++; mr = std::max(mr, iters[b]); }
+      for (int b = 0; b < B; b++) ma = std::max(ma, iters[b]);
+      g_bt.real_nodes += nreal; g_bt.max_real += mr; g_bt.max_all += ma;
+    }
     batches++; batched_nodes += B;
     return BQP_OK;
   }
@@ -300,7 +325,9 @@ struct Tree {
   }
   int run() {
     for (;;) {
+      const double t0 = g_bt.on ? bt_now() : 0.0;
       const int a = advance();
+      if (g_bt.on) g_bt.t_advance += bt_now() - t0;
       if (a <= 0) return a;
       const int rc = launch(); if (rc) return rc;
     }

@@ -137,6 +137,22 @@ struct HostGridL {
   long long iter_bytes(int npad) const { return (long long)npad * npad * 8 + 12LL * (long long)(avl.size() + tvl.size()); }
 };
 
+// ---- shared-memory-resident kernel for small problems (bqp_small.cu): npad <= 64 (BASELINE config 3: the power-converter
+// MPC, n = 60, m = 150; config 5: the max-iter pickles, n = 20, m = 70).  Same restated iteration as the dense kernels
+// (x~ = M b with the explicit reduced inverse, z~ = A x~, b' = sigma x - q + A'(rho z - y)); everything the ADMM loop reads
+// is ONE contiguous blob that a single TMA bulk copy stages into shared memory at the start of the launch and that stays there:
+//   Mf, Pf   M and P as FP64 mma.m8n8k4 A-fragments: [panel p][k-step s][lane] = X[8 p + (lane >> 2)][4 s + (lane & 3)]
+//   Av, Ac   A by rows as ELL, entry-major: Av[k * mp + r] (f64), Ac[k * mp + r] (u16 column), k < wa; padding 0.0 / column 0
+//   Tv, Tc   A' by rows (= A by columns) the same way: Tv[k * npad + j], Tc[k * npad + j] (u16 row of A), k < wt
+//   rho, rinv, E, Einv per row of A (mp entries each)
+struct HostSmall {
+  bool built = false;
+  int wa = 0, wt = 0, mp = 0;                       // ELL widths of A and A'; m rounded up to 8
+  int offP = 0, offAv = 0, offTv = 0, offRho = 0, offRinv = 0, offE = 0, offEinv = 0, offAc = 0, offTc = 0, bytes = 0;   // byte offsets into the blob (M at 0)
+  std::vector<unsigned char> blob;
+  long long iter_bytes() const { return bytes; }    // what one iteration reads -- from shared memory, not from HBM
+};
+
 // Everything the host computes once per (P, A): scaled data, rho typing, the LDL^T factor of the
 // KKT matrix in constraints-first order (L = [[I,0],[L21,L22]] with L21 = -A' diag(rho)
 // streamed as the A panels and the dense trailing supernode L22 D2 L22' = P + sigma I + A' diag(rho) A).
@@ -159,6 +175,7 @@ struct HostInstance {
   HostStream st;                         // streamed layout (built for problems large enough for the TMA kernel)
   HostPanels pn;                         // row-panel layout of the fused single-pass kernel (dense A, npad <= 512)
   HostGridL gd;                          // whole-GPU layout (npad > 512, memory permitting)
+  HostSmall sm;                          // shared-memory-resident layout (npad <= 64)
   // guard of the explicit reduced inverse: largest relative difference, over a few probe right-hand sides, between a KKT
   // solve through the panels (x~ = M b) and through the LDL' substitution; NaN when no panel layout was tried.  Above the
   // threshold (1e-10, BQP_INVERSE_TOL) the panel layout is dropped and the problem runs on the LDL' kernels
@@ -183,6 +200,8 @@ int host_stream_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_stream_matvec_P(const HostInstance *h, const double *in, double *out);
 int host_panel_kkt_solve(const HostInstance *h, double *rhs_xz);
 int host_grid_kkt_solve(const HostInstance *h, double *rhs_xz);
+int host_small_kkt_solve(const HostInstance *h, double *rhs_xz);
+int host_small_matvec_P(const HostInstance *h, const double *in, double *out);
 int host_panel_matvec_P(const HostInstance *h, const double *in, double *out);
 double host_panel_M(const HostInstance *h, int r, int c);      // entry (r, c) of the explicit reduced inverse
 
@@ -199,6 +218,8 @@ struct DevInstance {
   const double *g_M, *g_P; const int *g_arp, *g_aci, *g_trp, *g_tci; const double *g_avl, *g_tvl; int g_npm;
   // adaptive rho (spectral form): g_M = V' panels, g_V = V panels, g_mu = eigenvalues, g_rtype = row types
   const double *g_V, *g_mu; const int *g_rtype; int adaptive, adapt_interval; double adapt_tol;
+  // shared-memory-resident layout (bqp_small.cu): the blob and the byte offsets of its sections
+  const unsigned char *s_blob; int s_bytes, s_wa, s_wt, s_mp, s_offP, s_offAv, s_offTv, s_offRho, s_offRinv, s_offE, s_offEinv, s_offAc, s_offTc;
   DevMat At, Ab, Pm;
   const double *Lcol, *Lrow, *D2inv;
   const double *rho, *rho_inv, *q, *D, *Dinv, *E, *Einv;
@@ -259,6 +280,9 @@ size_t grid_smem_bytes(int npad, int m, int n, int nctas);                      
 int grid_max_ctas(int device, size_t smem_bytes);                                     // co-resident CTAs of the cooperative launch
 int launch_admm_grid(int nctas, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
                      double *d_work, NodeScalars *d_ns, int *d_tile_iters, unsigned *d_barrier, size_t smem_bytes, void *stream);
+size_t small_smem_bytes(int npad, int m, int blob_bytes);                             // bqp_small.cu
+int launch_admm_small(int npad, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
+                      NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu
 int launch_admm_stream(int tt, int slot_bytes, int nslots, int w_in_stage, double *d_state, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles,

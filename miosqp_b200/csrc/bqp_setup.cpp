@@ -622,6 +622,67 @@ void build_grid(HostInstance *h, const std::vector<Row> &arows, const std::vecto
   gd.built = true;
 }
 
+// shared-memory-resident layout (bqp_small.cu): M and P as mma A-fragments, A and A' as entry-major ELL, rho and 1 / rho
+// per row, in one blob (one TMA bulk copy).  Returns false when the problem does not qualify (the blob plus the kernel's
+// vectors must fit the shared memory of one CTA; columns are stored as u16)
+bool build_small(HostInstance *h, const std::vector<Row> &arows, const std::vector<Row> &atrows, const std::vector<Row> &prows,
+                 const std::vector<double> &S) {
+  const int n = h->n, m = h->m, np_ = h->npad;
+  HostSmall &sm = h->sm;
+  sm = HostSmall();
+  if (np_ > 64 || m > 60000) return false;
+  int wa = 1, wt = 1;
+  for (int r = 0; r < m; r++) wa = std::max(wa, (int)arows[r].size());
+  for (int j = 0; j < n; j++) wt = std::max(wt, (int)atrows[j].size());
+  // the kernel keeps a thread's ELL entries in registers: 3 rows of A with up to 4 entries, one row of A' with up to 8
+  // (config 3: 3 and 5).  Wider or taller problems stay on the direct-load kernel
+  if (wa > 4 || wt > 8 || m > 192) return false;
+  const int mp = std::max(8, (m + 7) / 8 * 8);
+  auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+  size_t off = 0;
+  const size_t offM = off; off += (size_t)np_ * np_ * 8;
+  const size_t offP = off; off += (size_t)np_ * np_ * 8;
+  const size_t offAv = off; off += (size_t)wa * mp * 8;
+  const size_t offTv = off; off += (size_t)wt * np_ * 8;
+  const size_t offRho = off; off += (size_t)mp * 8;
+  const size_t offRinv = off; off += (size_t)mp * 8;
+  const size_t offE = off; off += (size_t)mp * 8;
+  const size_t offEinv = off; off += (size_t)mp * 8;
+  const size_t offAc = off; off = align16(off + (size_t)wa * mp * 2);
+  const size_t offTc = off; off = align16(off + (size_t)wt * np_ * 2);
+  if (small_smem_bytes(np_, m, (int)off) > (size_t)kMaxSmem) return false;
+  sm.blob.assign(off, 0);
+  const std::vector<double> M = reduced_inverse(h, S);
+  std::vector<double> Pd((size_t)np_ * np_, 0.0);
+  for (int r = 0; r < n; r++)
+    for (auto &e : prows[r]) Pd[(size_t)r * np_ + e.first] = e.second;
+  auto frag = [&](const std::vector<double> &X, size_t o) {
+    double *dst = reinterpret_cast<double *>(sm.blob.data() + o);
+    const int ks = np_ / 4;
+    for (int p = 0; p < np_ / 8; p++)
+      for (int s = 0; s < ks; s++)
+        for (int lane = 0; lane < 32; lane++) dst[((size_t)p * ks + s) * 32 + lane] = X[(size_t)(8 * p + (lane >> 2)) * np_ + 4 * s + (lane & 3)];
+  };
+  frag(M, offM); frag(Pd, offP);
+  double *av = reinterpret_cast<double *>(sm.blob.data() + offAv), *tv = reinterpret_cast<double *>(sm.blob.data() + offTv);
+  double *rho = reinterpret_cast<double *>(sm.blob.data() + offRho), *rinv = reinterpret_cast<double *>(sm.blob.data() + offRinv);
+  uint16_t *ac = reinterpret_cast<uint16_t *>(sm.blob.data() + offAc), *tc = reinterpret_cast<uint16_t *>(sm.blob.data() + offTc);
+  for (int r = 0; r < m; r++)
+    for (size_t k = 0; k < arows[r].size(); k++) { av[k * mp + r] = arows[r][k].second; ac[k * mp + r] = (uint16_t)arows[r][k].first; }
+  for (int j = 0; j < n; j++)
+    for (size_t k = 0; k < atrows[j].size(); k++) { tv[k * np_ + j] = atrows[j][k].second; tc[k * np_ + j] = (uint16_t)atrows[j][k].first; }
+  double *es = reinterpret_cast<double *>(sm.blob.data() + offE), *eis = reinterpret_cast<double *>(sm.blob.data() + offEinv);
+  for (int r = 0; r < mp; r++) {
+    rho[r] = r < m ? h->rho[r] : 1.0; rinv[r] = r < m ? h->rho_inv[r] : 1.0;
+    es[r] = r < m ? h->E[r] : 1.0; eis[r] = r < m ? h->Einv[r] : 1.0;
+  }
+  sm.wa = wa; sm.wt = wt; sm.mp = mp;
+  sm.offP = (int)offP; sm.offAv = (int)offAv; sm.offTv = (int)offTv; sm.offRho = (int)offRho; sm.offRinv = (int)offRinv; sm.offE = (int)offE; sm.offEinv = (int)offEinv;
+  sm.offAc = (int)offAc; sm.offTc = (int)offTc; sm.bytes = (int)off;
+  sm.built = true;
+  return true;
+}
+
 }  // namespace
 
 void host_rescale_q(HostInstance *h, const double *q) {   // osqp update_lin_cost: q_scaled = c * D * q
@@ -861,6 +922,39 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
       if (!(worst <= tol)) { h->gd = HostGridL(); if (!h->pn.built) h->pn_rejected = true; }
     }
   }
+  // shared-memory-resident layout for small problems the dense kernels do not serve (configs 3 and 5); fixed rho typed at
+  // setup only.  Same guard of the explicit inverse; BQP_SMALL=0 keeps them on the direct-load LDL' kernel
+  h->sm = HostSmall();
+  {
+    int want = 1;
+    if (const char *e = std::getenv("BQP_SMALL")) want = std::atoi(e);
+    const bool also_dense = std::getenv("BQP_SMALL_ALL") && std::atoi(std::getenv("BQP_SMALL_ALL")) != 0;   // experiments: config 1 too
+    if (want && np_ <= 64 && (!h->pn.built || also_dense) && !h->pn_rejected && !s->adaptive_rho && s->eq_rho != 2 &&
+        build_small(h, arows, atrows, prows, S)) {
+      double tol = 1e-10;
+      if (const char *e = std::getenv("BQP_INVERSE_TOL")) tol = std::atof(e);
+      double worst = 0.0;
+      std::vector<double> r1((size_t)n + m), r2((size_t)n + m);
+      for (int probe = 0; probe < 4; probe++) {
+        uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)(probe + 1);
+        for (int k = 0; k < n + m; k++) {
+          double v;
+          if (probe == 0) v = 1.0;
+          else if (probe == 1) v = (k & 1) ? -1.0 : 1.0;
+          else { st ^= st << 13; st ^= st >> 7; st ^= st << 17; v = (double)(st >> 11) / 9007199254740992.0 - 0.5; }
+          r1[(size_t)k] = r2[(size_t)k] = v;
+        }
+        host_kkt_solve(h, r1.data());
+        host_small_kkt_solve(h, r2.data());
+        double nrm = 0.0, dif = 0.0;
+        for (int j = 0; j < n; j++) { nrm = std::max(nrm, std::fabs(r1[(size_t)j])); dif = std::max(dif, std::fabs(r1[(size_t)j] - r2[(size_t)j])); }
+        const double rel = dif / std::max(nrm, 1e-300);
+        worst = (rel == rel) ? std::max(worst, rel) : INFINITY;
+      }
+      if (!h->pn.built && !h->gd.built) h->pn_inverse_error = worst;
+      if (!(worst <= tol)) { h->sm = HostSmall(); if (!h->pn.built && !h->gd.built) h->pn_rejected = true; }
+    }
+  }
   if (s->adaptive_rho && !((h->gd.built && h->gd.spectral) || (h->pn.built && h->pn.spectral))) return BQP_E_UNSUPPORTED;
   h->mint.clear();
   if (s->eq_rho == 2) {
@@ -1085,6 +1179,50 @@ int host_grid_kkt_solve(const HostInstance *h, double *rhs) {
     rhs[n + i] = h->rho[i] * (acc - rhs[n + i]);
   }
   for (int j = 0; j < n; j++) rhs[j] = xt[j];
+  return BQP_OK;
+}
+
+// the same through the shared-memory-resident layout (fragment-ordered M, ELL A and A'): a layout check
+static inline double small_frag_at(const HostSmall &sm, int off, int np_, int r, int c) {
+  const double *X = reinterpret_cast<const double *>(sm.blob.data() + off);
+  return X[((size_t)(r >> 3) * (np_ / 4) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3)];
+}
+int host_small_kkt_solve(const HostInstance *h, double *rhs) {
+  const HostSmall &sm = h->sm;
+  if (!sm.built) return BQP_E_UNSUPPORTED;
+  const int n = h->n, m = h->m, np_ = h->npad, mp = sm.mp;
+  const double *av = reinterpret_cast<const double *>(sm.blob.data() + sm.offAv), *tv = reinterpret_cast<const double *>(sm.blob.data() + sm.offTv);
+  const double *rho = reinterpret_cast<const double *>(sm.blob.data() + sm.offRho);
+  const uint16_t *ac = reinterpret_cast<const uint16_t *>(sm.blob.data() + sm.offAc), *tc = reinterpret_cast<const uint16_t *>(sm.blob.data() + sm.offTc);
+  std::vector<double> b(np_, 0.0), xt(np_, 0.0);
+  for (int j = 0; j < n; j++) {
+    double acc = 0;
+    for (int k = 0; k < sm.wt; k++) { const int i = tc[(size_t)k * np_ + j]; acc = std::fma(tv[(size_t)k * np_ + j], rho[i] * rhs[n + i], acc); }
+    b[j] = rhs[j] + acc;
+  }
+  for (int r = 0; r < np_; r++) {
+    double acc = 0;
+    for (int j = 0; j < np_; j++) acc = std::fma(small_frag_at(sm, 0, np_, r, j), b[j], acc);
+    xt[r] = acc;
+  }
+  for (int i = 0; i < m; i++) {
+    double acc = 0;
+    for (int k = 0; k < sm.wa; k++) acc = std::fma(av[(size_t)k * mp + i], xt[ac[(size_t)k * mp + i]], acc);
+    rhs[n + i] = rho[i] * (acc - rhs[n + i]);
+  }
+  for (int j = 0; j < n; j++) rhs[j] = xt[j];
+  return BQP_OK;
+}
+
+int host_small_matvec_P(const HostInstance *h, const double *in, double *out) {
+  const HostSmall &sm = h->sm;
+  if (!sm.built) return BQP_E_UNSUPPORTED;
+  const int np_ = h->npad;
+  for (int r = 0; r < h->n; r++) {
+    double acc = 0;
+    for (int c = 0; c < h->n; c++) acc = std::fma(small_frag_at(sm, sm.offP, np_, r, c), in[c], acc);
+    out[r] = acc;
+  }
   return BQP_OK;
 }
 

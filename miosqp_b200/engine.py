@@ -105,7 +105,7 @@ EXPORTS = ["bqp_default_settings", "bqp_setup", "bqp_update_q", "bqp_solve_batch
            "bqp_batch_upload", "bqp_batch_run", "bqp_batch_download", "bqp_last_timing", "bqp_free",
            "bqp_set_tuning", "bqp_get_dims", "bqp_get_scaling", "bqp_device_count", "bqp_strerror",
            "bqp_version", "bqp_debug_host_setup", "bqp_debug_host_kkt_solve", "bqp_debug_host_stream_kkt_solve",
-           "bqp_debug_host_panel_kkt_solve",
+           "bqp_debug_host_panel_kkt_solve", "bqp_debug_host_small_kkt_solve",
            "bqp_debug_host_matvec", "bqp_bnb_solve", "bqp_bnb_solve_many", "bqp_setup_many", "bqp_bnb_solve_async",
            "bqp_ctx_create", "bqp_ctx_free", "bqp_ctx_solve_multi", "bqp_ctx_last_timing", "bqp_handle_device",
            "bqp_get_inverse_guard", "bqp_ctx_set_auto_cluster", "bqp_ctx_set_sm_share", "bqp_bnb_solve_rolling", "bqp_session_begin", "bqp_session_append", "bqp_session_round", "bqp_session_fetch"]
@@ -141,6 +141,7 @@ def lib():
         L.bqp_debug_host_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_stream_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_panel_kkt_solve.argtypes = [vp, _dp]
+        L.bqp_debug_host_small_kkt_solve.argtypes = [vp, _dp]
         L.bqp_debug_host_matvec.argtypes = [vp, C.c_int, _dp, _dp]
         L.bqp_setup_many.argtypes = [C.c_int, C.POINTER(C.POINTER(_Problem)), C.POINTER(_Settings), pp, C.c_int, C.c_int]
         L.bqp_bnb_solve_many.argtypes = [C.c_int, pp, C.POINTER(C.POINTER(_Problem)), C.POINTER(_BnbSettings), _pp_d, _dp, C.c_void_p, vp,
@@ -340,9 +341,14 @@ class BatchedQP(object):
         _check(lib().bqp_debug_host_panel_kkt_solve(self._h, _d(b)))
         return b
 
+    def debug_small_kkt_solve(self, rhs):
+        b = _f64(rhs).copy()
+        _check(lib().bqp_debug_host_small_kkt_solve(self._h, _d(b)))
+        return b
+
     def debug_matvec(self, which, v):
         v = _f64(v)
-        out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n, 4: self.n}[which])
+        out = np.zeros({0: self.m, 1: self.n, 2: self.n, 3: self.n, 4: self.n, 5: self.n}[which])
         _check(lib().bqp_debug_host_matvec(self._h, which, _d(v), _d(out)))
         return out
 

@@ -111,3 +111,56 @@ def test_adaptive_rho_settings_and_spectral_layout():
         e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, host_only=True, adaptive_rho=True, adaptive_rho_interval=25)
         err, in_use = e.inverse_guard()
         assert in_use and err < 1e-10, (shape, err)
+
+
+def _mpc_problem():
+    """BASELINE config 3: the power-converter MPC program (N = 10) at its initial state, extended by the integer rows."""
+    import scipy.sparse as spa
+    from miosqp_b200 import power_converter as pc
+    drive = pc.Drive(); system = pc.System(drive, 300, 5.5)
+    prog = pc.MpcProgram(system, 10, pc.TailCost(system, 0.95, "delta_550"))
+    q, l, u = prog.vectors(drive.initial_state())
+    ni = len(prog.i_idx)
+    I = spa.identity(prog.P.shape[0], format="csc")[prog.i_idx, :]
+    A = spa.vstack([prog.A, I]).tocsc()
+    return prog.P, q, A, np.append(l, prog.i_l), np.append(u, prog.i_u), np.asarray(prog.i_idx)
+
+
+@pytest.mark.parametrize("case", ["mpc", (60, 90, 6, 0.02, 4), (30, 60, 8, 0.04, 2), (64, 100, 4, 0.02, 3), (20, 40, 10, 0.08, 1), (60, 130, 60, 0.02, 2)])
+def test_small_layout_reproduces_oracle_kkt_solve(oracle_mod, case):
+    """Shared-memory-resident layout of small sparse problems (bqp_small.cu: config 3): mma fragments of the explicit reduced
+    inverse and of P, ELL A and A' -- KKT solves through it agree with the oracle's LDL', the guard reports it in use."""
+    if case == "mpc":
+        P, q, A, l, u, i_idx = _mpc_problem()
+    else:
+        n, m, p, d, seed = case
+        P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(n, m, p, d, seed=seed)[0])
+    n = P.shape[0]
+    o = oracle_mod.OSQP(); o.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3)
+    kw = {} if i_idx is None else {"i_idx": i_idx}
+    e = engine.BatchedQP().setup(P, q, A, l, u, host_only=True, eps_abs=1e-3, eps_rel=1e-3, **kw)
+    err, in_use = e.inverse_guard()
+    assert in_use and err < 1e-10, err
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(n + A.shape[0])
+    ref = o.kkt_solve(b)
+    assert np.abs(e.debug_small_kkt_solve(b) - ref).max() <= 1e-10 * np.abs(ref).max()
+    x = rng.standard_normal(n)
+    assert np.abs(e.debug_matvec(5, x) - e.debug_matvec(2, x)).max() <= 1e-12 * (1 + np.abs(e.debug_matvec(2, x)).max())
+
+
+def test_small_layout_not_built_for_wide_rows_or_dense_problems():
+    P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(130, 200, 10, 0.7, seed=4)[0])
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, host_only=True)
+    with pytest.raises(ValueError):
+        e.debug_small_kkt_solve(np.zeros(130 + A.shape[0]))
+    import os
+    from miosqp_b200 import maxiter_problems
+    pr = maxiter_problems.load_npz(os.path.join(os.path.dirname(__file__), "golden", "max_iter_examples.npz"))[0]       # config 5: A is dense
+    e = engine.BatchedQP().setup(pr["P"], pr["q"], pr["A"], pr["l"], pr["u"], host_only=True)
+    with pytest.raises(ValueError):
+        e.debug_small_kkt_solve(np.zeros(20 + 60))
+    P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(50, 100, 5, 0.7, seed=1)[0])        # config 1: served by the rows kernel
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, host_only=True)
+    with pytest.raises(ValueError):
+        e.debug_small_kkt_solve(np.zeros(50 + A.shape[0]))

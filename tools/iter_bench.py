@@ -22,8 +22,19 @@ ap.add_argument("--n", type=int, default=500)
 ap.add_argument("--m", type=int, default=1000)
 ap.add_argument("--p", type=int, default=50)
 ap.add_argument("--density", type=float, default=0.7)
+ap.add_argument("--mpc", action="store_true", help="BASELINE config 3: the power-converter MPC program (n = 60, m = 150) instead of a random MIQP")
 a = ap.parse_args()
-base = problems.extend(problems.random_miqp(a.n, a.m, a.p, a.density, seed=1, count=1)[0])
+if a.mpc:
+    import scipy.sparse as spa
+    from miosqp_b200 import power_converter as pc
+    drive = pc.Drive(); system = pc.System(drive, 300, 5.5)
+    prog = pc.MpcProgram(system, 10, pc.TailCost(system, 0.95, "delta_550"))
+    q, l, u = prog.vectors(drive.initial_state())
+    A = spa.vstack([prog.A, spa.identity(prog.P.shape[0], format="csc")[prog.i_idx, :]]).tocsc()
+    base = (prog.P, q, A, np.append(l, prog.i_l), np.append(u, prog.i_u), np.asarray(prog.i_idx))
+    a.n = 60
+else:
+    base = problems.extend(problems.random_miqp(a.n, a.m, a.p, a.density, seed=1, count=1)[0])
 P, q, A, l, u, i_idx = base
 rng = np.random.default_rng(0)
 st = dict(eps_abs=1e-12, eps_rel=1e-12, eps_prim_inf=1e-12, eps_dual_inf=1e-12, max_iter=a.iters, check_termination=a.iters)
