@@ -119,6 +119,7 @@ struct BatchCtx {
   // description of the resident batch
   int B = 0, ntiles = 0, tt = 0, threads = 0;
   bool use_grid = false; int grid_ctas = 0;
+  int small_mask = 0;             // widths (npad 32 / 64) among the problems of the planned launch: one kernel instantiation each
   bool use_small = false;         // every problem of the batch has the shared-memory-resident layout (npad <= 64) and no dense kernel serves it
   bool rows_ext = false;          // some problem of the batch uses eq_rho == 2 or adaptive rho: the rows kernel's extended instantiation
   bool use_stream = false, use_panel = false, use_rows = false, w_in_stage = false, round_ok = true; int nslots = 0, slot_bytes = 0, stage_bytes = 0, nw_max = 0, cs = 1;
@@ -597,6 +598,8 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
       g.tile_check_every.push_back(h.s.check_termination);
     }
   }
+  g.small_mask = 0;
+  if (g.use_small) for (const DevInstance &di : dinst) g.small_mask |= di.npad <= 32 ? 1 : 2;
   g.ntiles = (int)g.tiles.size(); g.tt = tt; g.smem = smem; g.nslots = nslots; g.slot_bytes = use_stream ? slot_size(tt) : slot_bytes;
   int rc;
   if ((rc = g.h_ti.reserve(sizeof(int) * (size_t)g.ntiles, g.stream))) return rc;
@@ -862,7 +865,7 @@ static int run_round(BatchCtx &g, std::vector<int> &alive, std::vector<int> &pro
                                 (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
                                 (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
        : g.use_small
-           ? launch_admm_small(64, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
+           ? launch_admm_small(g.small_mask, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles, (const double *)g.d_in.p,
                                (double *)g.d_out.p, (NodeScalars *)g.d_ns.p, (int *)g.d_ti.p, g.smem, g.stream)
            : launch_admm(g.tt, g.threads, (const DevInstance *)g.d_insts.p, (const DevTile *)g.d_tiles.p, g.ntiles,
                          (const double *)g.d_in.p, (double *)g.d_out.p, (double *)g.d_work.p, (NodeScalars *)g.d_ns.p,

@@ -281,7 +281,7 @@ int grid_max_ctas(int device, size_t smem_bytes);                               
 int launch_admm_grid(int nctas, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
                      double *d_work, NodeScalars *d_ns, int *d_tile_iters, unsigned *d_barrier, size_t smem_bytes, void *stream);
 size_t small_smem_bytes(int npad, int m, int blob_bytes);                             // bqp_small.cu
-int launch_admm_small(int npad, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
+int launch_admm_small(int npad_mask /* bit 0: npad 32 present, bit 1: npad 64 */, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
                       NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes, void *stream);
 size_t tile_smem_bytes(int n, int m, int tt, int threads);                           // bqp_kernels.cu
 size_t stream_smem_bytes(int n, int m, int tt, int slot_bytes, int nslots, int w_in_stage);          // bqp_stream.cu

@@ -11,18 +11,19 @@
 // into shared memory, and every iterate (x, z, y, l, u, w of the 8 leaves, [row][8] with the leaf index fastest) lives in
 // shared memory or registers for the whole solve.  The direct-load kernel this replaces for these shapes (bqp_kernels.cu)
 // re-reads the LDL' factor from L2 every iteration behind block-by-block triangular sweeps and keeps the iterates in global
-// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.5 - 1.7 us with 8).
+// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.47 us with 8).
 //
 // Thread map (256 threads): thread tid owns the leaf PAIR p = tid & 3 (leaves 2p, 2p + 1) of
 //   column-space row j = tid >> 2                (x, b, x~: 64 rows),  and of
 //   row-space rows  r = (tid >> 2) + 64 i, i < 3 (z, y, l, u, w),
 // which is also where the C fragment of mma.m8n8k4 puts the product rows of warp w's panel (rows 8 w + (lane >> 2),
 // columns 2 (lane & 3) + {0, 1}): x~ = M b comes out of the FP64 tensor pipe in the registers of the thread that owns x.
-// M's fragments (16 doubles per thread) and the thread's own ELL entries -- value and element offset of 3 rows of A x 4 entries
-// and one row of A' x 8 -- stay in registers for the whole launch: the first version read them from shared memory through a
-// generic predicated loop and spent 800 instructions per warp and iteration, mostly address arithmetic (ncu; the kernel is
-// bound by instruction issue and by the latency of its three short phases, not by memory).  P's fragments are read from
-// shared memory at the termination checks only.
+// The thread's own ELL entries -- value and byte offset of 3 rows of A x 4 entries and one row of A' x 8 -- stay in registers
+// for the whole launch, and the hot loop addresses shared memory by 32-bit address (ld.shared / st.shared): the first version
+// read the entries from shared memory through a generic predicated loop over 64-bit pointers and spent 800 instructions per
+// warp and iteration, now 377.  M's fragments are read from shared memory in the M b phase (in registers as well the kernel
+// spilled and ran at 2.1 us); P's at the termination checks only.  What bounds the kernel now is the shared-memory data pipe
+// (2133 wavefronts per iteration in ~2800 clk, profiles/r02_small_kernel_ncu.json).
 // Sums over rows use a fixed order (entries even / odd, per-thread rows ascending, xor butterflies over the 8 rows of a
 // warp, warps ascending) and every leaf's arithmetic is its own: a node's result does not depend on the other nodes of the
 // tile or on the launch.  Threads of leaf pairs without a leaf skip the vector phases.
@@ -82,6 +83,22 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// shared-memory accesses of the hot loop by 32-bit address: one instruction each (through generic 64-bit pointers every access
+// cost two or three more for the address)
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds1(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
 struct SmallShared {
   DevInstance I;
   DevTile tile;
@@ -112,10 +129,23 @@ __device__ __forceinline__ void red_put(double v0, double v1, double *red, int s
 // Every load is issued before the first use (index -> element -> fma one at a time is pure latency), even and odd entries
 // accumulate separately: the order of addition is the same wherever the row is used.
 template <int W>
-__device__ __forceinline__ double2 reg_dot(const double (&val)[W], const int (&off)[W], const double *__restrict__ v) {
+__device__ __forceinline__ double2 reg_dot(const double (&val)[W], const uint32_t (&off)[W], const double *__restrict__ v) {
   double2 x[W], e = make_double2(0.0, 0.0), o = e;
 #pragma unroll
-  for (int k = 0; k < W; k++) x[k] = *reinterpret_cast<const double2 *>(v + off[k]);
+  for (int k = 0; k < W; k++) x[k] = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(v) + off[k]);
+#pragma unroll
+  for (int k = 0; k < W; k += 2) {
+    e.x = fma(val[k], x[k].x, e.x); e.y = fma(val[k], x[k].y, e.y);
+    o.x = fma(val[k + 1], x[k + 1].x, o.x); o.y = fma(val[k + 1], x[k + 1].y, o.y);
+  }
+  return make_double2(e.x + o.x, e.y + o.y);
+}
+// the same arithmetic with the vector given by its 32-bit shared address (hot loop)
+template <int W>
+__device__ __forceinline__ double2 reg_dot_s(const double (&val)[W], const uint32_t (&off)[W], uint32_t v) {
+  double2 x[W], e = make_double2(0.0, 0.0), o = e;
+#pragma unroll
+  for (int k = 0; k < W; k++) x[k] = lds2(v + off[k]);
 #pragma unroll
   for (int k = 0; k < W; k += 2) {
     e.x = fma(val[k], x[k].x, e.x); e.y = fma(val[k], x[k].y, e.y);
@@ -137,6 +167,7 @@ __device__ __forceinline__ double2 frag_rows_smem(const double *__restrict__ F, 
   return make_double2(c0[0] + c1[0], c0[1] + c1[1]);
 }
 
+template <int NP>      // padded number of variables: 32 or 64 (a CTA whose problem has the other width leaves at once)
 __global__ void __launch_bounds__(kThreads, 1)
 admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restrict__ tiles, const double *__restrict__ in,
                   double *__restrict__ out, NodeScalars *__restrict__ ns, int *__restrict__ tile_iters) {
@@ -151,7 +182,9 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   if (tid < kT) { S.status[tid] = BQP_UNSOLVED; S.iters[tid] = 0; S.newly[tid] = 0; }
   __syncthreads();
   const DevInstance &I = S.I;
-  const int n = I.n, m = I.m, np = I.npad, nn = S.tile.nn, mp = I.s_mp, wa = I.s_wa, wt = I.s_wt, ks = np / 4;
+  if (I.npad != NP) return;
+  constexpr int np = NP, ks = NP / 4;
+  const int n = I.n, m = I.m, nn = S.tile.nn, mp = I.s_mp, wa = I.s_wa, wt = I.s_wt;
   unsigned char *blob = smem_raw + align16(sizeof(SmallShared));
   const double *Mf = reinterpret_cast<const double *>(blob), *Pf = reinterpret_cast<const double *>(blob + I.s_offP);
   const double *Av = reinterpret_cast<const double *>(blob + I.s_offAv), *Tv = reinterpret_cast<const double *>(blob + I.s_offTv);
@@ -218,21 +251,17 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   __syncthreads();                                    // barrier initialised, sx / sl / su / sy complete
   mbar_wait(bar, 0);
   const bool mwarp = warp < np / 8;                   // warps that own a row panel of P (and rows of M)
-  // M's fragments stay in registers for the whole launch
-  double mf[kKS];
-#pragma unroll
-  for (int s = 0; s < kKS; s++) mf[s] = (mwarp && s < ks) ? Mf[((size_t)warp * ks + s) * 32 + lane] : 0.0;
-  // ... and so do the thread's ELL entries when the rows are narrow (config 3: 3 entries per row of A, 5 per row of A'):
+  // The thread's ELL entries stay in registers for the whole launch (config 3: 3 entries per row of A, 5 per row of A'):
   // value + offset of the vector element, padding entries 0.0 * the zero row (reg_dot)
   // (host_setup builds the layout only for problems that fit: wa <= 4, wt <= 8, m <= 192; wider ones stay on bqp_kernels.cu)
   double tv[kRegWT], av[kRegRows][kRegWA], rho3[kRegRows], rinv3[kRegRows];
-  int to[kRegWT], ao[kRegRows][kRegWA];
+  uint32_t to[kRegWT], ao[kRegRows][kRegWA];          // byte offsets of the vector elements
   bool rv[kRegRows];
 #pragma unroll
   for (int k = 0; k < kRegWT; k++) {
     const bool ok = col && act && k < wt;
     tv[k] = ok ? Tv[k * np + j] : 0.0;
-    to[k] = (ok ? (int)Tc[k * np + j] : mp) * kT + 2 * p;
+    to[k] = (uint32_t)(((ok ? (int)Tc[k * np + j] : mp) * kT + 2 * p) * 8);
   }
 #pragma unroll
   for (int i = 0; i < kRegRows; i++) {
@@ -243,7 +272,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     for (int k = 0; k < kRegWA; k++) {
       const bool ok = rv[i] && k < wa;
       av[i][k] = ok ? Av[k * mp + r] : 0.0;
-      ao[i][k] = (ok ? (int)Ac[k * mp + r] : np) * kT + 2 * p;
+      ao[i][k] = (uint32_t)(((ok ? (int)Ac[k * mp + r] : np) * kT + 2 * p) * 8);
     }
   }
 #pragma unroll
@@ -264,9 +293,21 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
 #ifdef BQP_SMALL_DEBUG
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pl = clock64();
 #define PSTAMP(i) do { const long long now_ = clock64(); ph[i] += now_ - pl; pl = now_; } while (0)
+  long long ch[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int nchk = 0;
+#define CSTAMP(i) do { const long long now_ = clock64(); ch[i] += now_ - pl; pl = now_; } while (0)
 #else
 #define PSTAMP(i) do { } while (0)
+#define CSTAMP(i) do { } while (0)
 #endif
+  // 32-bit shared addresses of the hot loop
+  const uint32_t a_sw = smem_u32(sw), a_sb = smem_u32(sb), a_sxt = smem_u32(sxt), a_sx = smem_u32(sx), a_sdx = smem_u32(sdx),
+                 a_sz = smem_u32(sz), a_sy = smem_u32(sy), a_sl = smem_u32(sl), a_su = smem_u32(su), a_sdy = smem_u32(sdy);
+  const uint32_t e_col = (uint32_t)((j * kT + 2 * p) * 8);                                  // this thread's element of a column-space vector
+  uint32_t e_row[kRegRows];
+#pragma unroll
+  for (int i = 0; i < kRegRows; i++) e_row[i] = (uint32_t)(((j + (kThreads / 4) * i) * kT + 2 * p) * 8);
+  const uint32_t a_bfrag = a_sb + (uint32_t)(((lane & 3) * kT + (lane >> 2)) * 8);            // B fragments of b: + 256 bytes per k-step
+  const uint32_t a_mfrag = smem_u32(Mf) + (uint32_t)(((warp * ks) * 32 + lane) * 8);          // A fragments of this warp's panel of M
   int to_check = check_every;                         // iterations until the next termination check (no division in the loop)
   for (iter = 1; iter <= max_iter; iter++) {
     const bool do_check = (--to_check == 0) || iter == max_iter;
@@ -274,32 +315,32 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     PSTAMP(7);
     // b = sigma x - q + A'(rho z - y)
     if (col && act) {
-      const double2 aw = reg_dot<kRegWT>(tv, to, sw);
-      *reinterpret_cast<double2 *>(sb + (size_t)j * kT + 2 * p) = make_double2(sigma * xr.x - qj + aw.x, sigma * xr.y - qj + aw.y);
+      const double2 aw = reg_dot_s<kRegWT>(tv, to, a_sw);
+      sts2(a_sb + e_col, sigma * xr.x - qj + aw.x, sigma * xr.y - qj + aw.y);
     }
     PSTAMP(0);
     __syncthreads();
     PSTAMP(1);
-    // x~ = M b on the FP64 tensor pipe (M's fragments in registers; FP64 mma runs at 16 fma per clock and sub-partition, the
-    // plain fma pipe was measured no faster here and scales with the leaves); x update in the registers of the owner
+    // x~ = M b on the FP64 tensor pipe: 16 fma per clock and sub-partition, the rate of the plain fma pipe, but for all 8 leaves
+    // at once.  M's fragments come from shared memory every iteration (conflict-free 8-byte loads): holding them in registers
+    // was measured slower (2.1 instead of 1.5 us per iteration) -- the register file is what this kernel runs out of.  Every
+    // operand is loaded before the first mma: a load per mma serialises the chain.  x update in the registers of the owner.
     if (mwarp) {
-      double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
-      const double *b = sb + (lane & 3) * kT + (lane >> 2);
+      double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, bv[ks], mf[ks];
 #pragma unroll
-      for (int s = 0; s < kKS; s += 2) {
-        if (s < ks) {
-          dmma(c0, mf[s], b[s * 4 * kT]);
-          dmma(c1, mf[s + 1], b[(s + 1) * 4 * kT]);
-        }
+      for (int s = 0; s < ks; s++) { bv[s] = lds1(a_bfrag + (uint32_t)(s * 4 * kT * 8)); mf[s] = lds1(a_mfrag + (uint32_t)(s * 32 * 8)); }
+#pragma unroll
+      for (int s = 0; s < ks; s += 2) {
+        dmma(c0, mf[s], bv[s]);
+        dmma(c1, mf[s + 1], bv[s + 1]);
       }
       if (act) {
         const double2 xt = make_double2(c0[0] + c1[0], c0[1] + c1[1]);
         const double2 xn = make_double2(alpha * xt.x + (1.0 - alpha) * xr.x, alpha * xt.y + (1.0 - alpha) * xr.y);
-        const size_t e = (size_t)j * kT + 2 * p;
-        *reinterpret_cast<double2 *>(sxt + e) = xt;
+        sts2(a_sxt + e_col, xt.x, xt.y);
         if (do_check) {
-          *reinterpret_cast<double2 *>(sdx + e) = make_double2(xn.x - xr.x, xn.y - xr.y);
-          *reinterpret_cast<double2 *>(sx + e) = xn;
+          sts2(a_sdx + e_col, xn.x - xr.x, xn.y - xr.y);
+          sts2(a_sx + e_col, xn.x, xn.y);
         }
         xr = xn;
       }
@@ -308,31 +349,27 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     __syncthreads();
     PSTAMP(3);
     // z~ = A x~, projection, dual update, next w: the thread's rows j, j + 64, j + 128 together (loads first, then the updates)
-    {
-      if (act) {
-        double2 zt[kRegRows], zp[kRegRows], yv[kRegRows], lo[kRegRows], up[kRegRows];
+    if (act) {
+      double2 zt[kRegRows], zp[kRegRows], yv[kRegRows], lo[kRegRows], up[kRegRows];
 #pragma unroll
-        for (int i = 0; i < kRegRows; i++) {
-          zt[i] = reg_dot<kRegWA>(av[i], ao[i], sxt);       // padding rows: 0.0 * the zero row
-          if (rv[i]) {
-            const size_t e = (size_t)(j + (kThreads / 4) * i) * kT + 2 * p;
-            zp[i] = *reinterpret_cast<const double2 *>(sz + e); yv[i] = *reinterpret_cast<const double2 *>(sy + e);
-            lo[i] = *reinterpret_cast<const double2 *>(sl + e); up[i] = *reinterpret_cast<const double2 *>(su + e);
-          }
+      for (int i = 0; i < kRegRows; i++) {
+        zt[i] = reg_dot_s<kRegWA>(av[i], ao[i], a_sxt);       // padding rows: 0.0 * the zero row
+        if (rv[i]) {
+          zp[i] = lds2(a_sz + e_row[i]); yv[i] = lds2(a_sy + e_row[i]);
+          lo[i] = lds2(a_sl + e_row[i]); up[i] = lds2(a_su + e_row[i]);
         }
+      }
 #pragma unroll
-        for (int i = 0; i < kRegRows; i++) {
-          if (rv[i]) {
-            const size_t e = (size_t)(j + (kThreads / 4) * i) * kT + 2 * p;
-            const double zr0 = alpha * zt[i].x + (1.0 - alpha) * zp[i].x, zr1 = alpha * zt[i].y + (1.0 - alpha) * zp[i].y;
-            const double zn0 = fmin(fmax(zr0 + rinv3[i] * yv[i].x, lo[i].x), up[i].x), zn1 = fmin(fmax(zr1 + rinv3[i] * yv[i].y, lo[i].y), up[i].y);
-            const double dy0 = rho3[i] * (zr0 - zn0), dy1 = rho3[i] * (zr1 - zn1);
-            const double yn0 = yv[i].x + dy0, yn1 = yv[i].y + dy1;
-            *reinterpret_cast<double2 *>(sz + e) = make_double2(zn0, zn1);
-            *reinterpret_cast<double2 *>(sy + e) = make_double2(yn0, yn1);
-            *reinterpret_cast<double2 *>(sw + e) = make_double2(rho3[i] * zn0 - yn0, rho3[i] * zn1 - yn1);
-            if (do_check) *reinterpret_cast<double2 *>(sdy + e) = make_double2(dy0, dy1);
-          }
+      for (int i = 0; i < kRegRows; i++) {
+        if (rv[i]) {
+          const double zr0 = alpha * zt[i].x + (1.0 - alpha) * zp[i].x, zr1 = alpha * zt[i].y + (1.0 - alpha) * zp[i].y;
+          const double zn0 = fmin(fmax(zr0 + rinv3[i] * yv[i].x, lo[i].x), up[i].x), zn1 = fmin(fmax(zr1 + rinv3[i] * yv[i].y, lo[i].y), up[i].y);
+          const double dy0 = rho3[i] * (zr0 - zn0), dy1 = rho3[i] * (zr1 - zn1);
+          const double yn0 = yv[i].x + dy0, yn1 = yv[i].y + dy1;
+          sts2(a_sz + e_row[i], zn0, zn1);
+          sts2(a_sy + e_row[i], yn0, yn1);
+          sts2(a_sw + e_row[i], rho3[i] * zn0 - yn0, rho3[i] * zn1 - yn1);
+          if (do_check) sts2(a_sdy + e_row[i], dy0, dy1);
         }
       }
     }
@@ -359,6 +396,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
           qdx0 = qj * d.x; qdx1 = qj * d.y;
         }
       }
+      CSTAMP(0);
       red_put<0>(dr0, dr1, red, 0, warp, lane);
       red_put<0>(b10, b11, red, 1, warp, lane);
       red_put<0>(b20, b21, red, 2, warp, lane);
@@ -366,6 +404,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       red_put<1>(ln0, ln1, red, 4, warp, lane);
       red_put<0>(ndx0, ndx1, red, 10, warp, lane);
       red_put<1>(qdx0, qdx1, red, 11, warp, lane);
+      CSTAMP(1);
       // row space: A x -> primal residual and its norms; projected dy (certificate of primal infeasibility)
       double pr0 = 0, pr1 = 0, a10 = 0, a11 = 0, a20 = 0, a21 = 0, ndy0 = 0, ndy1 = 0, lh0 = 0, lh1 = 0;
 #pragma unroll
@@ -388,12 +427,14 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         ndy0 = fmax(ndy0, fabs(ei * d.x)); ndy1 = fmax(ndy1, fabs(ei * d.y));
         lh0 += up.x * fmax(d.x, 0.0) + lo.x * fmin(d.x, 0.0); lh1 += up.y * fmax(d.y, 0.0) + lo.y * fmin(d.y, 0.0);
       }
+      CSTAMP(2);
       red_put<0>(pr0, pr1, red, 5, warp, lane);
       red_put<0>(a10, a11, red, 6, warp, lane);
       red_put<0>(a20, a21, red, 7, warp, lane);
       red_put<0>(ndy0, ndy1, red, 8, warp, lane);
       red_put<1>(lh0, lh1, red, 9, warp, lane);
     }
+    CSTAMP(3);
     __syncthreads();                                  // projected dy complete
     {
       double t10 = 0, t11 = 0, t20 = 0, t21 = 0;
@@ -405,6 +446,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
           t20 = fabs(dinvj * pdx.x); t21 = fabs(dinvj * pdx.y);
         }
       }
+      CSTAMP(4);
       red_put<0>(t10, t11, red, 12, warp, lane);
       red_put<0>(t20, t21, red, 13, warp, lane);
       double vu0 = -INFINITY, vu1 = -INFINITY, vl0 = INFINITY, vl1 = INFINITY;
@@ -421,10 +463,12 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
         if (lo.x > -kInfty * kMinScaling) vl0 = fmin(vl0, v0);
         if (lo.y > -kInfty * kMinScaling) vl1 = fmin(vl1, v1);
       }
+      CSTAMP(5);
       red_put<0>(vu0, vu1, red, 14, warp, lane);
       red_put<2>(vl0, vl1, red, 15, warp, lane);
     }
     __syncthreads();
+    CSTAMP(6);
     if (tid < kSlots * kT) {                          // combine the per-warp partials in warp order
       const int slot = tid >> 3, t = tid & 7;
       const bool is_sum = (slot == 3 || slot == 4 || slot == 9 || slot == 11), is_min = (slot == 15);
@@ -486,6 +530,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       }
     }
     __syncthreads();
+    CSTAMP(7);
     // snapshot the iterates of nodes that just terminated (unscaled; NaN for certificates, as osqp returns)
     for (int t = 0; t < nn; t++) {
       if (!S.newly[t]) continue;
@@ -495,7 +540,10 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
       for (int c = tid; c < n; c += kThreads) ox[c] = bad ? NAN : __ldg(I.D + c) * sx[(size_t)c * kT + t];
       for (int i = tid; i < m; i += kThreads) oy[i] = bad ? NAN : I.cinv * __ldg(I.E + i) * sy[(size_t)i * kT + t];
     }
-    PSTAMP(6);
+    CSTAMP(8);
+#ifdef BQP_SMALL_DEBUG
+    nchk++;
+#endif
     if (S.remaining == 0) break;
   }
 #ifdef BQP_SMALL_DEBUG
@@ -503,6 +551,9 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     const double it = (double)(iter > max_iter ? max_iter : iter);
     printf("small kernel thread %d, %d iterations, clk per iteration: A' %.0f | wait %.0f | M b %.0f | wait %.0f | A + update %.0f | wait %.0f | checks (total) %lld | loop overhead %.0f\n",
            tid, (int)it, ph[0] / it, ph[1] / it, ph[2] / it, ph[3] / it, ph[4] / it, ph[5] / it, ph[6], ph[7] / it);
+    printf("  %d checks, clk per check: P x + A'y + column stats %lld | their reductions %lld | A x + row stats %lld | their reductions + wait %lld | "
+           "A'dy + P dx %lld | A dx + reductions %lld | wait %lld | combine + decision %lld | snapshot %lld\n", nchk, ch[0] / nchk, ch[1] / nchk, ch[2] / nchk,
+           ch[3] / nchk, ch[4] / nchk, ch[5] / nchk, ch[6] / nchk, ch[7] / nchk, ch[8] / nchk);
   }
 #endif
   __syncthreads();
@@ -558,16 +609,20 @@ size_t small_smem_bytes(int npad, int m, int blob_bytes) {
   return align16(sizeof(SmallShared)) + (size_t)blob_bytes + 8 * ((size_t)4 * (npad + 1) * kT + (size_t)7 * (mp + 1) * kT + (size_t)kSlots * kWarps * kT);
 }
 
-int launch_admm_small(int npad, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
+int launch_admm_small(int npad_mask, const DevInstance *d_insts, const DevTile *d_tiles, int ntiles, const double *d_in, double *d_out,
                       NodeScalars *d_ns, int *d_tile_iters, size_t smem_bytes, void *stream) {
-  if (npad > kNPmax || npad % 8 != 0 || smem_bytes > (size_t)kMaxSmem) return BQP_E_ARG;
+  // npad_mask: bit 0 -- some problem of the launch has npad = 32, bit 1 -- npad = 64.  One launch per width over ALL tiles: a CTA
+  // whose problem has the other width leaves at once
+  if (!(npad_mask & 3) || smem_bytes > (size_t)kMaxSmem) return BQP_E_ARG;
   // many host threads launch concurrently (one context each): raise the attribute once
   static std::atomic<int> attr_set{0};
   if (!attr_set.load()) {
-    if (cudaFuncSetAttribute(admm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem) != cudaSuccess) return BQP_E_CUDA;
+    if (cudaFuncSetAttribute(admm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem) != cudaSuccess) return BQP_E_CUDA;
+    if (cudaFuncSetAttribute(admm_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem) != cudaSuccess) return BQP_E_CUDA;
     attr_set.store(1);
   }
-  admm_small_kernel<<<ntiles, kThreads, smem_bytes, (cudaStream_t)stream>>>(d_insts, d_tiles, d_in, d_out, d_ns, d_tile_iters);
+  if (npad_mask & 1) admm_small_kernel<32><<<ntiles, kThreads, smem_bytes, (cudaStream_t)stream>>>(d_insts, d_tiles, d_in, d_out, d_ns, d_tile_iters);
+  if (npad_mask & 2) admm_small_kernel<64><<<ntiles, kThreads, smem_bytes, (cudaStream_t)stream>>>(d_insts, d_tiles, d_in, d_out, d_ns, d_tile_iters);
   return cudaGetLastError() == cudaSuccess ? BQP_OK : BQP_E_CUDA;
 }
 
