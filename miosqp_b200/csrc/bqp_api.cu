@@ -439,9 +439,10 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
         auto it = prio.find(key);
         if (it == prio.end()) prio[key] = remaining[b]; else it->second = std::max(it->second, remaining[b]);
       }
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return prio[std::make_pair(progress[a], g.node_inst[a])] > prio[std::make_pair(progress[b], g.node_inst[b])];
-      });
+      // one look-up per node, not two per comparison: with 800 running leaves the sort used to cost more than the launch overhead
+      std::vector<double> pr(g.node_inst.size(), 0.0);
+      for (int b : order) pr[(size_t)b] = prio[std::make_pair(progress[b], g.node_inst[b])];
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pr[(size_t)a] > pr[(size_t)b]; });
     }
     for (int b : order) {
       bqp_instance *h = g.node_inst[b];
@@ -494,7 +495,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
     if ((rc = g.d_gbar.reserve(sizeof(unsigned), g.stream))) return rc;
     CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
-    if (!g.fast) CK(ctx_sync(g));       // fast path: g.tiles / g.dinst_host live until the next plan, which comes after the launch's wait
+    // no wait here: g.tiles / g.dinst_host are members, overwritten by the next plan only -- after the wait that ends this round
     g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
     return BQP_OK;
   }
@@ -609,7 +610,7 @@ static int plan_round(BatchCtx &g, const std::vector<int> &alive, const std::vec
   if ((rc = g.d_insts.reserve(sizeof(DevInstance) * dinst.size(), g.stream))) return rc;
   CK(cudaMemcpyAsync(g.d_tiles.p, g.tiles.data(), sizeof(DevTile) * g.tiles.size(), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemcpyAsync(g.d_insts.p, dinst.data(), sizeof(DevInstance) * dinst.size(), cudaMemcpyHostToDevice, g.stream));
-  if (!g.fast) CK(ctx_sync(g));   // fast path: g.tiles / g.dinst_host live until the next plan, which comes after the launch's wait
+  // no wait here: g.tiles / g.dinst_host are members, overwritten by the next plan only -- after the wait that ends this round
   g.round_h2d_bytes = (long long)(sizeof(DevTile) * g.tiles.size() + sizeof(DevInstance) * dinst.size());
   return BQP_OK;
 }
