@@ -565,7 +565,17 @@ class ResidentBatch(object):
 
 
 def solve_multi(qps, l, u, x0, y0):
-    """Nodes of several set-up problems in ONE launch.  All arguments are sequences of length B."""
-    rb = ResidentBatch(qps, l, u, x0, y0)
-    rb.run()
-    return rb.download()
+    """Nodes of several set-up problems in ONE submission (bqp_solve_multi: upload, launches and read-back behind one C call; a
+    kernel that needs a single launch is waited for once).  All arguments are sequences of length B."""
+    qps = list(qps)
+    B = len(qps)
+    keep = [[_f64(a) for a in seq] for seq in (l, u, x0, y0)]
+    hs = (C.c_void_p * B)(*[q._h.value for q in qps])
+    xs = [np.empty(q.n) for q in qps]
+    ys = [np.empty(q.m) for q in qps]
+    sc = _Scalars()
+    sc.status = np.empty(B, np.int32); sc.iters = np.empty(B, np.int32)
+    sc.obj = np.empty(B); sc.pri_res = np.empty(B); sc.dua_res = np.empty(B); sc.lower = np.empty(B)
+    out = _node_out(sc)
+    _check(lib().bqp_solve_multi(B, hs, *[_ptr_array(k) for k in keep], _ptr_array(xs), _ptr_array(ys), C.byref(out)))
+    return xs, ys, sc

@@ -145,6 +145,28 @@ def test_small_kernel_results_do_not_depend_on_the_batch(oracle_mod):
         assert np.array_equal(one.x[0], full.x[b]) and np.array_equal(one.y[0], full.y[b]) and one.lower[0] == full.lower[b]
 
 
+@pytest.mark.parametrize("shape", [(60, 130, 60, 0.02, 2), (30, 60, 8, 0.5, 5), (600, 900, 20, 0.05, 12)])
+def test_single_wait_and_stepwise_submission_agree_bit_for_bit(shape):
+    """bqp_solve_multi waits once per single-launch batch (shared-memory-resident, direct-load and whole-GPU kernels); the staged
+    bqp_batch_upload / run / download calls wait after every step.  Same kernels, same inputs: identical bits."""
+    n, m, p, d, seed = shape
+    P, q, A, l, u, i_idx = problems.extend(problems.random_miqp(n, m, p, d, seed=seed)[0])
+    e = engine.BatchedQP().setup(P, q, A, l, u, i_idx=i_idx, **QP)
+    ls, us = problems.branched_nodes(l, u, len(i_idx), 9, np.random.default_rng(4))
+    qps = [e] * 9; X0 = [np.zeros(n)] * 9; Y0 = [np.zeros(A.shape[0])] * 9
+    xs, ys, sc = engine.solve_multi(qps, list(ls), list(us), X0, Y0)
+    kernel = engine.last_timing()["kernel"]
+    assert kernel in (0, 4, 5) and engine.last_timing()["launches"] == 1
+    rb = engine.ResidentBatch(qps, list(ls), list(us), X0, Y0)
+    rb.run()
+    xs2, ys2, sc2 = rb.download()
+    assert engine.last_timing()["kernel"] == kernel
+    assert list(sc.status) == list(sc2.status) and list(sc.iters) == list(sc2.iters)
+    for b in range(9):
+        assert np.array_equal(xs[b], xs2[b], equal_nan=True) and np.array_equal(ys[b], ys2[b], equal_nan=True)
+    assert np.array_equal(sc.lower, sc2.lower, equal_nan=True) and np.array_equal(sc.pri_res, sc2.pri_res, equal_nan=True)
+
+
 def test_wide_rows_stay_on_the_direct_load_kernel(oracle_mod):
     """More than 4 entries in a row of A (or 8 in a column): no shared-memory layout, the direct-load kernel serves it."""
     pr = problems.random_miqp(30, 60, 8, 0.5, seed=5)[0]
