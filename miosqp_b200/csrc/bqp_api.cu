@@ -746,8 +746,8 @@ static void select_kernel(BatchCtx &g) {
     g.use_grid = true; g.use_panel = g.use_stream = false; g.grid_ctas = sms;
     for (bqp_instance *inst : g.node_inst) if (!inst->h.gd.built) g.use_grid = false;
   }
-  // shared-memory-resident kernel: small problems (npad <= 64) that no dense kernel serves -- configs 3 and 5 -- or, with
-  // BQP_KERNEL=small, every batch whose problems all carry the layout (BQP_SMALL_ALL=1 at setup: config 1 too)
+  // shared-memory-resident kernel: every problem of the batch carries the layout (small sparse problems that no dense kernel
+  // serves: config 3) and no other kernel was asked for
   g.use_small = false;
   {
     const char *e = std::getenv("BQP_KERNEL");

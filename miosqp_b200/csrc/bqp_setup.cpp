@@ -922,14 +922,13 @@ int host_setup(const bqp_problem *p, const bqp_settings *s, HostInstance *h) {
       if (!(worst <= tol)) { h->gd = HostGridL(); if (!h->pn.built) h->pn_rejected = true; }
     }
   }
-  // shared-memory-resident layout for small problems the dense kernels do not serve (configs 3 and 5); fixed rho typed at
+  // shared-memory-resident layout for small sparse problems the dense kernels do not serve (config 3); fixed rho typed at
   // setup only.  Same guard of the explicit inverse; BQP_SMALL=0 keeps them on the direct-load LDL' kernel
   h->sm = HostSmall();
   {
     int want = 1;
     if (const char *e = std::getenv("BQP_SMALL")) want = std::atoi(e);
-    const bool also_dense = std::getenv("BQP_SMALL_ALL") && std::atoi(std::getenv("BQP_SMALL_ALL")) != 0;   // experiments: config 1 too
-    if (want && np_ <= 64 && (!h->pn.built || also_dense) && !h->pn_rejected && !s->adaptive_rho && s->eq_rho != 2 &&
+    if (want && np_ <= 64 && !h->pn.built && !h->pn_rejected && !s->adaptive_rho && s->eq_rho != 2 &&
         build_small(h, arows, atrows, prows, S)) {
       double tol = 1e-10;
       if (const char *e = std::getenv("BQP_INVERSE_TOL")) tol = std::atof(e);
