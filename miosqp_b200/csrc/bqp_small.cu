@@ -11,7 +11,7 @@
 // into shared memory, and every iterate (x, z, y, l, u, w of the 8 leaves, [row][8] with the leaf index fastest) lives in
 // shared memory or registers for the whole solve.  The direct-load kernel this replaces for these shapes (bqp_kernels.cu)
 // re-reads the LDL' factor from L2 every iteration behind block-by-block triangular sweeps and keeps the iterates in global
-// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.47 us with 8).
+// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.25 us with 8).
 //
 // Thread map (256 threads): thread tid owns the leaf PAIR p = tid & 3 (leaves 2p, 2p + 1) of
 //   column-space row j = tid >> 2                (x, b, x~: 64 rows),  and of
@@ -23,7 +23,8 @@
 // read the entries from shared memory through a generic predicated loop over 64-bit pointers and spent 800 instructions per
 // warp and iteration, now 377.  M's fragments are read from shared memory in the M b phase (in registers as well the kernel
 // spilled and ran at 2.1 us); P's at the termination checks only.  What bounds the kernel now is the shared-memory data pipe
-// (2133 wavefronts per iteration in ~2800 clk, profiles/r02_small_kernel_ncu.json).
+// (profiles/r02_small_kernel_ncu.json); the bounds l, u and the iterates z, y of the thread's own rows therefore live in
+// registers too -- shared memory sees z and y at the termination checks only.
 // Sums over rows use a fixed order (entries even / odd, per-thread rows ascending, xor butterflies over the 8 rows of a
 // warp, warps ascending) and every leaf's arithmetic is its own: a node's result does not depend on the other nodes of the
 // tile or on the launch.  Threads of leaf pairs without a leaf skip the vector phases.
@@ -308,6 +309,21 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   for (int i = 0; i < kRegRows; i++) e_row[i] = (uint32_t)(((j + (kThreads / 4) * i) * kT + 2 * p) * 8);
   const uint32_t a_bfrag = a_sb + (uint32_t)(((lane & 3) * kT + (lane >> 2)) * 8);            // B fragments of b: + 256 bytes per k-step
   const uint32_t a_mfrag = smem_u32(Mf) + (uint32_t)(((warp * ks) * 32 + lane) * 8);          // A fragments of this warp's panel of M
+  // the leaf pair's bounds of the thread's rows are constant over the solve: registers (1.40 -> 1.32 us per iteration)
+  double2 lo3[kRegRows], up3[kRegRows];
+#pragma unroll
+  for (int i = 0; i < kRegRows; i++) {
+    lo3[i] = rv[i] ? lds2(a_sl + e_row[i]) : make_double2(0.0, 0.0);
+    up3[i] = rv[i] ? lds2(a_su + e_row[i]) : make_double2(0.0, 0.0);
+  }
+  // ... and z, y of the thread's rows live in registers between the termination checks (1.32 -> 1.25 us): only their owner
+  // touches them in an iteration; shared memory sees them at the checks (A'y, the snapshot of a finished leaf)
+  double2 z3[kRegRows], y3[kRegRows];
+#pragma unroll
+  for (int i = 0; i < kRegRows; i++) {
+    z3[i] = rv[i] ? lds2(a_sz + e_row[i]) : make_double2(0.0, 0.0);
+    y3[i] = rv[i] ? lds2(a_sy + e_row[i]) : make_double2(0.0, 0.0);
+  }
   int to_check = check_every;                         // iterations until the next termination check (no division in the loop)
   for (iter = 1; iter <= max_iter; iter++) {
     const bool do_check = (--to_check == 0) || iter == max_iter;
@@ -350,24 +366,25 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
     PSTAMP(3);
     // z~ = A x~, projection, dual update, next w: the thread's rows j, j + 64, j + 128 together (loads first, then the updates)
     if (act) {
-      double2 zt[kRegRows], zp[kRegRows], yv[kRegRows], lo[kRegRows], up[kRegRows];
+      double2 zt[kRegRows], zp[kRegRows], yv[kRegRows];
 #pragma unroll
       for (int i = 0; i < kRegRows; i++) {
         zt[i] = reg_dot_s<kRegWA>(av[i], ao[i], a_sxt);       // padding rows: 0.0 * the zero row
-        if (rv[i]) {
-          zp[i] = lds2(a_sz + e_row[i]); yv[i] = lds2(a_sy + e_row[i]);
-          lo[i] = lds2(a_sl + e_row[i]); up[i] = lds2(a_su + e_row[i]);
-        }
+        zp[i] = z3[i]; yv[i] = y3[i];
       }
 #pragma unroll
       for (int i = 0; i < kRegRows; i++) {
         if (rv[i]) {
           const double zr0 = alpha * zt[i].x + (1.0 - alpha) * zp[i].x, zr1 = alpha * zt[i].y + (1.0 - alpha) * zp[i].y;
-          const double zn0 = fmin(fmax(zr0 + rinv3[i] * yv[i].x, lo[i].x), up[i].x), zn1 = fmin(fmax(zr1 + rinv3[i] * yv[i].y, lo[i].y), up[i].y);
+          // osqp's c_max / c_min are compare-and-select macros; FP64 fmax / fmin compile to a DSETP + SEL + FSEL + LOP3 sequence
+          // each (measured: 1.49 -> 1.40 us per iteration).  Same values for every comparable pair of operands
+          const double t0 = zr0 + rinv3[i] * yv[i].x, t1 = zr1 + rinv3[i] * yv[i].y;
+          const double m0 = t0 > lo3[i].x ? t0 : lo3[i].x, m1 = t1 > lo3[i].y ? t1 : lo3[i].y;
+          const double zn0 = m0 < up3[i].x ? m0 : up3[i].x, zn1 = m1 < up3[i].y ? m1 : up3[i].y;
           const double dy0 = rho3[i] * (zr0 - zn0), dy1 = rho3[i] * (zr1 - zn1);
           const double yn0 = yv[i].x + dy0, yn1 = yv[i].y + dy1;
-          sts2(a_sz + e_row[i], zn0, zn1);
-          sts2(a_sy + e_row[i], yn0, yn1);
+          z3[i] = make_double2(zn0, zn1); y3[i] = make_double2(yn0, yn1);
+          if (do_check) { sts2(a_sz + e_row[i], zn0, zn1); sts2(a_sy + e_row[i], yn0, yn1); }      // other threads read y at the checks only
           sts2(a_sw + e_row[i], rho3[i] * zn0 - yn0, rho3[i] * zn1 - yn1);
           if (do_check) sts2(a_sdy + e_row[i], dy0, dy1);
         }
