@@ -172,3 +172,43 @@ def test_wide_rows_stay_on_the_direct_load_kernel(oracle_mod):
     pr = problems.random_miqp(30, 60, 8, 0.5, seed=5)[0]
     _compare(pr, 5, 0, QP, oracle_mod=oracle_mod)
     assert engine.last_timing()["kernel"] == 0
+
+
+def test_small_problems_through_the_bnb_drivers():
+    """Branch and bound on small sparse MIQPs (shared-memory-resident kernel) through every driver: one tree at a time (native
+    replay, single-wait submissions), lock-step, one stream per tree, rolling session -- and the Python replay: same decisions,
+    node and ADMM iteration counts, incumbents to 1e-9."""
+    import miosqp_b200
+    cases = [(30, 60, 8, 0.04, 2), (20, 40, 10, 0.08, 1), (60, 130, 60, 0.02, 2)]
+
+    def trees(replay):
+        out = []
+        for n, m, p, d, seed in cases:
+            pr = problems.random_miqp(n, m, p, d, seed=seed)[0]
+            s = miosqp_b200.MIOSQP()
+            s.setup(pr['P'], pr['q'], pr['A'], pr['l'], pr['u'], pr['i_idx'], pr['i_l'], pr['i_u'],
+                    dict(problems.RANDOM_MIQP_SETTINGS, replay=replay, speculation=4), dict(problems.RANDOM_MIQP_QP_SETTINGS))
+            out.append(s)
+        return out
+
+    def sig(res, solvers):
+        return [(r.status, s.work.iter_num, int(s.work.osqp_iter), [tuple(d) for d in s.work.decisions]) for r, s in zip(res, solvers)]
+
+    runs = {}
+    for driver in ("single", "python", "lockstep", "async", "rolling"):
+        solvers = trees(None if driver == "python" else 'native')
+        if driver in ("single", "python"):
+            res = [s.solve() for s in solvers]
+            expect_small()
+        else:
+            res = miosqp_b200.solve_many(solvers, async_threads=(0 if driver == "async" else None), rolling=(driver == "rolling"))
+        runs[driver] = (sig(res, solvers), [float(r.upper_glob) for r in res], [np.array(r.x) for r in res])
+        for s in solvers:
+            s.work.solver.free()
+    ref = runs["single"]
+    assert all(it > 1 for _, it, _, _ in ref[0])                       # every tree branched at least once
+    for driver, run in runs.items():
+        assert run[0] == ref[0], driver
+        for k in range(len(cases)):
+            assert abs(run[1][k] - ref[1][k]) <= 1e-9 * (1 + abs(ref[1][k])), driver
+            assert np.abs(run[2][k] - ref[2][k]).max() <= 1e-9 * (1 + np.abs(ref[2][k]).max()), driver
