@@ -115,12 +115,23 @@ struct Tree {
     const unsigned hw = std::thread::hardware_concurrency();
     return (int)std::max(2u, std::min(16u, hw ? hw : 2u));
   }
+  // the same for a matrix that stores every entry (column j = M.x + j * rows): no index stream, the rows of the range vectorise
+  static void matvec_rows_dense(const Csc &M, const double *x, double *y, int r0, int r1) {
+    for (int r = r0; r < r1; r++) y[r] = 0.0;
+    const size_t rows = (size_t)M.rows;
+    for (int j = 0; j < M.cols; j++) {
+      const double xj = x[j];
+      const double *__restrict__ c = M.x + (size_t)j * rows;
+      for (int r = r0; r < r1; r++) y[r] += c[r] * xj;
+    }
+  }
   static void matvec(const Csc &M, const double *x, double *y, int threads = 0, bool dense = false) {
     if (threads > 1) {
       std::vector<std::thread> th;
+      auto fn = dense ? matvec_rows_dense : matvec_rows;
       for (int t = 1; t < threads; t++)
-        th.emplace_back(matvec_rows, std::cref(M), x, y, (int)((long long)M.rows * t / threads), (int)((long long)M.rows * (t + 1) / threads));
-      matvec_rows(M, x, y, 0, (int)((long long)M.rows / threads));
+        th.emplace_back(fn, std::cref(M), x, y, (int)((long long)M.rows * t / threads), (int)((long long)M.rows * (t + 1) / threads));
+      fn(M, x, y, 0, (int)((long long)M.rows / threads));
       for (auto &t : th) t.join();
       return;
     }
@@ -148,7 +159,7 @@ struct Tree {
   }
   double obj(const Vec &x) {                     // data.py:99-103
     tmp.resize(std::max(n, m_ext));
-    if (par_P < 0) { par_P = par_threads(P); dense_P = par_P == 0 && is_dense(P); }
+    if (par_P < 0) { par_P = par_threads(P); dense_P = is_dense(P); }
     matvec(P, x.data(), tmp.data(), par_P, dense_P);
     double a = 0.0, b = 0.0;
     for (int j = 0; j < n; j++) { a += x[j] * tmp[j]; b += q[j] * x[j]; }
