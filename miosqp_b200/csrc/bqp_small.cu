@@ -218,7 +218,7 @@ admm_small_kernel(const DevInstance *__restrict__ insts, const DevTile *__restri
   // ------------------------------------------------------------------ prologue (node.py:102-105), overlapping the copy
   const int p = tid & 3, j = tid >> 2;                // node pair; column-space row
   // pairs that hold a leaf: the others' threads skip the vector phases (a tile of 1 or 2 leaves moves a quarter of the
-  // shared-memory traffic of a full one; the host narrows the tiles when the launch has SMs to spare)
+  // shared-memory traffic of a full one -- its warps still issue every instruction, so the host does not narrow the tiles)
   const int npairs = (nn + 1) >> 1;
   const bool act = p < npairs;
   const bool col = j < np, colr = j < n;
