@@ -11,7 +11,7 @@
 // into shared memory, and every iterate (x, z, y, l, u, w of the 8 leaves, [row][8] with the leaf index fastest) lives in
 // shared memory or registers for the whole solve.  The direct-load kernel this replaces for these shapes (bqp_kernels.cu)
 // re-reads the LDL' factor from L2 every iteration behind block-by-block triangular sweeps and keeps the iterates in global
-// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.25 us with 8).
+// memory (3.9 us per iteration on the config-3 problem with ONE leaf per CTA; here 1.13 us with 8).
 //
 // Thread map (256 threads): thread tid owns the leaf PAIR p = tid & 3 (leaves 2p, 2p + 1) of
 //   column-space row j = tid >> 2                (x, b, x~: 64 rows),  and of
@@ -133,7 +133,10 @@ template <int W>
 __device__ __forceinline__ double2 reg_dot(const double (&val)[W], const uint32_t (&off)[W], const double *__restrict__ v) {
   double2 x[W], e = make_double2(0.0, 0.0), o = e;
 #pragma unroll
-  for (int k = 0; k < W; k++) x[k] = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(v) + off[k]);
+  for (int k = 0; k < W; k++) {
+    x[k] = make_double2(0.0, 0.0);
+    if (val[k] != 0.0) x[k] = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(v) + off[k]);
+  }
 #pragma unroll
   for (int k = 0; k < W; k += 2) {
     e.x = fma(val[k], x[k].x, e.x); e.y = fma(val[k], x[k].y, e.y);
@@ -146,7 +149,10 @@ template <int W>
 __device__ __forceinline__ double2 reg_dot_s(const double (&val)[W], const uint32_t (&off)[W], uint32_t v) {
   double2 x[W], e = make_double2(0.0, 0.0), o = e;
 #pragma unroll
-  for (int k = 0; k < W; k++) x[k] = lds2(v + off[k]);
+  for (int k = 0; k < W; k++) {      // padding entries (and explicit zeros) are not loaded: 1.25 -> 1.13 us per iteration at config 3, where
+    x[k] = make_double2(0.0, 0.0);   // 56 % of the 4-wide slots of A are padding
+    if (val[k] != 0.0) x[k] = lds2(v + off[k]);
+  }
 #pragma unroll
   for (int k = 0; k < W; k += 2) {
     e.x = fma(val[k], x[k].x, e.x); e.y = fma(val[k], x[k].y, e.y);
